@@ -1,0 +1,220 @@
+/*
+ * scn_b200.h -- C ABI of the B200-native sparse-convolution hot path.
+ *
+ * Drop-in boundary: the reference's ndsis/modules import the Python
+ * namespace `sparseconvnet` (module_factory.py:5, model.py:6, custom_operations.py:4,
+ * roi_select_sparse.py:3).  Upstream SparseConvNet binds that namespace to native code
+ * through a pybind11 module `sparseconvnet.SCN` whose free functions take a `Metadata<d>&`
+ * plus at::Tensors (`X_updateOutput / X_updateGradInput / X_backward`).  This header is
+ * what that binding layer is replaced with: plain pointers + sizes + a CUDA stream, no
+ * torch types.  Every entry point cites the reference call site it serves.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - features are row-major fp32 [rows, C] with an explicit leading dimension `ld` (floats);
+ *   - "keys" are packed voxel coordinates  b<<48 | x<<32 | y<<16 | z  (each field 16 bit);
+ *   - neighbour maps are offset-major int32 [K, n_out], -1 = inactive ("output-stationary
+ *     rulebook": map[o][r] is the input row that contributes to output row r through
+ *     kernel offset o; offsets enumerate the filter box with the LAST dimension fastest,
+ *     exactly like SparseConvNet's rulebooks);
+ *   - nothing here allocates: the caller owns every buffer (the Python host uses the torch
+ *     caching allocator); functions only enqueue work on `stream`;
+ *   - return value 0 = ok, otherwise an SCN_ERR_* code; scn_last_error() gives the text
+ *     (thread-local).  The library never aborts the process.
+ */
+#ifndef SCN_B200_H_
+#define SCN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* scn_stream_t; /* cudaStream_t */
+
+#define SCN_OK 0
+#define SCN_ERR_INVALID 1 /* bad argument (shape / alignment / unsupported size) */
+#define SCN_ERR_CUDA 2    /* a CUDA runtime call failed (incl. out of memory)   */
+
+#define SCN_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define SCN_SCAN_BLOCK 4096 /* items per scan block; tmp needs scn_scan_tmp_elems(n) ints */
+
+/* epilogue flags for the convolution kernels */
+#define SCN_EPI_RELU 1      /* out = max(out, 0)                      */
+#define SCN_EPI_ADD 2       /* out += residual[row] (same shape/ld)   */
+
+const char* scn_last_error(void);
+int scn_version(void);
+/* number of SMs / tcgen05 availability of the current device (0 if no device). */
+int scn_device_sm_count(void);
+int scn_device_is_sm100(void);
+/* number of kernels this library has launched in this process (monotonic; bench accounting) */
+int64_t scn_launch_count(void);
+
+/* ------------------------------------------------------------------ rulebook builder ------
+ * Replaces SparseConvNet Metadata<d> (CPU hash maps).  Call sites: CustomInputLayer.forward
+ * custom_operations.py:67-86; RawToTensor/TensorToTensor combiners roi_select_sparse.py:75-84,
+ * 113-122; get_spatial_locations custom_operations.py:26-30, roi_select_sparse.py:103. */
+
+/* coords int64 [P, ncol] (x,y,z[,b]); ncol 3 => b = 0.  err_flag (device int, caller zeroes it)
+ * is set to 1 if a coordinate is outside [0, 65534]. */
+int scn_pack_coords(const int64_t* coords, int P, int ncol, uint64_t* keys, int* err_flag,
+                    scn_stream_t stream);
+/* inverse: keys -> int64 [n,4] (x,y,z,b)  (get_spatial_locations) */
+int scn_unpack_keys(const uint64_t* keys, int n, int64_t* coords, scn_stream_t stream);
+
+/* open-addressing table: tab_keys[cap] (uint64), tab_vals[cap] (int32); cap = power of two */
+int scn_hash_clear(uint64_t* tab_keys, int32_t* tab_vals, uint32_t cap, scn_stream_t stream);
+/* insert keys[i] -> min(i)  (value = index of first appearance) */
+int scn_hash_insert_first(const uint64_t* keys, int P, uint64_t* tab_keys, int32_t* tab_vals,
+                          uint32_t cap, scn_stream_t stream);
+/* first[i] = 1 iff point i is the first appearance of its voxel */
+int scn_hash_first_flags(const uint64_t* keys, int P, const uint64_t* tab_keys,
+                         const int32_t* tab_vals, uint32_t cap, int32_t* first,
+                         scn_stream_t stream);
+/* exclusive prefix sum over n int32; out has n+1 entries (out[n] = total). */
+int64_t scn_scan_tmp_elems(int64_t n);
+int scn_exclusive_scan(const int32_t* in, int32_t* out, int64_t n, int32_t* tmp,
+                       scn_stream_t stream);
+/* point_row[i] = rank[first point of i's voxel]; row_keys[rank[i]] = keys[i] for first points.
+ * rank = exclusive scan of first[]. */
+int scn_hash_assign_rows(const uint64_t* keys, int P, const uint64_t* tab_keys,
+                         const int32_t* tab_vals, uint32_t cap, const int32_t* rank,
+                         int32_t* point_row, uint64_t* row_keys, scn_stream_t stream);
+/* tab_vals[s] = rank[tab_vals[s]] for occupied slots: the table now maps key -> row */
+int scn_hash_finalize(const uint64_t* tab_keys, int32_t* tab_vals, uint32_t cap,
+                      const int32_t* rank, scn_stream_t stream);
+/* rows[i] = lookup(keys[i]) or -1 */
+int scn_hash_lookup(const uint64_t* keys, int n, const uint64_t* tab_keys,
+                    const int32_t* tab_vals, uint32_t cap, int32_t* rows, scn_stream_t stream);
+
+/* CSR of the input rule (row -> its points, ascending point index): counts then fill.
+ * row_cnt[N] must be zeroed by the caller; row_ptr = exclusive scan of row_cnt (N+1);
+ * cursor[N] zeroed by the caller.  SparseConvNet InputLayer.h rule rows [count, idx...]. */
+int scn_rule_count(const int32_t* point_row, int P, int32_t* row_cnt, scn_stream_t stream);
+int scn_rule_fill(const int32_t* point_row, int P, const int32_t* row_ptr, int32_t* cursor,
+                  int32_t* row_pts, scn_stream_t stream);
+int scn_rule_sort(const int32_t* row_ptr, int N, int32_t* row_pts, scn_stream_t stream);
+
+/* submanifold neighbour map for an (fx,fy,fz) filter (odd sizes): map [fx*fy*fz, N].
+ * SubmanifoldConvolution call sites module_factory.py:377-414. */
+int scn_subm_map(const uint64_t* row_keys, int N, const uint64_t* tab_keys,
+                 const int32_t* tab_vals, uint32_t cap, int fx, int fy, int fz, int32_t* map,
+                 scn_stream_t stream);
+
+/* strided level (filter == stride): parent key and in-box offset index of every fine row.
+ * Convolution/Deconvolution/pooling call sites module_factory.py:221-271,315-354. */
+int scn_stride_keys(const uint64_t* row_keys, int N, int sx, int sy, int sz,
+                    uint64_t* parent_keys, int32_t* offs, scn_stream_t stream);
+/* cmap [K, n_out] (caller pre-fills with -1): cmap[offs[i]][parent_row[i]] = i
+ * dmap [K, n_in]: dmap[o][i] = (o == offs[i]) ? parent_row[i] : -1 */
+int scn_strided_maps(const int32_t* parent_row, const int32_t* offs, int n_in, int n_out, int K,
+                     int32_t* cmap, int32_t* dmap, scn_stream_t stream);
+
+/* ------------------------------------------------------------------ convolution family -----
+ * out[r] = bias + sum_o  in[map[o][r]] . W[o]      (SubmanifoldConvolution, Convolution,
+ * Deconvolution, NetworkInNetwork and all their input-gradients share this form).
+ * map == NULL means K == 1 with the identity map (NetworkInNetwork, module_factory.py:357-374). */
+
+/* bytes of the packed weight image for the tcgen05 kernel */
+int64_t scn_conv_weight_image_bytes(int K, int Cin, int Cout);
+/* w [K, Cin, Cout] fp32 (SparseConvNet layout [K, 1, Cin, Cout]).  transpose=1 packs W[o]^T
+ * (roles of Cin/Cout swapped: Cin is then the OUTPUT width); reverse=1 packs offset K-1-o at o
+ * (input-gradient of a submanifold convolution).  Values are rounded to TF32 (rna). */
+int scn_conv_pack_weights(const float* w, int K, int Cin, int Cout, int transpose, int reverse,
+                          void* image, scn_stream_t stream);
+/* TF32 tcgen05 implicit gather-GEMM (sm_100a).  Cin/Cout here are the GEMM's K/N widths, i.e.
+ * after any transpose.  residual (may be NULL) is [n_out, Cout] with leading dimension ld_res. */
+int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K,
+                      const void* image, const float* bias, const float* residual, int ld_res,
+                      float* out, int ld_out, int Cout, int epi_flags, scn_stream_t stream);
+/* exact fp32 FFMA path (verification mode, <=1e-5).  w is the raw [K, Cin_w, Cout_w] tensor;
+ * transpose/reverse as above. */
+int scn_conv_fwd_fp32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K,
+                      const float* w, int transpose, int reverse, const float* bias,
+                      const float* residual, int ld_res, float* out, int ld_out, int Cout,
+                      int epi_flags, scn_stream_t stream);
+/* grad_w[o] (+)= in[map[o][:]]^T . grad_out   (fp32 accumulate; grad_w must be zeroed) */
+int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const int32_t* map, int n_out,
+                        int K, const float* grad_out, int ld_go, int Cout, float* grad_w,
+                        int use_tf32, scn_stream_t stream);
+/* out[c] = sum_r in[r][c]   (bias gradient) */
+int scn_col_sum(const float* in, int ld, int n, int C, float* out, scn_stream_t stream);
+
+/* ------------------------------------------------------------------ elementwise ------------
+ * scn.ReLU module_factory.py:86-89; AddTable :51-57; BatchNorm(Leaky)ReLU :92-113. */
+int scn_relu_fwd(const float* in, float* out, int64_t n, scn_stream_t stream);
+int scn_relu_bwd(const float* out_or_in, const float* grad_out, float* grad_in, int64_t n,
+                 scn_stream_t stream);
+int scn_add(const float* a, const float* b, float* out, int64_t n, scn_stream_t stream);
+/* per-channel mean and biased variance over n rows (two-pass, deterministic) */
+int scn_bn_stats(const float* in, int n, int C, float* mean, float* var, scn_stream_t stream);
+/* y = leaky((x-mean)*rsqrt(var+eps)*gamma+beta) ; gamma/beta may be NULL */
+int scn_bn_apply(const float* in, int n, int C, const float* mean, const float* var,
+                 const float* gamma, const float* beta, float eps, float leak, float* out,
+                 scn_stream_t stream);
+/* backward of train-mode BN+leaky: needs x, y, dy; writes dx and (if non-NULL) dgamma, dbeta */
+int scn_bn_bwd(const float* x, const float* y, const float* dy, int n, int C, const float* mean,
+               const float* var, const float* gamma, float eps, float leak, int training,
+               float* dx, float* dgamma, float* dbeta, float* tmp2C, scn_stream_t stream);
+
+/* ------------------------------------------------------------------ io layers --------------
+ * InputLayerFunction custom_operations.py:74-82 (mode 4), roi_select_sparse.py:79-81,117-119;
+ * OutputLayerFunction custom_operations.py:7-10, model.py:461,576,600,643,658. */
+/* out[r] = reduce over the row's points (mode 1 last, 2 first, 3 sum, 4 mean) */
+int scn_input_fwd(const float* feats, int ld, int C, const int32_t* row_ptr,
+                  const int32_t* row_pts, int N, int mode, float* out, scn_stream_t stream);
+int scn_input_bwd(const float* grad_out, int C, const int32_t* point_row, const int32_t* row_ptr,
+                  const int32_t* row_pts, int P, int mode, float* grad_feats,
+                  scn_stream_t stream);
+/* out[i] = in[idx[i]]  (idx < 0 => zeros)   (OutputLayer forward, crop feature gather) */
+int scn_gather_rows(const float* in, int ld_in, const int32_t* idx, int n, int C, float* out,
+                    int ld_out, scn_stream_t stream);
+/* out[idx[i]] += in[i]  with atomics (backward of gather when no CSR exists) */
+int scn_scatter_add_rows(const float* in, const int32_t* idx, int n, int C, float* out,
+                         scn_stream_t stream);
+
+/* SparseToDense module_factory.py:429-435: out [B, C, X, Y, Z] incl. the zero fill */
+int scn_sparse_to_dense_fwd(const float* in, int C, const uint64_t* tab_keys,
+                            const int32_t* tab_vals, uint32_t cap, int B, int X, int Y, int Z,
+                            float* out, scn_stream_t stream);
+int scn_sparse_to_dense_bwd(const float* grad_dense, const uint64_t* row_keys, int N, int C,
+                            int X, int Y, int Z, float* grad_in, scn_stream_t stream);
+
+/* ------------------------------------------------------------------ pooling ----------------
+ * MaxPooling / AveragePooling module_factory.py:315-354 (cmap from scn_strided_maps);
+ * SparseGlobalPool custom_operations.py:42-59 (segment mean over batch-sorted rows). */
+int scn_pool_fwd(const float* in, int C, const int32_t* cmap, int n_out, int K, int is_max,
+                 float inv_volume, float* out, scn_stream_t stream);
+int scn_pool_bwd(const float* in, const float* out, const float* grad_out, int C,
+                 const int32_t* parent_row, int n_in, int is_max, float inv_volume,
+                 float* grad_in, scn_stream_t stream);
+int scn_segment_mean_fwd(const float* in, int C, const int32_t* seg_ptr, int n_seg, float* out,
+                         scn_stream_t stream);
+int scn_segment_mean_bwd(const float* grad_out, int C, const int32_t* seg_ptr, int n_seg,
+                         float* grad_in, scn_stream_t stream);
+/* seg_ptr[b] = first row whose batch field >= b (rows batch-sorted); n_seg+1 entries */
+int scn_batch_offsets(const uint64_t* row_keys, int N, int n_seg, int32_t* seg_ptr,
+                      scn_stream_t stream);
+
+/* ------------------------------------------------------------------ mask crop --------------
+ * roi_cut / get_inside_indicator / select_features / select_coords roi_select_sparse.py:125-180.
+ * boxes int32 [BB, 2, 3] (start, stop; half-open), box_sample[BB]; points given as keys with
+ * sample_ptr[B+1] (points are grouped by sample).  Output is in (box, point) order. */
+#define SCN_CROP_CHUNK 2048
+/* counts [BB, n_chunks] with n_chunks = ceil(max_sample_len / SCN_CROP_CHUNK) */
+int scn_crop_count(const uint64_t* keys, const int32_t* sample_ptr, const int32_t* boxes,
+                   const int32_t* box_sample, int BB, int n_chunks, int32_t* counts,
+                   scn_stream_t stream);
+/* offsets = exclusive scan of counts.  Writes sel_pt[total] (source point index), new_keys[total]
+ * (xyz absolute, batch field := box id) and, if non-NULL, is_inside [BB, P] bytes. */
+int scn_crop_select(const uint64_t* keys, const int32_t* sample_ptr, const int32_t* boxes,
+                    const int32_t* box_sample, int BB, int n_chunks, const int32_t* offsets,
+                    int P, int32_t* sel_pt, uint64_t* new_keys, uint8_t* is_inside,
+                    scn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCN_B200_H_ */

@@ -1,0 +1,83 @@
+// Shared helpers for the scn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/scn_b200.h"
+
+namespace scn {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define SCN_REQUIRE(cond, ...)                      \
+    do {                                            \
+        if (!(cond)) {                              \
+            scn::set_error(__VA_ARGS__);            \
+            return SCN_ERR_INVALID;                 \
+        }                                           \
+    } while (0)
+
+static inline cudaStream_t as_stream(scn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// grid size for grid-stride kernels: a multiple of the SM count (148 on B200), capped by work
+int sm_count();
+static inline int grid_for(int64_t work_items, int block, int ctas_per_sm = 8) {
+    int64_t need = (work_items + block - 1) / block;
+    int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// ---------------------------------------------------------------- packed voxel keys
+__host__ __device__ __forceinline__ uint64_t make_key(uint32_t x, uint32_t y, uint32_t z, uint32_t b) {
+    return ((uint64_t)b << 48) | ((uint64_t)x << 32) | ((uint64_t)y << 16) | (uint64_t)z;
+}
+__host__ __device__ __forceinline__ int key_x(uint64_t k) { return (int)((k >> 32) & 0xFFFF); }
+__host__ __device__ __forceinline__ int key_y(uint64_t k) { return (int)((k >> 16) & 0xFFFF); }
+__host__ __device__ __forceinline__ int key_z(uint64_t k) { return (int)(k & 0xFFFF); }
+__host__ __device__ __forceinline__ int key_b(uint64_t k) { return (int)((k >> 48) & 0xFFFF); }
+
+// ---------------------------------------------------------------- open-addressing hash
+__device__ __forceinline__ uint32_t hash_key(uint64_t k) {
+    // murmur3 fmix64
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return (uint32_t)k;
+}
+
+// returns slot of `key` (inserting it if absent)
+__device__ __forceinline__ uint32_t hash_insert_slot(uint64_t* tab_keys, uint32_t mask, uint64_t key) {
+    uint32_t s = hash_key(key) & mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(tab_keys + s),
+                                            (unsigned long long)SCN_EMPTY_KEY, (unsigned long long)key);
+        if (prev == SCN_EMPTY_KEY || prev == key) return s;
+        s = (s + 1) & mask;
+    }
+}
+
+// returns slot of key or 0xFFFFFFFF
+__device__ __forceinline__ uint32_t hash_find_slot(const uint64_t* __restrict__ tab_keys, uint32_t mask,
+                                                   uint64_t key) {
+    uint32_t s = hash_key(key) & mask;
+    while (true) {
+        uint64_t k = __ldg(tab_keys + s);
+        if (k == key) return s;
+        if (k == SCN_EMPTY_KEY) return 0xFFFFFFFFu;
+        s = (s + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ int hash_lookup(const uint64_t* __restrict__ tab_keys,
+                                           const int32_t* __restrict__ tab_vals, uint32_t mask,
+                                           uint64_t key) {
+    uint32_t s = hash_find_slot(tab_keys, mask, key);
+    return s == 0xFFFFFFFFu ? -1 : __ldg(tab_vals + s);
+}
+
+}  // namespace scn

@@ -1,0 +1,449 @@
+// TF32 implicit gather-GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   out[r, :] = epi( bias + sum_o  in[map[o][r], :] . W[o] )       r in [0, n_out)
+//
+// One persistent CTA per SM slot owns 128-row output tiles.  The reduction over (kernel offset o,
+// 32-channel k-block kb) is a stream of "units"; each unit is one pipeline stage:
+//     A stage : 128 gathered input rows x 32 fp32 (16 KB), K-major, 128B-swizzled, written by
+//               cp.async (16/8/4-byte, zero-fill for inactive neighbours) from 4 producer warps
+//     B stage : W[o][kb] as [Cout_pad x 32] fp32, K-major 128B-swizzled image pre-packed in HBM,
+//               fetched with one cp.async.bulk (TMA bulk engine) that completes on the mbarrier
+//     MMA     : one thread issues 1..4 tcgen05.mma.kind::tf32 (M=128, N=Cout_pad, K=8), fp32
+//               accumulation in TMEM across ALL units of the tile (no read-modify-write of out)
+// Accumulators are double buffered in TMEM so the epilogue (tcgen05.ld -> +bias/+residual/ReLU ->
+// global) of tile t overlaps the main loop of tile t+1.
+//
+// Warp roles (9 warps): 0-3 epilogue (TMEM lane quarter = warp id), 4-7 gather producers,
+// 8 MMA issuer + TMEM allocator.
+#include "common.cuh"
+
+namespace scn {
+
+constexpr int TILE_M = 128;
+constexpr int KB = 32;                  // fp32 per 128-byte swizzle row
+constexpr int A_STAGE_BYTES = TILE_M * 128;
+constexpr int N_PRODUCERS = 128;
+constexpr int CONV_THREADS = 288;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0) {
+            uint64_t t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) {
+                printf("scn_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                       threadIdx.x, bar, parity);
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src, bool valid) {
+    int sz = valid ? BYTES : 0;
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+    else if constexpr (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 in
+// [0,14), LBO>>4 in [16,30) (unused for swizzled K-major, set to 1), SBO>>4 in [32,46) = 1024 B
+// between 8-row groups, version=1 in [46,48), layout_type=2 (SWIZZLE_128B) in [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: c_format=F32 (1<<4), a/b_format=TF32 (2<<7, 2<<10),
+// K-major A and B (bits 15,16 = 0), n_dim=N>>3 at [17,23), m_dim=M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct ConvTcParams {
+    const float* in;
+    int ld_in, Cin;
+    const int32_t* map;
+    int n_out, K;
+    const uint8_t* image;
+    const float* bias;
+    const float* residual;
+    int ld_res;
+    float* out;
+    int ld_out, Cout, epi;
+    int cout_pad, n_kb, cin_pad8, stages, tmem_cols, n_tiles;
+};
+
+// one 16-byte chunk of a gathered row, split into VEC-float cp.asyncs
+template <int VEC>
+__device__ __forceinline__ void gather_chunk(uint32_t dst, const float* __restrict__ in, int64_t row_off, int src_row,
+                                             int col0, int Cin) {
+    constexpr int BYTES = VEC * 4;
+#pragma unroll
+    for (int j = 0; j < 4 / VEC; ++j) {
+        int col = col0 + j * VEC;
+        bool valid = src_row >= 0 && col < Cin;
+        const float* src = valid ? in + row_off + col : in;
+        cp_async<BYTES>(dst + j * BYTES, src, valid);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages;
+    const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.cout_pad * 128u;
+    const uint32_t bars = smem_base + (uint32_t)S * stage_bytes;  // 8-byte barriers
+    // layout: full[S], empty[S], acc_full[2], acc_empty[2], tmem_ptr
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+    auto accf_bar = [&](int b) { return bars + 8u * (2 * S + b); };
+    auto acce_bar = [&](int b) { return bars + 8u * (2 * S + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int units_per_tile = p.K * p.n_kb;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), N_PRODUCERS + 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accf_bar(b), 1);
+            mbar_init(acce_bar(b), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp >= 4 && warp < 8) {
+        // ===================== gather producers =====================
+        const int pt = tid - 128;
+        const int c = pt & 7, rbase = pt >> 3;
+        const uint32_t dst_in_stage = (uint32_t)rbase * 128u + (uint32_t)((c ^ (rbase & 7)) << 4);
+        const int look = S >= 4 ? 2 : 1;
+        int u = 0;            // units issued by this thread (global across tiles)
+        int signalled = 0;    // units whose full barrier this thread has arrived on
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int row0 = tile * TILE_M;
+            for (int o = 0; o < p.K; ++o) {
+                int idx[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    int r = row0 + rbase + 16 * i;
+                    int s = -1;
+                    if (r < p.n_out) s = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
+                    idx[i] = s;
+                }
+                for (int kb = 0; kb < p.n_kb; ++kb, ++u) {
+                    const int s = u % S;
+                    mbar_wait(empty_bar(s), ((u / S) & 1) ^ 1);
+                    const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
+                    if (pt == 0) {
+                        const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
+                        mbar_arrive_expect_tx(full_bar(s), wbytes);
+                        bulk_g2s(a_stage + A_STAGE_BYTES, p.image + (size_t)(o * p.n_kb + kb) * wbytes, wbytes,
+                                 full_bar(s));
+                    }
+                    const int col0 = kb * KB + c * 4;
+                    if (col0 < p.cin_pad8) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            gather_chunk<VEC>(a_stage + dst_in_stage + (uint32_t)i * 2048u, p.in,
+                                              (int64_t)idx[i] * p.ld_in, idx[i], col0, p.Cin);
+                    }
+                    cp_async_commit();
+                    if (u >= look) {
+                        if (look == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+                        fence_proxy_async();
+                        mbar_arrive(full_bar(signalled % S));
+                        ++signalled;
+                    }
+                }
+            }
+        }
+        // drain
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (; signalled < u; ++signalled) mbar_arrive(full_bar(signalled % S));
+    } else if (warp == 8) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TILE_M, p.cout_pad);
+            int u = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                const int b = it & 1;
+                mbar_wait(acce_bar(b), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(b * p.cout_pad);
+                for (int o = 0; o < p.K; ++o) {
+                    for (int kb = 0; kb < p.n_kb; ++kb, ++u) {
+                        const int s = u % S;
+                        mbar_wait(full_bar(s), (u / S) & 1);
+                        tc_fence_after();
+                        const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
+                        const uint64_t da = make_desc_sw128(a_stage);
+                        const uint64_t db = make_desc_sw128(a_stage + A_STAGE_BYTES);
+                        const int kcols = min(KB, p.cin_pad8 - kb * KB);
+                        for (int k = 0; k < kcols / 8; ++k) {
+                            // advance 32 bytes (8 tf32) inside the 128-byte swizzled row: +2 in the >>4 address field
+                            mma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                     (o | kb | k) != 0 ? 1u : 0u);
+                        }
+                        mma_commit(empty_bar(s));
+                    }
+                }
+                mma_commit(accf_bar(b));
+            }
+            (void)units_per_tile;
+        }
+    } else {
+        // ===================== epilogue warps 0..3 =====================
+        int it = 0;
+        const bool vec_ok = (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                            (!(p.epi & SCN_EPI_ADD) ||
+                             ((p.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int b = it & 1;
+            mbar_wait(accf_bar(b), (it >> 1) & 1);
+            tc_fence_after();
+            const int row = tile * TILE_M + warp * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * p.cout_pad);
+            for (int c0 = 0; c0 < p.cout_pad; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (row < p.n_out && c0 < p.Cout) {
+                    float* orow = p.out + (int64_t)row * p.ld_out + c0;
+                    const float* rrow = (p.epi & SCN_EPI_ADD) ? p.residual + (int64_t)row * p.ld_res + c0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (c0 + j < p.Cout) {
+                            float x = v[j];
+                            if (p.bias) x += __ldg(p.bias + c0 + j);
+                            v[j] = x;
+                        }
+                    }
+                    if (vec_ok && c0 + 16 <= p.Cout) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            if (rrow) {
+                                float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
+                                x.x += r4.x, x.y += r4.y, x.z += r4.z, x.w += r4.w;
+                            }
+                            if (p.epi & SCN_EPI_RELU)
+                                x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+                            *reinterpret_cast<float4*>(orow + j) = x;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (c0 + j < p.Cout) {
+                                float x = v[j];
+                                if (rrow) x += rrow[j];
+                                if (p.epi & SCN_EPI_RELU) x = fmaxf(x, 0.f);
+                                orow[j] = x;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acce_bar(b));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// pack W_eff[o][ci][co] into the kernel's B-stage images: [K][n_kb][cout_pad][32] fp32, element
+// (n, k) of a block at byte  n*128 + (((k>>2) ^ (n&7)) << 4) + (k&3)*4  (K-major SWIZZLE_128B).
+__global__ void k_pack_weights(const float* __restrict__ w, int K, int A, int B, int transpose, int reverse, int Cin,
+                               int Cout, int cout_pad, int n_kb, float* __restrict__ image) {
+    int64_t total = (int64_t)K * n_kb * cout_pad * KB;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int k = (int)(i % KB);
+        int n = (int)((i / KB) % cout_pad);
+        int kb = (int)((i / ((int64_t)KB * cout_pad)) % n_kb);
+        int o = (int)(i / ((int64_t)KB * cout_pad * n_kb));
+        int ci = kb * KB + k;
+        float v = 0.f;
+        if (ci < Cin && n < Cout) {
+            int oo = reverse ? K - 1 - o : o;
+            const float* pw = w + (int64_t)oo * A * B;
+            v = transpose ? pw[(int64_t)n * B + ci] : pw[(int64_t)ci * B + n];
+            uint32_t t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+            v = __uint_as_float(t);
+        }
+        int64_t blk = ((int64_t)o * n_kb + kb) * cout_pad * KB;
+        int off = n * KB + ((((k >> 2) ^ (n & 7)) << 2) | (k & 3));
+        image[blk + off] = v;
+    }
+}
+
+}  // namespace scn
+
+using namespace scn;
+
+static inline int pad16(int c) { return (c + 15) / 16 * 16; }
+static inline int n_kblocks(int cin) { return (cin + KB - 1) / KB; }
+
+extern "C" {
+
+int64_t scn_conv_weight_image_bytes(int K, int Cin, int Cout) {
+    return (int64_t)K * n_kblocks(Cin) * pad16(Cout) * 128;
+}
+
+int scn_conv_pack_weights(const float* w, int K, int Cin, int Cout, int transpose, int reverse, void* image,
+                          scn_stream_t stream) {
+    SCN_REQUIRE(K > 0 && Cin > 0 && Cout > 0, "pack_weights: bad shape");
+    int A = transpose ? Cout : Cin, B = transpose ? Cin : Cout;
+    int64_t total = scn_conv_weight_image_bytes(K, Cin, Cout) / 4;
+    k_pack_weights<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, K, A, B, transpose, reverse, Cin, Cout, pad16(Cout),
+                                                                        n_kblocks(Cin), reinterpret_cast<float*>(image));
+    return check_launch("pack_weights");
+}
+
+int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const void* image,
+                      const float* bias, const float* residual, int ld_res, float* out, int ld_out, int Cout,
+                      int epi_flags, scn_stream_t stream) {
+    SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0, "conv_fwd_tf32: bad shape Cin=%d Cout=%d K=%d", Cin, Cout, K);
+    SCN_REQUIRE(Cout <= 256, "conv_fwd_tf32: Cout > 256 not supported (got %d)", Cout);
+    SCN_REQUIRE(map || K == 1, "conv_fwd_tf32: identity map requires K == 1");
+    SCN_REQUIRE(!(epi_flags & SCN_EPI_ADD) || residual, "conv_fwd_tf32: SCN_EPI_ADD needs a residual pointer");
+    SCN_REQUIRE((reinterpret_cast<uintptr_t>(image) & 15) == 0, "conv_fwd_tf32: weight image must be 16-byte aligned");
+    SCN_REQUIRE((reinterpret_cast<uintptr_t>(in) & 3) == 0, "conv_fwd_tf32: input not 4-byte aligned");
+    if (n_out <= 0) return SCN_OK;
+    static int is100 = -1;
+    if (is100 < 0) is100 = scn_device_is_sm100();
+    SCN_REQUIRE(is100 == 1, "conv_fwd_tf32: needs an sm_100 device (tcgen05)");
+
+    ConvTcParams p;
+    p.in = in, p.ld_in = ld_in, p.Cin = Cin, p.map = map, p.n_out = n_out, p.K = K;
+    p.image = reinterpret_cast<const uint8_t*>(image), p.bias = bias, p.residual = residual, p.ld_res = ld_res;
+    p.out = out, p.ld_out = ld_out, p.Cout = Cout, p.epi = epi_flags;
+    p.cout_pad = pad16(Cout), p.n_kb = n_kblocks(Cin), p.cin_pad8 = (Cin + 7) / 8 * 8;
+    p.n_tiles = cdiv(n_out, TILE_M);
+    int cols = 2 * p.cout_pad, tc = 32;
+    while (tc < cols) tc <<= 1;
+    p.tmem_cols = tc;
+    const int stage_bytes = A_STAGE_BYTES + p.cout_pad * 128;
+    // two CTAs per SM when four stages fit in ~110 KB, else one CTA with as many stages (<= 4) as fit
+    int stages, ctas_per_sm;
+    if (4 * stage_bytes + 2048 <= 110 * 1024 && tc <= 256) {
+        stages = 4, ctas_per_sm = 2;
+    } else {
+        stages = (220 * 1024) / stage_bytes;
+        if (stages > 4) stages = 4;
+        ctas_per_sm = 1;
+    }
+    SCN_REQUIRE(stages >= 2, "conv_fwd_tf32: tile does not fit in shared memory");
+    p.stages = stages;
+    const int smem = stages * stage_bytes + 1024 + 256;
+    int vec = 1;
+    if (Cin % 4 == 0 && ld_in % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) vec = 4;
+    else if (Cin % 2 == 0 && ld_in % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0) vec = 2;
+    int grid = p.n_tiles < sm_count() * ctas_per_sm ? p.n_tiles : sm_count() * ctas_per_sm;
+    cudaError_t e;
+    auto launch = [&](auto kern) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return;
+        kern<<<grid, CONV_THREADS, smem, as_stream(stream)>>>(p);
+    };
+    if (vec == 4) launch(k_conv_tc<4>);
+    else if (vec == 2) launch(k_conv_tc<2>);
+    else launch(k_conv_tc<1>);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        scn::set_error("conv_fwd_tf32: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
+        return SCN_ERR_CUDA;
+    }
+    return check_launch("conv_fwd_tf32");
+}
+
+}  // extern "C"

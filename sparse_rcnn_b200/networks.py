@@ -1,0 +1,186 @@
+"""Host-side mirror of the reference's sparse network assembly for the hot path.
+
+/root/reference is not present on the GPU box, so the layer graphs that
+`ndsis/modules/module_factory.py` + `model.py` build for the shipped sparse configuration
+(scannet_config/run.py:515-815) are restated here, parameterised by the `scn` namespace
+(the B200 backend `sparse_rcnn_b200.scn`, or any other object exposing the same names --
+tests pass the CPU oracle).  Module nesting and attribute names follow the reference tree so
+that `state_dict()` keys are identical (tests/test_reference_graph.py checks this against the
+unmodified reference when it is available).
+
+Graph facts restated (with the reference line that produces them):
+  residual unit  : x + SubM3(ReLU(SubM3(ReLU(x))))          module_factory.py:127-183 (relu_first,
+                   main_path_relu=False, bottleneck_divisor=0), shortcut = Identity | NetworkInNetwork
+  encoder level  : [SubM 1^3 | Convolution 2^3/s2] + num_units residual units   :438-530
+  decoder level  : ReLU, Deconvolution 2^3/s2, JoinTable(up, skip), NetworkInNetwork, units  :533-578
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+# ----------------------------------------------------------------------------- containers
+class Interims(nn.Sequential):
+    """Sequential that returns every intermediate result (reference SequentialInterims)."""
+
+    def forward(self, x):
+        outs = []
+        for m in self._modules.values():
+            x = m(x)
+            outs.append(x)
+        return outs
+
+
+class SkipReunite(nn.Module):
+    """One decoder level (reference SkipConnectionReuniter, custom_container.py:68-83)."""
+
+    def __init__(self, input_stage, combiner, channel_changer, output_stage):
+        super().__init__()
+        self.input_stage, self.combiner = input_stage, combiner
+        self.channel_changer, self.output_stage = channel_changer, output_stage
+
+    def forward(self, x, skip):
+        return self.output_stage(self.channel_changer(self.combiner([self.input_stage(x), skip])))
+
+
+class ReuniteInterims(nn.Module):
+    def __init__(self, *mods):
+        super().__init__()
+        self.module_list = nn.ModuleList(mods)
+
+    def forward(self, x, skips):
+        assert len(skips) == len(self.module_list)
+        outs = []
+        for skip, m in zip(skips, self.module_list):
+            x = m(x, skip)
+            outs.append(x)
+        return outs
+
+
+class ReuniteLast(nn.Module):
+    """reference InverseSequentialInterims: only the final decoder output."""
+
+    def __init__(self, *mods):
+        super().__init__()
+        self.module_list = nn.ModuleList(mods)
+
+    def forward(self, x, skips):
+        assert len(skips) == len(self.module_list)
+        for skip, m in zip(skips, self.module_list):
+            x = m(x, skip)
+        return x
+
+
+class UNet(nn.Module):
+    def __init__(self, down, up):
+        super().__init__()
+        self.downsampling_layer, self.upsampling_layer = down, up
+
+    def forward(self, x):
+        *skip, out = self.downsampling_layer(x)
+        return self.upsampling_layer(out, skip[::-1])
+
+
+# ----------------------------------------------------------------------------- blocks
+def residual_unit(scn, cin, cout):
+    shortcut = scn.Identity() if cin == cout else scn.NetworkInNetwork(cin, cout, True)
+    inner = scn.Sequential(
+        scn.ReLU(), scn.SubmanifoldConvolution(3, cin, cout, 3, True),
+        scn.ReLU(), scn.SubmanifoldConvolution(3, cout, cout, 3, True))
+    return scn.Sequential(scn.ConcatTable(shortcut, inner), scn.AddTable())
+
+
+def unit_stage(scn, channels, num_units):
+    return scn.Sequential(*[residual_unit(scn, channels, channels) for _ in range(num_units)])
+
+
+def encoder_level(scn, cin, cout, stride, num_units):
+    if stride == 1:
+        entry = scn.Sequential(scn.SubmanifoldConvolution(3, cin, cout, 1, True))
+    else:
+        entry = scn.Sequential(scn.Convolution(3, cin, cout, (stride,) * 3, (stride,) * 3, True))
+    return scn.Sequential(entry, unit_stage(scn, cout, num_units))
+
+
+def decoder_level(scn, cin, skip, cout, stride, num_units):
+    up = scn.Sequential(scn.ReLU(), scn.Deconvolution(3, cin, cout, (stride,) * 3, (stride,) * 3, True))
+    changer = scn.NetworkInNetwork(cout + skip, cout, True)
+    return SkipReunite(up, scn.JoinTable(), changer, unit_stage(scn, cout, num_units))
+
+
+class InputStage(nn.Module):
+    """reference SparseInputStage + CustomInputLayer(mode=4) (model.py:248-258,
+    custom_operations.py:62-86)."""
+
+    def __init__(self, scn, mode=4):
+        super().__init__()
+        self.scn, self.mode = scn, mode
+
+    def forward(self, data):
+        coords, feats, spatial_size, batch_size = data[:4]
+        spatial_size = torch.as_tensor(spatial_size, dtype=torch.long)
+        if not len(coords):
+            return spatial_size, batch_size, None
+        md = self.scn.Metadata(3)
+        f = self.scn.ioLayers.InputLayerFunction.apply(3, md, spatial_size, coords.long(), feats, batch_size, self.mode)
+        t = self.scn.SparseConvNetTensor(features=f, metadata=md, spatial_size=spatial_size)
+        return spatial_size, t.batch_size(), t
+
+
+class FeatureExtractor(nn.Module):
+    """Sparse U-Net feature extractor (reference FeatureExtractor, model.py:261-446, built by
+    run.py:552-600 with include_unet=True).  encoder channels [32,48,64,80,96,112]."""
+
+    def __init__(self, scn, input_channels=6, channels=(32, 48, 64, 80, 96, 112), num_units=2, include_unet=True,
+                 class_output_index=-4, min_unet_channels=16):
+        super().__init__()
+        self.scn = scn
+        self.input_channels = input_channels
+        self.channels = list(channels)
+        self.input_stage = InputStage(scn)
+        levels, cin = [], input_channels
+        for i, c in enumerate(channels):
+            levels.append(encoder_level(scn, cin, c, 1 if i == 0 else 2, num_units))
+            cin = c
+        self.main_network = Interims(*levels)
+        self.class_output_index = class_output_index
+        self.include_unet = include_unet
+        main_channels = [input_channels] + self.channels
+        self.class_channels = main_channels[class_output_index]
+        self.class_stride = np.array([2 ** max(len(main_channels) + class_output_index - 1, 0)] * 3) \
+            if class_output_index < 0 else np.array([2 ** max(class_output_index - 1, 0)] * 3)
+        if include_unet:
+            rev = self.channels[::-1]
+            ups, c = [], rev[0]
+            for skip in rev[1:]:
+                out = max(skip, min_unet_channels)
+                ups.append(decoder_level(scn, c, skip, out, 2, num_units))
+                c = out
+            self.unet = ReuniteInterims(*ups)
+            self.unet_channels = [max(s, min_unet_channels) for s in rev[1:]]
+        else:
+            self.unet = None
+
+    def forward(self, data):
+        scene_size, batch_size, x = self.input_stage(data)
+        inter = self.main_network(x)
+        extended = [x] + inter
+        unet_out = self.unet(inter[-1], inter[:-1][::-1]) if self.include_unet else None
+        class_out = extended[self.class_output_index]
+        return scene_size, batch_size, [], class_out, inter, unet_out
+
+
+class SegmentationNetwork(nn.Module):
+    """reference SegmentationNetwork (model.py:449-467): SubM 1^3 C->classes + OutputLayer."""
+
+    def __init__(self, scn, channels=32, num_classes=20):
+        super().__init__()
+        self.channel_changer = scn.SubmanifoldConvolution(3, channels, num_classes, 1, True)
+        self.output_layer = scn.OutputLayer(3)
+
+    def forward(self, unet_feature_maps, scene=None):
+        return self.output_layer(self.channel_changer(unet_feature_maps[-1]))
+
+
+def count_parameters(m):
+    return sum(p.numel() for p in m.parameters())

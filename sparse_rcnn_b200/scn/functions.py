@@ -1,0 +1,305 @@
+"""autograd Functions of the sparse hot path; each forward/backward is one or two C-ABI calls.
+
+Upstream equivalents are the `X_updateOutput / X_updateGradInput / X_backward` triplets of
+SparseConvNet's pybind module; arithmetic follows SURVEY.md A5 (bias first, offsets accumulated
+in fp32).  All tensors are fp32 CUDA; there is no CPU path here.
+"""
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+from .metadata import _ptr, _stream
+
+EPI_RELU, EPI_ADD = 1, 2
+
+_state = {"precision": "tf32"}
+
+
+def set_precision(mode):
+    """'tf32' (tcgen05 tensor cores, rel <= 2e-3) or 'fp32' (exact FFMA verification mode, <= 1e-5)."""
+    if mode not in ("tf32", "fp32"):
+        raise ValueError("precision must be 'tf32' or 'fp32'")
+    _state["precision"] = mode
+
+
+def get_precision():
+    return _state["precision"]
+
+
+def _check(x):
+    if not x.is_cuda:
+        raise RuntimeError("sparse_rcnn_b200 ops need CUDA tensors (there is no CPU fallback)")
+    if x.dtype != torch.float32:
+        raise RuntimeError("features must be float32 (got %s)" % x.dtype)
+    return x.contiguous()
+
+
+def _image(weight, K, cin, cout, transpose, reverse):
+    """Packed (TF32-rounded, swizzled) weight image; cached on the tensor until it is modified."""
+    cache = getattr(weight, "_scn_img", None)
+    if cache is None:
+        cache = {}
+        try:
+            weight._scn_img = cache
+        except AttributeError:
+            pass
+    key = (transpose, reverse)
+    ver = (weight._version, weight.data_ptr())
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    nbytes = int(_lib.raw("scn_conv_weight_image_bytes")(K, cin, cout))
+    img = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    _lib.call("scn_conv_pack_weights", _ptr(weight), K, cin, cout, transpose, reverse, _ptr(img), _stream())
+    cache[key] = (ver, img)
+    return img
+
+
+def conv_gemm(x, weight, K, cin, cout, fmap, n_out, bias=None, transpose=0, reverse=0, residual=None, relu=False):
+    """out[r] = epi(bias + sum_o x[fmap[o][r]] . W_eff[o]);  W_eff = weight (transposed / offset-reversed).
+    cin/cout are the GEMM widths (after any transpose)."""
+    out = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
+    if n_out == 0:
+        return out
+    epi = (EPI_RELU if relu else 0) | (EPI_ADD if residual is not None else 0)
+    ld_res = residual.stride(0) if residual is not None else 0
+    s = _stream()
+    if _state["precision"] == "tf32" and cout <= 256:
+        img = _image(weight, K, cin, cout, transpose, reverse)
+        _lib.call("scn_conv_fwd_tf32", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(img), _ptr(bias),
+                  _ptr(residual), ld_res, _ptr(out), cout, cout, epi, s)
+    else:
+        _lib.call("scn_conv_fwd_fp32", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(weight), transpose,
+                  reverse, _ptr(bias), _ptr(residual), ld_res, _ptr(out), cout, cout, epi, s)
+    return out
+
+
+class ConvFunction(Function):
+    """Shared by SubmanifoldConvolution / Convolution / Deconvolution / NetworkInNetwork.
+
+    fmap [K, n_out]: forward map; bmap [K, n_in]: map of the input gradient (for a submanifold
+    conv bmap is fmap with the offsets reversed, expressed through `reverse_bwd`)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, fmap, bmap, n_out, reverse_bwd):
+        x = _check(x)
+        w = weight          # keep the Parameter object: the packed image is cached on it
+        K, cin, cout = w.shape[0] if w.dim() > 2 else 1, w.shape[-2], w.shape[-1]
+        if x.shape[1] != cin:
+            raise RuntimeError("convolution expects %d input planes, got %d" % (cin, x.shape[1]))
+        ctx.save_for_backward(x, weight)
+        ctx.maps = (fmap, bmap)
+        ctx.dims = (K, cin, cout, n_out, x.shape[0], reverse_bwd, bias is not None)
+        return conv_gemm(x, w, K, cin, cout, fmap, n_out, bias.detach() if bias is not None else None)
+
+    @staticmethod
+    def backward(ctx, go):
+        x, weight = ctx.saved_tensors
+        fmap, bmap = ctx.maps
+        K, cin, cout, n_out, n_in, reverse_bwd, has_bias = ctx.dims
+        go = _check(go)
+        w = weight
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = conv_gemm(go, w, K, cout, cin, bmap, n_in, None, transpose=1, reverse=reverse_bwd)
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros_like(w)
+            if n_out:
+                _lib.call("scn_conv_bwd_weight", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(go),
+                          go.stride(0), cout, _ptr(gw), 1 if _state["precision"] == "tf32" else 0, _stream())
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = torch.empty(cout, dtype=torch.float32, device=go.device)
+            if n_out:
+                _lib.call("scn_col_sum", _ptr(go), go.stride(0), n_out, cout, _ptr(gb), _stream())
+            else:
+                gb.zero_()
+        return gx, gw, gb, None, None, None, None
+
+
+class ReLUFunction(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _check(x)
+        y = torch.empty_like(x)
+        _lib.call("scn_relu_fwd", _ptr(x), _ptr(y), x.numel(), _stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, go):
+        y, = ctx.saved_tensors
+        go = _check(go)
+        gi = torch.empty_like(go)
+        _lib.call("scn_relu_bwd", _ptr(y), _ptr(go), _ptr(gi), go.numel(), _stream())
+        return gi
+
+
+class AddFunction(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _check(a), _check(b)
+        if a.shape != b.shape:
+            raise RuntimeError("AddTable: shape mismatch %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+        out = torch.empty_like(a)
+        _lib.call("scn_add", _ptr(a), _ptr(b), _ptr(out), a.numel(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        return go, go
+
+
+class InputLayerFunction(Function):
+    """scn.ioLayers.InputLayerFunction.apply(dimension, metadata, spatial_size, coords, features,
+    batch_size, mode)  (custom_operations.py:74-82, roi_select_sparse.py:79-81,117-119)."""
+
+    @staticmethod
+    def forward(ctx, dimension, metadata, spatial_size, coords, input_features, batch_size, mode):
+        f = _check(input_features)
+        n = metadata.set_input(spatial_size, coords, batch_size, mode, f.device)
+        if f.shape[0] != metadata.n_points:
+            raise RuntimeError("InputLayer: %d coords but %d feature rows" % (metadata.n_points, f.shape[0]))
+        ctx.md, ctx.mode, ctx.C = metadata, mode, f.shape[1]
+        if mode == 0:
+            return f.clone()
+        out = torch.empty((n, f.shape[1]), dtype=torch.float32, device=f.device)
+        _lib.call("scn_input_fwd", _ptr(f), f.stride(0), f.shape[1], _ptr(metadata.row_ptr), _ptr(metadata.row_pts),
+                  n, mode, _ptr(out), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        md = ctx.md
+        go = _check(go)
+        if ctx.mode == 0:
+            return None, None, None, None, go.clone(), None, None
+        gf = torch.empty((md.n_points, ctx.C), dtype=torch.float32, device=go.device)
+        _lib.call("scn_input_bwd", _ptr(go), ctx.C, _ptr(md.point_row), _ptr(md.row_ptr), _ptr(md.row_pts),
+                  md.n_points, ctx.mode, _ptr(gf), _stream())
+        return None, None, None, None, gf, None, None
+
+
+class OutputLayerFunction(Function):
+    """scn.ioLayers.OutputLayerFunction.apply(dimension, metadata, features)
+    (custom_operations.py:7-10): every original point receives its voxel's row."""
+
+    @staticmethod
+    def forward(ctx, dimension, metadata, input_features):
+        f = _check(input_features)
+        ctx.md, ctx.n, ctx.C = metadata, f.shape[0], f.shape[1]
+        out = torch.empty((metadata.n_points, f.shape[1]), dtype=torch.float32, device=f.device)
+        _lib.call("scn_gather_rows", _ptr(f), f.stride(0), _ptr(metadata.point_row), metadata.n_points, f.shape[1],
+                  _ptr(out), f.shape[1], _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        md = ctx.md
+        go = _check(go)
+        row_ptr, row_pts = md.rule_csr()
+        gi = torch.empty((ctx.n, ctx.C), dtype=torch.float32, device=go.device)
+        _lib.call("scn_input_fwd", _ptr(go), go.stride(0), ctx.C, _ptr(row_ptr), _ptr(row_pts), ctx.n, 3, _ptr(gi),
+                  _stream())
+        return None, None, gi
+
+
+class PoolFunction(Function):
+    @staticmethod
+    def forward(ctx, x, rules, n_out, is_max, inv_volume):
+        x = _check(x)
+        out = torch.empty((n_out, x.shape[1]), dtype=torch.float32, device=x.device)
+        _lib.call("scn_pool_fwd", _ptr(x), x.shape[1], _ptr(rules.cmap), n_out, rules.K, int(is_max), inv_volume,
+                  _ptr(out), _stream())
+        ctx.rules, ctx.cfg = rules, (is_max, inv_volume)
+        ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        x, out = ctx.saved_tensors
+        go = _check(go)
+        is_max, inv_volume = ctx.cfg
+        gi = torch.empty_like(x)
+        _lib.call("scn_pool_bwd", _ptr(x), _ptr(out), _ptr(go), x.shape[1], _ptr(ctx.rules.parent_row), x.shape[0],
+                  int(is_max), inv_volume, _ptr(gi), _stream())
+        return gi, None, None, None, None
+
+
+class SparseToDenseFunction(Function):
+    @staticmethod
+    def forward(ctx, x, level, n_samples, size):
+        x = _check(x)
+        C = x.shape[1]
+        out = torch.empty((n_samples, C, *size), dtype=torch.float32, device=x.device)
+        _lib.call("scn_sparse_to_dense_fwd", _ptr(x), C, _ptr(level.tab_keys), _ptr(level.tab_vals), level.cap,
+                  n_samples, size[0], size[1], size[2], _ptr(out), _stream())
+        ctx.level, ctx.size, ctx.shape = level, size, x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        go = _check(go)
+        n, C = ctx.shape
+        gi = torch.empty((n, C), dtype=torch.float32, device=go.device)
+        _lib.call("scn_sparse_to_dense_bwd", _ptr(go), _ptr(ctx.level.keys), n, C, ctx.size[0], ctx.size[1],
+                  ctx.size[2], _ptr(gi), _stream())
+        return gi, None, None, None
+
+
+class SegmentMeanFunction(Function):
+    """Per-sample mean over batch-sorted rows (replaces split_batch + torch.mean,
+    custom_operations.py:24-59, by one kernel)."""
+
+    @staticmethod
+    def forward(ctx, x, seg_ptr, n_seg):
+        x = _check(x)
+        out = torch.empty((n_seg, x.shape[1]), dtype=torch.float32, device=x.device)
+        _lib.call("scn_segment_mean_fwd", _ptr(x), x.shape[1], _ptr(seg_ptr), n_seg, _ptr(out), _stream())
+        ctx.seg, ctx.shape = (seg_ptr, n_seg), x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        go = _check(go)
+        seg_ptr, n_seg = ctx.seg
+        gi = torch.zeros(ctx.shape, dtype=torch.float32, device=go.device)
+        _lib.call("scn_segment_mean_bwd", _ptr(go), ctx.shape[1], _ptr(seg_ptr), n_seg, _ptr(gi), _stream())
+        return gi, None, None
+
+
+class BatchNormFunction(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, leak, training):
+        x = _check(x)
+        n, C = x.shape
+        s = _stream()
+        if training:
+            mean = torch.empty(C, dtype=torch.float32, device=x.device)
+            var = torch.empty(C, dtype=torch.float32, device=x.device)
+            _lib.call("scn_bn_stats", _ptr(x), n, C, _ptr(mean), _ptr(var), s)
+            running_mean.mul_(momentum).add_(mean, alpha=1 - momentum)
+            running_var.mul_(momentum).add_(var, alpha=1 - momentum)
+        else:
+            mean, var = running_mean, running_var
+        y = torch.empty_like(x)
+        w = weight.detach() if weight is not None else None
+        b = bias.detach() if bias is not None else None
+        _lib.call("scn_bn_apply", _ptr(x), n, C, _ptr(mean), _ptr(var), _ptr(w), _ptr(b), eps, leak, _ptr(y), s)
+        ctx.save_for_backward(x, y, mean, var, weight)
+        ctx.cfg = (eps, leak, training, weight is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, go):
+        x, y, mean, var, weight = ctx.saved_tensors
+        eps, leak, training, affine = ctx.cfg
+        go = _check(go)
+        n, C = x.shape
+        dx = torch.empty_like(x)
+        tmp = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        dg = torch.empty(C, dtype=torch.float32, device=x.device) if affine else None
+        db = torch.empty(C, dtype=torch.float32, device=x.device) if affine else None
+        _lib.call("scn_bn_bwd", _ptr(x), _ptr(y), _ptr(go), n, C, _ptr(mean), _ptr(var),
+                  _ptr(weight.detach()) if affine else 0, eps, leak, int(training), _ptr(dx), _ptr(dg), _ptr(db),
+                  _ptr(tmp), _stream())
+        return dx, dg, db, None, None, None, None, None, None

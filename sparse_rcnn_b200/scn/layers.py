@@ -1,0 +1,289 @@
+"""Module classes of the `sparseconvnet` namespace consumed by ndsis/modules
+(names, positional constructor signatures and parameter names/shapes as upstream, so that the
+reference's module_factory.py / model.py build unchanged and state_dicts stay loadable:
+SURVEY.md 8b).  Weight `[K^3, groups, Cin/g, Cout/g]`, bias `[Cout]`; NiN weight `[Cin, Cout]`;
+BN `weight, bias, running_mean, running_var`.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import functions as F
+from .metadata import Metadata, _triple, size_key
+
+
+class SparseConvNetTensor:
+    """Container (features, metadata, spatial_size); reference call sites:
+    custom_operations.py:19-21,83-85; roi_select_sparse.py:83-84,103-109."""
+
+    def __init__(self, features=None, metadata=None, spatial_size=None):
+        self.features = features
+        self.metadata = metadata
+        self.spatial_size = spatial_size
+
+    def get_spatial_locations(self, spatial_size=None):
+        """int64 CPU [N,4] (x,y,z,b), row-aligned with `features` (cached)."""
+        if spatial_size is None:
+            spatial_size = self.spatial_size
+        return self.metadata.level(spatial_size).locations()
+
+    def batch_size(self):
+        return self.metadata.n_samples
+
+    def cuda(self):
+        self.features = self.features.cuda()
+        return self
+
+    def cpu(self):
+        self.features = self.features.cpu()
+        return self
+
+    def __repr__(self):
+        return "SparseConvNetTensor<features=%s, spatial_size=%s>" % (
+            tuple(self.features.shape), size_key(self.spatial_size))
+
+
+def _like(x, features):
+    return SparseConvNetTensor(features, x.metadata, x.spatial_size)
+
+
+class Sequential(nn.Sequential):
+    def append(self, module):
+        self.add_module(str(len(self._modules)), module)
+        return self
+
+    def input_spatial_size(self, out_size):
+        for m in reversed(list(self._modules.values())):
+            out_size = m.input_spatial_size(out_size)
+        return out_size
+
+
+class Identity(nn.Module):
+    def forward(self, x):
+        return x
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+
+class ConcatTable(nn.Module):
+    def __init__(self, *modules):
+        super().__init__()
+        for i, m in enumerate(modules):
+            self.add_module(str(i), m)
+
+    def append(self, module):
+        self.add_module(str(len(self._modules)), module)
+        return self
+
+    def forward(self, x):
+        return [m(x) for m in self._modules.values()]
+
+
+class AddTable(nn.Module):
+    def forward(self, xs):
+        f = xs[0].features
+        for x in xs[1:]:
+            f = F.AddFunction.apply(f, x.features)
+        return _like(xs[0], f)
+
+
+class JoinTable(nn.Module):
+    def forward(self, xs):
+        return _like(xs[0], torch.cat([x.features for x in xs], 1))
+
+
+class ReLU(nn.Module):
+    def forward(self, x):
+        return _like(x, F.ReLUFunction.apply(x.features))
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+
+class BatchNormalization(nn.Module):
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9, affine=True, leakiness=1):
+        super().__init__()
+        self.nPlanes, self.eps, self.momentum, self.leakiness = nPlanes, eps, momentum, leakiness
+        self.register_buffer("running_mean", torch.zeros(nPlanes))
+        self.register_buffer("running_var", torch.ones(nPlanes))
+        if affine:
+            self.weight = nn.Parameter(torch.ones(nPlanes))
+            self.bias = nn.Parameter(torch.zeros(nPlanes))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+
+    def forward(self, x):
+        f = F.BatchNormFunction.apply(x.features, self.weight, self.bias, self.running_mean, self.running_var,
+                                      self.eps, self.momentum, float(self.leakiness), self.training)
+        return _like(x, f)
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+
+class BatchNormReLU(BatchNormalization):
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9):
+        super().__init__(nPlanes, eps, momentum, True, 0)
+
+
+class BatchNormLeakyReLU(BatchNormalization):
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9, leakiness=0.333):
+        super().__init__(nPlanes, eps, momentum, True, leakiness)
+
+
+def _conv_weight(volume, nin, nout, groups):
+    if groups != 1:
+        raise RuntimeError("groups != 1 is not implemented (ndsis builds groups=1: module_factory.py:152,404-406)")
+    std = math.sqrt(2.0 * groups / (nin * volume))
+    return nn.Parameter(torch.empty(volume, groups, nin // groups, nout // groups).normal_(0, std))
+
+
+class SubmanifoldConvolution(nn.Module):
+    """module_factory.py:377-414.  Output sites == input sites."""
+
+    def __init__(self, dimension, nIn, nOut, filter_size, bias, groups=1):
+        super().__init__()
+        self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
+        self.filter_size = _triple(filter_size)
+        if any(f % 2 == 0 for f in self.filter_size):
+            raise RuntimeError("SubmanifoldConvolution needs odd filter sizes")
+        self.weight = _conv_weight(self.filter_size[0] * self.filter_size[1] * self.filter_size[2], nIn, nOut, groups)
+        self.bias = nn.Parameter(torch.zeros(nOut)) if bias else None
+
+    def forward(self, x):
+        lvl = x.metadata.level(x.spatial_size)
+        m = lvl.subm_map(self.filter_size)
+        f = F.ConvFunction.apply(x.features, self.weight, self.bias, m, m, lvl.n, 1)
+        return _like(x, f)
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+
+ValidConvolution = SubmanifoldConvolution
+
+
+class Convolution(nn.Module):
+    """module_factory.py:221-241 (filter == stride)."""
+
+    def __init__(self, dimension, nIn, nOut, filter_size, filter_stride, bias, groups=1):
+        super().__init__()
+        self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
+        self.filter_size, self.filter_stride = _triple(filter_size), _triple(filter_stride)
+        self.weight = _conv_weight(self.filter_size[0] * self.filter_size[1] * self.filter_size[2], nIn, nOut, groups)
+        self.bias = nn.Parameter(torch.zeros(nOut)) if bias else None
+
+    def forward(self, x):
+        md = x.metadata
+        r = md.strided_rules(x.spatial_size, self.filter_size, self.filter_stride)
+        n_out = md.levels[r.out_key].n
+        f = F.ConvFunction.apply(x.features, self.weight, self.bias, r.cmap, r.dmap, n_out, 0)
+        return SparseConvNetTensor(f, md, torch.tensor(r.out_key, dtype=torch.long))
+
+    def input_spatial_size(self, out_size):
+        return (out_size - 1) * torch.tensor(self.filter_stride) + torch.tensor(self.filter_size)
+
+
+class Deconvolution(nn.Module):
+    """module_factory.py:244-271: transpose of Convolution; output active set = the finer grid
+    that must already exist in the Metadata."""
+
+    def __init__(self, dimension, nIn, nOut, filter_size, filter_stride, bias, groups=1):
+        super().__init__()
+        self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
+        self.filter_size, self.filter_stride = _triple(filter_size), _triple(filter_stride)
+        self.weight = _conv_weight(self.filter_size[0] * self.filter_size[1] * self.filter_size[2], nIn, nOut, groups)
+        self.bias = nn.Parameter(torch.zeros(nOut)) if bias else None
+
+    def forward(self, x):
+        md = x.metadata
+        in_size = size_key(x.spatial_size)
+        out_size = tuple((i - 1) * s + f for i, s, f in zip(in_size, self.filter_stride, self.filter_size))
+        if out_size not in md.levels:
+            raise RuntimeError("Deconvolution: no active set at spatial size %s in this Metadata" % (out_size,))
+        r = md.strided_rules(out_size, self.filter_size, self.filter_stride)
+        n_out = md.levels[out_size].n
+        f = F.ConvFunction.apply(x.features, self.weight, self.bias, r.dmap, r.cmap, n_out, 0)
+        return SparseConvNetTensor(f, md, torch.tensor(out_size, dtype=torch.long))
+
+
+class NetworkInNetwork(nn.Module):
+    """module_factory.py:357-374: out = x @ W + b."""
+
+    def __init__(self, nIn, nOut, bias):
+        super().__init__()
+        self.nIn, self.nOut = nIn, nOut
+        self.weight = nn.Parameter(torch.empty(nIn, nOut).normal_(0, math.sqrt(2.0 / nIn)))
+        self.bias = nn.Parameter(torch.zeros(nOut)) if bias else None
+
+    def forward(self, x):
+        f = F.ConvFunction.apply(x.features, self.weight, self.bias, None, None, x.features.shape[0], 0)
+        return _like(x, f)
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+
+class _Pooling(nn.Module):
+    IS_MAX = True
+
+    def __init__(self, dimension, pool_size, pool_stride, nFeaturesToDrop=0):
+        super().__init__()
+        self.pool_size, self.pool_stride = _triple(pool_size), _triple(pool_stride)
+
+    def forward(self, x):
+        md = x.metadata
+        r = md.strided_rules(x.spatial_size, self.pool_size, self.pool_stride)
+        n_out = md.levels[r.out_key].n
+        vol = self.pool_size[0] * self.pool_size[1] * self.pool_size[2]
+        f = F.PoolFunction.apply(x.features, r, n_out, self.IS_MAX, 1.0 / vol)
+        return SparseConvNetTensor(f, md, torch.tensor(r.out_key, dtype=torch.long))
+
+
+class MaxPooling(_Pooling):
+    """module_factory.py:315-333: max over ACTIVE children."""
+    IS_MAX = True
+
+
+class AveragePooling(_Pooling):
+    """module_factory.py:336-354: sum over active children / pool VOLUME."""
+    IS_MAX = False
+
+
+class SparseToDense(nn.Module):
+    """module_factory.py:429-435 -> [B, C, X, Y, Z]."""
+
+    def __init__(self, dimension, nPlanes):
+        super().__init__()
+        self.nPlanes = nPlanes
+
+    def forward(self, x):
+        md = x.metadata
+        return F.SparseToDenseFunction.apply(x.features, md.level(x.spatial_size), md.n_samples,
+                                             size_key(x.spatial_size))
+
+
+class OutputLayer(nn.Module):
+    def __init__(self, dimension):
+        super().__init__()
+        self.dimension = dimension
+
+    def forward(self, x):
+        return F.OutputLayerFunction.apply(self.dimension, x.metadata, x.features)
+
+
+class InputLayer(nn.Module):
+    def __init__(self, dimension, spatial_size, mode=3):
+        super().__init__()
+        self.dimension, self.mode = dimension, mode
+        self.spatial_size = torch.as_tensor(spatial_size, dtype=torch.long)
+
+    def forward(self, inp):
+        coords, feats = inp[0], inp[1]
+        bs = inp[2] if len(inp) > 2 else 0
+        md = Metadata(self.dimension)
+        f = F.InputLayerFunction.apply(self.dimension, md, self.spatial_size, coords, feats, bs, self.mode)
+        return SparseConvNetTensor(f, md, self.spatial_size)

@@ -1,0 +1,225 @@
+"""Device-resident Metadata: the B200 replacement of SparseConvNet's `Metadata<d>`.
+
+Reference usage: one fresh `scn.Metadata(dim)` per input layer / crop
+(/root/reference ndsis/modules/custom_operations.py:70, roi_select_sparse.py:77,115),
+shared by every SparseConvNetTensor derived from it.  Upstream keeps per-scale CPU
+hash maps and std::vector rulebooks that are re-uploaded on every convolution call;
+here every scale is a `Level` living in HBM: packed row keys, an open-addressing
+table key->row, and cached output-stationary neighbour maps.  All buffers are torch
+tensors (caching allocator); the C ABI only sees raw pointers.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def size_key(size):
+    if isinstance(size, torch.Tensor):
+        return tuple(int(s) for s in size.reshape(-1).tolist())
+    return tuple(int(s) for s in np.asarray(size).reshape(-1))
+
+
+def _triple(v):
+    return tuple(int(a) for a in np.broadcast_to(np.asarray(v), (3,)))
+
+
+def exclusive_scan(x):
+    """int32 [n] -> int32 [n+1] exclusive prefix sum (own kernel, no CUB)."""
+    n = x.numel()
+    out = torch.empty(n + 1, dtype=torch.int32, device=x.device)
+    tmp = torch.empty(int(_lib.raw("scn_scan_tmp_elems")(n)), dtype=torch.int32, device=x.device)
+    _lib.call("scn_exclusive_scan", _ptr(x), _ptr(out), n, _ptr(tmp), _stream())
+    return out
+
+
+class Level:
+    """One spatial scale: rows <-> voxel coordinates."""
+
+    def __init__(self, keys, tab_keys, tab_vals, cap, n):
+        self.keys = keys              # int64 storage of uint64 packed (b,x,y,z), [n]
+        self.tab_keys = tab_keys
+        self.tab_vals = tab_vals
+        self.cap = cap
+        self.n = n
+        self.subm = {}                # filter triple -> int32 [K, n] (None for 1x1x1 = identity)
+        self._locations = None
+        self._batch_ptr = {}
+
+    def locations(self):
+        """int64 CPU [n, 4] (x,y,z,b), row aligned (reference contract: custom_operations.py:26-32)."""
+        if self._locations is None:
+            out = torch.empty((self.n, 4), dtype=torch.int64, device=self.keys.device)
+            _lib.call("scn_unpack_keys", _ptr(self.keys), self.n, _ptr(out), _stream())
+            self._locations = out.cpu()
+        return self._locations
+
+    def batch_ptr(self, n_seg):
+        """int32 [n_seg+1]: first row of every sample (rows are batch-sorted)."""
+        if n_seg not in self._batch_ptr:
+            p = torch.empty(n_seg + 1, dtype=torch.int32, device=self.keys.device)
+            _lib.call("scn_batch_offsets", _ptr(self.keys), self.n, n_seg, _ptr(p), _stream())
+            self._batch_ptr[n_seg] = p
+        return self._batch_ptr[n_seg]
+
+    def subm_map(self, filter_size):
+        f = _triple(filter_size)
+        if f not in self.subm:
+            if f == (1, 1, 1):
+                self.subm[f] = None
+            else:
+                K = f[0] * f[1] * f[2]
+                m = torch.empty((K, self.n), dtype=torch.int32, device=self.keys.device)
+                _lib.call("scn_subm_map", _ptr(self.keys), self.n, _ptr(self.tab_keys), _ptr(self.tab_vals),
+                          self.cap, f[0], f[1], f[2], _ptr(m), _stream())
+                self.subm[f] = m
+        return self.subm[f]
+
+
+def build_level(keys):
+    """keys int64[P] (packed) -> (Level, point_row int32 [P]).  Rows are numbered by first
+    appearance (SparseConvNet InputLayer.h).  One host sync (the active count)."""
+    dev = keys.device
+    P = keys.numel()
+    cap = 64
+    while cap < 2 * P:
+        cap <<= 1
+    tab_keys = torch.empty(cap, dtype=torch.int64, device=dev)
+    tab_vals = torch.empty(cap, dtype=torch.int32, device=dev)
+    s = _stream()
+    _lib.call("scn_hash_clear", _ptr(tab_keys), _ptr(tab_vals), cap, s)
+    _lib.call("scn_hash_insert_first", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, s)
+    first = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    _lib.call("scn_hash_first_flags", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(first), s)
+    rank = exclusive_scan(first[:P])
+    n = int(rank[P].item())
+    point_row = torch.empty(P, dtype=torch.int32, device=dev)
+    row_keys = torch.empty(n, dtype=torch.int64, device=dev)
+    _lib.call("scn_hash_assign_rows", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(rank),
+              _ptr(point_row), _ptr(row_keys), s)
+    _lib.call("scn_hash_finalize", _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(rank), s)
+    return Level(row_keys, tab_keys, tab_vals, cap, n), point_row
+
+
+class Strided:
+    """Rulebook of a (filter == stride) convolution between two levels."""
+
+    def __init__(self, out_key, cmap, dmap, parent_row, K):
+        self.out_key, self.cmap, self.dmap, self.parent_row, self.K = out_key, cmap, dmap, parent_row, K
+
+
+class Metadata:
+    def __init__(self, dimension=3):
+        if dimension != 3:
+            raise RuntimeError("sparse_rcnn_b200 implements the 3-D path only (ndsis uses num_dims=3)")
+        self.dimension = dimension
+        self.levels = {}
+        self.strided = {}
+        self.point_row = None
+        self.row_ptr = None
+        self.row_pts = None
+        self.n_points = 0
+        self.n_samples = 0
+        self.mode = None
+        self.input_size = None
+
+    # ---------------------------------------------------------------- input layer rule
+    def set_input(self, spatial_size, coords, batch_size, mode, device):
+        """coords: int64 [P, 3|4] on CPU or device, or already-packed keys (int64 [P], device) when
+        `coords.dim() == 1` (device-side crop path).  Returns the number of active rows."""
+        s = _stream()
+        if coords.dim() == 1:
+            keys = coords
+            max_b = None
+        else:
+            if coords.dtype != torch.int64:
+                coords = coords.long()
+            P, ncol = coords.shape
+            if ncol not in (3, 4):
+                raise RuntimeError("coords must be [P, 3] or [P, 4] (x,y,z[,b])")
+            max_b = 0
+            if ncol == 4 and P:
+                max_b = int(coords[:, 3].max())          # CPU in the reference contract => no device sync
+            cdev = coords.to(device, non_blocking=True).contiguous()
+            keys = torch.empty(P, dtype=torch.int64, device=device)
+            err = torch.zeros(1, dtype=torch.int32, device=device)
+            _lib.call("scn_pack_coords", _ptr(cdev), P, ncol, _ptr(keys), _ptr(err), s)
+            self._err = err
+        level, point_row = build_level(keys)
+        if coords.dim() != 1 and int(self._err.item()):
+            raise RuntimeError("InputLayer: coordinate outside [0, 65534]")
+        if max_b is None:
+            max_b = int((keys.max().item() >> 48) & 0xFFFF) if keys.numel() else 0
+        P = keys.numel()
+        if mode == 0 and level.n != P:
+            raise RuntimeError("InputLayer mode 0 requires unique coordinates (%d points, %d voxels)" % (P, level.n))
+        self.input_size = size_key(spatial_size)
+        self.levels[self.input_size] = level
+        self.point_row, self.n_points, self.mode = point_row, P, mode
+        self.n_samples = max(int(batch_size), max_b + 1, 1)
+        if mode != 0:
+            n = level.n
+            cnt = torch.zeros(n, dtype=torch.int32, device=device)
+            _lib.call("scn_rule_count", _ptr(point_row), P, _ptr(cnt), s)
+            self.row_ptr = exclusive_scan(cnt)
+            cnt.zero_()
+            self.row_pts = torch.empty(P, dtype=torch.int32, device=device)
+            _lib.call("scn_rule_fill", _ptr(point_row), P, _ptr(self.row_ptr), _ptr(cnt), _ptr(self.row_pts), s)
+            _lib.call("scn_rule_sort", _ptr(self.row_ptr), n, _ptr(self.row_pts), s)
+        return level.n
+
+    def level(self, spatial_size):
+        k = size_key(spatial_size)
+        if k not in self.levels:
+            raise RuntimeError("Metadata has no active set at spatial size %s" % (k,))
+        return self.levels[k]
+
+    def rule_csr(self):
+        """(row_ptr, row_pts) of the input rule; built lazily for mode 0 (identity)."""
+        if self.row_ptr is None:
+            dev = self.point_row.device
+            self.row_ptr = torch.arange(self.n_points + 1, dtype=torch.int32, device=dev)
+            self.row_pts = torch.arange(self.n_points, dtype=torch.int32, device=dev)
+        return self.row_ptr, self.row_pts
+
+    # ---------------------------------------------------------------- strided rulebooks
+    def strided_rules(self, in_size, filter_size, stride):
+        f, st = _triple(filter_size), _triple(stride)
+        ik = size_key(in_size)
+        key = (ik, f, st)
+        if key in self.strided:
+            return self.strided[key]
+        if f != st:
+            raise RuntimeError("only filter_size == filter_stride is implemented (the form ndsis uses)")
+        out_size = tuple((i - a) // b + 1 for i, a, b in zip(ik, f, st))
+        if any((o - 1) * b + a != i for o, a, b, i in zip(out_size, f, st, ik)):
+            raise RuntimeError("spatial size %s incompatible with filter %s / stride %s" % (ik, f, st))
+        lin = self.level(ik)
+        dev = lin.keys.device
+        s = _stream()
+        K = f[0] * f[1] * f[2]
+        pkeys = torch.empty(lin.n, dtype=torch.int64, device=dev)
+        offs = torch.empty(lin.n, dtype=torch.int32, device=dev)
+        _lib.call("scn_stride_keys", _ptr(lin.keys), lin.n, st[0], st[1], st[2], _ptr(pkeys), _ptr(offs), s)
+        if out_size in self.levels:
+            lout = self.levels[out_size]
+            parent_row = torch.empty(lin.n, dtype=torch.int32, device=dev)
+            _lib.call("scn_hash_lookup", _ptr(pkeys), lin.n, _ptr(lout.tab_keys), _ptr(lout.tab_vals), lout.cap,
+                      _ptr(parent_row), s)
+        else:
+            lout, parent_row = build_level(pkeys)
+            self.levels[out_size] = lout
+        cmap = torch.full((K, lout.n), -1, dtype=torch.int32, device=dev)
+        dmap = torch.empty((K, lin.n), dtype=torch.int32, device=dev)
+        _lib.call("scn_strided_maps", _ptr(parent_row), _ptr(offs), lin.n, lout.n, K, _ptr(cmap), _ptr(dmap), s)
+        r = Strided(out_size, cmap, dmap, parent_row, K)
+        self.strided[key] = r
+        return r

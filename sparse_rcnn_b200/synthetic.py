@@ -1,0 +1,116 @@
+"""Synthetic "ScanNet-shaped" scenes.
+
+Produces the 5-tuple the hot path consumes, in the format of the reference's
+`collate_fn` (/root/reference ndsis/data/data.py:88-115):
+``(coords [P,4] int64 CPU (x,y,z,b), feats [P,C] fp32, spatial_size [3] long,
+batch_size, batch_splits)``.  A scene is a room shell (floor + 4 walls) plus
+random furniture boxes (5 faces each) sampled as jittered surface points, so
+that the active set has the 2-D-manifold neighbourhood statistics of a scan
+(mean 3^3 occupancy ~10-18 instead of 27) and ~1.6-2 points per voxel.
+"""
+import numpy as np
+import torch
+
+# anchor shapes in metres (reference scannet_config/network.py:5-19); used for proposal boxes
+ANCHORS_M = np.array([
+    [0.3752, 0.3752, 0.4221], [0.6566, 0.6566, 0.5159], [0.6566, 0.6566, 0.9380],
+    [0.4221, 0.4221, 1.6415], [0.1876, 1.3132, 1.0318], [0.3283, 0.9849, 1.8291],
+    [0.7035, 1.5008, 0.8442], [1.3132, 0.1876, 1.0318], [0.9849, 0.3283, 1.7822],
+    [1.5008, 0.7035, 0.8442], [0.8442, 2.1574, 0.3752], [2.1574, 0.8442, 0.3752],
+    [2.4857, 1.1256, 1.0318], [1.1256, 2.4857, 1.0318]])
+VOXEL_M = 0.0375       # reference scannet_config/run.py:357-370
+
+
+def _face(rng, origin, u, v, normal, density, jitter):
+    """Sample a rectangle origin + a*u + b*v (a,b in [0,1]) with `density` points per voxel^2."""
+    area = np.linalg.norm(u) * np.linalg.norm(v)
+    n = max(int(area * density), 1)
+    a, b = rng.random(n), rng.random(n)
+    p = origin[None] + a[:, None] * u[None] + b[:, None] * v[None]
+    p = p + rng.normal(0, jitter, (n, 1)) * normal[None]
+    return p, np.repeat(normal[None], n, 0)
+
+
+def _box_faces(lo, hi, with_bottom):
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    d = hi - lo
+    ex, ey, ez = np.array([d[0], 0, 0]), np.array([0, d[1], 0]), np.array([0, 0, d[2]])
+    faces = [
+        (lo, ey, ez, np.array([-1., 0, 0])), (lo + ex, ey, ez, np.array([1., 0, 0])),
+        (lo, ex, ez, np.array([0, -1., 0])), (lo + ey, ex, ez, np.array([0, 1., 0])),
+        (lo + ez, ex, ey, np.array([0, 0, 1.])),
+    ]
+    if with_bottom:
+        faces.append((lo, ex, ey, np.array([0, 0, -1.])))
+    return faces
+
+
+def make_scene(seed=0, spatial_size=(256, 256, 128), room=(176, 176, 88), room_offset=(32, 32, 8),
+               n_furniture=24, density=1.5, jitter=0.1, in_channels=6, scale=1.0):
+    """One sample: (coords [P,3] int64, feats [P,C] fp32).  `scale` rescales the room (and
+    the furniture) to steer the active-voxel count; scale=1 gives N ~ 150-180k."""
+    rng = np.random.default_rng(seed)
+    size = np.asarray(spatial_size)
+    room = np.minimum(np.asarray(room, float) * scale, size - 2 * 4).astype(float)
+    off = np.minimum(np.asarray(room_offset, float), size - room - 1)
+    lo, hi = off, off + room
+    pts, nrm = [], []
+    # room shell: floor + 4 walls, normals pointing inwards
+    ex, ey, ez = np.array([room[0], 0, 0]), np.array([0, room[1], 0]), np.array([0, 0, room[2]])
+    shell = [(lo, ex, ey, np.array([0, 0, 1.])),
+             (lo, ey, ez, np.array([1., 0, 0])), (lo + ex, ey, ez, np.array([-1., 0, 0])),
+             (lo, ex, ez, np.array([0, 1., 0])), (lo + ey, ex, ez, np.array([0, -1., 0]))]
+    for f in shell:
+        p, n = _face(rng, *f, density, jitter)
+        pts.append(p), nrm.append(n)
+    for _ in range(n_furniture):
+        e = rng.uniform(8, 48, 3) * scale
+        e = np.minimum(e, room - 2)
+        p0 = lo + np.array([rng.uniform(1, room[0] - e[0] - 1), rng.uniform(1, room[1] - e[1] - 1), 0.0])
+        for f in _box_faces(p0, p0 + e, with_bottom=False):
+            p, n = _face(rng, *f, density, jitter)
+            pts.append(p), nrm.append(n)
+    p = np.concatenate(pts)
+    n = np.concatenate(nrm)
+    c = np.floor(p).astype(np.int64)
+    keep = ((c >= 0) & (c < size[None])).all(1)
+    c, n = c[keep], n[keep]
+    perm = rng.permutation(len(c))          # a scan has no spatial order
+    c, n = c[perm], n[perm]
+    rgb = rng.uniform(-1, 1, (len(c), 3))
+    n = n + rng.normal(0, 0.05, n.shape)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    feats = np.concatenate([rgb, n], 1).astype(np.float32)
+    if in_channels > 6:
+        feats = np.concatenate([feats, np.ones((len(c), in_channels - 6), np.float32)], 1)
+    feats = feats[:, :in_channels]
+    return torch.from_numpy(c), torch.from_numpy(np.ascontiguousarray(feats))
+
+
+def make_batch(n_scenes=1, seed=0, spatial_size=(256, 256, 128), **kw):
+    """Batch in collate_fn format (data.py:95-107)."""
+    coords, feats, splits = [], [], []
+    for i in range(n_scenes):
+        c, f = make_scene(seed + i, spatial_size, **kw)
+        coords.append(torch.nn.functional.pad(c, (0, 1), value=i))
+        feats.append(f)
+        splits.append(len(c))
+    return (torch.cat(coords), torch.cat(feats), torch.tensor(spatial_size, dtype=torch.long),
+            n_scenes, splits)
+
+
+def make_boxes(coords, n_boxes=256, seed=0, spatial_size=(256, 256, 128)):
+    """Proposal-like boxes per sample: list over samples of [n_i, 2, 3] fp32 (start, stop) in voxels.
+    Centres on random points, edges from the 14 anchor shapes x U[0.8,1.2]."""
+    rng = np.random.default_rng(seed + 7919)
+    coords = coords.numpy() if isinstance(coords, torch.Tensor) else coords
+    n_samples = int(coords[:, 3].max()) + 1 if len(coords) else 1
+    out = []
+    for b in range(n_samples):
+        c = coords[coords[:, 3] == b, :3]
+        ctr = c[rng.integers(0, len(c), n_boxes)].astype(np.float64) + 0.5
+        edge = ANCHORS_M[rng.integers(0, len(ANCHORS_M), n_boxes)] / VOXEL_M * rng.uniform(0.8, 1.2, (n_boxes, 1))
+        box = np.stack([ctr - edge / 2, ctr + edge / 2], 1)
+        box = np.clip(box, 0, np.asarray(spatial_size, float)[None, None])
+        out.append(torch.from_numpy(box.astype(np.float32)))
+    return out

@@ -1,0 +1,48 @@
+"""GPU parity: whole sparse U-Net feature extractor (BASELINE config 1 graph) forward + backward
+vs the oracle on a reduced scene, in both precisions."""
+import pytest
+import torch
+
+import scn_oracle as O
+from sparse_rcnn_b200 import networks
+from sparse_rcnn_b200.synthetic import make_batch
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_batch(n_scenes=2):
+    return make_batch(n_scenes, 3, spatial_size=(64, 64, 32), room=(44, 44, 22), room_offset=(8, 8, 2), n_furniture=4)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("tf32", 2e-3)])
+def test_feature_extractor_fwd_bwd(cuda, precision, tol):
+    from sparse_rcnn_b200 import scn
+    scn.set_precision(precision)
+    torch.manual_seed(0)
+    ref = networks.FeatureExtractor(O)
+    seg_o = networks.SegmentationNetwork(O)
+    net = networks.FeatureExtractor(scn)
+    seg_g = networks.SegmentationNetwork(scn)
+    net.load_state_dict(ref.state_dict()), seg_g.load_state_dict(seg_o.state_dict())
+    net.to(cuda), seg_g.to(cuda)
+    coords, feats, size, bs, splits = _small_batch()
+    fo = feats.clone().requires_grad_(True)
+    fg = feats.to(cuda).requires_grad_(True)
+    out_o = ref((coords, fo, size, bs, splits))
+    out_g = net((coords, fg, size, bs, splits))
+    assert out_g[1] == out_o[1] == 2
+    for lo, lg in zip(out_o[4] + out_o[5], out_g[4] + out_g[5]):
+        assert lo.features.shape == lg.features.shape
+        assert torch.equal(lo.get_spatial_locations(), lg.get_spatial_locations())
+        assert rel_err(lg.features, lo.features) <= tol, rel_err(lg.features, lo.features)
+    so, sg = seg_o(out_o[5]), seg_g(out_g[5])
+    assert so.shape == sg.shape == (len(coords), 20)
+    assert rel_err(sg, so) <= tol
+    g = torch.randn_like(so)
+    so.backward(g)
+    sg.backward(g.to(cuda))
+    assert rel_err(fg.grad, fo.grad) <= 5 * tol, rel_err(fg.grad, fo.grad)
+    worst = max(rel_err(pg.grad, po.grad) for (_, po), (_, pg) in zip(ref.named_parameters(), net.named_parameters())
+                if po.grad is not None)
+    assert worst <= 10 * tol, worst

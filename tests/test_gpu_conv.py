@@ -1,0 +1,111 @@
+"""GPU parity: convolution family (SubM / Convolution / Deconvolution / NiN) forward and backward
+vs the oracle.  fp32 verification mode: rel <= 1e-5; TF32 tcgen05 path: rel <= 2e-3 (north_star)."""
+import pytest
+import torch
+
+import scn_oracle as O
+from tests.util import copy_params, make_pair, random_scene, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-5, "tf32": 2e-3}
+
+
+def _scn(precision):
+    from sparse_rcnn_b200 import scn
+    scn.set_precision(precision)
+    return scn
+
+
+def _run(layer_o, layer_g, to, tg, tol):
+    xo = to.features.clone().requires_grad_(True)
+    xg = tg.features.clone().requires_grad_(True)
+    yo = layer_o(O.SparseConvNetTensor(xo, to.metadata, to.spatial_size))
+    yg = layer_g(type(tg)(xg, tg.metadata, tg.spatial_size))
+    fo = yo.features if hasattr(yo, "features") else yo
+    fg = yg.features if hasattr(yg, "features") else yg
+    assert fo.shape == fg.shape
+    assert rel_err(fg, fo) <= tol, ("fwd", rel_err(fg, fo))
+    go = torch.randn_like(fo)
+    fo.backward(go)
+    fg.backward(go.to(fg.device))
+    assert rel_err(xg.grad, xo.grad) <= tol, ("dx", rel_err(xg.grad, xo.grad))
+    for (n, po), (_, pg) in zip(layer_o.named_parameters(), layer_g.named_parameters()):
+        assert rel_err(pg.grad, po.grad) <= 5 * tol, (n, rel_err(pg.grad, po.grad))
+    return yo, yg
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("cin,cout,fs", [(5, 7, 3), (32, 32, 3), (6, 32, 1), (48, 80, 3), (22, 22, 3), (44, 24, 3),
+                                         (128, 128, 3), (16, 256, 3), (7, 18, 3)])
+def test_submanifold(cuda, precision, cin, cout, fs):
+    scn = _scn(precision)
+    torch.manual_seed(0)
+    coords, feats, size = random_scene(cin * 31 + cout, channels=cin)
+    to, tg = make_pair(scn, coords, feats, size, cuda)
+    lo = O.SubmanifoldConvolution(3, cin, cout, fs, True)
+    lo.bias.data.normal_()
+    lg = copy_params(lo, scn.SubmanifoldConvolution(3, cin, cout, fs, True), cuda)
+    _run(lo, lg, to, tg, TOL[precision])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("cin,cout", [(32, 48), (22, 32), (6, 16)])
+def test_strided_conv_and_deconv(cuda, precision, cin, cout):
+    scn = _scn(precision)
+    torch.manual_seed(1)
+    coords, feats, size = random_scene(cin + cout, size=(24, 20, 16), channels=cin)
+    to, tg = make_pair(scn, coords, feats, size, cuda)
+    lo = O.Convolution(3, cin, cout, 2, 2, True)
+    lo.bias.data.normal_()
+    lg = copy_params(lo, scn.Convolution(3, cin, cout, 2, 2, True), cuda)
+    yo, yg = _run(lo, lg, to, tg, TOL[precision])
+    assert tuple(yg.spatial_size.tolist()) == tuple(yo.spatial_size.tolist())
+    do = O.Deconvolution(3, cout, cin, 2, 2, True)
+    do.bias.data.normal_()
+    dg = copy_params(do, scn.Deconvolution(3, cout, cin, 2, 2, True), cuda)
+    yo2 = O.SparseConvNetTensor(yo.features.detach(), yo.metadata, yo.spatial_size)
+    yg2 = type(yg)(yo.features.detach().to(cuda), yg.metadata, yg.spatial_size)
+    _run(do, dg, yo2, yg2, TOL[precision])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_network_in_network(cuda, precision):
+    scn = _scn(precision)
+    torch.manual_seed(2)
+    coords, feats, size = random_scene(9, channels=44)
+    to, tg = make_pair(scn, coords, feats, size, cuda)
+    lo = O.NetworkInNetwork(44, 22, True)
+    lo.bias.data.normal_()
+    lg = copy_params(lo, scn.NetworkInNetwork(44, 22, True), cuda)
+    _run(lo, lg, to, tg, TOL[precision])
+
+
+def test_no_bias_and_empty_rows(cuda):
+    scn = _scn("tf32")
+    coords, feats, size = random_scene(4, channels=16)
+    to, tg = make_pair(scn, coords, feats, size, cuda)
+    lo = O.SubmanifoldConvolution(3, 16, 16, 3, False)
+    lg = copy_params(lo, scn.SubmanifoldConvolution(3, 16, 16, 3, False), cuda)
+    _run(lo, lg, to, tg, TOL["tf32"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_large_layer_linearity(cuda, precision):
+    """BASELINE-size single layer (config 3): conv(a*x + y) == a*conv(x) + conv(y) and parity of the
+    two precisions with each other (no oracle at this size)."""
+    scn = _scn(precision)
+    from sparse_rcnn_b200.synthetic import make_batch
+    coords, feats, size, bs, _ = make_batch(1, 0)
+    torch.manual_seed(3)
+    md = scn.Metadata(3)
+    f6 = scn.ioLayers.InputLayerFunction.apply(3, md, size, coords, feats.to(cuda), bs, 4)
+    n = f6.shape[0]
+    conv = scn.SubmanifoldConvolution(3, 32, 32, 3, False).to(cuda)
+    x, y = torch.randn(n, 32, device=cuda), torch.randn(n, 32, device=cuda)
+    T = lambda f: scn.SparseConvNetTensor(f, md, size)
+    with torch.no_grad():
+        cx, cy, cxy = conv(T(x)).features, conv(T(y)).features, conv(T(2.5 * x + y)).features
+        assert rel_err(cxy, 2.5 * cx + cy) <= (1e-5 if precision == "fp32" else 4e-3)
+        scn.set_precision("fp32")
+        ref = conv(T(x)).features
+        assert rel_err(cx, ref) <= TOL[precision]
