@@ -144,9 +144,13 @@ int scn_col_sum(const float* in, int ld, int n, int C, float* out, scn_stream_t 
 
 /* ------------------------------------------------------------------ elementwise ------------
  * scn.ReLU module_factory.py:86-89; AddTable :51-57; BatchNorm(Leaky)ReLU :92-113. */
-int scn_relu_fwd(const float* in, float* out, int64_t n, scn_stream_t stream);
+/* round_tf32 != 0: the result is additionally rounded (to nearest, ties away) to TF32 so that a
+ * following tcgen05 kind::tf32 MMA, which TRUNCATES fp32 operands, reads it exactly. */
+int scn_relu_fwd(const float* in, float* out, int64_t n, int round_tf32, scn_stream_t stream);
 int scn_relu_bwd(const float* out_or_in, const float* grad_out, float* grad_in, int64_t n,
-                 scn_stream_t stream);
+                 int round_tf32, scn_stream_t stream);
+/* out = rna_tf32(in) */
+int scn_round_tf32(const float* in, float* out, int64_t n, scn_stream_t stream);
 int scn_add(const float* a, const float* b, float* out, int64_t n, scn_stream_t stream);
 /* per-channel mean and biased variance over n rows (two-pass, deterministic) */
 int scn_bn_stats(const float* in, int n, int C, float* mean, float* var, scn_stream_t stream);

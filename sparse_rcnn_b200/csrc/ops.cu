@@ -9,6 +9,19 @@ namespace scn {
 constexpr int TB = 256;
 
 // ------------------------------------------------------------------------------ elementwise
+__device__ __forceinline__ float rna_tf32(float v) {
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+    return __uint_as_float(t);
+}
+// MODE 0: relu, 1: relu + tf32 rounding, 2: tf32 rounding only
+template <int MODE>
+__device__ __forceinline__ float ew(float v) {
+    if (MODE != 2) v = fmaxf(v, 0.f);
+    if (MODE != 0) v = rna_tf32(v);
+    return v;
+}
+template <int MODE>
 __global__ void k_relu_fwd(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
     int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
@@ -16,16 +29,20 @@ __global__ void k_relu_fwd(const float* __restrict__ in, float* __restrict__ out
     for (; i < n; i += stride) {
         if (vec && i + 3 < n) {
             float4 v = *reinterpret_cast<const float4*>(in + i);
-            v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+            v.x = ew<MODE>(v.x), v.y = ew<MODE>(v.y), v.z = ew<MODE>(v.z), v.w = ew<MODE>(v.w);
             *reinterpret_cast<float4*>(out + i) = v;
         } else {
-            for (int j = 0; j < 4 && i + j < n; ++j) out[i + j] = fmaxf(in[i + j], 0.f);
+            for (int j = 0; j < 4 && i + j < n; ++j) out[i + j] = ew<MODE>(in[i + j]);
         }
     }
 }
+template <bool ROUND>
 __global__ void k_relu_bwd(const float* __restrict__ y, const float* __restrict__ go, float* __restrict__ gi, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i < n; i += (int64_t)gridDim.x * blockDim.x) gi[i] = y[i] > 0.f ? go[i] : 0.f;
+    for (; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float g = y[i] > 0.f ? go[i] : 0.f;
+        gi[i] = ROUND ? rna_tf32(g) : g;
+    }
 }
 __global__ void k_add(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -404,15 +421,26 @@ constexpr int NSLAB = 296;  // 2 x 148 SMs
 
 extern "C" {
 
-int scn_relu_fwd(const float* in, float* out, int64_t n, scn_stream_t stream) {
+int scn_relu_fwd(const float* in, float* out, int64_t n, int round_tf32, scn_stream_t stream) {
     if (n <= 0) return SCN_OK;
-    k_relu_fwd<<<grid_for((n + 3) / 4, TB), TB, 0, as_stream(stream)>>>(in, out, n);
+    if (round_tf32)
+        k_relu_fwd<1><<<grid_for((n + 3) / 4, TB), TB, 0, as_stream(stream)>>>(in, out, n);
+    else
+        k_relu_fwd<0><<<grid_for((n + 3) / 4, TB), TB, 0, as_stream(stream)>>>(in, out, n);
     return check_launch("relu_fwd");
 }
-int scn_relu_bwd(const float* y, const float* go, float* gi, int64_t n, scn_stream_t stream) {
+int scn_relu_bwd(const float* y, const float* go, float* gi, int64_t n, int round_tf32, scn_stream_t stream) {
     if (n <= 0) return SCN_OK;
-    k_relu_bwd<<<grid_for(n, TB), TB, 0, as_stream(stream)>>>(y, go, gi, n);
+    if (round_tf32)
+        k_relu_bwd<true><<<grid_for(n, TB), TB, 0, as_stream(stream)>>>(y, go, gi, n);
+    else
+        k_relu_bwd<false><<<grid_for(n, TB), TB, 0, as_stream(stream)>>>(y, go, gi, n);
     return check_launch("relu_bwd");
+}
+int scn_round_tf32(const float* in, float* out, int64_t n, scn_stream_t stream) {
+    if (n <= 0) return SCN_OK;
+    k_relu_fwd<2><<<grid_for((n + 3) / 4, TB), TB, 0, as_stream(stream)>>>(in, out, n);
+    return check_launch("round_tf32");
 }
 int scn_add(const float* a, const float* b, float* out, int64_t n, scn_stream_t stream) {
     if (n <= 0) return SCN_OK;

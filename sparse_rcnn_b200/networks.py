@@ -184,3 +184,112 @@ class SegmentationNetwork(nn.Module):
 
 def count_parameters(m):
     return sum(p.numel() for p in m.parameters())
+
+
+# ----------------------------------------------------------------------------- heads on crops
+class SparseGlobalPool(nn.Module):
+    """Per-box mean over the rows of each sample (reference SparseGlobalPool / split_batch,
+    custom_operations.py:24-59, which builds a [B, N] mask and loops in Python).  On the B200
+    backend this is one segment-mean kernel over the batch-sorted rows."""
+
+    def __init__(self, scn):
+        super().__init__()
+        self.scn = scn
+
+    def forward(self, x):
+        if getattr(self.scn, "BACKEND", "") == "b200-cuda":
+            from .scn.functions import SegmentMeanFunction
+            md = x.metadata
+            n_seg = md.n_samples
+            ptr = md.level(x.spatial_size).batch_ptr(n_seg)
+            return SegmentMeanFunction.apply(x.features, ptr, n_seg)
+        # generic namespace (e.g. the CPU oracle in tests): reference algorithm
+        b = x.get_spatial_locations()[:, -1]
+        n = x.batch_size()
+        out = x.features.new_zeros((n, x.features.shape[1]))
+        cnt = torch.bincount(b, minlength=n).clamp(min=1).to(out.dtype)
+        out.index_add_(0, b.to(x.features.device), x.features)
+        return out / cnt[:, None].to(out.device)
+
+
+def linear_stack(cin, channel_list, start_relu):
+    """reference get_linear_layer_network (module_factory.py:676-693), end_relu=False."""
+    layers = [nn.ReLU()] if start_relu else []
+    layers.append(nn.Linear(cin, channel_list[0]))
+    c = channel_list[0]
+    for ch in channel_list[1:]:
+        layers += [nn.ReLU(inplace=True), nn.Linear(c, ch)]
+        c = ch
+    return nn.Sequential(*layers)
+
+
+class ClassNetwork(nn.Module):
+    """Sparse branch of the reference ClassNetwork (model.py:470-569) as configured by
+    run.py:640-718: level-2 map (64 ch, stride 4) -> [SubM1 64->32 + 1 unit] -> SparseRoiCut
+    (Tensor->Tensor, boxes / stride, clipped) -> [Conv s2 32->64 + unit] -> [Conv s2 64->128 + unit]
+    -> per-box mean -> ReLU, Linear 128->64, ReLU, Linear 64->classes."""
+
+    def __init__(self, scn, roi_cut_factory, input_channels=64, stride=4, mid=32, out_channels=(64, 128),
+                 linear_channels=(64,), num_classes=18):
+        super().__init__()
+        self.input_conv_layer = scn.Sequential(encoder_level(scn, input_channels, mid, 1, 1))
+        self.roi_getter = roi_cut_factory(raw_scene=False, clip_boxes=True, resize_boxes=[stride] * 3)
+        levels, c = [], mid
+        for oc in out_channels:
+            levels.append(encoder_level(scn, c, oc, 2, 1))
+            c = oc
+        self.output_conv_layer = scn.Sequential(*levels)
+        self.vectorice_layer = SparseGlobalPool(scn)
+        self.linear_layer = linear_stack(c, list(linear_channels) + [num_classes], start_relu=True)
+
+    def forward(self, feature_map, roi_bbox):
+        x = self.input_conv_layer(feature_map)
+        boxes, selection = self.roi_getter(x, roi_bbox)
+        y = self.output_conv_layer(boxes)
+        return self.linear_layer(self.vectorice_layer(y)), selection
+
+
+class SparseMaskNetwork(nn.Module):
+    """reference SparseMaskNetwork (model.py:572-782) as configured by run.py:722-800
+    (use_unet_features, use_raw_features, internal U-Net, no skip features):
+      input convs on the last U-Net map (SubM1 32->16 + 2 units) -> OutputLayer to points, cat raw
+      point features (16+C_in) -> SparseRoiCut on the raw scene with spatial size + 32 (mode 4,
+      batch = boxes) -> internal U-Net 22->32->48->64->48->32->22 -> OutputLayer -> Linear 22->32->classes."""
+
+    def __init__(self, scn, roi_cut_factory, input_channels=6, unet_channels=32, mid=16, levels=(32, 48, 64),
+                 channel_list=(32, 18), extension=32, min_unet_channels=16):
+        super().__init__()
+        self.scn = scn
+        self.extension = extension
+        self.input_conv_layer = scn.Sequential(encoder_level(scn, unet_channels, mid, 1, 2))
+        self.point_layer = scn.OutputLayer(3)
+        self.output_roi_cut = roi_cut_factory(raw_scene=True, clip_boxes=False, resize_boxes=None)
+        c0 = mid + input_channels
+        down, c = [scn.Identity()], c0
+        for ch in levels:
+            down.append(encoder_level(scn, c, ch, 2, 2))
+            c = ch
+        chans = [c0] + list(levels)
+        rev = chans[::-1]
+        ups, c = [], rev[0]
+        for skip in rev[1:]:
+            out = max(skip, min_unet_channels)
+            ups.append(decoder_level(scn, c, skip, out, 2, 2))
+            c = out
+        self.output_conv_layer = UNet(Interims(*down), ReuniteLast(*ups))
+        self.final_point_layer = scn.OutputLayer(3)
+        self.classes = channel_list[-1]
+        self.linear_layer = linear_stack(c, list(channel_list), start_relu=False)
+
+    def forward(self, scene, unet_feature_maps, roi_bbox):
+        coords, feats, spatial_size, *other, batch_splits = scene
+        x = self.input_conv_layer(unet_feature_maps[-1])
+        point_feats = self.point_layer(x)
+        combined = torch.cat((point_feats, feats.to(point_feats.device)), dim=-1)
+        size = torch.as_tensor(spatial_size, dtype=torch.long) + self.extension
+        new_scene = (coords, combined, size, *other, batch_splits)
+        boxes_tensor, selection = self.output_roi_cut(new_scene, roi_bbox)
+        if boxes_tensor.features.shape[0] == 0:
+            return combined.new_zeros((0, self.classes)), selection
+        y = self.output_conv_layer(boxes_tensor)
+        return self.linear_layer(self.final_point_layer(y)), selection

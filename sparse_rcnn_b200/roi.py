@@ -1,0 +1,223 @@
+"""Per-proposal sparse crop ("mask crop"): host-side mirror of the reference's
+ndsis/modules/roi_select_sparse.py + roi_select_bbox_transform.py on top of the crop kernels.
+
+Reference behaviour restated (file:line in /root/reference):
+  * BBoxTransformerSlice (roi_select_bbox_transform.py:87-97): cat boxes, optional divide by the
+    feature stride, floor(start)/ceil(stop) -> int64 (utils/bbox.py:87-106), optional asymmetric
+    clip start in [0,S-1], stop in [1,S] (utils/bbox.py:62-84); returns (boxes, counts, sample ids).
+  * get_inside_indicator (roi_select_sparse.py:157-167): half-open integer box test AND sample match.
+  * select_features / select_coords (:125-149): gather in (box, point) order; xyz stay ABSOLUTE,
+    the batch column becomes the box index.
+  * combiners (:55-122): Raw->Tensor uses InputLayer mode 4 with batch_size = #boxes; Tensor->Tensor
+    uses mode 0.
+The reference materialises a dense [BB, P] comparison, boolean-mask gathers and moves `is_inside`
+and the cropped coords to the CPU (:180).  Here only the points of the box's own sample are tested,
+the selection is compacted on the device (count -> scan -> ordered select) and the cropped keys feed
+the device hash builder directly; `is_inside` is produced on the device (optionally copied to the
+CPU to keep the reference's return format).
+"""
+import weakref
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _lib
+from .scn.metadata import _ptr, _stream, exclusive_scan, size_key
+
+CROP_CHUNK = 2048      # SCN_CROP_CHUNK
+
+
+def round_bbox(boxes):
+    start, stop = boxes.unbind(-2)
+    return torch.stack((start.floor(), stop.ceil()), dim=-2).long()
+
+
+def clip_boxes_asymmetric(boxes, scene_shape):
+    lo = boxes.new_tensor([[0], [1]])
+    hi = torch.stack((scene_shape - 1, scene_shape))
+    return torch.max(torch.min(boxes, hi), lo)
+
+
+class BBoxTransformerSlice(nn.Module):
+    def __init__(self, clip=False, resize=None):
+        super().__init__()
+        self.clip, self.resize = clip, resize
+
+    def forward(self, bbox_batch, shape=None):
+        counts = [len(b) for b in bbox_batch]
+        raw = torch.cat(list(bbox_batch))
+        if self.resize is not None:
+            raw = raw / raw.new_tensor(self.resize)
+        boxes = round_bbox(raw)
+        if self.clip:
+            boxes = clip_boxes_asymmetric(boxes, boxes.new_tensor(tuple(int(s) for s in shape)))
+        assoc = torch.cat([torch.full((c,), i, dtype=torch.long) for i, c in enumerate(counts)]) \
+            if counts else torch.zeros(0, dtype=torch.long)
+        return boxes, counts, assoc
+
+
+# ------------------------------------------------------------------------------- key cache
+_KEY_CACHE = {}
+
+
+def _packed_keys(coords, device):
+    """Packed device keys of a raw [P,4] coordinate tensor (cached per tensor object)."""
+    k = id(coords)
+    hit = _KEY_CACHE.get(k)
+    if hit is not None and hit[0]() is coords:
+        return hit[1]
+    P, ncol = coords.shape
+    cdev = coords.to(device, non_blocking=True).contiguous()
+    keys = torch.empty(P, dtype=torch.int64, device=device)
+    err = torch.zeros(1, dtype=torch.int32, device=device)
+    _lib.call("scn_pack_coords", _ptr(cdev), P, ncol, _ptr(keys), _ptr(err), _stream())
+    if len(_KEY_CACHE) > 64:
+        _KEY_CACHE.clear()
+    _KEY_CACHE[k] = (weakref.ref(coords), keys)
+    return keys
+
+
+class GatherRowsFunction(Function):
+    """out[i] = x[idx[i]]; backward scatter-adds (boxes may overlap)."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        x = x.contiguous()
+        n, C = idx.numel(), x.shape[1]
+        out = torch.empty((n, C), dtype=torch.float32, device=x.device)
+        _lib.call("scn_gather_rows", _ptr(x), x.stride(0), _ptr(idx), n, C, _ptr(out), C, _stream())
+        ctx.idx, ctx.shape = idx, x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        go = go.contiguous()
+        gi = torch.zeros(ctx.shape, dtype=torch.float32, device=go.device)
+        _lib.call("scn_scatter_add_rows", _ptr(go), _ptr(ctx.idx), ctx.idx.numel(), ctx.shape[1], _ptr(gi), _stream())
+        return gi, None
+
+
+class CropSelection:
+    """Result of one crop: which source points fall into which box, in (box, point) order."""
+
+    def __init__(self, sel_pt, new_keys, box_ptr, n_boxes, n_points, is_inside, bbox_sample_count, batch_splits):
+        self.sel_pt, self.new_keys, self.box_ptr = sel_pt, new_keys, box_ptr
+        self.n_boxes, self.n_points = n_boxes, n_points
+        self._is_inside = is_inside
+        self.bbox_sample_count, self.batch_splits = bbox_sample_count, batch_splits
+
+    @property
+    def total(self):
+        return self.sel_pt.numel()
+
+    def is_inside(self, cpu=False):
+        m = self._is_inside.view(self.n_boxes, self.n_points).bool()
+        return m.cpu() if cpu else m
+
+    def as_reference_tuple(self, cpu=True):
+        """(is_inside, bbox_sample_count, batch_splits) -- the reference's `selection` triple."""
+        return self.is_inside(cpu), self.bbox_sample_count, self.batch_splits
+
+    def __iter__(self):
+        return iter(self.as_reference_tuple())
+
+    def __len__(self):
+        return 3
+
+
+def crop(point_keys, sample_ptr, max_sample_len, boxes, box_sample, want_is_inside=True):
+    """point_keys int64[P] (device, grouped by sample), sample_ptr int32 [B+1] (device),
+    boxes int64 [BB,2,3] (any device), box_sample int64 [BB].  One host sync (the selected count)."""
+    dev = point_keys.device
+    P, BB = point_keys.numel(), boxes.shape[0]
+    s = _stream()
+    b32 = boxes.to(device=dev, dtype=torch.int32).contiguous()
+    bs32 = box_sample.to(device=dev, dtype=torch.int32).contiguous()
+    n_chunks = max((max_sample_len + CROP_CHUNK - 1) // CROP_CHUNK, 1)
+    counts = torch.empty(BB * n_chunks, dtype=torch.int32, device=dev)
+    _lib.call("scn_crop_count", _ptr(point_keys), _ptr(sample_ptr), _ptr(b32), _ptr(bs32), BB, n_chunks,
+              _ptr(counts), s)
+    offsets = exclusive_scan(counts)
+    total = int(offsets[-1].item()) if BB else 0
+    sel_pt = torch.empty(total, dtype=torch.int32, device=dev)
+    new_keys = torch.empty(total, dtype=torch.int64, device=dev)
+    inside = torch.zeros(BB * P, dtype=torch.uint8, device=dev) if want_is_inside else None
+    _lib.call("scn_crop_select", _ptr(point_keys), _ptr(sample_ptr), _ptr(b32), _ptr(bs32), BB, n_chunks,
+              _ptr(offsets), P, _ptr(sel_pt), _ptr(new_keys), _ptr(inside), s)
+    box_ptr = offsets[::n_chunks].contiguous() if BB else offsets          # [BB+1] first slot of every box
+    return sel_pt, new_keys, box_ptr, total, inside
+
+
+# ------------------------------------------------------------------------------- extractor / combiners
+class RawScene:
+    """extract() of the reference's Raw* combiners: scene = (coords, feats, spatial_size, ..., batch_splits)."""
+    NEED_COORDS = True
+
+    @staticmethod
+    def extract(feature_map, device):
+        coords, feats, spatial_size, *_, batch_splits = feature_map
+        keys = _packed_keys(coords, device)
+        splits = [int(v) for v in batch_splits]
+        ptr = torch.tensor([0] + list(torch.tensor(splits).cumsum(0).tolist()), dtype=torch.int32).to(device)
+        return keys, feats, spatial_size, splits, ptr, (max(splits) if splits else 0)
+
+
+class TensorScene:
+    """extract() of TensorToTensorFeatureExtractorCombiner (roi_select_sparse.py:100-110)."""
+    NEED_COORDS = True
+
+    @staticmethod
+    def extract(feature_map, device):
+        md = feature_map.metadata
+        lvl = md.level(feature_map.spatial_size)
+        ptr = lvl.batch_ptr(md.n_samples)
+        splits = (ptr[1:] - ptr[:-1]).tolist()                 # host copy of B+1 ints (reference: bincount)
+        return lvl.keys, feature_map.features, feature_map.spatial_size, splits, ptr, (max(splits) if splits else 0)
+
+
+class SparseRoiCut(nn.Module):
+    """SparseRoiCut (roi_select_sparse.py:29-52).  `scn` is the namespace used to build the cropped
+    tensor; `raw_scene` selects RawToTensor (InputLayer mode 4) vs TensorToTensor (mode 0);
+    `combine` in {'tensor','features','raw'}."""
+
+    def __init__(self, scn, raw_scene=True, clip_boxes=False, resize_boxes=None, combine="tensor",
+                 cpu_selection=False):
+        super().__init__()
+        self.scn = scn
+        self.raw_scene = raw_scene
+        self.bbox_transformer = BBoxTransformerSlice(clip=clip_boxes, resize=resize_boxes)
+        self.combine, self.cpu_selection = combine, cpu_selection
+
+    def forward(self, feature_map, bbox_batch):
+        feats0 = feature_map[1] if self.raw_scene else feature_map.features
+        dev = feats0.device
+        keys, feats, spatial_size, splits, ptr, max_len = (RawScene if self.raw_scene else TensorScene).extract(
+            feature_map, dev)
+        boxes, counts, assoc = self.bbox_transformer(bbox_batch, spatial_size)
+        sel_pt, new_keys, box_ptr, total, inside = crop(keys, ptr, max_len, boxes, assoc)
+        sel = CropSelection(sel_pt, new_keys, box_ptr, boxes.shape[0], keys.numel(), inside, counts, splits)
+        new_feats = GatherRowsFunction.apply(feats, sel_pt)
+        out = combine_crop(self.scn, self.combine, new_keys, new_feats, spatial_size, boxes.shape[0],
+                           mode=4 if self.raw_scene else 0)
+        return out, sel
+
+
+def combine_crop(scn, how, new_keys, new_feats, spatial_size, n_boxes, mode):
+    if how == "features":
+        return new_feats
+    if how == "raw":
+        return new_keys, new_feats, spatial_size, n_boxes
+    md = scn.Metadata(3)
+    size = torch.as_tensor(spatial_size, dtype=torch.long)
+    f = scn.ioLayers.InputLayerFunction.apply(3, md, size, new_keys, new_feats, n_boxes, mode)
+    return scn.SparseConvNetTensor(features=f, metadata=md, spatial_size=size)
+
+
+class SparseRoiExtraCut(nn.Module):
+    """SparseRoiExtraCut (roi_select_sparse.py:8-26): reuse a selection to gather another per-point
+    feature tensor (RawToFeatures combiner => plain features)."""
+
+    def forward(self, feature_map, selection):
+        feats = feature_map[1]
+        return GatherRowsFunction.apply(feats, selection.sel_pt)

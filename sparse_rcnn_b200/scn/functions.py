@@ -66,12 +66,31 @@ def conv_gemm(x, weight, K, cin, cout, fmap, n_out, bias=None, transpose=0, reve
     s = _stream()
     if _state["precision"] == "tf32" and cout <= 256:
         img = _image(weight, K, cin, cout, transpose, reverse)
+        x = tf32_exact(x)
         _lib.call("scn_conv_fwd_tf32", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(img), _ptr(bias),
                   _ptr(residual), ld_res, _ptr(out), cout, cout, epi, s)
     else:
         _lib.call("scn_conv_fwd_fp32", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(weight), transpose,
                   reverse, _ptr(bias), _ptr(residual), ld_res, _ptr(out), cout, cout, epi, s)
     return out
+
+
+def tf32_exact(x):
+    """tcgen05 kind::tf32 truncates its fp32 operands (a systematic shrink of ~3e-4 per layer).  The
+    gathered operand is therefore required to be TF32-representable: tensors produced by kernels
+    that already round (ReLU in tf32 mode) carry a mark, anything else gets one rounding pass."""
+    if getattr(x, "_scn_tf32", False):
+        return x
+    y = torch.empty_like(x)
+    _lib.call("scn_round_tf32", _ptr(x), _ptr(y), x.numel(), _stream())
+    y._scn_tf32 = True
+    return y
+
+
+def _mark(t):
+    if _state["precision"] == "tf32":
+        t._scn_tf32 = True
+    return t
 
 
 class ConvFunction(Function):
@@ -121,7 +140,7 @@ class ReLUFunction(Function):
     def forward(ctx, x):
         x = _check(x)
         y = torch.empty_like(x)
-        _lib.call("scn_relu_fwd", _ptr(x), _ptr(y), x.numel(), _stream())
+        _lib.call("scn_relu_fwd", _ptr(x), _ptr(y), x.numel(), int(_state["precision"] == "tf32"), _stream())
         ctx.save_for_backward(y)
         return y
 
@@ -130,8 +149,9 @@ class ReLUFunction(Function):
         y, = ctx.saved_tensors
         go = _check(go)
         gi = torch.empty_like(go)
-        _lib.call("scn_relu_bwd", _ptr(y), _ptr(go), _ptr(gi), go.numel(), _stream())
-        return gi
+        _lib.call("scn_relu_bwd", _ptr(y), _ptr(go), _ptr(gi), go.numel(), int(_state["precision"] == "tf32"),
+                  _stream())
+        return _mark(gi)
 
 
 class AddFunction(Function):

@@ -96,7 +96,7 @@ class JoinTable(nn.Module):
 
 class ReLU(nn.Module):
     def forward(self, x):
-        return _like(x, F.ReLUFunction.apply(x.features))
+        return _like(x, F._mark(F.ReLUFunction.apply(x.features)))
 
     def input_spatial_size(self, out_size):
         return out_size

@@ -138,7 +138,8 @@ class Metadata:
         s = _stream()
         if coords.dim() == 1:
             keys = coords
-            max_b = None
+            # device-side crop path: batch ids are box ids < batch_size (no host sync needed)
+            max_b = int(batch_size) - 1 if int(batch_size) > 0 else None
         else:
             if coords.dtype != torch.int64:
                 coords = coords.long()
