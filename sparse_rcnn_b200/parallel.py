@@ -1,0 +1,91 @@
+"""Multi-GPU plumbing for the two ways the path shards.
+
+* Inference: scenes are independent (own hash grids) -> scene i goes to rank i mod world,
+  NO collective (`shard_scenes`).
+* Training: data parallel over the batch with ONE collective, the gradient allreduce.  The
+  reference has no distributed code at all (single process, scannet_config/run.py:498-499);
+  the hook point is right before `optimizer.step()` (ndsis/training/training.py:458-460).
+  Gradients live as views into two flat fp32 buckets (decoder-side parameters finish first in
+  backward), each bucket is all-reduced asynchronously as soon as its last gradient has been
+  accumulated, so the first allreduce overlaps the rest of backward.  NVSwitch gives every GPU
+  full bandwidth to every peer, so buckets are sized for launch latency/overlap, not link count.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_scenes(n_scenes, rank, world):
+    """Indices of the scenes this rank owns (round robin; weak scaling keeps len() fixed)."""
+    return list(range(rank, n_scenes, world))
+
+
+class GradientBuckets:
+    """Flat gradient buckets with overlapped asynchronous allreduce (mean)."""
+
+    def __init__(self, params, n_buckets=2, process_group=None):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        params = [p for p in params if p.requires_grad]
+        # reverse registration order ~ order in which backward produces gradients
+        order = list(reversed(params))
+        total = sum(p.numel() for p in order)
+        target = (total + n_buckets - 1) // n_buckets
+        self.buckets, cur, cur_n = [], [], 0
+        for p in order:
+            cur.append(p)
+            cur_n += p.numel()
+            if cur_n >= target and len(self.buckets) < n_buckets - 1:
+                self.buckets.append(cur)
+                cur, cur_n = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.flats, self._pending, self._handles = [], [], []
+        for bi, bucket in enumerate(self.buckets):
+            n = sum(p.numel() for p in bucket)
+            flat = torch.zeros(n, dtype=bucket[0].dtype, device=bucket[0].device)
+            off = 0
+            for p in bucket:
+                p.grad = flat[off:off + p.numel()].view_as(p)      # autograd accumulates in place
+                off += p.numel()
+                p.register_post_accumulate_grad_hook(self._make_hook(bi))
+            self.flats.append(flat)
+            self._pending.append(len(bucket))
+        self.enabled = True
+
+    def _make_hook(self, bi):
+        def hook(param):
+            if not self.enabled:
+                return
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0:
+                self._launch(bi)
+        return hook
+
+    def _launch(self, bi):
+        if self.world > 1:
+            self._handles.append(dist.all_reduce(self.flats[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def zero(self):
+        """Zero the flat buckets (instead of optimizer.zero_grad(set_to_none=True), which would
+        detach the gradient views)."""
+        for f in self.flats:
+            f.zero_()
+        self._pending = [len(b) for b in self.buckets]
+        self._handles = []
+
+    def finish(self):
+        """Call after backward, before optimizer.step(): launches buckets whose hooks did not all
+        fire (unused parameters), waits for the collectives and turns the sums into means."""
+        for bi, left in enumerate(self._pending):
+            if left > 0:
+                self._pending[bi] = 0
+                self._launch(bi)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        if self.world > 1:
+            for f in self.flats:
+                f.div_(self.world)
+
+    def nbytes(self):
+        return sum(f.numel() * f.element_size() for f in self.flats)

@@ -1,0 +1,79 @@
+"""Public entry points of the hot path: a training step of the sparse backbone and the sparse
+inference pass (backbone + segmentation + class network + sparse mask network).
+
+These are the calls bench.py and __graft_entry__.smoke() time / exercise.  Inputs follow the
+reference's `collate_fn` 5-tuple (ndsis/data/data.py:88-115): coords stay int64 on the HOST,
+features may be host (pinned) or device tensors; the host->device copies happen inside.
+"""
+import torch
+import torch.nn as nn
+
+from . import networks, roi, scn
+from .parallel import GradientBuckets
+
+
+def _to_device(data, device):
+    coords, feats, size, bs, splits = data
+    return coords, feats.to(device, non_blocking=True), size, bs, splits
+
+
+class BackboneTrainer(nn.Module):
+    """fwd + point-wise cross-entropy on the segmentation head + bwd (+ gradient allreduce) + Adam,
+    i.e. the sparse part of ndsis/training/training.py:428-460 for the shipped sparse U-Net."""
+
+    def __init__(self, device, in_channels=6, num_classes=20, lr=1e-3, distributed=False, seed=0):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.device = device
+        self.backbone = networks.FeatureExtractor(scn, input_channels=in_channels)
+        self.seg = networks.SegmentationNetwork(scn, 32, num_classes)
+        self.to(device)
+        self.buckets = GradientBuckets(list(self.parameters()), n_buckets=2)
+        self.buckets.enabled = True
+        self.optimizer = torch.optim.Adam(self.parameters(), lr=lr, foreach=True)
+        self.distributed = distributed
+
+    def step(self, data, labels):
+        """data: collate_fn 5-tuple, labels int64 [P] (host or device).  Returns the loss (device scalar)."""
+        data = _to_device(data, self.device)
+        labels = labels.to(self.device, non_blocking=True)
+        self.buckets.zero()
+        out = self.backbone(data)
+        logits = self.seg(out[5])
+        loss = nn.functional.cross_entropy(logits, labels)
+        loss.backward()
+        self.buckets.finish()
+        self.optimizer.step()
+        self.last_active = out[4][0].features.shape[0]
+        return loss.detach()
+
+
+class SparseInference(nn.Module):
+    """Sparse inference pass on given proposal boxes (the dense RPN trunk / NMS that would produce
+    them is out of scope): feature extractor -> segmentation logits per point,
+    class logits per box, mask logits per (box, point)."""
+
+    def __init__(self, device, in_channels=6, num_seg_classes=20, num_classes=18, seed=0):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.device = device
+        cut = lambda **kw: roi.SparseRoiCut(scn, **kw)
+        self.backbone = networks.FeatureExtractor(scn, input_channels=in_channels)
+        self.seg = networks.SegmentationNetwork(scn, 32, num_seg_classes)
+        self.class_network = networks.ClassNetwork(scn, cut, input_channels=64, stride=4, num_classes=num_classes)
+        self.mask_network = networks.SparseMaskNetwork(scn, cut, input_channels=in_channels,
+                                                       channel_list=(32, num_classes))
+        self.to(device)
+        self.eval()
+
+    @torch.no_grad()
+    def forward(self, data, boxes):
+        data = _to_device(data, self.device)
+        roi.clear_key_cache()
+        scene_size, batch_size, _, class_map, inter, unet = self.backbone(data)
+        roi.register_keys(data[0], inter[0].metadata.point_keys)     # packed once per forward
+        seg = self.seg(unet)
+        cls, cls_sel = self.class_network(class_map, boxes)
+        mask, mask_sel = self.mask_network(data, unet, boxes)
+        return dict(segmentation=seg, mpn_class=cls, mpn_mask=mask, class_selection=cls_sel, mask_selection=mask_sel,
+                    n_active=inter[0].features.shape[0])

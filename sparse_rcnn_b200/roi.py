@@ -78,6 +78,17 @@ def _packed_keys(coords, device):
     return keys
 
 
+def register_keys(coords, keys):
+    """Let a crop reuse the keys the input layer already packed for the same coords tensor."""
+    if len(_KEY_CACHE) > 64:
+        _KEY_CACHE.clear()
+    _KEY_CACHE[id(coords)] = (weakref.ref(coords), keys)
+
+
+def clear_key_cache():
+    _KEY_CACHE.clear()
+
+
 class GatherRowsFunction(Function):
     """out[i] = x[idx[i]]; backward scatter-adds (boxes may overlap)."""
 

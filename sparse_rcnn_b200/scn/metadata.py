@@ -165,6 +165,7 @@ class Metadata:
         self.input_size = size_key(spatial_size)
         self.levels[self.input_size] = level
         self.point_row, self.n_points, self.mode = point_row, P, mode
+        self.point_keys = keys
         self.n_samples = max(int(batch_size), max_b + 1, 1)
         if mode != 0:
             n = level.n

@@ -1,0 +1,102 @@
+"""CPU: the oracle (and the host-side graph mirror running on it) against golden vectors produced
+by the UNMODIFIED reference (oracle/make_golden.py, run in the build container)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import scn_oracle as O
+from scn_oracle import roi_ref
+from sparse_rcnn_b200 import networks
+from sparse_rcnn_b200.synthetic import make_batch, make_boxes
+from tests.util import reinit_by_name
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["crop_raw", "crop_stride4"])
+def test_oracle_crop_matches_reference_roi_cut(name):
+    g = torch.load(os.path.join(G, name + ".pt"), weights_only=False)
+    coords, feats = g["coords"].long(), g["feats"]
+    boxes, counts, assoc = roi_ref.transform_boxes(g["boxes"], g["size"], g["clip"], g["resize"])
+    assert torch.equal(boxes, g["box_tensor"]) and counts == g["counts"] and torch.equal(assoc, g["assoc"])
+    nc, nf, inside = roi_ref.roi_cut(coords, feats, boxes, assoc)
+    assert torch.equal(nc, g["new_coords"].long())
+    assert np.array_equal(np.packbits(inside.numpy(), axis=1), g["inside_packed"])
+    assert tuple(inside.shape) == g["inside_shape"]
+    assert torch.equal(nf[:32], g["new_feats_head"]) and abs(float(nf.double().sum()) - g["new_feats_sum"]) < 1e-6
+    # product-side box transformer (pure host logic) agrees with the reference too
+    from sparse_rcnn_b200.roi import BBoxTransformerSlice
+    b2, c2, a2 = BBoxTransformerSlice(clip=g["clip"], resize=g["resize"])(g["boxes"], g["size"])
+    assert torch.equal(b2, g["box_tensor"]) and c2 == g["counts"] and torch.equal(a2, g["assoc"])
+
+
+@pytest.fixture(scope="module")
+def graph():
+    return torch.load(os.path.join(G, "ref_graph.pt"), weights_only=False)
+
+
+def _nets():
+    cut = lambda **kw: roi_ref.OracleRoiCut(O, **kw)
+    fe = networks.FeatureExtractor(O)
+    seg = networks.SegmentationNetwork(O)
+    cls = networks.ClassNetwork(O, cut)
+    mask = networks.SparseMaskNetwork(O, cut)
+    for m in (fe, seg, cls, mask):
+        reinit_by_name(m).eval()
+    return fe, seg, cls, mask
+
+
+def test_graph_mirror_has_reference_state_dict(graph):
+    fe, seg, cls, mask = _nets()
+    for name, m in (("fe", fe), ("seg", seg), ("cls", cls), ("mask", mask)):
+        mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert mine == graph["state"][name], (name, set(mine) ^ set(graph["state"][name]))
+        wsum = float(sum(v.double().sum() for v in m.state_dict().values()))
+        assert abs(wsum - graph["weight_sums"][name]) < 1e-6 * max(1, abs(wsum))
+
+
+def test_graph_mirror_reproduces_reference_outputs(graph):
+    fe, seg, cls, mask = _nets()
+    data = make_batch(2, graph["scene_seed"], spatial_size=(64, 64, 32), room=(44, 44, 22), room_offset=(8, 8, 2),
+                      n_furniture=3)
+    boxes = make_boxes(data[0], 5, graph["box_seed"], (64, 64, 32))
+    with torch.no_grad():
+        _, bs, _, class_map, inter, unet = fe(data)
+        assert [t.features.shape[0] for t in inter] == graph["level_rows"]
+        u = unet[-1].features
+        assert torch.allclose(u[:64], graph["unet_last_head"], rtol=1e-4, atol=1e-4 * graph["unet_last_absmax"])
+        assert abs(float(u.double().sum()) - graph["unet_last_sum"]) <= 1e-5 * u.numel() * graph["unet_last_absmax"]
+        s = seg(unet)
+        assert torch.allclose(s[:64], graph["seg_head"], rtol=1e-4, atol=1e-3)
+        c, csel = cls(class_map, boxes)
+        assert torch.allclose(c, graph["cls_out"], rtol=1e-4, atol=1e-3 * float(graph["cls_out"].abs().max()))
+        assert int(csel.is_inside().sum()) == graph["cls_inside_count"]
+        m, msel = mask(data, unet, boxes)
+        assert m.shape[0] == graph["mask_rows"] and int(msel.is_inside().sum()) == graph["mask_inside_count"]
+        assert torch.allclose(m[:64], graph["mask_head"], rtol=1e-4, atol=1e-3 * float(graph["mask_head"].abs().max()))
+
+
+def test_reference_graph_live_when_available():
+    """When /root/reference is present (build container), rebuild the reference modules on the oracle and
+    compare state_dict keys live (guards against stale goldens)."""
+    if not os.path.isdir("/root/reference/ndsis"):
+        pytest.skip("reference checkout not present")
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path[:0]=[%r, %r, '/root/reference']\n"
+        "import scn_oracle; sys.modules['sparseconvnet']=scn_oracle\n"
+        "import importlib.util, torch\n"
+        "spec=importlib.util.spec_from_file_location('mg', %r); mg=importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)\n"
+        "from ndsis.modules.model import FeatureExtractor\n"
+        "from sparse_rcnn_b200 import networks\n"
+        "fe_p, unet_p, _, _ = mg.reference_configs()\n"
+        "ref = FeatureExtractor(**fe_p, include_unet=True, unet_params=unet_p)\n"
+        "mine = networks.FeatureExtractor(scn_oracle)\n"
+        "a={k:tuple(v.shape) for k,v in ref.state_dict().items()}; b={k:tuple(v.shape) for k,v in mine.state_dict().items()}\n"
+        "assert a==b, set(a)^set(b)\nprint('OK', len(a))\n") % (root, os.path.join(root, "oracle"),
+                                                                 os.path.join(root, "oracle", "make_golden.py"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK 120" in r.stdout, r.stdout + r.stderr

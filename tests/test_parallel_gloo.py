@@ -1,0 +1,81 @@
+"""CPU, world_size 2 over gloo: the data-parallel gradient buckets (the only collective on the path)
+and the no-collective scene sharding."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+from sparse_rcnn_b200.parallel import GradientBuckets, shard_scenes
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(6, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 3))
+    buckets = GradientBuckets(list(net.parameters()), n_buckets=2)
+    assert len(buckets.buckets) == 2 and sum(len(b) for b in buckets.buckets) == 6
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(100 + rank)          # every rank sees different data
+    for step in range(3):
+        x, y = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
+        buckets.zero()
+        ((net(x) - y) ** 2).mean().backward()
+        buckets.finish()
+        opt.step()
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    q.put((rank, float((gathered[0] - gathered[1]).abs().max()), flat.tolist() if rank == 0 else None))
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_match_single_process_mean():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] == 0.0 for r in res)                   # replicas stay bit-identical
+    got = torch.tensor(next(r[2] for r in res if r[2] is not None))
+    # single-process reference: average the two ranks' gradients by hand
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(6, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 3))
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    gens = [torch.Generator().manual_seed(100 + r) for r in range(2)]
+    for step in range(3):
+        grads = None
+        for g in gens:
+            x, y = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
+            net.zero_grad()
+            ((net(x) - y) ** 2).mean().backward()
+            cur = [p.grad.clone() for p in net.parameters()]
+            grads = cur if grads is None else [a + b for a, b in zip(grads, cur)]
+        for p, gr in zip(net.parameters(), grads):
+            p.grad = gr / 2
+        opt.step()
+    ref = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    assert torch.allclose(got, ref, atol=1e-6)
+
+
+def test_scene_sharding_is_a_partition():
+    for world in (1, 2, 4, 8):
+        shards = [shard_scenes(19, r, world) for r in range(world)]
+        assert sorted(sum(shards, [])) == list(range(19))
+        assert max(map(len, shards)) - min(map(len, shards)) <= 1

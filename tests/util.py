@@ -48,3 +48,19 @@ def copy_params(src, dst, device=None):
     if device is not None:
         dst.to(device)
     return dst
+
+
+def reinit_by_name(module, scale=1.0):
+    """Deterministic, construction-order independent weights: every parameter is redrawn from a
+    generator seeded by the crc32 of its state_dict key, keeping the std of its initialiser
+    (biases: 0.05).  Lets goldens be regenerated without committing megabytes of weights.
+    std depends only on the shape: sqrt(2 / (numel / shape[-1])) for matrices, 0.05 for vectors."""
+    import zlib
+    with torch.no_grad():
+        for k, v in sorted(module.state_dict().items()):
+            if not v.is_floating_point():
+                continue
+            g = torch.Generator().manual_seed(zlib.crc32(k.encode()))
+            std = (2.0 / max(v.numel() // v.shape[-1], 1)) ** 0.5 if v.dim() >= 2 else 0.05
+            v.copy_(torch.randn(v.shape, generator=g) * std * scale)
+    return module
