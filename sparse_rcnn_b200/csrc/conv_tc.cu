@@ -204,17 +204,26 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
         const int look = S >= 4 ? 2 : 1;
         int u = 0;            // units issued by this thread (global across tiles)
         int signalled = 0;    // units whose full barrier this thread has arrived on
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        // neighbour indices are fetched one (tile, offset) ahead of the copies that depend on them, so
+        // the L2 latency of the map read overlaps the cp.async issue of the previous offset
+        auto load_idx = [&](int tile, int o, int (&dst)[8]) {
             const int row0 = tile * TILE_M;
-            for (int o = 0; o < p.K; ++o) {
-                int idx[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    int r = row0 + rbase + 16 * i;
-                    int s = -1;
-                    if (r < p.n_out) s = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
-                    idx[i] = s;
-                }
+            for (int i = 0; i < 8; ++i) {
+                int r = row0 + rbase + 16 * i;
+                int s = -1;
+                if (tile < p.n_tiles && r < p.n_out) s = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
+                dst[i] = s;
+            }
+        };
+        int idx[8], idx_next[8];
+        load_idx(blockIdx.x, 0, idx_next);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int o = 0; o < p.K; ++o) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) idx[i] = idx_next[i];
+                if (o + 1 < p.K) load_idx(tile, o + 1, idx_next);
+                else load_idx(tile + gridDim.x, 0, idx_next);
                 for (int kb = 0; kb < p.n_kb; ++kb, ++u) {
                     const int s = u % S;
                     mbar_wait(empty_bar(s), ((u / S) & 1) ^ 1);
