@@ -191,9 +191,8 @@ int scn_conv_fwd_fp32(const float* in, int ld_in, int Cin, const int32_t* map, i
     return check_launch("conv_fwd_fp32");
 }
 
-int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const float* grad_out,
-                        int ld_go, int Cout, float* grad_w, int use_tf32, scn_stream_t stream) {
-    (void)use_tf32;
+int scn_conv_bwd_weight_fp32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K,
+                             const float* grad_out, int ld_go, int Cout, float* grad_w, scn_stream_t stream) {
     SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0, "conv_bwd_weight: bad shape");
     SCN_REQUIRE(map || K == 1, "conv_bwd_weight: identity map requires K == 1");
     SCN_REQUIRE(K <= 65535, "conv_bwd_weight: K too large");

@@ -1,0 +1,307 @@
+// Weight gradient of the convolution family on tcgen05 (TF32, fp32 accumulate in TMEM):
+//
+//   gw[o] (Cin x Cout) = sum_r  in[map[o][r], :]^T (x) go[r, :]
+//
+// The reduction dimension is the ROW index, so both operands are "MN-major" for the tensor core:
+// the gathered tile [128 rows][32 ch] (one 128-byte swizzled row per output row) is exactly the
+// canonical MN-major SWIZZLE_128B layout with K = row.  One MMA (K=8) consumes one 8-row swizzle
+// atom; M = 128 input channels (4 channel blocks 16 KB apart), N = up to 128 output channels.
+//
+// Work split: grid = (row chunks) x (offset group, 128-wide Cin half, 128-wide Cout half).  A CTA keeps
+// the accumulators of ALL its offsets in TMEM across ALL its tiles and adds them to gw with one
+// round of atomics at the very end.  The grad-out tile is staged once per tile and reused by every
+// offset of the group.  8 producer warps (cp.async gather, zero fill for inactive rows) + 1 MMA warp.
+#include "tc_common.cuh"
+
+namespace scn {
+
+constexpr int WG_PRODUCERS = 256;
+constexpr int WG_THREADS = 288;
+
+struct WgradParams {
+    const float* in;
+    int ld_in, Cin;
+    const int32_t* map;
+    int n_out, K;
+    const float* go;
+    int ld_go, Cout;
+    float* gw;
+    int n_tiles, tiles_per_chunk;
+    int opg, n_ogroups, n_mhalves;
+    int a_stages, g_stages, a_stage_bytes, g_stage_bytes, tmem_cols;
+};
+
+template <int VEC>
+__device__ __forceinline__ void wg_chunk(uint32_t dst, const float* __restrict__ base, int64_t row_off, bool row_ok,
+                                         int col0, int C) {
+    constexpr int BYTES = VEC * 4;
+#pragma unroll
+    for (int j = 0; j < 4 / VEC; ++j) {
+        int col = col0 + j * VEC;
+        bool valid = row_ok && col < C;
+        const float* src = valid ? base + row_off + col : base;
+        cp_async<BYTES>(dst + j * BYTES, src, valid);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradParams p) {
+    const int chunk = blockIdx.x;
+    const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+    if (t0 >= t1) return;
+    const int og = blockIdx.y % p.n_ogroups;
+    const int rest = blockIdx.y / p.n_ogroups;
+    const int mh = rest % p.n_mhalves, nh = rest / p.n_mhalves;
+    const int o0 = og * p.opg, nO = min(p.K, o0 + p.opg) - o0;
+    if (nO <= 0) return;
+    const int cin0 = mh * 128, cin_h = min(128, p.Cin - cin0), nblk_a = (cin_h + 31) / 32;
+    const int cout0 = nh * 128, cout_h = min(128, p.Cout - cout0), npad = (cout_h + 15) / 16 * 16;
+    const int nblk_g = (npad + 31) / 32;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int AS = p.a_stages, GS = p.g_stages;
+    const uint32_t g_base = smem_base + (uint32_t)AS * p.a_stage_bytes;
+    const uint32_t bars = g_base + (uint32_t)GS * p.g_stage_bytes;
+    auto a_full = [&](int s) { return bars + 8u * s; };
+    auto a_empty = [&](int s) { return bars + 8u * (AS + s); };
+    auto g_full = [&](int s) { return bars + 8u * (2 * AS + s); };
+    auto g_empty = [&](int s) { return bars + 8u * (2 * AS + GS + s); };
+    const uint32_t done_bar = bars + 8u * (2 * AS + 2 * GS);
+    const uint32_t tmem_slot = done_bar + 8u;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < AS; ++s) {
+            mbar_init(a_full(s), WG_PRODUCERS);
+            mbar_init(a_empty(s), 1);
+        }
+        for (int s = 0; s < GS; ++s) {
+            mbar_init(g_full(s), WG_PRODUCERS);
+            mbar_init(g_empty(s), 1);
+        }
+        mbar_init(done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp < 8) {
+        // ===================== producers =====================
+        const int c = tid & 7, rbase = tid >> 3;        // rows rbase + 32 i
+        const uint32_t dst_in_blk = (uint32_t)rbase * 128u + (uint32_t)((c ^ (rbase & 7)) << 4);
+        const int look = AS >= 3 ? 2 : 1;
+        auto load_idx = [&](int tile, int o, int (&dst)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int r = tile * TILE_M + rbase + 32 * i;
+                int s = -1;
+                if (tile < t1 && r < p.n_out) s = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
+                dst[i] = s;
+            }
+        };
+        int idx[4], idx_next[4];
+        load_idx(t0, o0, idx_next);
+        int ua = 0, ug = 0, signalled = 0;
+        auto signal = [&]() {
+            fence_proxy_async();
+            if (signalled % nO == 0) mbar_arrive(g_full((signalled / nO) % GS));
+            mbar_arrive(a_full(signalled % AS));
+            ++signalled;
+        };
+        for (int tile = t0; tile < t1; ++tile, ++ug) {
+            const int gs = ug % GS;
+            {
+                // the grad-out stage being reused belongs to tile ug-GS: every unit of that tile must have been
+                // signalled, otherwise the MMA warp can never release the stage (look-ahead signalling lags by
+                // `look` units, which matters when a tile has fewer units than that, e.g. K == 1)
+                const int need = (ug - GS + 1) * nO;
+                if (signalled < need) {
+                    cp_async_wait<0>();
+                    while (signalled < need) signal();
+                }
+            }
+            mbar_wait(g_empty(gs), ((ug / GS) & 1) ^ 1);
+            {
+                const uint32_t gst = g_base + (uint32_t)gs * p.g_stage_bytes;
+                for (int blk = 0; blk < nblk_g; ++blk) {
+                    const int col0 = cout0 + blk * KB + c * 4;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = tile * TILE_M + rbase + 32 * i;
+                        wg_chunk<VEC>(gst + (uint32_t)blk * A_STAGE_BYTES + dst_in_blk + (uint32_t)i * 4096u, p.go,
+                                      (int64_t)r * p.ld_go, r < p.n_out, col0, min(p.Cout, cout0 + 128));
+                    }
+                }
+            }
+            for (int oi = 0; oi < nO; ++oi, ++ua) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) idx[i] = idx_next[i];
+                if (oi + 1 < nO) load_idx(tile, o0 + oi + 1, idx_next);
+                else load_idx(tile + 1, o0, idx_next);
+                const int s = ua % AS;
+                mbar_wait(a_empty(s), ((ua / AS) & 1) ^ 1);
+                const uint32_t ast = smem_base + (uint32_t)s * p.a_stage_bytes;
+                for (int kb = 0; kb < nblk_a; ++kb) {
+                    const int col0 = cin0 + kb * KB + c * 4;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        wg_chunk<VEC>(ast + (uint32_t)kb * A_STAGE_BYTES + dst_in_blk + (uint32_t)i * 4096u, p.in,
+                                      (int64_t)idx[i] * p.ld_in, idx[i] >= 0, col0, min(p.Cin, cin0 + 128));
+                }
+                cp_async_commit();
+                if (ua >= look) {
+                    if (look == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+                    signal();
+                }
+            }
+        }
+        cp_async_wait<0>();
+        while (signalled < ua) signal();
+    } else if (lane == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_tf32_mn(TILE_M, npad);
+        int ua = 0, ug = 0;
+        for (int tile = t0; tile < t1; ++tile, ++ug) {
+            const int gs = ug % GS;
+            mbar_wait(g_full(gs), (ug / GS) & 1);
+            const uint32_t gst = g_base + (uint32_t)gs * p.g_stage_bytes;
+            for (int oi = 0; oi < nO; ++oi, ++ua) {
+                const int s = ua % AS;
+                mbar_wait(a_full(s), (ua / AS) & 1);
+                tc_fence_after();
+                const uint32_t ast = smem_base + (uint32_t)s * p.a_stage_bytes;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(oi * npad);
+#pragma unroll 4
+                for (int j = 0; j < TILE_M / 8; ++j) {
+                    const uint64_t da = make_desc_mn_sw128(ast + (uint32_t)j * 1024u, A_STAGE_BYTES, 1024);
+                    const uint64_t db = make_desc_mn_sw128(gst + (uint32_t)j * 1024u, A_STAGE_BYTES, 1024);
+                    mma_tf32(tmem_d, da, db, idesc, (tile != t0 || j != 0) ? 1u : 0u);
+                }
+                mma_commit(a_empty(s));
+            }
+            mma_commit(g_empty(gs));
+        }
+        mma_commit(done_bar);
+    }
+
+    if (warp < 4) {
+        // ===================== epilogue: TMEM -> atomics into gw =====================
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        const int ci = cin0 + warp * 32 + lane;
+        for (int oi = 0; oi < nO; ++oi) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(oi * npad);
+            float* dst = p.gw + ((int64_t)(o0 + oi) * p.Cin + ci) * p.Cout + cout0;
+            for (int c0 = 0; c0 < npad; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (ci < p.Cin) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < cout_h) atomicAdd(dst + c0 + j, v[j]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace scn
+
+using namespace scn;
+
+extern "C" int scn_conv_bwd_weight_fp32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K,
+                                        const float* grad_out, int ld_go, int Cout, float* grad_w, scn_stream_t stream);
+
+extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K,
+                                   const float* grad_out, int ld_go, int Cout, float* grad_w, int use_tf32,
+                                   scn_stream_t stream) {
+    SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0, "conv_bwd_weight: bad shape");
+    SCN_REQUIRE(map || K == 1, "conv_bwd_weight: identity map requires K == 1");
+    if (n_out <= 0) return SCN_OK;
+    static int is100 = -1;
+    if (is100 < 0) is100 = scn_device_is_sm100();
+    if (!use_tf32 || !is100 || Cin > 512 || Cout > 512)
+        return scn_conv_bwd_weight_fp32(in, ld_in, Cin, map, n_out, K, grad_out, ld_go, Cout, grad_w, stream);
+
+    WgradParams p;
+    p.in = in, p.ld_in = ld_in, p.Cin = Cin, p.map = map, p.n_out = n_out, p.K = K;
+    p.go = grad_out, p.ld_go = ld_go, p.Cout = Cout, p.gw = grad_w;
+    p.n_tiles = cdiv(n_out, TILE_M);
+    const int cin_h = Cin < 128 ? Cin : 128, cout_h = Cout < 128 ? Cout : 128;
+    const int npad = (cout_h + 15) / 16 * 16;
+    p.n_mhalves = cdiv(Cin, 128);
+    const int n_nhalves = cdiv(Cout, 128);
+    p.a_stage_bytes = cdiv(cin_h, 32) * A_STAGE_BYTES;
+    p.g_stage_bytes = cdiv(npad, 32) * A_STAGE_BYTES;
+    // offsets per group: accumulators of one group must fit 256 TMEM columns (two CTAs per SM) when
+    // the tiles are narrow, 512 otherwise
+    int budget_cols = (p.a_stage_bytes + p.g_stage_bytes <= 32 * 1024) ? 256 : 512;
+    p.opg = budget_cols / npad;
+    if (p.opg > K) p.opg = K;
+    if (p.opg < 1) p.opg = 1;
+    p.n_ogroups = cdiv(K, p.opg);
+    p.opg = cdiv(K, p.n_ogroups);          // balance the groups
+    int tc = 32;
+    while (tc < p.opg * npad) tc <<= 1;
+    p.tmem_cols = tc;
+    // shared memory: 2 grad-out stages if they fit, then as many A stages (<= 4) as fit.  M = 128 always
+    // reads a 64 KB window (4 channel blocks) from an A stage base, so the allocation must reach
+    // (a_stages - 1) * a_stage_bytes + 64 KB even when the stage itself is narrower.
+    const int budget = (tc <= 256 ? 112 : 224) * 1024;
+    int smem = 0;
+    p.a_stages = 0;
+    for (int gs = 2; gs >= 1 && p.a_stages < 2; --gs) {
+        for (int as = 4; as >= 2; --as) {
+            int total = as * p.a_stage_bytes + gs * p.g_stage_bytes;
+            int window_end = (as - 1) * p.a_stage_bytes + 4 * A_STAGE_BYTES;
+            if (total < window_end) total = window_end;
+            if (total <= budget) {
+                p.a_stages = as, p.g_stages = gs, smem = total;
+                break;
+            }
+        }
+    }
+    SCN_REQUIRE(p.a_stages >= 2, "conv_bwd_weight: tile does not fit in shared memory (Cin=%d Cout=%d)", Cin, Cout);
+    smem += 1024 + 256;
+    const int groups_y = p.n_ogroups * p.n_mhalves * n_nhalves;
+    const int ctas_per_sm = (tc <= 256 && smem <= 113 * 1024) ? 2 : 1;
+    int n_chunks = (sm_count() * ctas_per_sm + groups_y - 1) / groups_y;
+    if (n_chunks > p.n_tiles) n_chunks = p.n_tiles;
+    if (n_chunks < 1) n_chunks = 1;
+    p.tiles_per_chunk = cdiv(p.n_tiles, n_chunks);
+    n_chunks = cdiv(p.n_tiles, p.tiles_per_chunk);
+    int vec = 1;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(grad_out);
+    if (Cin % 4 == 0 && Cout % 4 == 0 && ld_in % 4 == 0 && ld_go % 4 == 0 && (al & 15) == 0) vec = 4;
+    else if (Cin % 2 == 0 && Cout % 2 == 0 && ld_in % 2 == 0 && ld_go % 2 == 0 && (al & 7) == 0) vec = 2;
+    dim3 grid(n_chunks, groups_y);
+    cudaError_t e = cudaSuccess;
+    auto launch = [&](auto kern) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return;
+        kern<<<grid, WG_THREADS, smem, as_stream(stream)>>>(p);
+    };
+    if (vec == 4) launch(k_conv_wgrad_tc<4>);
+    else if (vec == 2) launch(k_conv_wgrad_tc<2>);
+    else launch(k_conv_wgrad_tc<1>);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        scn::set_error("conv_bwd_weight: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
+        return SCN_ERR_CUDA;
+    }
+    return check_launch("conv_bwd_weight_tc");
+}

@@ -77,12 +77,21 @@ __global__ void k_col_partial(const float* __restrict__ in, int ld, int n, int C
         partial[(int64_t)blockIdx.x * C + c] = s;
     }
 }
+// final pass: block (32 channels x 8 slab lanes), shared-memory tree over the lanes (deterministic)
 __global__ void k_col_final(const float* __restrict__ partial, int nslab, int C, float scale, float* __restrict__ out) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ float sm[8][33];
+    int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    for (int j = 0; j < nslab; ++j) s += partial[(int64_t)j * C + c];
-    out[c] = s * scale;
+    if (c < C)
+        for (int j = threadIdx.y; j < nslab; j += 8) s += partial[(int64_t)j * C + c];
+    sm[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+        out[c] = t * scale;
+    }
 }
 
 __global__ void k_bn_apply(const float* __restrict__ in, int64_t total, int C, const float* __restrict__ mean,
@@ -396,7 +405,7 @@ static int col_reduce(const float* in, int ld, int n, int C, const float* mean, 
         k_col_partial<false><<<grid, block, 0, st>>>(in, ld, n, C, nullptr, partial);
     int rc = check_launch("col_partial");
     if (rc) return rc;
-    k_col_final<<<cdiv(C, 128), 128, 0, st>>>(partial, nslab, C, scale, out);
+    k_col_final<<<cdiv(C, 32), dim3(32, 8), 0, st>>>(partial, nslab, C, scale, out);
     return check_launch("col_final");
 }
 
