@@ -3,9 +3,9 @@
 //   gw[o] (Cin x Cout) = sum_r  in[map[o][r], :]^T (x) go[r, :]
 //
 // The reduction dimension is the ROW index, so both operands are "MN-major" for the tensor core:
-// the gathered tile [128 rows][32 ch] (one 128-byte swizzled row per output row) is exactly the
-// canonical MN-major SWIZZLE_128B layout with K = row.  One MMA (K=8) consumes one 8-row swizzle
-// atom; M = 128 input channels (4 channel blocks 16 KB apart), N = up to 128 output channels.
+// the gathered tile [128 rows][32 ch] (one 128-byte row per output row, 32-byte chunks XOR-ed with
+// row & 3) is the canonical MN-major SW128_32B layout with K = row.  One MMA (K=8) consumes two 4-row
+// swizzle atoms; M = 128 input channels (4 channel blocks 16 KB apart), N = up to 128 output channels.
 //
 // Work split: grid = (row chunks) x (offset group, 128-wide Cin half, 128-wide Cout half).  A CTA keeps
 // the accumulators of ALL its offsets in TMEM across ALL its tiles and adds them to gw with one
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
     if (warp < 8) {
         // ===================== producers =====================
         const int c = tid & 7, rbase = tid >> 3;        // rows rbase + 32 i
-        const uint32_t dst_in_blk = (uint32_t)rbase * 128u + (uint32_t)((c ^ (rbase & 7)) << 4);
+        const uint32_t dst_in_blk = swz_mn32b(rbase, c);      // (rbase + 32 i) & 3 == rbase & 3
         const int look = AS >= 3 ? 2 : 1;
         auto load_idx = [&](int tile, int o, int (&dst)[4]) {
 #pragma unroll
@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                 const uint32_t tmem_d = tmem_base + (uint32_t)(oi * npad);
 #pragma unroll 4
                 for (int j = 0; j < TILE_M / 8; ++j) {
-                    const uint64_t da = make_desc_mn_sw128(ast + (uint32_t)j * 1024u, A_STAGE_BYTES, 1024);
-                    const uint64_t db = make_desc_mn_sw128(gst + (uint32_t)j * 1024u, A_STAGE_BYTES, 1024);
+                    const uint64_t da = make_desc_mn_sw128_32b(ast + (uint32_t)j * 1024u, A_STAGE_BYTES, 512);
+                    const uint64_t db = make_desc_mn_sw128_32b(gst + (uint32_t)j * 1024u, A_STAGE_BYTES, 512);
                     mma_tf32(tmem_d, da, db, idesc, (tile != t0 || j != 0) ? 1u : 0u);
                 }
                 mma_commit(a_empty(s));
@@ -261,20 +261,20 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
     // shared memory: 2 grad-out stages if they fit, then as many A stages (<= 4) as fit.  M = 128 always
     // reads a 64 KB window (4 channel blocks) from an A stage base, so the allocation must reach
     // (a_stages - 1) * a_stage_bytes + 64 KB even when the stage itself is narrower.
-    const int budget = (tc <= 256 ? 112 : 224) * 1024;
     int smem = 0;
     p.a_stages = 0;
-    for (int gs = 2; gs >= 1 && p.a_stages < 2; --gs) {
-        for (int as = 4; as >= 2; --as) {
-            int total = as * p.a_stage_bytes + gs * p.g_stage_bytes;
-            int window_end = (as - 1) * p.a_stage_bytes + 4 * A_STAGE_BYTES;
-            if (total < window_end) total = window_end;
-            if (total <= budget) {
-                p.a_stages = as, p.g_stages = gs, smem = total;
-                break;
+    const int budgets[2] = {tc <= 256 ? 112 * 1024 : 0, 224 * 1024};      // two CTAs per SM first, else one
+    for (int b = 0; b < 2 && p.a_stages < 2; ++b)
+        for (int gs = 2; gs >= 1 && p.a_stages < 2; --gs)
+            for (int as = 4; as >= 2; --as) {
+                int total = as * p.a_stage_bytes + gs * p.g_stage_bytes;
+                int window_end = (as - 1) * p.a_stage_bytes + 4 * A_STAGE_BYTES;
+                if (total < window_end) total = window_end;
+                if (total <= budgets[b]) {
+                    p.a_stages = as, p.g_stages = gs, smem = total;
+                    break;
+                }
             }
-        }
-    }
     SCN_REQUIRE(p.a_stages >= 2, "conv_bwd_weight: tile does not fit in shared memory (Cin=%d Cout=%d)", Cin, Cout);
     smem += 1024 + 256;
     const int groups_y = p.n_ogroups * p.n_mhalves * n_nhalves;

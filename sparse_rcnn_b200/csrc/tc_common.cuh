@@ -115,12 +115,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 
-// MN-major SWIZZLE_128B descriptor: 32 fp32 of the M/N dimension are contiguous (one 128-byte row
-// per K index); LBO = byte distance between consecutive 32-element M/N groups, SBO = byte distance
-// between 8-row K groups.
-__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major descriptor for 32-bit operands.  CUTLASS: "for mn-major tf32 operands, SW128_32B is the only
+// available smem layout" (UMMA::Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> o (1024 bit, 4):(1, 1024 bit)):
+// one 128-byte row (32 fp32 of the M/N dimension) per K index, byte-address bits [5,7) ^= bits [7,9),
+// i.e. the 32-byte chunk index is XOR-ed with (k_row & 3); K atom = 4 rows = 512 B.
+// layout_type = 1 (SWIZZLE_128B_BASE32B); LBO = byte distance between 32-element M/N groups,
+// SBO = byte distance between 4-row K groups.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (1ull << 61);
+}
+// position of 16-byte chunk c (0..7) of row r inside a 128-byte row under that swizzle
+__device__ __forceinline__ uint32_t swz_mn32b(int r, int c) {
+    return (uint32_t)r * 128u + (uint32_t)((((((c >> 1) ^ (r & 3)) << 1) | (c & 1))) << 4);
 }
 // kind::tf32 instruction descriptor with both operands MN-major (bits 15 and 16 set)
 __device__ __forceinline__ uint32_t make_idesc_tf32_mn(int M, int N) {
