@@ -94,9 +94,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
         const int pt = tid - 128;
         const int c = pt & 7, rbase = pt >> 3;
         const uint32_t dst_in_stage = (uint32_t)rbase * 128u + (uint32_t)((c ^ (rbase & 7)) << 4);
-        const int look = S >= 4 ? 2 : 1;
-        int u = 0;            // units issued by this thread (global across tiles)
-        int signalled = 0;    // units whose full barrier this thread has arrived on
+        int s = 0;
+        uint32_t ph = 0;      // ring position / phase of this thread's unit stream
         // neighbour indices are fetched one (tile, offset) ahead of the copies that depend on them, so
         // the L2 latency of the map read overlaps the cp.async issue of the previous offset
         auto load_idx = [&](int tile, int o, int (&dst)[8]) {
@@ -104,25 +103,24 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 int r = row0 + rbase + 16 * i;
-                int s = -1;
-                if (tile < p.n_tiles && r < p.n_out) s = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
-                dst[i] = s;
+                int v = -1;
+                if (tile < p.n_tiles && r < p.n_out) v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
+                dst[i] = v;
             }
         };
         int idx[8], idx_next[8];
         load_idx(blockIdx.x, 0, idx_next);
+        const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             for (int o = 0; o < p.K; ++o) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) idx[i] = idx_next[i];
                 if (o + 1 < p.K) load_idx(tile, o + 1, idx_next);
                 else load_idx(tile + gridDim.x, 0, idx_next);
-                for (int kb = 0; kb < p.n_kb; ++kb, ++u) {
-                    const int s = u % S;
-                    mbar_wait(empty_bar(s), ((u / S) & 1) ^ 1);
+                for (int kb = 0; kb < p.n_kb; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
                     const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
                     if (pt == 0) {
-                        const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
                         mbar_arrive_expect_tx(full_bar(s), wbytes);
                         bulk_g2s(a_stage + A_STAGE_BYTES, p.image + (size_t)(o * p.n_kb + kb) * wbytes, wbytes,
                                  full_bar(s));
@@ -134,34 +132,28 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
                             gather_chunk<VEC>(a_stage + dst_in_stage + (uint32_t)i * 2048u, p.in,
                                               (int64_t)idx[i] * p.ld_in, idx[i], col0, p.Cin);
                     }
-                    cp_async_commit();
-                    if (u >= look) {
-                        if (look == 2) cp_async_wait<2>(); else cp_async_wait<1>();
-                        fence_proxy_async();
-                        mbar_arrive(full_bar(signalled % S));
-                        ++signalled;
-                    }
+                    // the stage's full barrier receives this thread's arrival when its copies have landed;
+                    // up to S units are in flight per CTA and the producer only ever waits for a free slot
+                    cp_async_mbar_arrive_noinc(full_bar(s));
+                    if (++s == S) s = 0, ph ^= 1;
                 }
             }
         }
-        // drain
         cp_async_wait<0>();
-        fence_proxy_async();
-        for (; signalled < u; ++signalled) mbar_arrive(full_bar(signalled % S));
     } else if (warp == 8) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TILE_M, p.cout_pad);
-            int u = 0, it = 0;
+            int s = 0, it = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const int b = it & 1;
                 mbar_wait(acce_bar(b), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(b * p.cout_pad);
                 for (int o = 0; o < p.K; ++o) {
-                    for (int kb = 0; kb < p.n_kb; ++kb, ++u) {
-                        const int s = u % S;
-                        mbar_wait(full_bar(s), (u / S) & 1);
+                    for (int kb = 0; kb < p.n_kb; ++kb) {
+                        mbar_wait(full_bar(s), ph);
                         tc_fence_after();
                         const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
                         const uint64_t da = make_desc_sw128(a_stage);
@@ -173,6 +165,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
                                      (o | kb | k) != 0 ? 1u : 0u);
                         }
                         mma_commit(empty_bar(s));
+                        if (++s == S) s = 0, ph ^= 1;
                     }
                 }
                 mma_commit(accf_bar(b));
@@ -315,13 +308,15 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, const int32_t* map, i
     while (tc < cols) tc <<= 1;
     p.tmem_cols = tc;
     const int stage_bytes = A_STAGE_BYTES + p.cout_pad * 128;
-    // two CTAs per SM when four stages fit in ~110 KB, else one CTA with as many stages (<= 4) as fit
+    // ring depth = units in flight per CTA (the gather is latency bound, so deeper is better): two CTAs
+    // per SM when at least four stages fit in ~110 KB each, otherwise one CTA with up to eight stages
     int stages, ctas_per_sm;
-    if (4 * stage_bytes + 2048 <= 110 * 1024 && tc <= 256) {
-        stages = 4, ctas_per_sm = 2;
+    const int s2 = (110 * 1024) / stage_bytes;
+    if (s2 >= 4 && tc <= 256) {
+        stages = s2 > 8 ? 8 : s2, ctas_per_sm = 2;
     } else {
         stages = (220 * 1024) / stage_bytes;
-        if (stages > 4) stages = 4;
+        if (stages > 8) stages = 8;
         ctas_per_sm = 1;
     }
     SCN_REQUIRE(stages >= 2, "conv_fwd_tf32: tile does not fit in shared memory");

@@ -98,40 +98,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
         // ===================== producers =====================
         const int c = tid & 7, rbase = tid >> 3;        // rows rbase + 32 i
         const uint32_t dst_in_blk = swz_mn32b(rbase, c);      // (rbase + 32 i) & 3 == rbase & 3
-        const int look = AS >= 3 ? 2 : 1;
         auto load_idx = [&](int tile, int o, int (&dst)[4]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 int r = tile * TILE_M + rbase + 32 * i;
-                int s = -1;
-                if (tile < t1 && r < p.n_out) s = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
-                dst[i] = s;
+                int v = -1;
+                if (tile < t1 && r < p.n_out) v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
+                dst[i] = v;
             }
         };
         int idx[4], idx_next[4];
         load_idx(t0, o0, idx_next);
-        int ua = 0, ug = 0, signalled = 0;
-        auto signal = [&]() {
-            fence_proxy_async();
-            if (signalled % nO == 0) mbar_arrive(g_full((signalled / nO) % GS));
-            mbar_arrive(a_full(signalled % AS));
-            ++signalled;
-        };
-        for (int tile = t0; tile < t1; ++tile, ++ug) {
-            const int gs = ug % GS;
+        int sa = 0, sg = 0;
+        uint32_t pha = 0, phg = 0;
+        for (int tile = t0; tile < t1; ++tile) {
+            // grad-out tile: staged once per tile, shared by every offset of the group
+            mbar_wait(g_empty(sg), phg ^ 1);
             {
-                // the grad-out stage being reused belongs to tile ug-GS: every unit of that tile must have been
-                // signalled, otherwise the MMA warp can never release the stage (look-ahead signalling lags by
-                // `look` units, which matters when a tile has fewer units than that, e.g. K == 1)
-                const int need = (ug - GS + 1) * nO;
-                if (signalled < need) {
-                    cp_async_wait<0>();
-                    while (signalled < need) signal();
-                }
-            }
-            mbar_wait(g_empty(gs), ((ug / GS) & 1) ^ 1);
-            {
-                const uint32_t gst = g_base + (uint32_t)gs * p.g_stage_bytes;
+                const uint32_t gst = g_base + (uint32_t)sg * p.g_stage_bytes;
                 for (int blk = 0; blk < nblk_g; ++blk) {
                     const int col0 = cout0 + blk * KB + c * 4;
 #pragma unroll
@@ -141,15 +125,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                                       (int64_t)r * p.ld_go, r < p.n_out, col0, min(p.Cout, cout0 + 128));
                     }
                 }
+                cp_async_mbar_arrive_noinc(g_full(sg));      // fires when this thread's copies have landed
+                if (++sg == GS) sg = 0, phg ^= 1;
             }
-            for (int oi = 0; oi < nO; ++oi, ++ua) {
+            for (int oi = 0; oi < nO; ++oi) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) idx[i] = idx_next[i];
                 if (oi + 1 < nO) load_idx(tile, o0 + oi + 1, idx_next);
                 else load_idx(tile + 1, o0, idx_next);
-                const int s = ua % AS;
-                mbar_wait(a_empty(s), ((ua / AS) & 1) ^ 1);
-                const uint32_t ast = smem_base + (uint32_t)s * p.a_stage_bytes;
+                mbar_wait(a_empty(sa), pha ^ 1);
+                const uint32_t ast = smem_base + (uint32_t)sa * p.a_stage_bytes;
                 for (int kb = 0; kb < nblk_a; ++kb) {
                     const int col0 = cin0 + kb * KB + c * 4;
 #pragma unroll
@@ -157,28 +142,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                         wg_chunk<VEC>(ast + (uint32_t)kb * A_STAGE_BYTES + dst_in_blk + (uint32_t)i * 4096u, p.in,
                                       (int64_t)idx[i] * p.ld_in, idx[i] >= 0, col0, min(p.Cin, cin0 + 128));
                 }
-                cp_async_commit();
-                if (ua >= look) {
-                    if (look == 2) cp_async_wait<2>(); else cp_async_wait<1>();
-                    signal();
-                }
+                cp_async_mbar_arrive_noinc(a_full(sa));
+                if (++sa == AS) sa = 0, pha ^= 1;
             }
         }
         cp_async_wait<0>();
-        while (signalled < ua) signal();
     } else if (lane == 0) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = make_idesc_tf32_mn(TILE_M, npad);
-        int ua = 0, ug = 0;
-        for (int tile = t0; tile < t1; ++tile, ++ug) {
-            const int gs = ug % GS;
-            mbar_wait(g_full(gs), (ug / GS) & 1);
-            const uint32_t gst = g_base + (uint32_t)gs * p.g_stage_bytes;
-            for (int oi = 0; oi < nO; ++oi, ++ua) {
-                const int s = ua % AS;
-                mbar_wait(a_full(s), (ua / AS) & 1);
+        int sa = 0, sg = 0;
+        uint32_t pha = 0, phg = 0;
+        for (int tile = t0; tile < t1; ++tile) {
+            mbar_wait(g_full(sg), phg);
+            const uint32_t gst = g_base + (uint32_t)sg * p.g_stage_bytes;
+            for (int oi = 0; oi < nO; ++oi) {
+                mbar_wait(a_full(sa), pha);
                 tc_fence_after();
-                const uint32_t ast = smem_base + (uint32_t)s * p.a_stage_bytes;
+                const uint32_t ast = smem_base + (uint32_t)sa * p.a_stage_bytes;
                 const uint32_t tmem_d = tmem_base + (uint32_t)(oi * npad);
 #pragma unroll 4
                 for (int j = 0; j < TILE_M / 8; ++j) {
@@ -186,9 +166,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                     const uint64_t db = make_desc_mn_sw128_32b(gst + (uint32_t)j * 1024u, A_STAGE_BYTES, 512);
                     mma_tf32(tmem_d, da, db, idesc, (tile != t0 || j != 0) ? 1u : 0u);
                 }
-                mma_commit(a_empty(s));
+                mma_commit(a_empty(sa));
+                if (++sa == AS) sa = 0, pha ^= 1;
             }
-            mma_commit(g_empty(gs));
+            mma_commit(g_empty(sg));
+            if (++sg == GS) sg = 0, phg ^= 1;
         }
         mma_commit(done_bar);
     }
@@ -258,15 +240,15 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
     int tc = 32;
     while (tc < p.opg * npad) tc <<= 1;
     p.tmem_cols = tc;
-    // shared memory: 2 grad-out stages if they fit, then as many A stages (<= 4) as fit.  M = 128 always
+    // shared memory: 2 grad-out stages if they fit, then as many A stages (<= 6) as fit.  M = 128 always
     // reads a 64 KB window (4 channel blocks) from an A stage base, so the allocation must reach
     // (a_stages - 1) * a_stage_bytes + 64 KB even when the stage itself is narrower.
     int smem = 0;
     p.a_stages = 0;
-    const int budgets[2] = {tc <= 256 ? 112 * 1024 : 0, 224 * 1024};      // two CTAs per SM first, else one
+    const int budgets[2] = {tc <= 256 ? 108 * 1024 : 0, 224 * 1024};      // two CTAs per SM first, else one
     for (int b = 0; b < 2 && p.a_stages < 2; ++b)
         for (int gs = 2; gs >= 1 && p.a_stages < 2; --gs)
-            for (int as = 4; as >= 2; --as) {
+            for (int as = 6; as >= 2; --as) {
                 int total = as * p.a_stage_bytes + gs * p.g_stage_bytes;
                 int window_end = (as - 1) * p.a_stage_bytes + 4 * A_STAGE_BYTES;
                 if (total < window_end) total = window_end;
@@ -278,7 +260,7 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
     SCN_REQUIRE(p.a_stages >= 2, "conv_bwd_weight: tile does not fit in shared memory (Cin=%d Cout=%d)", Cin, Cout);
     smem += 1024 + 256;
     const int groups_y = p.n_ogroups * p.n_mhalves * n_nhalves;
-    const int ctas_per_sm = (tc <= 256 && smem <= 113 * 1024) ? 2 : 1;
+    const int ctas_per_sm = (tc <= 256 && smem <= 112 * 1024) ? 2 : 1;
     int n_chunks = (sm_count() * ctas_per_sm + groups_y - 1) / groups_y;
     if (n_chunks > p.n_tiles) n_chunks = p.n_tiles;
     if (n_chunks < 1) n_chunks = 1;

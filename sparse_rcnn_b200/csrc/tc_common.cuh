@@ -71,6 +71,12 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// arrive on the mbarrier when all cp.async issued so far by this thread have landed (the arrival is one
+// of the barrier's expected arrivals: .noinc).  Same mechanism as CUTLASS' sm100 cp.async collective
+// (cutlass::arch::cpasync_barrier_arrive_noinc): the producer never blocks on its own copies.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
