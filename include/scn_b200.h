@@ -119,14 +119,18 @@ int scn_strided_maps(const int32_t* parent_row, const int32_t* offs, int n_in, i
 
 /* bytes of the packed weight image for the tcgen05 kernel */
 int64_t scn_conv_weight_image_bytes(int K, int Cin, int Cout);
-/* w [K, Cin, Cout] fp32 (SparseConvNet layout [K, 1, Cin, Cout]).  transpose=1 packs W[o]^T
- * (roles of Cin/Cout swapped: Cin is then the OUTPUT width); reverse=1 packs offset K-1-o at o
- * (input-gradient of a submanifold convolution).  Values are rounded to TF32 (rna). */
+/* Cin/Cout are the GEMM widths of the image (reduction width, output width).  transpose=0: w is
+ * [K, Cin, Cout] (SparseConvNet layout [K, 1, Cin, Cout]); transpose=1: w is [K, Cout, Cin] and
+ * W[o]^T is packed (input gradients); reverse=1 packs offset K-1-o at o (input gradient of a
+ * submanifold convolution).  Values are rounded to TF32 (rna). */
 int scn_conv_pack_weights(const float* w, int K, int Cin, int Cout, int transpose, int reverse,
                           void* image, scn_stream_t stream);
 /* TF32 tcgen05 implicit gather-GEMM (sm_100a).  Cin/Cout here are the GEMM's K/N widths, i.e.
- * after any transpose.  residual (may be NULL) is [n_out, Cout] with leading dimension ld_res. */
-int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K,
+ * after any transpose; n_in = rows of `in`.  residual (may be NULL) is [n_out, Cout] with leading
+ * dimension ld_res.  When `in` and its row stride are 16-byte aligned the rows are gathered by TMA
+ * (tile::gather4, fp32->TF32 round-to-nearest on load), otherwise by cp.async (operand truncated:
+ * round it first with scn_round_tf32). */
+int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32_t* map, int n_out, int K,
                       const void* image, const float* bias, const float* residual, int ld_res,
                       float* out, int ld_out, int Cout, int epi_flags, scn_stream_t stream);
 /* exact fp32 FFMA path (verification mode, <=1e-5).  w is the raw [K, Cin_w, Cout_w] tensor;

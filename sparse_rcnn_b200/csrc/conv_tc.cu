@@ -15,6 +15,8 @@
 //
 // Warp roles (9 warps): 0-3 epilogue (TMEM lane quarter = warp id), 4-7 gather producers,
 // 8 MMA issuer + TMEM allocator.
+#include <cuda.h>   // CUtensorMap types only; the driver entry point is resolved at run time
+#include <string.h>
 #include "tc_common.cuh"
 
 namespace scn {
@@ -50,8 +52,16 @@ __device__ __forceinline__ void gather_chunk(uint32_t dst, const float* __restri
     }
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams p) {
+// TMA = true : the A stage is filled by ONE producer warp with `cp.async.bulk.tensor.2d ... tile::gather4`
+//              (SASS UTMALDG): lane L gathers rows 4L..4L+3 of the tile by index, the hardware applies the
+//              128B swizzle, zero-fills index -1 / out-of-range columns, rounds fp32 -> TF32 (to nearest)
+//              and completes the bytes on the stage mbarrier.  6 warps.
+// TMA = false: cp.async producers (4 warps, 16/8/4-byte copies) for feature tensors whose row stride is not
+//              a multiple of 16 bytes.  9 warps.
+template <int VEC, bool TMA>
+__global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const __grid_constant__ CUtensorMap tmap,
+                                                                        const ConvTcParams p) {
+    constexpr int MMA_WARP = TMA ? 5 : 8;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int S = p.stages;
@@ -69,7 +79,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), N_PRODUCERS + 1);
+            mbar_init(full_bar(s), TMA ? 1 : N_PRODUCERS + 1);
             mbar_init(empty_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -78,7 +88,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -89,7 +99,49 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp >= 4 && warp < 8) {
+    if (TMA && warp == 4) {
+        // ===================== TMA gather producer (one warp) =====================
+        if constexpr (TMA) {
+            int s = 0;
+            uint32_t ph = 0;
+            auto load_idx = [&](int tile, int o, int (&dst)[4]) {
+                const int row0 = tile * TILE_M + 4 * lane;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int r = row0 + i;
+                    int v = -1;
+                    if (tile < p.n_tiles && r < p.n_out) v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
+                    dst[i] = v;
+                }
+            };
+            int idx[4], idx_next[4];
+            load_idx(blockIdx.x, 0, idx_next);
+            const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int o = 0; o < p.K; ++o) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) idx[i] = idx_next[i];
+                    if (o + 1 < p.K) load_idx(tile, o + 1, idx_next);
+                    else load_idx(tile + gridDim.x, 0, idx_next);
+                    for (int kb = 0; kb < p.n_kb; ++kb) {
+                        mbar_wait(empty_bar(s), ph ^ 1);
+                        const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)A_STAGE_BYTES + wbytes);
+                            bulk_g2s(a_stage + A_STAGE_BYTES, p.image + (size_t)(o * p.n_kb + kb) * wbytes, wbytes,
+                                     full_bar(s));
+                        }
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+                            "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(a_stage + (uint32_t)lane * 512u),
+                            "l"(&tmap), "r"(kb * KB), "r"(idx[0]), "r"(idx[1]), "r"(idx[2]), "r"(idx[3]), "r"(full_bar(s))
+                            : "memory");
+                        if (++s == S) s = 0, ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (!TMA && warp >= 4 && warp < 8) {
         // ===================== gather producers =====================
         const int pt = tid - 128;
         const int c = pt & 7, rbase = pt >> 3;
@@ -140,7 +192,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
             }
         }
         cp_async_wait<0>();
-    } else if (warp == 8) {
+    } else if (warp == MMA_WARP) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TILE_M, p.cout_pad);
@@ -172,7 +224,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
             }
             (void)units_per_tile;
         }
-    } else {
+    } else if (warp < 4) {
         // ===================== epilogue warps 0..3 =====================
         int it = 0;
         const bool vec_ok = (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
@@ -230,7 +282,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv_tc(const ConvTcParams 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
@@ -265,6 +317,47 @@ __global__ void k_pack_weights(const float* __restrict__ w, int K, int A, int B,
 
 using namespace scn;
 
+// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        cudaDriverEntryPointQueryResult q;
+        void* ptr = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// 2-D map over a row-major fp32 feature tensor [rows, C] for tile::gather4: box = 32 columns x 1 row,
+// TFLOAT32 (round-to-nearest conversion on load), out-of-bounds -> zeros.
+int scn::make_gather_tmap(CUtensorMap* tm, const float* base, int rows, int C, int ld, CUtensorMapSwizzle swz) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return SCN_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)(rows > 0 ? rows : 1)};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32u, 1u};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%d C=%d ld=%d", (int)rc, rows, C, ld);
+        return SCN_ERR_CUDA;
+    }
+    return SCN_OK;
+}
+
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 static inline int n_kblocks(int cin) { return (cin + KB - 1) / KB; }
 
@@ -284,7 +377,7 @@ int scn_conv_pack_weights(const float* w, int K, int Cin, int Cout, int transpos
     return check_launch("pack_weights");
 }
 
-int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const void* image,
+int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32_t* map, int n_out, int K, const void* image,
                       const float* bias, const float* residual, int ld_res, float* out, int ld_out, int Cout,
                       int epi_flags, scn_stream_t stream) {
     SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0, "conv_fwd_tf32: bad shape Cin=%d Cout=%d K=%d", Cin, Cout, K);
@@ -325,16 +418,25 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, const int32_t* map, i
     int vec = 1;
     if (Cin % 4 == 0 && ld_in % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) vec = 4;
     else if (Cin % 2 == 0 && ld_in % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0) vec = 2;
+    // TMA gather needs a 16-byte aligned base and row stride
+    const bool use_tma = (ld_in % 4 == 0) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && n_in > 0;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (use_tma) {
+        int rc = scn::make_gather_tmap(&tmap, in, n_in, Cin, ld_in, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
     int grid = p.n_tiles < sm_count() * ctas_per_sm ? p.n_tiles : sm_count() * ctas_per_sm;
     cudaError_t e;
-    auto launch = [&](auto kern) {
+    auto launch = [&](auto kern, int threads) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return;
-        kern<<<grid, CONV_THREADS, smem, as_stream(stream)>>>(p);
+        kern<<<grid, threads, smem, as_stream(stream)>>>(tmap, p);
     };
-    if (vec == 4) launch(k_conv_tc<4>);
-    else if (vec == 2) launch(k_conv_tc<2>);
-    else launch(k_conv_tc<1>);
+    if (use_tma) launch(k_conv_tc<4, true>, 192);
+    else if (vec == 4) launch(k_conv_tc<4, false>, CONV_THREADS);
+    else if (vec == 2) launch(k_conv_tc<2, false>, CONV_THREADS);
+    else launch(k_conv_tc<1, false>, CONV_THREADS);
     if (e != cudaSuccess) {
         cudaGetLastError();
         scn::set_error("conv_fwd_tf32: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));

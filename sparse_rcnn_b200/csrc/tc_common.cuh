@@ -2,9 +2,12 @@
 // tcgen05.mma / commit / ld.  Bit layouts follow cute/arch/mma_sm100_desc.hpp (CUTLASS), which is
 // only consulted as documentation -- nothing here includes CUTLASS.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace scn {
+
+int make_gather_tmap(CUtensorMap* tm, const float* base, int rows, int C, int ld, CUtensorMapSwizzle swz);
 
 constexpr int TILE_M = 128;
 constexpr int KB = 32;                  // fp32 per 128-byte swizzle row
