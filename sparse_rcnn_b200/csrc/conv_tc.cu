@@ -16,6 +16,7 @@
 // Warp roles (9 warps): 0-3 epilogue (TMEM lane quarter = warp id), 4-7 gather producers,
 // 8 MMA issuer + TMEM allocator.
 #include <cuda.h>   // CUtensorMap types only; the driver entry point is resolved at run time
+#include <stdlib.h>
 #include <string.h>
 #include "tc_common.cuh"
 
@@ -179,10 +180,27 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                     }
                     const int col0 = kb * KB + c * 4;
                     if (col0 < p.cin_pad8) {
+                        if constexpr (VEC == 4) {
+                            // lean path: one IMAD.WIDE + one LDGSTS per 16-byte chunk; inactive rows (and the
+                            // all-padding chunk of a Cin that is not a multiple of 8) use src-size 0 = zero fill
+                            const float* colp = p.in + col0;
+                            const int full = col0 < p.Cin ? 16 : 0;
+                            const uint32_t dst = a_stage + dst_in_stage;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            gather_chunk<VEC>(a_stage + dst_in_stage + (uint32_t)i * 2048u, p.in,
-                                              (int64_t)idx[i] * p.ld_in, idx[i], col0, p.Cin);
+                            for (int i = 0; i < 8; ++i) {
+                                const int r = idx[i];
+                                const float* src = colp + (int64_t)max(r, 0) * p.ld_in;
+                                const int sz = r >= 0 ? full : 0;
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)i * 2048u),
+                                             "l"(src), "r"(sz)
+                                             : "memory");
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                gather_chunk<VEC>(a_stage + dst_in_stage + (uint32_t)i * 2048u, p.in,
+                                                  (int64_t)idx[i] * p.ld_in, idx[i], col0, p.Cin);
+                        }
                     }
                     // the stage's full barrier receives this thread's arrival when its copies have landed;
                     // up to S units are in flight per CTA and the producer only ever waits for a free slot
@@ -232,7 +250,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                              ((p.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int b = it & 1;
-            mbar_wait(accf_bar(b), (it >> 1) & 1);
+            mbar_wait<200>(accf_bar(b), (it >> 1) & 1);      // epilogue warps wait a whole tile: long back-off
             tc_fence_after();
             const int row = tile * TILE_M + warp * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * p.cout_pad);
@@ -419,7 +437,15 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     if (Cin % 4 == 0 && ld_in % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) vec = 4;
     else if (Cin % 2 == 0 && ld_in % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0) vec = 2;
     // TMA gather needs a 16-byte aligned base and row stride
-    const bool use_tma = (ld_in % 4 == 0) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && n_in > 0;
+    // Measured on B200 (profiles/r1_c_tma_gather4.md): the TMA unit retires ~one 128-byte row per 14 cycles per
+    // SM and spends the same on zero-filled (inactive) rows, so tile::gather4 is 2.2x SLOWER than the cp.async
+    // producers for this access pattern.  It stays available as an opt-in (SCN_CONV_TMA=1).
+    static int want_tma = -1;
+    if (want_tma < 0) {
+        const char* e = getenv("SCN_CONV_TMA");
+        want_tma = (e && e[0] == '1') ? 1 : 0;
+    }
+    const bool use_tma = want_tma && (ld_in % 4 == 0) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && n_in > 0;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (use_tma) {

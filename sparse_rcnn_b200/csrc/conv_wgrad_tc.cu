@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
 
     if (warp < 4) {
         // ===================== epilogue: TMEM -> atomics into gw =====================
-        mbar_wait(done_bar, 0);
+        mbar_wait<500>(done_bar, 0);
         tc_fence_after();
         const int ci = cin0 + warp * 32 + lane;
         for (int oi = 0; oi < nO; ++oi) {

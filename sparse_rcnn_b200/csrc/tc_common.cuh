@@ -37,13 +37,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.  After the first
+// failed probe the warp backs off with nanosleep so that waiting roles (epilogue, MMA issuer, producers
+// waiting for a free stage) do not steal issue slots from the warps doing the copies.
+template <int SLEEP_NS = 32>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint64_t t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(SLEEP_NS);
         if ((++spins & 1023u) == 0) {
             uint64_t t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));

@@ -66,8 +66,7 @@ def conv_gemm(x, weight, K, cin, cout, fmap, n_out, bias=None, transpose=0, reve
     s = _stream()
     if _state["precision"] == "tf32" and cout <= 256:
         img = _image(weight, K, cin, cout, transpose, reverse)
-        if x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0:
-            x = tf32_exact(x)       # cp.async path truncates; the TMA path rounds on load
+        x = tf32_exact(x)           # cp.async gathers are truncated by the MMA: round the operand once
         _lib.call("scn_conv_fwd_tf32", _ptr(x), x.stride(0), cin, x.shape[0], _ptr(fmap), n_out, K, _ptr(img), _ptr(bias),
                   _ptr(residual), ld_res, _ptr(out), cout, cout, epi, s)
     else:
