@@ -37,6 +37,9 @@ struct ConvTcParams {
     float* out;
     int ld_out, Cout, epi;
     int cout_pad, n_kb, cin_pad8, stages, tmem_cols, n_tiles;
+    int smap;             // 1 = neighbour map of a tile is staged in shared memory one tile ahead
+    long long* dbg_buf;   // SCN_CONV_TRACE: per-unit clock64 timestamps of CTA 0 (4 per unit), NULL = off
+    int debug;   // timing experiments only (SCN_CONV_DEBUG): 1 = no gather traffic, 2 = 16-byte weight copies, 4 = no MMA
 };
 
 // one 16-byte chunk of a gathered row, split into VEC-float cp.asyncs
@@ -149,37 +152,79 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
         const uint32_t dst_in_stage = (uint32_t)rbase * 128u + (uint32_t)((c ^ (rbase & 7)) << 4);
         int s = 0;
         uint32_t ph = 0;      // ring position / phase of this thread's unit stream
-        // neighbour indices are fetched one (tile, offset) ahead of the copies that depend on them, so
-        // the L2 latency of the map read overlaps the cp.async issue of the previous offset
-        auto load_idx = [&](int tile, int o, int (&dst)[8]) {
+        // The neighbour indices of a whole tile (K x 128 ints) are staged in shared memory ONE TILE ahead with
+        // cp.async (double buffered).  Measured with the clock64 trace (profiles/r1_d_producer_trace.md): reading
+        // them from global memory one unit ahead made every unit wait ~1000 cycles for that load.
+        const uint32_t map_smem = bars + 256u;
+        const int32_t* sm_map = reinterpret_cast<const int32_t*>(smem_raw + (map_smem - smem_u32(smem_raw)));
+        const bool map_vec = ((p.n_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.map) & 15) == 0);
+        auto stage_map = [&](int tile, int buf) {
+            if (p.smap && tile < p.n_tiles) {
+                const int row0 = tile * TILE_M;
+                const uint32_t dst0 = map_smem + (uint32_t)(buf * p.K) * 512u;
+                if (map_vec && row0 + TILE_M <= p.n_out) {
+                    for (int ch = pt; ch < p.K * 32; ch += N_PRODUCERS) {
+                        const int o = ch >> 5, q = ch & 31;
+                        cp_async<16>(dst0 + (uint32_t)o * 512u + (uint32_t)q * 16u,
+                                     p.map + (int64_t)o * p.n_out + row0 + q * 4, true);
+                    }
+                } else {
+                    int32_t* dstp = const_cast<int32_t*>(sm_map) + buf * p.K * TILE_M;
+                    for (int e = pt; e < p.K * TILE_M; e += N_PRODUCERS) {
+                        const int o = e >> 7, r = e & 127;
+                        dstp[e] = (row0 + r < p.n_out) ? __ldg(p.map + (int64_t)o * p.n_out + row0 + r) : -1;
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+        auto producers_sync = [&]() {
+            cp_async_wait<0>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        auto load_idx = [&](int tile, int o, int buf, int (&dst)[8]) {
             const int row0 = tile * TILE_M;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                int r = row0 + rbase + 16 * i;
-                int v = -1;
-                if (tile < p.n_tiles && r < p.n_out) v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
+                const int r = rbase + 16 * i;
+                int v;
+                if (p.smap) v = sm_map[(buf * p.K + o) * TILE_M + r];
+                else if (row0 + r >= p.n_out) v = -1;
+                else v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + row0 + r) : row0 + r;
                 dst[i] = v;
             }
         };
-        int idx[8], idx_next[8];
-        load_idx(blockIdx.x, 0, idx_next);
-        const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        int idx[8];
+        int ucount = 0, it = 0;
+        stage_map(blockIdx.x, 0);
+        producers_sync();
+        const uint32_t wbytes = (p.debug & 2) ? 16u : (uint32_t)p.cout_pad * 128u;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            stage_map(tile + gridDim.x, (it + 1) & 1);
             for (int o = 0; o < p.K; ++o) {
+                load_idx(tile, o, it & 1, idx);
+                if (p.debug & 1) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) idx[i] = idx_next[i];
-                if (o + 1 < p.K) load_idx(tile, o + 1, idx_next);
-                else load_idx(tile + gridDim.x, 0, idx_next);
+                    for (int i = 0; i < 8; ++i) idx[i] = -1;
+                }
                 for (int kb = 0; kb < p.n_kb; ++kb) {
+                    const bool trace = p.dbg_buf && blockIdx.x == 0 && pt == 0 && ucount < 256;
+                    if (trace) p.dbg_buf[ucount * 4 + 0] = clock64();
                     mbar_wait(empty_bar(s), ph ^ 1);
+                    if (trace) p.dbg_buf[ucount * 4 + 1] = clock64();
+                    ++ucount;
                     const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
                     if (pt == 0) {
-                        mbar_arrive_expect_tx(full_bar(s), wbytes);
-                        bulk_g2s(a_stage + A_STAGE_BYTES, p.image + (size_t)(o * p.n_kb + kb) * wbytes, wbytes,
-                                 full_bar(s));
+                        if (p.debug & 8) {
+                            mbar_arrive(full_bar(s));          // timing experiment: no bulk copy at all
+                        } else {
+                            mbar_arrive_expect_tx(full_bar(s), wbytes);
+                            bulk_g2s(a_stage + A_STAGE_BYTES, p.image + (size_t)(o * p.n_kb + kb) * wbytes, wbytes,
+                                     full_bar(s));
+                        }
                     }
                     const int col0 = kb * KB + c * 4;
-                    if (col0 < p.cin_pad8) {
+                    if (col0 < p.cin_pad8 && !(p.debug & 16)) {
                         if constexpr (VEC == 4) {
                             // lean path: one IMAD.WIDE + one LDGSTS per 16-byte chunk; inactive rows (and the
                             // all-padding chunk of a Cin that is not a multiple of 8) use src-size 0 = zero fill
@@ -208,13 +253,14 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                     if (++s == S) s = 0, ph ^= 1;
                 }
             }
+            producers_sync();       // next tile's map slice has landed and is visible to all producer threads
         }
         cp_async_wait<0>();
     } else if (warp == MMA_WARP) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TILE_M, p.cout_pad);
-            int s = 0, it = 0;
+            int s = 0, it = 0, ucount = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const int b = it & 1;
@@ -223,13 +269,17 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                 const uint32_t tmem_d = tmem_base + (uint32_t)(b * p.cout_pad);
                 for (int o = 0; o < p.K; ++o) {
                     for (int kb = 0; kb < p.n_kb; ++kb) {
+                        const bool trace = p.dbg_buf && blockIdx.x == 0 && ucount < 256;
+                        if (trace) p.dbg_buf[ucount * 4 + 2] = clock64();
                         mbar_wait(full_bar(s), ph);
+                        if (trace) p.dbg_buf[ucount * 4 + 3] = clock64();
+                        ++ucount;
                         tc_fence_after();
                         const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
                         const uint64_t da = make_desc_sw128(a_stage);
                         const uint64_t db = make_desc_sw128(a_stage + A_STAGE_BYTES);
                         const int kcols = min(KB, p.cin_pad8 - kb * KB);
-                        for (int k = 0; k < kcols / 8; ++k) {
+                        for (int k = 0; k < ((p.debug & 4) ? 0 : kcols / 8); ++k) {
                             // advance 32 bytes (8 tf32) inside the 128-byte swizzled row: +2 in the >>4 address field
                             mma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                      (o | kb | k) != 0 ? 1u : 0u);
@@ -376,6 +426,14 @@ int scn::make_gather_tmap(CUtensorMap* tm, const float* base, int rows, int C, i
     return SCN_OK;
 }
 
+static long long* g_trace_buf = nullptr;
+extern "C" int scn_debug_trace(long long* host_out) {
+    if (!g_trace_buf) return 1;
+    cudaDeviceSynchronize();
+    cudaMemcpy(host_out, g_trace_buf, 256 * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return 0;
+}
+
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 static inline int n_kblocks(int cin) { return (cin + KB - 1) / KB; }
 
@@ -415,24 +473,40 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     p.out = out, p.ld_out = ld_out, p.Cout = Cout, p.epi = epi_flags;
     p.cout_pad = pad16(Cout), p.n_kb = n_kblocks(Cin), p.cin_pad8 = (Cin + 7) / 8 * 8;
     p.n_tiles = cdiv(n_out, TILE_M);
+    {
+        const char* e = getenv("SCN_CONV_DEBUG");
+        p.debug = e ? atoi(e) : 0;
+        p.dbg_buf = nullptr;
+        const char* t = getenv("SCN_CONV_TRACE");
+        if (t && t[0] == '1') {
+            static long long* buf = nullptr;
+            if (!buf) cudaMalloc(&buf, 256 * 4 * sizeof(long long));
+            cudaMemsetAsync(buf, 0, 256 * 4 * sizeof(long long), as_stream(stream));
+            p.dbg_buf = buf;
+            g_trace_buf = buf;
+        }
+    }
     int cols = 2 * p.cout_pad, tc = 32;
     while (tc < cols) tc <<= 1;
     p.tmem_cols = tc;
     const int stage_bytes = A_STAGE_BYTES + p.cout_pad * 128;
-    // ring depth = units in flight per CTA (the gather is latency bound, so deeper is better): two CTAs
-    // per SM when at least four stages fit in ~110 KB each, otherwise one CTA with up to eight stages
+    // neighbour-map staging buffers (2 x K x 512 B) live behind the stage ring
+    p.smap = (map != nullptr && K <= 32) ? 1 : 0;
+    const int map_bytes = p.smap ? 2 * K * 512 : 0;
+    // ring depth = units in flight per CTA: two CTAs per SM when at least four stages fit in ~110 KB each,
+    // otherwise one CTA with up to eight stages
     int stages, ctas_per_sm;
-    const int s2 = (110 * 1024) / stage_bytes;
+    const int s2 = (110 * 1024 - map_bytes) / stage_bytes;
     if (s2 >= 4 && tc <= 256) {
         stages = s2 > 8 ? 8 : s2, ctas_per_sm = 2;
     } else {
-        stages = (220 * 1024) / stage_bytes;
+        stages = (220 * 1024 - map_bytes) / stage_bytes;
         if (stages > 8) stages = 8;
         ctas_per_sm = 1;
     }
     SCN_REQUIRE(stages >= 2, "conv_fwd_tf32: tile does not fit in shared memory");
     p.stages = stages;
-    const int smem = stages * stage_bytes + 1024 + 256;
+    const int smem = stages * stage_bytes + 1024 + 256 + map_bytes;
     int vec = 1;
     if (Cin % 4 == 0 && ld_in % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) vec = 4;
     else if (Cin % 2 == 0 && ld_in % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0) vec = 2;
