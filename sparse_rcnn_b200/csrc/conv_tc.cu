@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), TMA ? 1 : N_PRODUCERS + 1);
+            mbar_init(full_bar(s), TMA ? 1 : N_PRODUCERS / 32 + 1);   // one arrival per producer WARP + weights
             mbar_init(empty_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -194,6 +194,19 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                 dst[i] = v;
             }
         };
+        // Stage completion is signalled ONCE PER WARP: every thread commits its copies as a cp.async group,
+        // waits until the group issued `look` units earlier has landed, the warp converges and lane 0 arrives.
+        // (128 per-thread arrivals on one mbarrier serialise like same-address shared-memory atomics: measured
+        // ~1000 cycles per unit, the whole kernel time -- profiles/r1_d_producer_trace.md.)
+        const int look = S - 1 < 6 ? S - 1 : 6;
+        int sig_s = 0, pending = 0;
+        auto signal_oldest = [&]() {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(sig_s));
+            if (++sig_s == S) sig_s = 0;
+            --pending;
+        };
         int idx[8];
         int ucount = 0, it = 0;
         stage_map(blockIdx.x, 0);
@@ -247,13 +260,17 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                                                   (int64_t)idx[i] * p.ld_in, idx[i], col0, p.Cin);
                         }
                     }
-                    // the stage's full barrier receives this thread's arrival when its copies have landed;
-                    // up to S units are in flight per CTA and the producer only ever waits for a free slot
-                    cp_async_mbar_arrive_noinc(full_bar(s));
+                    cp_async_commit();
+                    ++pending;
+                    if (pending > look) {
+                        cp_async_wait_dyn(look);
+                        signal_oldest();
+                    }
                     if (++s == S) s = 0, ph ^= 1;
                 }
             }
             producers_sync();       // next tile's map slice has landed and is visible to all producer threads
+            while (pending > 0) signal_oldest();      // everything issued so far has landed (wait_group 0 above)
         }
         cp_async_wait<0>();
     } else if (warp == MMA_WARP) {
