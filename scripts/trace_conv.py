@@ -16,17 +16,20 @@ t = scn.SparseConvNetTensor(Fn.tf32_exact(torch.randn(n, C, device=dev)), md, si
 with torch.no_grad():
     for _ in range(3): conv(t)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 1024)()
+buf = (ctypes.c_longlong * 2048)()
 dll = ctypes.CDLL(_lib.LIB_PATH)
 print("rc", dll.scn_debug_trace(buf))
-a = np.array(buf[:]).reshape(256, 4)
+a = np.array(buf[:]).reshape(256, 8)
 a = a[a[:, 0] > 0]
-t0 = a[0, 0]
-print("units traced", len(a))
-print("unit | prod: wait_start wait_end (wait) | mma: wait_start wait_end (wait) | prod per-unit period | mma period")
-for i in range(min(len(a), 140)):
-    if i < 40 or i % 10 == 0:
-        print("%4d | %8d %8d (%6d) | %8d %8d (%6d) | %6d | %6d" % (i, a[i,0]-t0, a[i,1]-t0, a[i,1]-a[i,0], a[i,2]-t0, a[i,3]-t0, a[i,3]-a[i,2],
-              a[i,0]-a[i-1,0] if i else 0, a[i,3]-a[i-1,3] if i else 0))
-pw = (a[:,1]-a[:,0]); mw = (a[:,3]-a[:,2])
-print("mean producer wait-for-empty %.0f cyc, mean MMA wait-for-full %.0f cyc, mean unit period %.0f cyc" % (pw[8:].mean(), mw[8:].mean(), np.diff(a[8:,0]).mean()))
+print("units traced", len(a), "debug", os.environ.get("SCN_CONV_DEBUG", "0"))
+d = a[8:]
+print("producer (thread 0 of warp 4), mean cycles per unit:")
+print("  wait empty        %7.0f" % (d[:,1]-d[:,0]).mean())
+print("  weights issue     %7.0f" % (d[:,2]-d[:,1]).mean())
+print("  8x LDGSTS issue   %7.0f" % (d[:,3]-d[:,2]).mean())
+print("  arrive            %7.0f" % (d[:,4]-d[:,3]).mean())
+print("  loop tail -> next %7.0f" % (d[1:,0]-d[:-1,4]).mean())
+print("  unit period       %7.0f" % np.diff(d[:,0]).mean())
+print("MMA thread: wait full %7.0f, period %7.0f" % ((d[:,7]-d[:,6]).mean(), np.diff(d[:,7]).mean()))
+for i in range(20, 32):
+    r = a[i]; print(i, [int(x - a[20,0]) for x in r])

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), TMA ? 1 : N_PRODUCERS / 32 + 1);   // one arrival per producer WARP + weights
+            mbar_init(full_bar(s), TMA ? 1 : 32 + 1);   // the owning producer warp's 32 lanes + the weights expect_tx
             mbar_init(empty_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -146,33 +146,51 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
             }
         }
     } else if (!TMA && warp >= 4 && warp < 8) {
-        // ===================== gather producers =====================
-        const int pt = tid - 128;
-        const int c = pt & 7, rbase = pt >> 3;
-        const uint32_t dst_in_stage = (uint32_t)rbase * 128u + (uint32_t)((c ^ (rbase & 7)) << 4);
-        int s = 0;
-        uint32_t ph = 0;      // ring position / phase of this thread's unit stream
-        // The neighbour indices of a whole tile (K x 128 ints) are staged in shared memory ONE TILE ahead with
-        // cp.async (double buffered).  Measured with the clock64 trace (profiles/r1_d_producer_trace.md): reading
-        // them from global memory one unit ahead made every unit wait ~1000 cycles for that load.
+        // ===================== cp.async gather producers =====================
+        // Each producer warp OWNS whole units (warp w takes units w, w+4, ... of the CTA's unit stream): the
+        // fixed per-unit costs measured with the clock64 trace (mbarrier try_wait ~120 cycles, weights issue
+        // ~190, loop control ~600 of serial constant-bank loads) are paid by one warp per unit instead of by
+        // all four, and four stages are being filled concurrently.  Lane L copies 16-byte chunk (L & 7) of rows
+        // (L >> 3) + 4 i, i = 0..31.  Kernel parameters are laundered into registers so the loop does not
+        // re-read them from the constant bank.
+        const int pw = warp - 4, pt = tid - 128;
+        const int c = lane & 7, rsub = lane >> 3;
+        int K, n_kb, n_tiles, n_out, cin, cin_pad8, ld_in, nS;
+        asm volatile("mov.u32 %0, %1;" : "=r"(K) : "r"(p.K));
+        asm volatile("mov.u32 %0, %1;" : "=r"(n_kb) : "r"(p.n_kb));
+        asm volatile("mov.u32 %0, %1;" : "=r"(n_tiles) : "r"(p.n_tiles));
+        asm volatile("mov.u32 %0, %1;" : "=r"(n_out) : "r"(p.n_out));
+        asm volatile("mov.u32 %0, %1;" : "=r"(cin) : "r"(p.Cin));
+        asm volatile("mov.u32 %0, %1;" : "=r"(cin_pad8) : "r"(p.cin_pad8));
+        asm volatile("mov.u32 %0, %1;" : "=r"(ld_in) : "r"(p.ld_in));
+        asm volatile("mov.u32 %0, %1;" : "=r"(nS) : "r"(p.stages));
+        const bool smap = p.smap != 0;
+        const float* in = p.in;
+        const int32_t* gmap = p.map;
+        const uint8_t* image = p.image;
+        const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
+        const uint32_t dstA = (uint32_t)rsub * 128u + (uint32_t)((c ^ rsub) << 4);            // rows with (r & 4) == 0
+        const uint32_t dstB = (uint32_t)rsub * 128u + (uint32_t)((c ^ (rsub + 4)) << 4);      // rows with (r & 4) != 0
+
+        // neighbour indices of a whole tile (K x 128 ints) are staged in shared memory ONE TILE ahead (double buffer)
         const uint32_t map_smem = bars + 256u;
         const int32_t* sm_map = reinterpret_cast<const int32_t*>(smem_raw + (map_smem - smem_u32(smem_raw)));
-        const bool map_vec = ((p.n_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.map) & 15) == 0);
+        const bool map_vec = ((n_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(gmap) & 15) == 0);
         auto stage_map = [&](int tile, int buf) {
-            if (p.smap && tile < p.n_tiles) {
+            if (smap && tile < n_tiles) {
                 const int row0 = tile * TILE_M;
-                const uint32_t dst0 = map_smem + (uint32_t)(buf * p.K) * 512u;
-                if (map_vec && row0 + TILE_M <= p.n_out) {
-                    for (int ch = pt; ch < p.K * 32; ch += N_PRODUCERS) {
+                const uint32_t dst0 = map_smem + (uint32_t)(buf * K) * 512u;
+                if (map_vec && row0 + TILE_M <= n_out) {
+                    for (int ch = pt; ch < K * 32; ch += N_PRODUCERS) {
                         const int o = ch >> 5, q = ch & 31;
-                        cp_async<16>(dst0 + (uint32_t)o * 512u + (uint32_t)q * 16u,
-                                     p.map + (int64_t)o * p.n_out + row0 + q * 4, true);
+                        cp_async<16>(dst0 + (uint32_t)o * 512u + (uint32_t)q * 16u, gmap + (int64_t)o * n_out + row0 + q * 4,
+                                     true);
                     }
                 } else {
-                    int32_t* dstp = const_cast<int32_t*>(sm_map) + buf * p.K * TILE_M;
-                    for (int e = pt; e < p.K * TILE_M; e += N_PRODUCERS) {
+                    int32_t* dstp = const_cast<int32_t*>(sm_map) + buf * K * TILE_M;
+                    for (int e = pt; e < K * TILE_M; e += N_PRODUCERS) {
                         const int o = e >> 7, r = e & 127;
-                        dstp[e] = (row0 + r < p.n_out) ? __ldg(p.map + (int64_t)o * p.n_out + row0 + r) : -1;
+                        dstp[e] = (row0 + r < n_out) ? __ldg(gmap + (int64_t)o * n_out + row0 + r) : -1;
                     }
                 }
             }
@@ -182,102 +200,72 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
             cp_async_wait<0>();
             asm volatile("bar.sync 1, 128;" ::: "memory");
         };
-        auto load_idx = [&](int tile, int o, int buf, int (&dst)[8]) {
-            const int row0 = tile * TILE_M;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 16 * i;
-                int v;
-                if (p.smap) v = sm_map[(buf * p.K + o) * TILE_M + r];
-                else if (row0 + r >= p.n_out) v = -1;
-                else v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + row0 + r) : row0 + r;
-                dst[i] = v;
-            }
-        };
-        // Stage completion is signalled ONCE PER WARP: every thread commits its copies as a cp.async group,
-        // waits until the group issued `look` units earlier has landed, the warp converges and lane 0 arrives.
-        // (128 per-thread arrivals on one mbarrier serialise like same-address shared-memory atomics: measured
-        // ~1000 cycles per unit, the whole kernel time -- profiles/r1_d_producer_trace.md.)
-        const int look = S - 1 < 6 ? S - 1 : 6;
-        int sig_s = 0, pending = 0;
-        auto signal_oldest = [&]() {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(sig_s));
-            if (++sig_s == S) sig_s = 0;
-            --pending;
-        };
-        int idx[8];
-        int ucount = 0, it = 0;
+        // ring position of this warp's next unit: unit index u = pw, pw + 4, ...
+        int s = pw % nS;
+        uint32_t ph = (uint32_t)(pw / nS) & 1u;
+        int ucur = 0;                    // index (within the CTA's unit stream) of the next unit of ANY warp
+        int mine = pw;                   // next unit index owned by this warp
+        int it = 0;
         stage_map(blockIdx.x, 0);
         producers_sync();
-        const uint32_t wbytes = (p.debug & 2) ? 16u : (uint32_t)p.cout_pad * 128u;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             stage_map(tile + gridDim.x, (it + 1) & 1);
-            for (int o = 0; o < p.K; ++o) {
-                load_idx(tile, o, it & 1, idx);
-                if (p.debug & 1) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) idx[i] = -1;
-                }
-                for (int kb = 0; kb < p.n_kb; ++kb) {
-                    const bool trace = p.dbg_buf && blockIdx.x == 0 && pt == 0 && ucount < 256;
-                    if (trace) p.dbg_buf[ucount * 4 + 0] = clock64();
+            const int row0 = tile * TILE_M;
+            const int32_t* tmap_s = sm_map + (it & 1) * K * TILE_M;
+            for (int o = 0; o < K; ++o) {
+                for (int kb = 0; kb < n_kb; ++kb, ++ucur) {
+                    if (ucur != mine) continue;
+                    mine += 4;
                     mbar_wait(empty_bar(s), ph ^ 1);
-                    if (trace) p.dbg_buf[ucount * 4 + 1] = clock64();
-                    ++ucount;
                     const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
-                    if (pt == 0) {
-                        if (p.debug & 8) {
-                            mbar_arrive(full_bar(s));          // timing experiment: no bulk copy at all
-                        } else {
-                            mbar_arrive_expect_tx(full_bar(s), wbytes);
-                            bulk_g2s(a_stage + A_STAGE_BYTES, p.image + (size_t)(o * p.n_kb + kb) * wbytes, wbytes,
-                                     full_bar(s));
-                        }
+                    const uint32_t fb = full_bar(s);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(fb, wbytes);
+                        bulk_g2s(a_stage + A_STAGE_BYTES, image + (size_t)(o * n_kb + kb) * wbytes, wbytes, fb);
                     }
                     const int col0 = kb * KB + c * 4;
-                    if (col0 < p.cin_pad8 && !(p.debug & 16)) {
+                    if (col0 < cin_pad8) {
                         if constexpr (VEC == 4) {
-                            // lean path: one IMAD.WIDE + one LDGSTS per 16-byte chunk; inactive rows (and the
-                            // all-padding chunk of a Cin that is not a multiple of 8) use src-size 0 = zero fill
-                            const float* colp = p.in + col0;
-                            const int full = col0 < p.Cin ? 16 : 0;
-                            const uint32_t dst = a_stage + dst_in_stage;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int r = idx[i];
-                                const float* src = colp + (int64_t)max(r, 0) * p.ld_in;
+                            const float* colp = in + col0;
+                            const int full = col0 < cin ? 16 : 0;
+#pragma unroll 8
+                            for (int i = 0; i < 32; ++i) {
+                                const int rr = rsub + 4 * i;
+                                int r;
+                                if (smap) r = tmap_s[o * TILE_M + rr];
+                                else r = (row0 + rr < n_out) ? (gmap ? __ldg(gmap + (int64_t)o * n_out + row0 + rr) : row0 + rr) : -1;
+                                const float* src = colp + (int64_t)max(r, 0) * ld_in;
                                 const int sz = r >= 0 ? full : 0;
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)i * 2048u),
-                                             "l"(src), "r"(sz)
+                                const uint32_t dst = a_stage + (uint32_t)i * 512u + ((i & 1) ? dstB : dstA);
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz)
                                              : "memory");
                             }
                         } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                gather_chunk<VEC>(a_stage + dst_in_stage + (uint32_t)i * 2048u, p.in,
-                                                  (int64_t)idx[i] * p.ld_in, idx[i], col0, p.Cin);
+#pragma unroll 4
+                            for (int i = 0; i < 32; ++i) {
+                                const int rr = rsub + 4 * i;
+                                int r;
+                                if (smap) r = tmap_s[o * TILE_M + rr];
+                                else r = (row0 + rr < n_out) ? (gmap ? __ldg(gmap + (int64_t)o * n_out + row0 + rr) : row0 + rr) : -1;
+                                gather_chunk<VEC>(a_stage + (uint32_t)i * 512u + ((i & 1) ? dstB : dstA), in, (int64_t)r * ld_in,
+                                                  r, col0, cin);
+                            }
                         }
                     }
-                    cp_async_commit();
-                    ++pending;
-                    if (pending > look) {
-                        cp_async_wait_dyn(look);
-                        signal_oldest();
-                    }
-                    if (++s == S) s = 0, ph ^= 1;
+                    // this thread's arrival on the stage's full barrier fires when its copies have landed
+                    cp_async_mbar_arrive_noinc(fb);
+                    s += 4;
+                    while (s >= nS) s -= nS, ph ^= 1;
                 }
             }
             producers_sync();       // next tile's map slice has landed and is visible to all producer threads
-            while (pending > 0) signal_oldest();      // everything issued so far has landed (wait_group 0 above)
         }
         cp_async_wait<0>();
     } else if (warp == MMA_WARP) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TILE_M, p.cout_pad);
-            int s = 0, it = 0, ucount = 0;
+            int s = 0, it = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const int b = it & 1;
@@ -286,17 +274,13 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                 const uint32_t tmem_d = tmem_base + (uint32_t)(b * p.cout_pad);
                 for (int o = 0; o < p.K; ++o) {
                     for (int kb = 0; kb < p.n_kb; ++kb) {
-                        const bool trace = p.dbg_buf && blockIdx.x == 0 && ucount < 256;
-                        if (trace) p.dbg_buf[ucount * 4 + 2] = clock64();
                         mbar_wait(full_bar(s), ph);
-                        if (trace) p.dbg_buf[ucount * 4 + 3] = clock64();
-                        ++ucount;
                         tc_fence_after();
                         const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
                         const uint64_t da = make_desc_sw128(a_stage);
                         const uint64_t db = make_desc_sw128(a_stage + A_STAGE_BYTES);
                         const int kcols = min(KB, p.cin_pad8 - kb * KB);
-                        for (int k = 0; k < ((p.debug & 4) ? 0 : kcols / 8); ++k) {
+                        for (int k = 0; k < kcols / 8; ++k) {
                             // advance 32 bytes (8 tf32) inside the 128-byte swizzled row: +2 in the >>4 address field
                             mma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                      (o | kb | k) != 0 ? 1u : 0u);
@@ -447,7 +431,7 @@ static long long* g_trace_buf = nullptr;
 extern "C" int scn_debug_trace(long long* host_out) {
     if (!g_trace_buf) return 1;
     cudaDeviceSynchronize();
-    cudaMemcpy(host_out, g_trace_buf, 256 * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(host_out, g_trace_buf, 256 * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
     return 0;
 }
 
@@ -497,8 +481,8 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
         const char* t = getenv("SCN_CONV_TRACE");
         if (t && t[0] == '1') {
             static long long* buf = nullptr;
-            if (!buf) cudaMalloc(&buf, 256 * 4 * sizeof(long long));
-            cudaMemsetAsync(buf, 0, 256 * 4 * sizeof(long long), as_stream(stream));
+            if (!buf) cudaMalloc(&buf, 256 * 8 * sizeof(long long));
+            cudaMemsetAsync(buf, 0, 256 * 8 * sizeof(long long), as_stream(stream));
             p.dbg_buf = buf;
             g_trace_buf = buf;
         }

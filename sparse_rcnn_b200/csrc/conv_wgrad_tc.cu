@@ -73,11 +73,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < AS; ++s) {
-            mbar_init(a_full(s), WG_PRODUCERS / 32);      // one arrival per producer warp
+            mbar_init(a_full(s), WG_PRODUCERS);
             mbar_init(a_empty(s), 1);
         }
         for (int s = 0; s < GS; ++s) {
-            mbar_init(g_full(s), WG_PRODUCERS / 32);
+            mbar_init(g_full(s), WG_PRODUCERS);
             mbar_init(g_empty(s), 1);
         }
         mbar_init(done_bar, 1);
@@ -137,21 +137,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                 dst[i] = v;
             }
         };
-        // one mbarrier arrival per WARP per unit (see conv_tc.cu): commit groups + look-ahead wait + lane-0 arrive
-        const int look = AS - 1 < 6 ? AS - 1 : 6;
-        int sig_a = 0, sig_g = 0, sig_oi = 0, pending = 0;
-        auto signal_oldest = [&]() {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                if (sig_oi == 0) mbar_arrive(g_full(sig_g));      // first unit of a tile carries the grad-out tile
-                mbar_arrive(a_full(sig_a));
-            }
-            if (sig_oi == 0 && ++sig_g == GS) sig_g = 0;
-            if (++sig_oi == nO) sig_oi = 0;
-            if (++sig_a == AS) sig_a = 0;
-            --pending;
-        };
         int idx[4];
         int it = 0;
         stage_map(t0, 0);
@@ -173,7 +158,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                                       (int64_t)r * p.ld_go, r < p.n_out, col0, min(p.Cout, cout0 + 128));
                     }
                 }
-                if (++sg == GS) sg = 0, phg ^= 1;      // committed together with the tile's first A unit
+                cp_async_mbar_arrive_noinc(g_full(sg));      // fires when this thread's copies have landed
+                if (++sg == GS) sg = 0, phg ^= 1;
             }
             for (int oi = 0; oi < nO; ++oi) {
                 load_idx(tile, oi, it & 1, idx);
@@ -186,16 +172,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                         wg_chunk<VEC>(ast + (uint32_t)kb * A_STAGE_BYTES + dst_in_blk + (uint32_t)i * 4096u, p.in,
                                       (int64_t)idx[i] * p.ld_in, idx[i] >= 0, col0, min(p.Cin, cin0 + 128));
                 }
-                cp_async_commit();
-                ++pending;
-                if (pending > look) {
-                    cp_async_wait_dyn(look);
-                    signal_oldest();
-                }
+                cp_async_mbar_arrive_noinc(a_full(sa));
                 if (++sa == AS) sa = 0, pha ^= 1;
             }
             producers_sync();       // next tile's map slice has landed and is visible to all producers
-            while (pending > 0) signal_oldest();
         }
     } else if (lane == 0) {
         // ===================== MMA issuer =====================
