@@ -219,10 +219,11 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                     mbar_wait(empty_bar(s), ph ^ 1);
                     const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
                     const uint32_t fb = full_bar(s);
-                    if (lane == 0) {
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(fb, wbytes);
                         bulk_g2s(a_stage + A_STAGE_BYTES, image + (size_t)(o * n_kb + kb) * wbytes, wbytes, fb);
                     }
+                    __syncwarp();
                     const int col0 = kb * KB + c * 4;
                     if (col0 < cin_pad8) {
                         if constexpr (VEC == 4) {
@@ -263,35 +264,46 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
         cp_async_wait<0>();
     } else if (warp == MMA_WARP) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TILE_M, p.cout_pad);
+        // The whole warp runs the loop (warp-uniform control flow); one elected lane issues the tcgen05 ops.
+        {
+            int nS, K, n_kb, n_tiles, cin_pad8, cout_pad;
+            asm volatile("mov.u32 %0, %1;" : "=r"(nS) : "r"(p.stages));
+            asm volatile("mov.u32 %0, %1;" : "=r"(K) : "r"(p.K));
+            asm volatile("mov.u32 %0, %1;" : "=r"(n_kb) : "r"(p.n_kb));
+            asm volatile("mov.u32 %0, %1;" : "=r"(n_tiles) : "r"(p.n_tiles));
+            asm volatile("mov.u32 %0, %1;" : "=r"(cin_pad8) : "r"(p.cin_pad8));
+            asm volatile("mov.u32 %0, %1;" : "=r"(cout_pad) : "r"(p.cout_pad));
+            const uint32_t idesc = make_idesc_tf32(TILE_M, cout_pad);
             int s = 0, it = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const int b = it & 1;
                 mbar_wait(acce_bar(b), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(b * p.cout_pad);
-                for (int o = 0; o < p.K; ++o) {
-                    for (int kb = 0; kb < p.n_kb; ++kb) {
+                const uint32_t tmem_d = tmem_base + (uint32_t)(b * cout_pad);
+                for (int o = 0; o < K; ++o) {
+                    for (int kb = 0; kb < n_kb; ++kb) {
                         mbar_wait(full_bar(s), ph);
                         tc_fence_after();
                         const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
                         const uint64_t da = make_desc_sw128(a_stage);
                         const uint64_t db = make_desc_sw128(a_stage + A_STAGE_BYTES);
-                        const int kcols = min(KB, p.cin_pad8 - kb * KB);
-                        for (int k = 0; k < kcols / 8; ++k) {
+                        const int nk = min(KB, cin_pad8 - kb * KB) >> 3;
+                        if (elect_one()) {
                             // advance 32 bytes (8 tf32) inside the 128-byte swizzled row: +2 in the >>4 address field
-                            mma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                     (o | kb | k) != 0 ? 1u : 0u);
+                            mma_tf32(tmem_d, da, db, idesc, (o | kb) != 0 ? 1u : 0u);
+                            if (nk > 1) mma_tf32(tmem_d, da + 2, db + 2, idesc, 1u);
+                            if (nk > 2) mma_tf32(tmem_d, da + 4, db + 4, idesc, 1u);
+                            if (nk > 3) mma_tf32(tmem_d, da + 6, db + 6, idesc, 1u);
+                            mma_commit(empty_bar(s));
                         }
-                        mma_commit(empty_bar(s));
-                        if (++s == S) s = 0, ph ^= 1;
+                        __syncwarp();
+                        if (++s == nS) s = 0, ph ^= 1;
                     }
                 }
-                mma_commit(accf_bar(b));
+                if (elect_one()) mma_commit(accf_bar(b));
+                __syncwarp();
             }
-            (void)units_per_tile;
         }
     } else if (warp < 4) {
         // ===================== epilogue warps 0..3 =====================
