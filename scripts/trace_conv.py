@@ -20,16 +20,20 @@ buf = (ctypes.c_longlong * 2048)()
 dll = ctypes.CDLL(_lib.LIB_PATH)
 print("rc", dll.scn_debug_trace(buf))
 a = np.array(buf[:]).reshape(256, 8)
-a = a[a[:, 0] > 0]
-print("units traced", len(a), "debug", os.environ.get("SCN_CONV_DEBUG", "0"))
-d = a[8:]
-print("producer (thread 0 of warp 4), mean cycles per unit:")
-print("  wait empty        %7.0f" % (d[:,1]-d[:,0]).mean())
-print("  weights issue     %7.0f" % (d[:,2]-d[:,1]).mean())
-print("  8x LDGSTS issue   %7.0f" % (d[:,3]-d[:,2]).mean())
-print("  arrive            %7.0f" % (d[:,4]-d[:,3]).mean())
-print("  loop tail -> next %7.0f" % (d[1:,0]-d[:-1,4]).mean())
-print("  unit period       %7.0f" % np.diff(d[:,0]).mean())
-print("MMA thread: wait full %7.0f, period %7.0f" % ((d[:,7]-d[:,6]).mean(), np.diff(d[:,7]).mean()))
-for i in range(20, 32):
-    r = a[i]; print(i, [int(x - a[20,0]) for x in r])
+nz = int((a[:, 7] > 0).sum())
+a = a[:nz]
+t0 = a[a[:, 0] > 0][0, 0]
+print("units with MMA trace", nz)
+print("unit | producer(warp4 only: every 4th): t_start wait issueW ldgsts arrive | MMA: wait_start wait_end(+wait) done(+busy)")
+for i in range(16, 60):
+    r = a[i]
+    if r[0] > 0:
+        ps = "%7d w%5d W%5d L%5d a%4d" % (r[0]-t0, r[1]-r[0], r[2]-r[1], r[3]-r[2], r[4]-r[3])
+    else:
+        ps = " " * 36
+    print("%3d | %s | %7d %7d (+%5d) %7d (+%5d)" % (i, ps, r[6]-t0, r[7]-t0, r[7]-r[6], r[5]-t0, r[5]-r[7]))
+m = a[16:]
+print("MMA: mean wait %.0f, mean busy %.0f, period %.0f" % ((m[:,7]-m[:,6]).mean(), (m[:,5]-m[:,7]).mean(), np.diff(m[:,7]).mean()))
+pr = m[m[:,0] > 0]
+print("producer warp 4: mean wait %.0f, weights %.0f, ldgsts %.0f, arrive %.0f, period(4 units) %.0f" % (
+    (pr[:,1]-pr[:,0]).mean(), (pr[:,2]-pr[:,1]).mean(), (pr[:,3]-pr[:,2]).mean(), (pr[:,4]-pr[:,3]).mean(), np.diff(pr[:,0]).mean()))

@@ -172,33 +172,43 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
         const uint32_t dstA = (uint32_t)rsub * 128u + (uint32_t)((c ^ rsub) << 4);            // rows with (r & 4) == 0
         const uint32_t dstB = (uint32_t)rsub * 128u + (uint32_t)((c ^ (rsub + 4)) << 4);      // rows with (r & 4) != 0
 
-        // neighbour indices of a whole tile (K x 128 ints) are staged in shared memory ONE TILE ahead (double buffer)
+        // Neighbour indices are staged in shared memory ONE TILE ahead (double buffer [2][K][128] ints).  Every
+        // producer warp stages only the 512-byte map rows of the units IT owns (one 16-byte cp.async per lane and
+        // unit), so the hand-over needs a warp-level sync only: a CTA-wide producer barrier cost ~9000 cycles per
+        // tile because 27 units do not divide evenly over 4 warps (clock64 trace, profiles/r1_d_producer_trace.md).
         const uint32_t map_smem = bars + 256u;
         const int32_t* sm_map = reinterpret_cast<const int32_t*>(smem_raw + (map_smem - smem_u32(smem_raw)));
         const bool map_vec = ((n_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(gmap) & 15) == 0);
-        auto stage_map = [&](int tile, int buf) {
+        const int upt = K * n_kb;        // units per tile
+        auto stage_map = [&](int tile, int it_t, int buf) {
+            // units of tile number it_t (in this CTA's sequence) have stream indices it_t*upt + j; mine: == pw mod 4
             if (smap && tile < n_tiles) {
                 const int row0 = tile * TILE_M;
-                const uint32_t dst0 = map_smem + (uint32_t)(buf * K) * 512u;
-                if (map_vec && row0 + TILE_M <= n_out) {
-                    for (int ch = pt; ch < K * 32; ch += N_PRODUCERS) {
-                        const int o = ch >> 5, q = ch & 31;
-                        cp_async<16>(dst0 + (uint32_t)o * 512u + (uint32_t)q * 16u, gmap + (int64_t)o * n_out + row0 + q * 4,
-                                     true);
-                    }
-                } else {
-                    int32_t* dstp = const_cast<int32_t*>(sm_map) + buf * K * TILE_M;
-                    for (int e = pt; e < K * TILE_M; e += N_PRODUCERS) {
-                        const int o = e >> 7, r = e & 127;
-                        dstp[e] = (row0 + r < n_out) ? __ldg(gmap + (int64_t)o * n_out + row0 + r) : -1;
+                const bool fast = map_vec && row0 + TILE_M <= n_out;
+                int j = (pw - (it_t * upt) % 4 + 4) % 4;           // first unit of that tile owned by this warp
+                int o_prev = -1;
+                for (; j < upt; j += 4) {
+                    const int o = j / n_kb;
+                    if (o == o_prev) continue;
+                    o_prev = o;
+                    const uint32_t dst = map_smem + (uint32_t)((buf * K + o) * TILE_M) * 4u + (uint32_t)lane * 16u;
+                    if (fast) {
+                        cp_async<16>(dst, gmap + (int64_t)o * n_out + row0 + lane * 4, true);
+                    } else {
+                        int32_t* dp = const_cast<int32_t*>(sm_map) + (buf * K + o) * TILE_M + lane * 4;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int r = row0 + lane * 4 + q;
+                            dp[q] = r < n_out ? __ldg(gmap + (int64_t)o * n_out + r) : -1;
+                        }
                     }
                 }
             }
             cp_async_commit();
         };
-        auto producers_sync = [&]() {
+        auto warp_sync_map = [&]() {
             cp_async_wait<0>();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            __syncwarp();
         };
         // ring position of this warp's next unit: unit index u = pw, pw + 4, ...
         int s = pw % nS;
@@ -206,17 +216,21 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
         int ucur = 0;                    // index (within the CTA's unit stream) of the next unit of ANY warp
         int mine = pw;                   // next unit index owned by this warp
         int it = 0;
-        stage_map(blockIdx.x, 0);
-        producers_sync();
+        const int skip_zero = p.debug & 32;      // timing experiment only: do not zero-fill inactive rows
+        stage_map(blockIdx.x, 0, 0);
+        warp_sync_map();
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            stage_map(tile + gridDim.x, (it + 1) & 1);
+            stage_map(tile + gridDim.x, it + 1, (it + 1) & 1);
             const int row0 = tile * TILE_M;
             const int32_t* tmap_s = sm_map + (it & 1) * K * TILE_M;
             for (int o = 0; o < K; ++o) {
                 for (int kb = 0; kb < n_kb; ++kb, ++ucur) {
                     if (ucur != mine) continue;
                     mine += 4;
+                    const bool trace = p.dbg_buf && blockIdx.x == 0 && pt == 0 && ucur < 256;
+                    if (trace) p.dbg_buf[ucur * 8 + 0] = clock64();
                     mbar_wait(empty_bar(s), ph ^ 1);
+                    if (trace) p.dbg_buf[ucur * 8 + 1] = clock64();
                     const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
                     const uint32_t fb = full_bar(s);
                     if (elect_one()) {
@@ -224,6 +238,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                         bulk_g2s(a_stage + A_STAGE_BYTES, image + (size_t)(o * n_kb + kb) * wbytes, wbytes, fb);
                     }
                     __syncwarp();
+                    if (trace) p.dbg_buf[ucur * 8 + 2] = clock64();
                     const int col0 = kb * KB + c * 4;
                     if (col0 < cin_pad8) {
                         if constexpr (VEC == 4) {
@@ -238,8 +253,9 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                                 const float* src = colp + (int64_t)max(r, 0) * ld_in;
                                 const int sz = r >= 0 ? full : 0;
                                 const uint32_t dst = a_stage + (uint32_t)i * 512u + ((i & 1) ? dstB : dstA);
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz)
-                                             : "memory");
+                                if (!skip_zero || r >= 0)
+                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz)
+                                                 : "memory");
                             }
                         } else {
 #pragma unroll 4
@@ -253,13 +269,15 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                             }
                         }
                     }
+                    if (trace) p.dbg_buf[ucur * 8 + 3] = clock64();
                     // this thread's arrival on the stage's full barrier fires when its copies have landed
                     cp_async_mbar_arrive_noinc(fb);
+                    if (trace) p.dbg_buf[ucur * 8 + 4] = clock64();
                     s += 4;
                     while (s >= nS) s -= nS, ph ^= 1;
                 }
             }
-            producers_sync();       // next tile's map slice has landed and is visible to all producer threads
+            warp_sync_map();        // this warp's share of the next tile's map slice has landed
         }
         cp_async_wait<0>();
     } else if (warp == MMA_WARP) {
@@ -283,7 +301,11 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                 const uint32_t tmem_d = tmem_base + (uint32_t)(b * cout_pad);
                 for (int o = 0; o < K; ++o) {
                     for (int kb = 0; kb < n_kb; ++kb) {
+                        const int uidx = (it * K + o) * n_kb + kb;
+                        const bool trace = p.dbg_buf && blockIdx.x == 0 && lane == 0 && uidx < 256;
+                        if (trace) p.dbg_buf[uidx * 8 + 6] = clock64();
                         mbar_wait(full_bar(s), ph);
+                        if (trace) p.dbg_buf[uidx * 8 + 7] = clock64();
                         tc_fence_after();
                         const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
                         const uint64_t da = make_desc_sw128(a_stage);
@@ -298,6 +320,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
                             mma_commit(empty_bar(s));
                         }
                         __syncwarp();
+                        if (trace) p.dbg_buf[uidx * 8 + 5] = clock64();
                         if (++s == nS) s = 0, ph ^= 1;
                     }
                 }
