@@ -37,9 +37,6 @@ struct ConvTcParams {
     float* out;
     int ld_out, Cout, epi;
     int cout_pad, n_kb, cin_pad8, stages, tmem_cols, n_tiles;
-    int smap;             // 1 = neighbour map of a tile is staged in shared memory one tile ahead
-    long long* dbg_buf;   // SCN_CONV_TRACE: per-unit clock64 timestamps of CTA 0 (4 per unit), NULL = off
-    int debug;   // timing experiments only (SCN_CONV_DEBUG): 1 = no gather traffic, 2 = 16-byte weight copies, 4 = no MMA
 };
 
 // one 16-byte chunk of a gathered row, split into VEC-float cp.asyncs
@@ -83,7 +80,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), TMA ? 1 : 32 + 1);   // the owning producer warp's 32 lanes + the weights expect_tx
+            mbar_init(full_bar(s), TMA ? 1 : N_PRODUCERS + 1);
             mbar_init(empty_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -146,187 +143,104 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const _
             }
         }
     } else if (!TMA && warp >= 4 && warp < 8) {
-        // ===================== cp.async gather producers =====================
-        // Each producer warp OWNS whole units (warp w takes units w, w+4, ... of the CTA's unit stream): the
-        // fixed per-unit costs measured with the clock64 trace (mbarrier try_wait ~120 cycles, weights issue
-        // ~190, loop control ~600 of serial constant-bank loads) are paid by one warp per unit instead of by
-        // all four, and four stages are being filled concurrently.  Lane L copies 16-byte chunk (L & 7) of rows
-        // (L >> 3) + 4 i, i = 0..31.  Kernel parameters are laundered into registers so the loop does not
-        // re-read them from the constant bank.
-        const int pw = warp - 4, pt = tid - 128;
-        const int c = lane & 7, rsub = lane >> 3;
-        int K, n_kb, n_tiles, n_out, cin, cin_pad8, ld_in, nS;
-        asm volatile("mov.u32 %0, %1;" : "=r"(K) : "r"(p.K));
-        asm volatile("mov.u32 %0, %1;" : "=r"(n_kb) : "r"(p.n_kb));
-        asm volatile("mov.u32 %0, %1;" : "=r"(n_tiles) : "r"(p.n_tiles));
-        asm volatile("mov.u32 %0, %1;" : "=r"(n_out) : "r"(p.n_out));
-        asm volatile("mov.u32 %0, %1;" : "=r"(cin) : "r"(p.Cin));
-        asm volatile("mov.u32 %0, %1;" : "=r"(cin_pad8) : "r"(p.cin_pad8));
-        asm volatile("mov.u32 %0, %1;" : "=r"(ld_in) : "r"(p.ld_in));
-        asm volatile("mov.u32 %0, %1;" : "=r"(nS) : "r"(p.stages));
-        const bool smap = p.smap != 0;
-        const float* in = p.in;
-        const int32_t* gmap = p.map;
-        const uint8_t* image = p.image;
-        const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
-        const uint32_t dstA = (uint32_t)rsub * 128u + (uint32_t)((c ^ rsub) << 4);            // rows with (r & 4) == 0
-        const uint32_t dstB = (uint32_t)rsub * 128u + (uint32_t)((c ^ (rsub + 4)) << 4);      // rows with (r & 4) != 0
-
-        // Neighbour indices are staged in shared memory ONE TILE ahead (double buffer [2][K][128] ints).  Every
-        // producer warp stages only the 512-byte map rows of the units IT owns (one 16-byte cp.async per lane and
-        // unit), so the hand-over needs a warp-level sync only: a CTA-wide producer barrier cost ~9000 cycles per
-        // tile because 27 units do not divide evenly over 4 warps (clock64 trace, profiles/r1_d_producer_trace.md).
-        const uint32_t map_smem = bars + 256u;
-        const int32_t* sm_map = reinterpret_cast<const int32_t*>(smem_raw + (map_smem - smem_u32(smem_raw)));
-        const bool map_vec = ((n_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(gmap) & 15) == 0);
-        const int upt = K * n_kb;        // units per tile
-        auto stage_map = [&](int tile, int it_t, int buf) {
-            // units of tile number it_t (in this CTA's sequence) have stream indices it_t*upt + j; mine: == pw mod 4
-            if (smap && tile < n_tiles) {
-                const int row0 = tile * TILE_M;
-                const bool fast = map_vec && row0 + TILE_M <= n_out;
-                int j = (pw - (it_t * upt) % 4 + 4) % 4;           // first unit of that tile owned by this warp
-                int o_prev = -1;
-                for (; j < upt; j += 4) {
-                    const int o = j / n_kb;
-                    if (o == o_prev) continue;
-                    o_prev = o;
-                    const uint32_t dst = map_smem + (uint32_t)((buf * K + o) * TILE_M) * 4u + (uint32_t)lane * 16u;
-                    if (fast) {
-                        cp_async<16>(dst, gmap + (int64_t)o * n_out + row0 + lane * 4, true);
-                    } else {
-                        int32_t* dp = const_cast<int32_t*>(sm_map) + (buf * K + o) * TILE_M + lane * 4;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int r = row0 + lane * 4 + q;
-                            dp[q] = r < n_out ? __ldg(gmap + (int64_t)o * n_out + r) : -1;
-                        }
-                    }
-                }
-            }
-            cp_async_commit();
-        };
-        auto warp_sync_map = [&]() {
-            cp_async_wait<0>();
-            __syncwarp();
-        };
-        // ring position of this warp's next unit: unit index u = pw, pw + 4, ...
-        int s = pw % nS;
-        uint32_t ph = (uint32_t)(pw / nS) & 1u;
-        int ucur = 0;                    // index (within the CTA's unit stream) of the next unit of ANY warp
-        int mine = pw;                   // next unit index owned by this warp
-        int it = 0;
-        const int skip_zero = p.debug & 32;      // timing experiment only: do not zero-fill inactive rows
-        stage_map(blockIdx.x, 0, 0);
-        warp_sync_map();
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            stage_map(tile + gridDim.x, it + 1, (it + 1) & 1);
+        // ===================== gather producers =====================
+        const int pt = tid - 128;
+        const int c = pt & 7, rbase = pt >> 3;
+        const uint32_t dst_in_stage = (uint32_t)rbase * 128u + (uint32_t)((c ^ (rbase & 7)) << 4);
+        int s = 0;
+        uint32_t ph = 0;      // ring position / phase of this thread's unit stream
+        // neighbour indices are fetched one (tile, offset) ahead of the copies that depend on them, so
+        // the L2 latency of the map read overlaps the cp.async issue of the previous offset
+        auto load_idx = [&](int tile, int o, int (&dst)[8]) {
             const int row0 = tile * TILE_M;
-            const int32_t* tmap_s = sm_map + (it & 1) * K * TILE_M;
-            for (int o = 0; o < K; ++o) {
-                for (int kb = 0; kb < n_kb; ++kb, ++ucur) {
-                    if (ucur != mine) continue;
-                    mine += 4;
-                    const bool trace = p.dbg_buf && blockIdx.x == 0 && pt == 0 && ucur < 256;
-                    if (trace) p.dbg_buf[ucur * 8 + 0] = clock64();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int r = row0 + rbase + 16 * i;
+                int v = -1;
+                if (tile < p.n_tiles && r < p.n_out) v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
+                dst[i] = v;
+            }
+        };
+        int idx[8], idx_next[8];
+        load_idx(blockIdx.x, 0, idx_next);
+        const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int o = 0; o < p.K; ++o) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) idx[i] = idx_next[i];
+                if (o + 1 < p.K) load_idx(tile, o + 1, idx_next);
+                else load_idx(tile + gridDim.x, 0, idx_next);
+                for (int kb = 0; kb < p.n_kb; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1);
-                    if (trace) p.dbg_buf[ucur * 8 + 1] = clock64();
                     const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
-                    const uint32_t fb = full_bar(s);
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx(fb, wbytes);
-                        bulk_g2s(a_stage + A_STAGE_BYTES, image + (size_t)(o * n_kb + kb) * wbytes, wbytes, fb);
+                    if (pt == 0) {
+                        mbar_arrive_expect_tx(full_bar(s), wbytes);
+                        bulk_g2s(a_stage + A_STAGE_BYTES, p.image + (size_t)(o * p.n_kb + kb) * wbytes, wbytes,
+                                 full_bar(s));
                     }
-                    __syncwarp();
-                    if (trace) p.dbg_buf[ucur * 8 + 2] = clock64();
                     const int col0 = kb * KB + c * 4;
-                    if (col0 < cin_pad8) {
+                    if (col0 < p.cin_pad8) {
                         if constexpr (VEC == 4) {
-                            const float* colp = in + col0;
-                            const int full = col0 < cin ? 16 : 0;
-#pragma unroll 8
-                            for (int i = 0; i < 32; ++i) {
-                                const int rr = rsub + 4 * i;
-                                int r;
-                                if (smap) r = tmap_s[o * TILE_M + rr];
-                                else r = (row0 + rr < n_out) ? (gmap ? __ldg(gmap + (int64_t)o * n_out + row0 + rr) : row0 + rr) : -1;
-                                const float* src = colp + (int64_t)max(r, 0) * ld_in;
+                            // lean path: one IMAD.WIDE + one LDGSTS per 16-byte chunk; inactive rows (and the
+                            // all-padding chunk of a Cin that is not a multiple of 8) use src-size 0 = zero fill
+                            const float* colp = p.in + col0;
+                            const int full = col0 < p.Cin ? 16 : 0;
+                            const uint32_t dst = a_stage + dst_in_stage;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int r = idx[i];
+                                const float* src = colp + (int64_t)max(r, 0) * p.ld_in;
                                 const int sz = r >= 0 ? full : 0;
-                                const uint32_t dst = a_stage + (uint32_t)i * 512u + ((i & 1) ? dstB : dstA);
-                                if (!skip_zero || r >= 0)
-                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz)
-                                                 : "memory");
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)i * 2048u),
+                                             "l"(src), "r"(sz)
+                                             : "memory");
                             }
                         } else {
-#pragma unroll 4
-                            for (int i = 0; i < 32; ++i) {
-                                const int rr = rsub + 4 * i;
-                                int r;
-                                if (smap) r = tmap_s[o * TILE_M + rr];
-                                else r = (row0 + rr < n_out) ? (gmap ? __ldg(gmap + (int64_t)o * n_out + row0 + rr) : row0 + rr) : -1;
-                                gather_chunk<VEC>(a_stage + (uint32_t)i * 512u + ((i & 1) ? dstB : dstA), in, (int64_t)r * ld_in,
-                                                  r, col0, cin);
-                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                gather_chunk<VEC>(a_stage + dst_in_stage + (uint32_t)i * 2048u, p.in,
+                                                  (int64_t)idx[i] * p.ld_in, idx[i], col0, p.Cin);
                         }
                     }
-                    if (trace) p.dbg_buf[ucur * 8 + 3] = clock64();
-                    // this thread's arrival on the stage's full barrier fires when its copies have landed
-                    cp_async_mbar_arrive_noinc(fb);
-                    if (trace) p.dbg_buf[ucur * 8 + 4] = clock64();
-                    s += 4;
-                    while (s >= nS) s -= nS, ph ^= 1;
+                    // the stage's full barrier receives this thread's arrival when its copies have landed;
+                    // up to S units are in flight per CTA and the producer only ever waits for a free slot
+                    cp_async_mbar_arrive_noinc(full_bar(s));
+                    if (++s == S) s = 0, ph ^= 1;
                 }
             }
-            warp_sync_map();        // this warp's share of the next tile's map slice has landed
         }
         cp_async_wait<0>();
     } else if (warp == MMA_WARP) {
         // ===================== MMA issuer =====================
-        // The whole warp runs the loop (warp-uniform control flow); one elected lane issues the tcgen05 ops.
-        {
-            int nS, K, n_kb, n_tiles, cin_pad8, cout_pad;
-            asm volatile("mov.u32 %0, %1;" : "=r"(nS) : "r"(p.stages));
-            asm volatile("mov.u32 %0, %1;" : "=r"(K) : "r"(p.K));
-            asm volatile("mov.u32 %0, %1;" : "=r"(n_kb) : "r"(p.n_kb));
-            asm volatile("mov.u32 %0, %1;" : "=r"(n_tiles) : "r"(p.n_tiles));
-            asm volatile("mov.u32 %0, %1;" : "=r"(cin_pad8) : "r"(p.cin_pad8));
-            asm volatile("mov.u32 %0, %1;" : "=r"(cout_pad) : "r"(p.cout_pad));
-            const uint32_t idesc = make_idesc_tf32(TILE_M, cout_pad);
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TILE_M, p.cout_pad);
             int s = 0, it = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const int b = it & 1;
                 mbar_wait(acce_bar(b), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(b * cout_pad);
-                for (int o = 0; o < K; ++o) {
-                    for (int kb = 0; kb < n_kb; ++kb) {
-                        const int uidx = (it * K + o) * n_kb + kb;
-                        const bool trace = p.dbg_buf && blockIdx.x == 0 && lane == 0 && uidx < 256;
-                        if (trace) p.dbg_buf[uidx * 8 + 6] = clock64();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(b * p.cout_pad);
+                for (int o = 0; o < p.K; ++o) {
+                    for (int kb = 0; kb < p.n_kb; ++kb) {
                         mbar_wait(full_bar(s), ph);
-                        if (trace) p.dbg_buf[uidx * 8 + 7] = clock64();
                         tc_fence_after();
                         const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
                         const uint64_t da = make_desc_sw128(a_stage);
                         const uint64_t db = make_desc_sw128(a_stage + A_STAGE_BYTES);
-                        const int nk = min(KB, cin_pad8 - kb * KB) >> 3;
-                        if (elect_one()) {
+                        const int kcols = min(KB, p.cin_pad8 - kb * KB);
+                        for (int k = 0; k < kcols / 8; ++k) {
                             // advance 32 bytes (8 tf32) inside the 128-byte swizzled row: +2 in the >>4 address field
-                            mma_tf32(tmem_d, da, db, idesc, (o | kb) != 0 ? 1u : 0u);
-                            if (nk > 1) mma_tf32(tmem_d, da + 2, db + 2, idesc, 1u);
-                            if (nk > 2) mma_tf32(tmem_d, da + 4, db + 4, idesc, 1u);
-                            if (nk > 3) mma_tf32(tmem_d, da + 6, db + 6, idesc, 1u);
-                            mma_commit(empty_bar(s));
+                            mma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                     (o | kb | k) != 0 ? 1u : 0u);
                         }
-                        __syncwarp();
-                        if (trace) p.dbg_buf[uidx * 8 + 5] = clock64();
-                        if (++s == nS) s = 0, ph ^= 1;
+                        mma_commit(empty_bar(s));
+                        if (++s == S) s = 0, ph ^= 1;
                     }
                 }
-                if (elect_one()) mma_commit(accf_bar(b));
-                __syncwarp();
+                mma_commit(accf_bar(b));
             }
+            (void)units_per_tile;
         }
     } else if (warp < 4) {
         // ===================== epilogue warps 0..3 =====================
@@ -462,14 +376,6 @@ int scn::make_gather_tmap(CUtensorMap* tm, const float* base, int rows, int C, i
     return SCN_OK;
 }
 
-static long long* g_trace_buf = nullptr;
-extern "C" int scn_debug_trace(long long* host_out) {
-    if (!g_trace_buf) return 1;
-    cudaDeviceSynchronize();
-    cudaMemcpy(host_out, g_trace_buf, 256 * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
-    return 0;
-}
-
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 static inline int n_kblocks(int cin) { return (cin + KB - 1) / KB; }
 
@@ -509,40 +415,24 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     p.out = out, p.ld_out = ld_out, p.Cout = Cout, p.epi = epi_flags;
     p.cout_pad = pad16(Cout), p.n_kb = n_kblocks(Cin), p.cin_pad8 = (Cin + 7) / 8 * 8;
     p.n_tiles = cdiv(n_out, TILE_M);
-    {
-        const char* e = getenv("SCN_CONV_DEBUG");
-        p.debug = e ? atoi(e) : 0;
-        p.dbg_buf = nullptr;
-        const char* t = getenv("SCN_CONV_TRACE");
-        if (t && t[0] == '1') {
-            static long long* buf = nullptr;
-            if (!buf) cudaMalloc(&buf, 256 * 8 * sizeof(long long));
-            cudaMemsetAsync(buf, 0, 256 * 8 * sizeof(long long), as_stream(stream));
-            p.dbg_buf = buf;
-            g_trace_buf = buf;
-        }
-    }
     int cols = 2 * p.cout_pad, tc = 32;
     while (tc < cols) tc <<= 1;
     p.tmem_cols = tc;
     const int stage_bytes = A_STAGE_BYTES + p.cout_pad * 128;
-    // neighbour-map staging buffers (2 x K x 512 B) live behind the stage ring
-    p.smap = (map != nullptr && K <= 32) ? 1 : 0;
-    const int map_bytes = p.smap ? 2 * K * 512 : 0;
-    // ring depth = units in flight per CTA: two CTAs per SM when at least four stages fit in ~110 KB each,
-    // otherwise one CTA with up to eight stages
+    // ring depth = units in flight per CTA (the gather is latency bound, so deeper is better): two CTAs
+    // per SM when at least four stages fit in ~110 KB each, otherwise one CTA with up to eight stages
     int stages, ctas_per_sm;
-    const int s2 = (110 * 1024 - map_bytes) / stage_bytes;
+    const int s2 = (110 * 1024) / stage_bytes;
     if (s2 >= 4 && tc <= 256) {
         stages = s2 > 8 ? 8 : s2, ctas_per_sm = 2;
     } else {
-        stages = (220 * 1024 - map_bytes) / stage_bytes;
+        stages = (220 * 1024) / stage_bytes;
         if (stages > 8) stages = 8;
         ctas_per_sm = 1;
     }
     SCN_REQUIRE(stages >= 2, "conv_fwd_tf32: tile does not fit in shared memory");
     p.stages = stages;
-    const int smem = stages * stage_bytes + 1024 + 256 + map_bytes;
+    const int smem = stages * stage_bytes + 1024 + 256;
     int vec = 1;
     if (Cin % 4 == 0 && ld_in % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) vec = 4;
     else if (Cin % 2 == 0 && ld_in % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0) vec = 2;

@@ -98,53 +98,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
         // ===================== producers =====================
         const int c = tid & 7, rbase = tid >> 3;        // rows rbase + 32 i
         const uint32_t dst_in_blk = swz_mn32b(rbase, c);      // (rbase + 32 i) & 3 == rbase & 3
-        // neighbour indices of a tile (nO x 128 ints) are staged in shared memory one tile ahead (see conv_tc.cu)
-        const uint32_t map_smem = (tmem_slot + 31u) & ~15u;      // 16-byte aligned for cp.async
-        const int32_t* sm_map = reinterpret_cast<const int32_t*>(smem_raw + (map_smem - smem_u32(smem_raw)));
-        const bool smap = p.map != nullptr;
-        const bool map_vec = ((p.n_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.map) & 15) == 0);
-        auto stage_map = [&](int tile, int buf) {
-            if (smap && tile < t1) {
-                const int row0 = tile * TILE_M;
-                const uint32_t dst0 = map_smem + (uint32_t)(buf * p.opg) * 512u;
-                if (map_vec && row0 + TILE_M <= p.n_out) {
-                    for (int ch = tid; ch < nO * 32; ch += WG_PRODUCERS) {
-                        const int o = ch >> 5, q = ch & 31;
-                        cp_async<16>(dst0 + (uint32_t)o * 512u + (uint32_t)q * 16u,
-                                     p.map + (int64_t)(o0 + o) * p.n_out + row0 + q * 4, true);
-                    }
-                } else {
-                    int32_t* dstp = const_cast<int32_t*>(sm_map) + buf * p.opg * TILE_M;
-                    for (int e = tid; e < nO * TILE_M; e += WG_PRODUCERS) {
-                        const int o = e >> 7, r = e & 127;
-                        dstp[e] = (row0 + r < p.n_out) ? __ldg(p.map + (int64_t)(o0 + o) * p.n_out + row0 + r) : -1;
-                    }
-                }
-            }
-            cp_async_commit();
-        };
-        auto producers_sync = [&]() {
-            cp_async_wait<0>();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-        };
-        auto load_idx = [&](int tile, int oi, int buf, int (&dst)[4]) {
+        auto load_idx = [&](int tile, int o, int (&dst)[4]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = rbase + 32 * i;
-                int v;
-                if (smap) v = sm_map[(buf * p.opg + oi) * TILE_M + r];
-                else v = (tile * TILE_M + r < p.n_out) ? tile * TILE_M + r : -1;
+                int r = tile * TILE_M + rbase + 32 * i;
+                int v = -1;
+                if (tile < t1 && r < p.n_out) v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
                 dst[i] = v;
             }
         };
-        int idx[4];
-        int it = 0;
-        stage_map(t0, 0);
-        producers_sync();
+        int idx[4], idx_next[4];
+        load_idx(t0, o0, idx_next);
         int sa = 0, sg = 0;
         uint32_t pha = 0, phg = 0;
-        for (int tile = t0; tile < t1; ++tile, ++it) {
-            stage_map(tile + 1, (it + 1) & 1);
+        for (int tile = t0; tile < t1; ++tile) {
             // grad-out tile: staged once per tile, shared by every offset of the group
             mbar_wait(g_empty(sg), phg ^ 1);
             {
@@ -162,7 +129,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                 if (++sg == GS) sg = 0, phg ^= 1;
             }
             for (int oi = 0; oi < nO; ++oi) {
-                load_idx(tile, oi, it & 1, idx);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) idx[i] = idx_next[i];
+                if (oi + 1 < nO) load_idx(tile, o0 + oi + 1, idx_next);
+                else load_idx(tile + 1, o0, idx_next);
                 mbar_wait(a_empty(sa), pha ^ 1);
                 const uint32_t ast = smem_base + (uint32_t)sa * p.a_stage_bytes;
                 for (int kb = 0; kb < nblk_a; ++kb) {
@@ -175,8 +145,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                 cp_async_mbar_arrive_noinc(a_full(sa));
                 if (++sa == AS) sa = 0, pha ^= 1;
             }
-            producers_sync();       // next tile's map slice has landed and is visible to all producers
         }
+        cp_async_wait<0>();
     } else if (lane == 0) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = make_idesc_tf32_mn(TILE_M, npad);
@@ -275,8 +245,7 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
     // (a_stages - 1) * a_stage_bytes + 64 KB even when the stage itself is narrower.
     int smem = 0;
     p.a_stages = 0;
-    const int map_bytes = map ? 2 * p.opg * 512 : 0;
-    const int budgets[2] = {tc <= 256 ? 108 * 1024 - map_bytes : 0, 222 * 1024 - map_bytes};      // two CTAs per SM first, else one
+    const int budgets[2] = {tc <= 256 ? 108 * 1024 : 0, 224 * 1024};      // two CTAs per SM first, else one
     for (int b = 0; b < 2 && p.a_stages < 2; ++b)
         for (int gs = 2; gs >= 1 && p.a_stages < 2; --gs)
             for (int as = 6; as >= 2; --as) {
@@ -289,7 +258,7 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
                 }
             }
     SCN_REQUIRE(p.a_stages >= 2, "conv_bwd_weight: tile does not fit in shared memory (Cin=%d Cout=%d)", Cin, Cout);
-    smem += 1024 + 256 + 32 + (map ? 2 * p.opg * 512 : 0);
+    smem += 1024 + 256;
     const int groups_y = p.n_ogroups * p.n_mhalves * n_nhalves;
     const int ctas_per_sm = (tc <= 256 && smem <= 112 * 1024) ? 2 : 1;
     int n_chunks = (sm_count() * ctas_per_sm + groups_y - 1) / groups_y;
