@@ -60,7 +60,7 @@ __device__ __forceinline__ void gather_chunk(uint32_t dst, const float* __restri
 // TMA = false: cp.async producers (4 warps, 16/8/4-byte copies) for feature tensors whose row stride is not
 //              a multiple of 16 bytes.  9 warps.
 template <int VEC, bool TMA>
-__global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, 2) k_conv_tc(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_tc(const __grid_constant__ CUtensorMap tmap,
                                                                         const ConvTcParams p) {
     constexpr int MMA_WARP = TMA ? 5 : 8;
     extern __shared__ uint8_t smem_raw[];
@@ -421,14 +421,22 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     const int stage_bytes = A_STAGE_BYTES + p.cout_pad * 128;
     // ring depth = units in flight per CTA (the gather is latency bound, so deeper is better): two CTAs
     // per SM when at least four stages fit in ~110 KB each, otherwise one CTA with up to eight stages
+    // The kernel is bound by a per-CTA latency chain (profiles/r1_d_producer_trace.md: identical per-CTA unit period
+    // at one and two CTAs per SM), so residency beats ring depth: prefer three CTAs per SM with >= 3 stages, then two
+    // CTAs with >= 3 stages, else one CTA with up to eight stages.
     int stages, ctas_per_sm;
-    const int s2 = (110 * 1024) / stage_bytes;
-    if (s2 >= 4 && tc <= 256) {
-        stages = s2 > 8 ? 8 : s2, ctas_per_sm = 2;
-    } else {
-        stages = (220 * 1024) / stage_bytes;
-        if (stages > 8) stages = 8;
-        ctas_per_sm = 1;
+    static int max_ctas = -1;
+    if (max_ctas < 0) {
+        const char* e = getenv("SCN_CONV_CTAS");
+        max_ctas = e ? atoi(e) : 3;
+    }
+    // candidates: (CTAs per SM, smem budget per CTA); every CTA needs >= 3 stages (>= 2 for the 4-CTA case is not enough
+    // to overlap gather, MMA and hand-over) and its TMEM columns must fit 512 / CTAs
+    stages = 0, ctas_per_sm = 1;
+    const int budgets[4] = {220 * 1024, 110 * 1024, 72 * 1024, 54 * 1024};
+    for (int c = (max_ctas > 4 ? 4 : max_ctas); c >= 1 && !stages; --c) {
+        const int st = budgets[c - 1] / stage_bytes;
+        if ((st >= 3 || c == 1) && c * tc <= 512) stages = st > 8 ? 8 : st, ctas_per_sm = c;
     }
     SCN_REQUIRE(stages >= 2, "conv_fwd_tf32: tile does not fit in shared memory");
     p.stages = stages;
