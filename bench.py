@@ -265,9 +265,41 @@ def main():
         achieved = alg_bytes / (kms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "k_conv_tc<4> SubM 3^3 32->32, N=%d, %d pairs" % (n0, pairs),
                 "achieved": achieved, "peak": peak, "peak_source": "measured" if peaks else "fallback",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this layer from the ncu --set full
+                # capture summarised in profiles/r1_b_ncu_full_conv_c32.md (39.62 MB + 0.49 MB; the output stays in L2)
+                "traffic": 40.11e6,
                 "ms_per_launch": kms, "algorithmic_bytes": alg_bytes,
                 "tflops_useful": flops / (kms * 1e-3) / 1e12, "l2": "flushed between launches"}
+
+    # metric part (ii): sparse inference scenes/s (backbone + segmentation + class network + sparse mask network on
+    # 256 proposal boxes per scene), every rank runs its own scenes (no collective), pinned host inputs.
+    from sparse_rcnn_b200.synthetic import make_boxes
+    infer = pipeline.SparseInference(dev)
+    boxes = [make_boxes(d[0], 256, 7 + i) for i, (d, _) in enumerate(host)]
+    n_inf = max(K // 2, 3)
+    for i in range(3):
+        infer(pinned[i % n_distinct][0], boxes[i % n_distinct])
+    barrier()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.raw("scn_launch_count")()
+    i0.record()
+    mask_pts = 0
+    for i in range(n_inf):
+        res = infer(pinned[i % n_distinct][0], boxes[i % n_distinct])
+        mask_pts += int(res["mpn_mask"].shape[0])
+        res["mpn_class"].argmax(1).cpu()                   # D2H of the per-box class decision
+    i1.record()
+    barrier()
+    inf_ms = i0.elapsed_time(i1)
+    inf_launches = _lib.raw("scn_launch_count")() - l0
+    if world > 1:
+        tmax = torch.tensor([inf_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        inf_ms = float(tmax[0])
+    inference = {"scenes_per_sec": world * n_inf / (inf_ms * 1e-3), "ms_per_scene": inf_ms / n_inf, "boxes_per_scene": 256,
+                 "mask_points_per_scene": mask_pts // n_inf, "scn_launches_per_scene": int(inf_launches // n_inf),
+                 "scope": "sparse path only: backbone+seg+class net+mask net on given boxes (dense RPN/NMS out of scope)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -289,7 +321,7 @@ def main():
                        "precision": args.precision},
             "e2e": {"value": vox_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "inference": inference,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
