@@ -41,8 +41,11 @@ typedef void* scn_stream_t; /* cudaStream_t */
 #define SCN_SCAN_BLOCK 4096 /* items per scan block; tmp needs scn_scan_tmp_elems(n) ints */
 
 /* epilogue flags for the convolution kernels */
-#define SCN_EPI_RELU 1      /* out = max(out, 0)                      */
-#define SCN_EPI_ADD 2       /* out += residual[row] (same shape/ld)   */
+/* order of application: bias, MASK, ADD, RELU, ROUND */
+#define SCN_EPI_RELU 1      /* out = max(out, 0)                                        */
+#define SCN_EPI_ADD 2       /* out += residual[row] (same shape, leading dim ld_res)    */
+#define SCN_EPI_MASK 4      /* out = mask[row][col] > 0 ? out : 0  (ReLU backward)      */
+#define SCN_EPI_ROUND 8     /* out = rna_tf32(out): ready to be a tcgen05 TF32 operand  */
 
 const char* scn_last_error(void);
 int scn_version(void);
@@ -132,13 +135,14 @@ int scn_conv_pack_weights(const float* w, int K, int Cin, int Cout, int transpos
  * round it first with scn_round_tf32). */
 int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32_t* map, int n_out, int K,
                       const void* image, const float* bias, const float* residual, int ld_res,
-                      float* out, int ld_out, int Cout, int epi_flags, scn_stream_t stream);
+                      const float* mask, int ld_mask, float* out, int ld_out, int Cout, int epi_flags,
+                      scn_stream_t stream);
 /* exact fp32 FFMA path (verification mode, <=1e-5).  w is the raw [K, Cin_w, Cout_w] tensor;
  * transpose/reverse as above. */
 int scn_conv_fwd_fp32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K,
                       const float* w, int transpose, int reverse, const float* bias,
-                      const float* residual, int ld_res, float* out, int ld_out, int Cout,
-                      int epi_flags, scn_stream_t stream);
+                      const float* residual, int ld_res, const float* mask, int ld_mask, float* out,
+                      int ld_out, int Cout, int epi_flags, scn_stream_t stream);
 /* grad_w[o] (+)= in[map[o][:]]^T . grad_out   (fp32 accumulate; grad_w must be zeroed) */
 int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const int32_t* map, int n_out,
                         int K, const float* grad_out, int ld_go, int Cout, float* grad_w,

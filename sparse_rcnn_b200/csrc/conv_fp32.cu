@@ -23,7 +23,8 @@ struct WView {
 __global__ void __launch_bounds__(256) k_conv_fp32(const float* __restrict__ in, int ld_in, int Cin,
                                                    const int32_t* __restrict__ map, int n_out, int K, WView wv,
                                                    const float* __restrict__ bias, const float* __restrict__ residual,
-                                                   int ld_res, float* __restrict__ out, int ld_out, int Cout, int epi) {
+                                                   int ld_res, const float* __restrict__ mask, int ld_mask,
+                                                   float* __restrict__ out, int ld_out, int Cout, int epi) {
     __shared__ float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN];
     __shared__ int s_row[BM];
@@ -89,9 +90,10 @@ __global__ void __launch_bounds__(256) k_conv_fp32(const float* __restrict__ in,
             if (c >= Cout) continue;
             float v = acc[i][j];
             if (bias) v += bias[c];
+            if ((epi & SCN_EPI_MASK) && !(mask[(int64_t)r * ld_mask + c] > 0.f)) v = 0.f;
             if (epi & SCN_EPI_ADD) v += residual[(int64_t)r * ld_res + c];
             if (epi & SCN_EPI_RELU) v = fmaxf(v, 0.f);
-            out[(int64_t)r * ld_out + c] = v;
+            out[(int64_t)r * ld_out + c] = v;       // SCN_EPI_ROUND is a no-op in the exact-fp32 mode
         }
     }
 }
@@ -174,11 +176,13 @@ using namespace scn;
 extern "C" {
 
 int scn_conv_fwd_fp32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const float* w,
-                      int transpose, int reverse, const float* bias, const float* residual, int ld_res, float* out,
-                      int ld_out, int Cout, int epi_flags, scn_stream_t stream) {
+                      int transpose, int reverse, const float* bias, const float* residual, int ld_res,
+                      const float* mask, int ld_mask, float* out, int ld_out, int Cout, int epi_flags,
+                      scn_stream_t stream) {
     SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0, "conv_fwd_fp32: bad shape Cin=%d Cout=%d K=%d", Cin, Cout, K);
     SCN_REQUIRE(map || K == 1, "conv_fwd_fp32: identity map requires K == 1");
     SCN_REQUIRE(!(epi_flags & SCN_EPI_ADD) || residual, "conv_fwd_fp32: SCN_EPI_ADD needs a residual pointer");
+    SCN_REQUIRE(!(epi_flags & SCN_EPI_MASK) || mask, "conv_fwd_fp32: SCN_EPI_MASK needs a mask pointer");
     if (n_out <= 0) return SCN_OK;
     WView wv;
     wv.w = w, wv.K = K, wv.transpose = transpose, wv.reverse = reverse;
@@ -186,8 +190,8 @@ int scn_conv_fwd_fp32(const float* in, int ld_in, int Cin, const int32_t* map, i
     wv.A = transpose ? Cout : Cin;
     wv.B = transpose ? Cin : Cout;
     dim3 grid(cdiv(n_out, BM), cdiv(Cout, BN));
-    k_conv_fp32<<<grid, 256, 0, as_stream(stream)>>>(in, ld_in, Cin, map, n_out, K, wv, bias, residual, ld_res, out,
-                                                      ld_out, Cout, epi_flags);
+    k_conv_fp32<<<grid, 256, 0, as_stream(stream)>>>(in, ld_in, Cin, map, n_out, K, wv, bias, residual, ld_res, mask, ld_mask,
+                                                      out, ld_out, Cout, epi_flags);
     return check_launch("conv_fwd_fp32");
 }
 

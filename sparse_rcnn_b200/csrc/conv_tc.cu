@@ -34,6 +34,8 @@ struct ConvTcParams {
     const float* bias;
     const float* residual;
     int ld_res;
+    const float* mask;
+    int ld_mask;
     float* out;
     int ld_out, Cout, epi;
     int cout_pad, n_kb, cin_pad8, stages, tmem_cols, n_tiles;
@@ -245,9 +247,24 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
     } else if (warp < 4) {
         // ===================== epilogue warps 0..3 =====================
         int it = 0;
+        const int epi = p.epi;
         const bool vec_ok = (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
-                            (!(p.epi & SCN_EPI_ADD) ||
-                             ((p.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
+                            (!(epi & SCN_EPI_ADD) ||
+                             ((p.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
+                            (!(epi & SCN_EPI_MASK) ||
+                             ((p.ld_mask % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+        // order: bias, MASK (aux > 0 ? x : 0), ADD residual, RELU, ROUND (rna to TF32)
+        auto finish = [&](float x, float m, float r) {
+            if ((epi & SCN_EPI_MASK) && !(m > 0.f)) x = 0.f;
+            if (epi & SCN_EPI_ADD) x += r;
+            if (epi & SCN_EPI_RELU) x = fmaxf(x, 0.f);
+            if (epi & SCN_EPI_ROUND) {
+                uint32_t t;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+                x = __uint_as_float(t);
+            }
+            return x;
+        };
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int b = it & 1;
             mbar_wait<200>(accf_bar(b), (it >> 1) & 1);      // epilogue warps wait a whole tile: long back-off
@@ -259,37 +276,27 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                 tmem_ld16(taddr + c0, v);
                 if (row < p.n_out && c0 < p.Cout) {
                     float* orow = p.out + (int64_t)row * p.ld_out + c0;
-                    const float* rrow = (p.epi & SCN_EPI_ADD) ? p.residual + (int64_t)row * p.ld_res + c0 : nullptr;
+                    const float* rrow = (epi & SCN_EPI_ADD) ? p.residual + (int64_t)row * p.ld_res + c0 : nullptr;
+                    const float* mrow = (epi & SCN_EPI_MASK) ? p.mask + (int64_t)row * p.ld_mask + c0 : nullptr;
+                    if (p.bias) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (c0 + j < p.Cout) {
-                            float x = v[j];
-                            if (p.bias) x += __ldg(p.bias + c0 + j);
-                            v[j] = x;
-                        }
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < p.Cout) v[j] += __ldg(p.bias + c0 + j);
                     }
                     if (vec_ok && c0 + 16 <= p.Cout) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            if (rrow) {
-                                float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
-                                x.x += r4.x, x.y += r4.y, x.z += r4.z, x.w += r4.w;
-                            }
-                            if (p.epi & SCN_EPI_RELU)
-                                x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+                            float4 r4 = rrow ? *reinterpret_cast<const float4*>(rrow + j) : make_float4(0, 0, 0, 0);
+                            float4 m4 = mrow ? *reinterpret_cast<const float4*>(mrow + j) : make_float4(1, 1, 1, 1);
+                            float4 x;
+                            x.x = finish(v[j], m4.x, r4.x), x.y = finish(v[j + 1], m4.y, r4.y);
+                            x.z = finish(v[j + 2], m4.z, r4.z), x.w = finish(v[j + 3], m4.w, r4.w);
                             *reinterpret_cast<float4*>(orow + j) = x;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (c0 + j < p.Cout) {
-                                float x = v[j];
-                                if (rrow) x += rrow[j];
-                                if (p.epi & SCN_EPI_RELU) x = fmaxf(x, 0.f);
-                                orow[j] = x;
-                            }
-                        }
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < p.Cout) orow[j] = finish(v[j], mrow ? mrow[j] : 1.f, rrow ? rrow[j] : 0.f);
                     }
                 }
             }
@@ -396,12 +403,13 @@ int scn_conv_pack_weights(const float* w, int K, int Cin, int Cout, int transpos
 }
 
 int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32_t* map, int n_out, int K, const void* image,
-                      const float* bias, const float* residual, int ld_res, float* out, int ld_out, int Cout,
-                      int epi_flags, scn_stream_t stream) {
+                      const float* bias, const float* residual, int ld_res, const float* mask, int ld_mask, float* out,
+                      int ld_out, int Cout, int epi_flags, scn_stream_t stream) {
     SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0, "conv_fwd_tf32: bad shape Cin=%d Cout=%d K=%d", Cin, Cout, K);
     SCN_REQUIRE(Cout <= 256, "conv_fwd_tf32: Cout > 256 not supported (got %d)", Cout);
     SCN_REQUIRE(map || K == 1, "conv_fwd_tf32: identity map requires K == 1");
     SCN_REQUIRE(!(epi_flags & SCN_EPI_ADD) || residual, "conv_fwd_tf32: SCN_EPI_ADD needs a residual pointer");
+    SCN_REQUIRE(!(epi_flags & SCN_EPI_MASK) || mask, "conv_fwd_tf32: SCN_EPI_MASK needs a mask pointer");
     SCN_REQUIRE((reinterpret_cast<uintptr_t>(image) & 15) == 0, "conv_fwd_tf32: weight image must be 16-byte aligned");
     SCN_REQUIRE((reinterpret_cast<uintptr_t>(in) & 3) == 0, "conv_fwd_tf32: input not 4-byte aligned");
     if (n_out <= 0) return SCN_OK;
@@ -412,6 +420,7 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     ConvTcParams p;
     p.in = in, p.ld_in = ld_in, p.Cin = Cin, p.map = map, p.n_out = n_out, p.K = K;
     p.image = reinterpret_cast<const uint8_t*>(image), p.bias = bias, p.residual = residual, p.ld_res = ld_res;
+    p.mask = mask, p.ld_mask = ld_mask;
     p.out = out, p.ld_out = ld_out, p.Cout = Cout, p.epi = epi_flags;
     p.cout_pad = pad16(Cout), p.n_kb = n_kblocks(Cin), p.cin_pad8 = (Cin + 7) / 8 * 8;
     p.n_tiles = cdiv(n_out, TILE_M);

@@ -82,12 +82,42 @@ class UNet(nn.Module):
 
 
 # ----------------------------------------------------------------------------- blocks
+FUSE = {"residual": True}      # set False to run the unfused scn.* module graph (identical numerics in fp32 mode)
+
+
 def residual_unit(scn, cin, cout):
     shortcut = scn.Identity() if cin == cout else scn.NetworkInNetwork(cin, cout, True)
     inner = scn.Sequential(
         scn.ReLU(), scn.SubmanifoldConvolution(3, cin, cout, 3, True),
         scn.ReLU(), scn.SubmanifoldConvolution(3, cout, cout, 3, True))
-    return scn.Sequential(scn.ConcatTable(shortcut, inner), scn.AddTable())
+    unit = scn.Sequential(scn.ConcatTable(shortcut, inner), scn.AddTable())
+    if getattr(scn, "BACKEND", "") == "b200-cuda" and cin == cout:
+        unit.__class__ = _fused_class(scn)
+    return unit
+
+
+_FUSED_CLASSES = {}
+
+
+def _fused_class(scn):
+    """Same module tree (=> same state_dict keys) as the reference's residual unit, but forward runs
+    scn.functions.ResidualUnitFunction: two convolution launches + one elementwise pass."""
+    if scn not in _FUSED_CLASSES:
+        from .scn.functions import ResidualUnitFunction
+
+        class FusedResidualUnit(scn.Sequential):
+            def forward(self, x):
+                if not FUSE["residual"]:
+                    return super().forward(x)
+                inner = self[0]._modules["1"]
+                c1, c2 = inner[1], inner[3]
+                lvl = x.metadata.level(x.spatial_size)
+                f = ResidualUnitFunction.apply(x.features, c1.weight, c1.bias, c2.weight, c2.bias,
+                                               lvl.subm_map(c1.filter_size), lvl.n)
+                return scn.SparseConvNetTensor(f, x.metadata, x.spatial_size)
+
+        _FUSED_CLASSES[scn] = FusedResidualUnit
+    return _FUSED_CLASSES[scn]
 
 
 def unit_stage(scn, channels, num_units):

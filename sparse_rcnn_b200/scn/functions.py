@@ -10,7 +10,7 @@ from torch.autograd import Function
 from .. import _lib
 from .metadata import _ptr, _stream
 
-EPI_RELU, EPI_ADD = 1, 2
+EPI_RELU, EPI_ADD, EPI_MASK, EPI_ROUND = 1, 2, 4, 8
 
 _state = {"precision": "tf32"}
 
@@ -55,23 +55,30 @@ def _image(weight, K, cin, cout, transpose, reverse):
     return img
 
 
-def conv_gemm(x, weight, K, cin, cout, fmap, n_out, bias=None, transpose=0, reverse=0, residual=None, relu=False):
+def conv_gemm(x, weight, K, cin, cout, fmap, n_out, bias=None, transpose=0, reverse=0, residual=None, relu=False,
+              mask=None, round_out=False):
     """out[r] = epi(bias + sum_o x[fmap[o][r]] . W_eff[o]);  W_eff = weight (transposed / offset-reversed).
-    cin/cout are the GEMM widths (after any transpose)."""
+    cin/cout are the GEMM widths (after any transpose).  Epilogue order: bias, mask (mask > 0 ? v : 0), + residual,
+    ReLU, TF32 rounding (tf32 mode only; the result is then marked as a valid tensor-core operand)."""
     out = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
     if n_out == 0:
         return out
-    epi = (EPI_RELU if relu else 0) | (EPI_ADD if residual is not None else 0)
+    tf32 = _state["precision"] == "tf32" and cout <= 256
+    epi = (EPI_RELU if relu else 0) | (EPI_ADD if residual is not None else 0) | (EPI_MASK if mask is not None else 0) | \
+        (EPI_ROUND if (round_out and tf32) else 0)
     ld_res = residual.stride(0) if residual is not None else 0
+    ld_mask = mask.stride(0) if mask is not None else 0
     s = _stream()
-    if _state["precision"] == "tf32" and cout <= 256:
+    if tf32:
         img = _image(weight, K, cin, cout, transpose, reverse)
         x = tf32_exact(x)           # cp.async gathers are truncated by the MMA: round the operand once
         _lib.call("scn_conv_fwd_tf32", _ptr(x), x.stride(0), cin, x.shape[0], _ptr(fmap), n_out, K, _ptr(img), _ptr(bias),
-                  _ptr(residual), ld_res, _ptr(out), cout, cout, epi, s)
+                  _ptr(residual), ld_res, _ptr(mask), ld_mask, _ptr(out), cout, cout, epi, s)
+        if round_out:
+            out._scn_tf32 = True
     else:
         _lib.call("scn_conv_fwd_fp32", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(weight), transpose,
-                  reverse, _ptr(bias), _ptr(residual), ld_res, _ptr(out), cout, cout, epi, s)
+                  reverse, _ptr(bias), _ptr(residual), ld_res, _ptr(mask), ld_mask, _ptr(out), cout, cout, epi, s)
     return out
 
 
@@ -133,6 +140,68 @@ class ConvFunction(Function):
             else:
                 gb.zero_()
         return gx, gw, gb, None, None, None, None
+
+
+def _wgrad(x, fmap, go, K, cin, cout, n_out, like):
+    gw = torch.zeros_like(like)
+    if n_out:
+        _lib.call("scn_conv_bwd_weight", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(go), go.stride(0), cout,
+                  _ptr(gw), 1 if _state["precision"] == "tf32" else 0, _stream())
+    return gw
+
+
+def _bgrad(go, n, cout):
+    gb = torch.empty(cout, dtype=torch.float32, device=go.device)
+    if n:
+        _lib.call("scn_col_sum", _ptr(go), go.stride(0), n, cout, _ptr(gb), _stream())
+    else:
+        gb.zero_()
+    return gb
+
+
+def relu_round(x):
+    """r = relu(x), additionally rounded to TF32 (and marked) in tf32 mode."""
+    y = torch.empty_like(x)
+    tf32 = _state["precision"] == "tf32"
+    _lib.call("scn_relu_fwd", _ptr(x), _ptr(y), x.numel(), int(tf32), _stream())
+    if tf32:
+        y._scn_tf32 = True
+    return y
+
+
+class ResidualUnitFunction(Function):
+    """y = x + conv2(relu(conv1(relu(x))))  -- the residual unit of the reference's sparse networks
+    (module_factory.py:127-183 with relu_first, identity shortcut) as TWO convolution launches plus one
+    elementwise pass: ReLU / residual add / TF32 rounding ride in the convolution epilogues
+    (SCN_EPI_RELU|ROUND on conv1, SCN_EPI_ADD on conv2; backward: SCN_EPI_MASK|ROUND and SCN_EPI_MASK|ADD)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, fmap, n):
+        x = _check(x)
+        K, c = w1.shape[0], w1.shape[-1]
+        r = relu_round(x)
+        h = conv_gemm(r, w1, K, c, c, fmap, n, b1, relu=True, round_out=True)
+        y = conv_gemm(h, w2, K, c, c, fmap, n, b2, residual=x)
+        ctx.save_for_backward(r, h, w1, w2)
+        ctx.cfg = (fmap, n, K, c, b1 is not None, b2 is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        r, h, w1, w2 = ctx.saved_tensors
+        fmap, n, K, c, has_b1, has_b2 = ctx.cfg
+        gy = _check(gy)
+        gyr = tf32_exact(gy) if _state["precision"] == "tf32" else gy
+        # d/dh' through conv2, masked by relu'(conv1 out) = (h > 0); rounded so it can feed the next MMA directly
+        gh = conv_gemm(gyr, w2, K, c, c, fmap, n, None, transpose=1, reverse=1, mask=h, round_out=True)
+        gw2 = _wgrad(h, fmap, gyr, K, c, c, n, w2) if ctx.needs_input_grad[3] else None
+        gb2 = _bgrad(gy, n, c) if has_b2 and ctx.needs_input_grad[4] else None
+        # d/dx = gy + relu'(x) * conv1^T(gh)
+        gx = conv_gemm(gh, w1, K, c, c, fmap, n, None, transpose=1, reverse=1, mask=r, residual=gy) \
+            if ctx.needs_input_grad[0] else None
+        gw1 = _wgrad(r, fmap, gh, K, c, c, n, w1) if ctx.needs_input_grad[1] else None
+        gb1 = _bgrad(gh, n, c) if has_b1 and ctx.needs_input_grad[2] else None
+        return gx, gw1, gb1, gw2, gb2, None, None
 
 
 class ReLUFunction(Function):

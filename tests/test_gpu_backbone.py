@@ -68,3 +68,33 @@ def test_feature_extractor_fwd_bwd(cuda, precision, tol):
     worst = max(l2_err(pg.grad, po.grad) for (_, po), (_, pg) in zip(ref.named_parameters(), net.named_parameters())
                 if po.grad is not None)
     assert worst <= GRAD_L2[precision], worst
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 2e-3)])
+def test_fused_residual_unit_equals_module_graph(cuda, precision, tol):
+    """networks.residual_unit on the B200 backend runs ResidualUnitFunction (2 conv launches + 1 elementwise pass);
+    it must agree with the unfused scn.* module graph it replaces, forward and backward."""
+    from sparse_rcnn_b200 import scn
+    from tests.util import make_pair, random_scene
+    scn.set_precision(precision)
+    torch.manual_seed(0)
+    coords, feats, size = random_scene(3, channels=32, size=(28, 24, 16))
+    _, tg = make_pair(scn, coords, feats, size, cuda)
+    unit = networks.residual_unit(scn, 32, 32).to(cuda)
+    assert type(unit).__name__ == "FusedResidualUnit"
+    outs, grads = [], []
+    for fuse in (True, False):
+        networks.FUSE["residual"] = fuse
+        try:
+            x = tg.features.clone().requires_grad_(True)
+            unit.zero_grad()
+            y = unit(scn.SparseConvNetTensor(x, tg.metadata, size)).features
+            torch.manual_seed(1)
+            y.backward(torch.randn_like(y))
+            outs.append(y.detach())
+            grads.append([x.grad.clone()] + [p.grad.clone() for p in unit.parameters()])
+        finally:
+            networks.FUSE["residual"] = True
+    assert rel_err(outs[0], outs[1]) <= tol
+    for a, b in zip(grads[0], grads[1]):
+        assert l2_err(a, b) <= (1e-5 if precision == "fp32" else 3e-2), l2_err(a, b)
