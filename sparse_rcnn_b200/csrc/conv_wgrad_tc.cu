@@ -147,32 +147,42 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
             }
         }
         cp_async_wait<0>();
-    } else if (lane == 0) {
+    } else {
         // ===================== MMA issuer =====================
+        // Whole warp 8 runs the loop (warp-uniform control flow); one elected lane issues the 16 MMAs of a unit
+        // back to back (no per-instruction vote loops).
         const uint32_t idesc = make_idesc_tf32_mn(TILE_M, npad);
+        int AS_r, GS_r;
+        asm volatile("mov.u32 %0, %1;" : "=r"(AS_r) : "r"(AS));
+        asm volatile("mov.u32 %0, %1;" : "=r"(GS_r) : "r"(GS));
+        const uint32_t a_bytes = (uint32_t)p.a_stage_bytes, g_bytes = (uint32_t)p.g_stage_bytes;
         int sa = 0, sg = 0;
         uint32_t pha = 0, phg = 0;
         for (int tile = t0; tile < t1; ++tile) {
             mbar_wait(g_full(sg), phg);
-            const uint32_t gst = g_base + (uint32_t)sg * p.g_stage_bytes;
+            const uint64_t db0 = make_desc_mn_sw128_32b(g_base + (uint32_t)sg * g_bytes, A_STAGE_BYTES, 512);
             for (int oi = 0; oi < nO; ++oi) {
                 mbar_wait(a_full(sa), pha);
                 tc_fence_after();
-                const uint32_t ast = smem_base + (uint32_t)sa * p.a_stage_bytes;
+                const uint64_t da0 = make_desc_mn_sw128_32b(smem_base + (uint32_t)sa * a_bytes, A_STAGE_BYTES, 512);
                 const uint32_t tmem_d = tmem_base + (uint32_t)(oi * npad);
-#pragma unroll 4
-                for (int j = 0; j < TILE_M / 8; ++j) {
-                    const uint64_t da = make_desc_mn_sw128_32b(ast + (uint32_t)j * 1024u, A_STAGE_BYTES, 512);
-                    const uint64_t db = make_desc_mn_sw128_32b(gst + (uint32_t)j * 1024u, A_STAGE_BYTES, 512);
-                    mma_tf32(tmem_d, da, db, idesc, (tile != t0 || j != 0) ? 1u : 0u);
+                const uint32_t acc0 = tile != t0 ? 1u : 0u;
+                if (elect_one()) {
+                    mma_tf32(tmem_d, da0, db0, idesc, acc0);
+#pragma unroll
+                    for (int j = 1; j < TILE_M / 8; ++j)      // one 8-row K step = 1024 bytes = +64 in the >>4 address field
+                        mma_tf32(tmem_d, da0 + (uint64_t)(64 * j), db0 + (uint64_t)(64 * j), idesc, 1u);
+                    mma_commit(a_empty(sa));
                 }
-                mma_commit(a_empty(sa));
-                if (++sa == AS) sa = 0, pha ^= 1;
+                __syncwarp();
+                if (++sa == AS_r) sa = 0, pha ^= 1;
             }
-            mma_commit(g_empty(sg));
-            if (++sg == GS) sg = 0, phg ^= 1;
+            if (elect_one()) mma_commit(g_empty(sg));
+            __syncwarp();
+            if (++sg == GS_r) sg = 0, phg ^= 1;
         }
-        mma_commit(done_bar);
+        if (elect_one()) mma_commit(done_bar);
+        __syncwarp();
     }
 
     if (warp < 4) {

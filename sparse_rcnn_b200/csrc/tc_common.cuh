@@ -59,6 +59,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// One lane of a CONVERGED warp (cute::elect_one_sync).  Single-thread instructions (tcgen05.mma / commit,
+// bulk copies) should be issued as `if (elect_one()) ...` from warp-uniform control flow: issued from a divergent
+// `if (lane == 0)` region the compiler cannot prove their uniform-register operands warp-uniform and wraps
+// every one of them in a vote loop (SASS `BRA.U.ANY`).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
