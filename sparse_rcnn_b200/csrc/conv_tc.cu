@@ -39,6 +39,7 @@ struct ConvTcParams {
     float* out;
     int ld_out, Cout, epi;
     int cout_pad, n_kb, cin_pad8, stages, tmem_cols, n_tiles;
+    int osplit, opg;      // offsets of a tile are split over `osplit` work items of `opg` offsets each (small levels)
 };
 
 // one 16-byte chunk of a gathered row, split into VEC-float cp.asyncs
@@ -118,14 +119,19 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                 }
             };
             int idx[4], idx_next[4];
-            load_idx(blockIdx.x, 0, idx_next);
+            const int n_work = p.n_tiles * p.osplit;
+            load_idx(blockIdx.x / p.osplit, (blockIdx.x % p.osplit) * p.opg, idx_next);
             const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int o = 0; o < p.K; ++o) {
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int tile = w / p.osplit, o_lo = (w % p.osplit) * p.opg, o_hi = min(p.K, o_lo + p.opg);
+                for (int o = o_lo; o < o_hi; ++o) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) idx[i] = idx_next[i];
-                    if (o + 1 < p.K) load_idx(tile, o + 1, idx_next);
-                    else load_idx(tile + gridDim.x, 0, idx_next);
+                    if (o + 1 < o_hi) load_idx(tile, o + 1, idx_next);
+                    else {
+                        const int wn = w + gridDim.x;
+                        load_idx(wn < n_work ? wn / p.osplit : p.n_tiles, (wn % p.osplit) * p.opg, idx_next);
+                    }
                     for (int kb = 0; kb < p.n_kb; ++kb) {
                         mbar_wait(empty_bar(s), ph ^ 1);
                         const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
@@ -218,12 +224,14 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             const uint32_t idesc = make_idesc_tf32(TILE_M, p.cout_pad);
             int s = 0, it = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int n_work = p.n_tiles * p.osplit;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+                const int o_lo = (w % p.osplit) * p.opg, o_hi = min(p.K, o_lo + p.opg);
                 const int b = it & 1;
                 mbar_wait(acce_bar(b), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(b * p.cout_pad);
-                for (int o = 0; o < p.K; ++o) {
+                for (int o = o_lo; o < o_hi; ++o) {
                     for (int kb = 0; kb < p.n_kb; ++kb) {
                         mbar_wait(full_bar(s), ph);
                         tc_fence_after();
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                         for (int k = 0; k < kcols / 8; ++k) {
                             // advance 32 bytes (8 tf32) inside the 128-byte swizzled row: +2 in the >>4 address field
                             mma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                     (o | kb | k) != 0 ? 1u : 0u);
+                                     ((o - o_lo) | kb | k) != 0 ? 1u : 0u);
                         }
                         mma_commit(empty_bar(s));
                         if (++s == S) s = 0, ph ^= 1;
@@ -265,7 +273,9 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             }
             return x;
         };
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int n_work = p.n_tiles * p.osplit;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int tile = w / p.osplit;
             const int b = it & 1;
             mbar_wait<200>(accf_bar(b), (it >> 1) & 1);      // epilogue warps wait a whole tile: long back-off
             tc_fence_after();
@@ -274,7 +284,16 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             for (int c0 = 0; c0 < p.cout_pad; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
-                if (row < p.n_out && c0 < p.Cout) {
+                if (p.osplit > 1) {
+                    // split-offset mode: this work item holds a PARTIAL sum; accumulate into the bias-prefilled output
+                    // (the epilogue flags are applied by k_conv_post once all partials have landed)
+                    if (row < p.n_out) {
+                        float* orow = p.out + (int64_t)row * p.ld_out + c0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < p.Cout) atomicAdd(orow + j, v[j]);
+                    }
+                } else if (row < p.n_out && c0 < p.Cout) {
                     float* orow = p.out + (int64_t)row * p.ld_out + c0;
                     const float* rrow = (epi & SCN_EPI_ADD) ? p.residual + (int64_t)row * p.ld_res + c0 : nullptr;
                     const float* mrow = (epi & SCN_EPI_MASK) ? p.mask + (int64_t)row * p.ld_mask + c0 : nullptr;
@@ -309,6 +328,32 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
     __syncthreads();
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// split-offset mode helpers: out = bias (before the partial sums are accumulated) / the epilogue flags afterwards
+__global__ void k_conv_prefill(float* __restrict__ out, int ld, const float* __restrict__ bias, int n, int C) {
+    int64_t total = (int64_t)n * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / C), c = (int)(i % C);
+        out[(int64_t)r * ld + c] = bias ? bias[c] : 0.f;
+    }
+}
+__global__ void k_conv_post(float* __restrict__ out, int ld, const float* __restrict__ mask, int ld_mask,
+                            const float* __restrict__ residual, int ld_res, int n, int C, int epi) {
+    int64_t total = (int64_t)n * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / C), c = (int)(i % C);
+        float x = out[(int64_t)r * ld + c];
+        if ((epi & SCN_EPI_MASK) && !(mask[(int64_t)r * ld_mask + c] > 0.f)) x = 0.f;
+        if (epi & SCN_EPI_ADD) x += residual[(int64_t)r * ld_res + c];
+        if (epi & SCN_EPI_RELU) x = fmaxf(x, 0.f);
+        if (epi & SCN_EPI_ROUND) {
+            uint32_t t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+            x = __uint_as_float(t);
+        }
+        out[(int64_t)r * ld + c] = x;
     }
 }
 
@@ -469,7 +514,25 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
         int rc = scn::make_gather_tmap(&tmap, in, n_in, Cin, ld_in, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    int grid = p.n_tiles < sm_count() * ctas_per_sm ? p.n_tiles : sm_count() * ctas_per_sm;
+    // small levels: one CTA would walk all K * n_kb units of its tile serially (~0.6 us each) while most SMs idle
+    // (profiles/r1_e_launches_fused.md: 40-60 us per layer at 1..122 tiles).  Split the offsets of a tile over
+    // several work items; partial sums are accumulated with fp32 atomics into the bias-prefilled output.
+    const int slots = sm_count() * ctas_per_sm;
+    p.osplit = 1, p.opg = K;
+    if (K > 1 && p.n_tiles * 2 <= slots) {
+        int g = slots / p.n_tiles;
+        if (g > K) g = K;
+        p.opg = cdiv(K, g);
+        p.osplit = cdiv(K, p.opg);
+    }
+    const int n_work = p.n_tiles * p.osplit;
+    int grid = n_work < slots ? n_work : slots;
+    if (p.osplit > 1) {
+        k_conv_prefill<<<grid_for((int64_t)n_out * Cout, 256), 256, 0, as_stream(stream)>>>(out, ld_out, bias, n_out, Cout);
+        int rc = check_launch("conv_prefill");
+        if (rc) return rc;
+        p.bias = nullptr;
+    }
     cudaError_t e;
     auto launch = [&](auto kern, int threads) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -485,7 +548,14 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
         scn::set_error("conv_fwd_tf32: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
         return SCN_ERR_CUDA;
     }
-    return check_launch("conv_fwd_tf32");
+    int rc = check_launch("conv_fwd_tf32");
+    if (rc) return rc;
+    if (p.osplit > 1 && epi_flags) {
+        k_conv_post<<<grid_for((int64_t)n_out * Cout, 256), 256, 0, as_stream(stream)>>>(out, ld_out, mask, ld_mask, residual,
+                                                                                          ld_res, n_out, Cout, epi_flags);
+        rc = check_launch("conv_post");
+    }
+    return rc;
 }
 
 }  // extern "C"

@@ -272,7 +272,10 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
     const int groups_y = p.n_ogroups * p.n_mhalves * n_nhalves;
     const int ctas_per_sm = (tc <= 256 && smem <= 112 * 1024) ? 2 : 1;
     int n_chunks = (sm_count() * ctas_per_sm + groups_y - 1) / groups_y;
-    if (n_chunks > p.n_tiles) n_chunks = p.n_tiles;
+    // every CTA ends with opg x Cin x Cout atomics into gw: keep at least 4 tiles per chunk so that the final
+    // reduction does not dominate small levels (profiles/r1_e_launches_fused.md)
+    const int max_chunks = p.n_tiles >= 8 ? p.n_tiles / 4 : (p.n_tiles >= 2 ? 2 : 1);
+    if (n_chunks > max_chunks) n_chunks = max_chunks;
     if (n_chunks < 1) n_chunks = 1;
     p.tiles_per_chunk = cdiv(p.n_tiles, n_chunks);
     n_chunks = cdiv(p.n_tiles, p.tiles_per_chunk);

@@ -232,3 +232,43 @@ class SparseRoiExtraCut(nn.Module):
     def forward(self, feature_map, selection):
         feats = feature_map[1]
         return GatherRowsFunction.apply(feats, selection.sel_pt)
+
+
+class SparseMaskPredictor(nn.Module):
+    """Consumer of the crop selection (reference SparseMaskPredictor, model.py:859-882; format of
+    `split_select_nd`, utils/basic_functions.py:177-216): for every box pick the logit column of its
+    predicted class, sigmoid, and scatter back to a per-sample [n_boxes_i, P_i] point mask.  The reference
+    splits the dense [BB, P] `is_inside` matrix block-diagonally on the CPU and loops over boxes in Python;
+    here the (box, point) CSR produced by the crop kernel is used directly on the device."""
+
+    def __init__(self, num_valid=0):
+        super().__init__()
+        self.num_valid = num_valid
+
+    @torch.no_grad()
+    def forward(self, mask_logits, selection, class_indices):
+        """mask_logits [sum n_b, classes]; selection: CropSelection; class_indices int64 [BB] (device or CPU).
+        Returns a list over samples of float masks [n_boxes_i, P_i]."""
+        dev = mask_logits.device
+        box_ptr = selection.box_ptr.long()
+        n_rows = mask_logits.shape[0]
+        cls = class_indices.to(dev).long()
+        valid = cls >= 0
+        if self.num_valid:
+            valid &= cls < self.num_valid
+        rows = torch.arange(n_rows, device=dev)
+        box_of_row = torch.searchsorted(box_ptr, rows, right=True) - 1
+        c = cls.clamp(min=0)[box_of_row]
+        val = torch.sigmoid(mask_logits.detach()[rows, c]) * valid[box_of_row].to(mask_logits.dtype)
+        counts, splits = selection.bbox_sample_count, selection.batch_splits
+        pt = selection.sel_pt.long()
+        out, b0, p0 = [], 0, 0
+        for nb, npts in zip(counts, splits):
+            m = torch.zeros((nb, npts), dtype=mask_logits.dtype, device=dev)
+            if nb:
+                lo, hi = int(box_ptr[b0]), int(box_ptr[b0 + nb])
+                m[box_of_row[lo:hi] - b0, pt[lo:hi] - p0] = val[lo:hi]
+            out.append(m)
+            b0 += nb
+            p0 += npts
+        return out

@@ -98,3 +98,32 @@ def test_global_pool_segment_mean(cuda):
     xo = to.features.clone().requires_grad_(True)
     (networks.SparseGlobalPool(O)(O.SparseConvNetTensor(xo, to.metadata, size)) * w.cpu()).sum().backward()
     assert rel_err(x.grad, xo.grad) <= 1e-6
+
+
+def test_mask_predictor_matches_reference_algorithm(cuda):
+    """Device-side consumer of the crop CSR vs the reference SparseMaskPredictor algorithm (model.py:859-882)
+    restated with the dense is_inside matrix on the CPU."""
+    from sparse_rcnn_b200 import roi, scn
+    coords, feats, size, bs, splits = make_batch(2, 4, spatial_size=(32, 32, 16), room=(22, 22, 11),
+                                                 room_offset=(4, 4, 1), n_furniture=1, density=1.0)
+    boxes = make_boxes(coords, 3, 5, (32, 32, 16))
+    scene = (coords, feats.to(cuda), size, bs, splits)
+    _, sel = roi.SparseRoiCut(scn, raw_scene=True, combine="features")(scene, boxes)
+    torch.manual_seed(0)
+    logits = torch.randn(sel.total, 18, device=cuda)
+    cls = torch.tensor([2, 17, -1, 0, 5, 9])
+    got = roi.SparseMaskPredictor(18)(logits, sel, cls)
+    inside = sel.is_inside(cpu=True)
+    lg = logits.cpu()
+    row, b0, p0 = 0, 0, 0
+    for s, (nb, npts) in enumerate(zip(sel.bbox_sample_count, sel.batch_splits)):
+        ref = torch.zeros(nb, npts)
+        for b in range(nb):
+            m = inside[b0 + b, p0:p0 + npts]
+            n = int(m.sum())
+            c = int(cls[b0 + b])
+            ref[b, m] = torch.sigmoid(lg[row:row + n, c]) if 0 <= c < 18 else 0.0
+            row += n
+        assert torch.allclose(got[s].cpu(), ref, atol=1e-6)
+        b0 += nb
+        p0 += npts
