@@ -170,14 +170,19 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             }
         };
         int idx[8], idx_next[8];
-        load_idx(blockIdx.x, 0, idx_next);
+        const int n_work = p.n_tiles * p.osplit;
+        load_idx(blockIdx.x / p.osplit, (blockIdx.x % p.osplit) * p.opg, idx_next);
         const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            for (int o = 0; o < p.K; ++o) {
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int tile = w / p.osplit, o_lo = (w % p.osplit) * p.opg, o_hi = min(p.K, o_lo + p.opg);
+            for (int o = o_lo; o < o_hi; ++o) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) idx[i] = idx_next[i];
-                if (o + 1 < p.K) load_idx(tile, o + 1, idx_next);
-                else load_idx(tile + gridDim.x, 0, idx_next);
+                if (o + 1 < o_hi) load_idx(tile, o + 1, idx_next);
+                else {
+                    const int wn = w + gridDim.x;
+                    load_idx(wn < n_work ? wn / p.osplit : p.n_tiles, (wn % p.osplit) * p.opg, idx_next);
+                }
                 for (int kb = 0; kb < p.n_kb; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1);
                     const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
