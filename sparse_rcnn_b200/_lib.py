@@ -48,6 +48,7 @@ class _Lib:
     def __init__(self):
         self._dll = None
         self._protos = None
+        self._fns = {}
 
     def load(self):
         if self._dll is not None:
@@ -65,23 +66,36 @@ class _Lib:
         self._dll = dll
         return dll
 
+    def fn(self, name):
+        f = self._fns.get(name)
+        if f is None:
+            f = getattr(self.load(), name)
+            self._fns[name] = f
+        return f
+
     def call(self, name, *args):
-        dll = self.load()
-        rc = getattr(dll, name)(*args)
+        rc = self.fn(name)(*args)
         if rc != 0:
-            msg = dll.scn_last_error()
+            msg = self.load().scn_last_error()
             raise RuntimeError("%s failed (%d): %s" % (name, rc, msg.decode() if msg else "?"))
 
     def raw(self, name):
-        return getattr(self.load(), name)
+        return self.fn(name)
 
 
 LIB = _Lib()
+_FNS = LIB._fns
 
 
 def call(name, *args):
-    LIB.call(name, *args)
+    f = _FNS.get(name)
+    if f is None:
+        f = LIB.fn(name)
+    rc = f(*args)
+    if rc != 0:
+        msg = LIB.load().scn_last_error()
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, msg.decode() if msg else "?"))
 
 
 def raw(name):
-    return LIB.raw(name)
+    return LIB.fn(name)

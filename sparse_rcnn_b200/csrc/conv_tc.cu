@@ -524,7 +524,12 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     // several work items; partial sums are accumulated with fp32 atomics into the bias-prefilled output.
     const int slots = sm_count() * ctas_per_sm;
     p.osplit = 1, p.opg = K;
-    if (K > 1 && p.n_tiles * 2 <= slots) {
+    static int no_split = -1;
+    if (no_split < 0) {
+        const char* e = getenv("SCN_CONV_NOSPLIT");
+        no_split = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!no_split && K > 1 && p.n_tiles * 2 <= slots) {
         int g = slots / p.n_tiles;
         if (g > K) g = K;
         p.opg = cdiv(K, g);
@@ -540,8 +545,15 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     }
     cudaError_t e;
     auto launch = [&](auto kern, int threads) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return;
+        // the attribute only has to grow: remember the largest value set per instantiation (a driver call per
+        // launch costs several microseconds of host time and this path is host bound for small levels)
+        static int smem_set = 0;
+        e = cudaSuccess;
+        if (smem > smem_set) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return;
+            smem_set = smem;
+        }
         kern<<<grid, threads, smem, as_stream(stream)>>>(tmap, p);
     };
     if (use_tma) launch(k_conv_tc<4, true>, 192);

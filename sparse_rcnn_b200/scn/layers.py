@@ -181,7 +181,7 @@ class Convolution(nn.Module):
         r = md.strided_rules(x.spatial_size, self.filter_size, self.filter_stride)
         n_out = md.levels[r.out_key].n
         f = F.ConvFunction.apply(x.features, self.weight, self.bias, r.cmap, r.dmap, n_out, 0)
-        return SparseConvNetTensor(f, md, torch.tensor(r.out_key, dtype=torch.long))
+        return SparseConvNetTensor(f, md, r.out_size)
 
     def input_spatial_size(self, out_size):
         return (out_size - 1) * torch.tensor(self.filter_stride) + torch.tensor(self.filter_size)
@@ -205,9 +205,11 @@ class Deconvolution(nn.Module):
         if out_size not in md.levels:
             raise RuntimeError("Deconvolution: no active set at spatial size %s in this Metadata" % (out_size,))
         r = md.strided_rules(out_size, self.filter_size, self.filter_stride)
-        n_out = md.levels[out_size].n
-        f = F.ConvFunction.apply(x.features, self.weight, self.bias, r.dmap, r.cmap, n_out, 0)
-        return SparseConvNetTensor(f, md, torch.tensor(out_size, dtype=torch.long))
+        lvl = md.levels[out_size]
+        if getattr(lvl, "size_tensor", None) is None:
+            lvl.size_tensor = torch.tensor(out_size, dtype=torch.long)
+        f = F.ConvFunction.apply(x.features, self.weight, self.bias, r.dmap, r.cmap, lvl.n, 0)
+        return SparseConvNetTensor(f, md, lvl.size_tensor)
 
 
 class NetworkInNetwork(nn.Module):
@@ -240,7 +242,7 @@ class _Pooling(nn.Module):
         n_out = md.levels[r.out_key].n
         vol = self.pool_size[0] * self.pool_size[1] * self.pool_size[2]
         f = F.PoolFunction.apply(x.features, r, n_out, self.IS_MAX, 1.0 / vol)
-        return SparseConvNetTensor(f, md, torch.tensor(r.out_key, dtype=torch.long))
+        return SparseConvNetTensor(f, md, r.out_size)
 
 
 class MaxPooling(_Pooling):
