@@ -23,6 +23,9 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // grid size for grid-stride kernels: a multiple of the SM count (148 on B200), capped by work
 int sm_count();
+// cudaFuncAttributeMaxDynamicSharedMemorySize only has to grow: remember the largest value set per kernel (a driver
+// call per launch costs microseconds of host time and the small levels are host bound).  Returns a cudaError_t.
+int ensure_dynamic_smem(const void* kernel, int bytes);
 static inline int grid_for(int64_t work_items, int block, int ctas_per_sm = 8) {
     int64_t need = (work_items + block - 1) / block;
     int64_t cap = (int64_t)sm_count() * ctas_per_sm;

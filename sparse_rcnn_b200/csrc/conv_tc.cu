@@ -545,15 +545,8 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     }
     cudaError_t e;
     auto launch = [&](auto kern, int threads) {
-        // the attribute only has to grow: remember the largest value set per instantiation (a driver call per
-        // launch costs several microseconds of host time and this path is host bound for small levels)
-        static int smem_set = 0;
-        e = cudaSuccess;
-        if (smem > smem_set) {
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return;
-            smem_set = smem;
-        }
+        e = (cudaError_t)scn::ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
+        if (e != cudaSuccess) return;
         kern<<<grid, threads, smem, as_stream(stream)>>>(tmap, p);
     };
     if (use_tma) launch(k_conv_tc<4, true>, 192);

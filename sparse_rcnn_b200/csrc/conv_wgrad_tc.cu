@@ -286,12 +286,8 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
     dim3 grid(n_chunks, groups_y);
     cudaError_t e = cudaSuccess;
     auto launch = [&](auto kern) {
-        static int smem_set = 0;      // per instantiation (generic lambda): the attribute only has to grow
-        if (smem > smem_set) {
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return;
-            smem_set = smem;
-        }
+        e = (cudaError_t)scn::ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
+        if (e != cudaSuccess) return;
         kern<<<grid, WG_THREADS, smem, as_stream(stream)>>>(p);
     };
     if (vec == 4) launch(k_conv_wgrad_tc<4>);

@@ -41,6 +41,21 @@ int sm_count() {
     return n;
 }
 
+int ensure_dynamic_smem(const void* kernel, int bytes) {
+    static const void* fns[32];
+    static int vals[32];
+    static int n = 0;
+    int i = 0;
+    for (; i < n; ++i)
+        if (fns[i] == kernel) break;
+    if (i < n && vals[i] >= bytes) return (int)cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    if (i == n && n < 32) fns[n++] = kernel;
+    if (i < 32) vals[i] = bytes;
+    return (int)cudaSuccess;
+}
+
 // ------------------------------------------------------------------------------ kernels
 __global__ void k_pack_coords(const int64_t* __restrict__ coords, int P, int ncol, uint64_t* __restrict__ keys,
                               int* __restrict__ err) {
