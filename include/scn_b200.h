@@ -147,6 +147,20 @@ int scn_conv_fwd_fp32(const float* in, int ld_in, int Cin, const int32_t* map, i
 int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const int32_t* map, int n_out,
                         int K, const float* grad_out, int ld_go, int Cout, float* grad_w,
                         int use_tf32, scn_stream_t stream);
+/* Residual unit  y = x + conv2(relu(conv1(relu(x))))  (module_factory.py:127-183, relu_first, identity shortcut;
+ * both convolutions C -> C over the same map) as ONE call that enqueues all kernels (relu+round, two gather-GEMMs
+ * with fused ReLU / residual-add epilogues); r = relu(x) and h = relu(conv1) are kept for the backward.  img1/img2:
+ * caller-owned packed-weight buffers (scn_conv_weight_image_bytes), re-packed here when repack != 0.  All tensors
+ * are dense [n, C] with leading dimension C. */
+int scn_residual_unit_fwd(const float* x, int n, int C, const int32_t* map, int K, const float* w1,
+                          const float* b1, const float* w2, const float* b2, void* img1, void* img2,
+                          int repack, float* r, float* h, float* y, int use_tf32, scn_stream_t stream);
+/* backward of the unit: gx = gy + relu'(x) * conv1^T(relu'(h) * conv2^T(gy)); weight / bias gradients (any of the
+ * g* outputs may be NULL).  gyr [n, C] is scratch (TF32-rounded gy), gh [n, C] receives d/dh. */
+int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n, int C, const int32_t* map,
+                          int K, const float* w1, const float* w2, void* img1t, void* img2t, int repack,
+                          float* gyr, float* gh, float* gx, float* gw1, float* gb1, float* gw2, float* gb2,
+                          int use_tf32, scn_stream_t stream);
 /* out[c] = sum_r in[r][c]   (bias gradient) */
 int scn_col_sum(const float* in, int ld, int n, int C, float* out, scn_stream_t stream);
 

@@ -49,16 +49,17 @@ __global__ void k_add(const float* __restrict__ a, const float* __restrict__ b, 
     for (; i < n; i += (int64_t)gridDim.x * blockDim.x) o[i] = a[i] + b[i];
 }
 
-// column sums: block handles a slab of rows, threads (cx, ry); smem reduce over ry; atomicAdd per block.
-// Deterministic variant: two-stage (partials [gridDim.x, C] then a final pass).
+// Column reductions (bias gradients, BatchNorm statistics): ONE launch, deterministic.  Blocks (32 channels x 8 row
+// lanes) write slab partials; the last block of every channel group to finish (ticket counter, self resetting) adds the
+// partials in slab order.
 template <bool SQ_DIFF>
-__global__ void k_col_partial(const float* __restrict__ in, int ld, int n, int C, const float* __restrict__ mean,
-                              float* __restrict__ partial) {
-    // blockDim = (32, 8): 32 channels x 8 row lanes; grid = (slabs, ceil(C/32))
+__global__ void k_col_reduce(const float* __restrict__ in, int ld, int n, int C, const float* __restrict__ mean, float scale,
+                             float* __restrict__ partial, unsigned int* __restrict__ tickets, float* __restrict__ out) {
     __shared__ float sm[8][33];
-    int c = blockIdx.y * 32 + threadIdx.x;
+    __shared__ bool last;
+    const int c = blockIdx.y * 32 + threadIdx.x;
     float acc = 0.f;
-    float m = (SQ_DIFF && c < C) ? mean[c] : 0.f;
+    const float m = (SQ_DIFF && c < C) ? mean[c] : 0.f;
     if (c < C)
         for (int r = blockIdx.x * 8 + threadIdx.y; r < n; r += gridDim.x * 8) {
             float v = in[(int64_t)r * ld + c];
@@ -76,14 +77,19 @@ __global__ void k_col_partial(const float* __restrict__ in, int ld, int n, int C
         for (int j = 0; j < 8; ++j) s += sm[j][threadIdx.x];
         partial[(int64_t)blockIdx.x * C + c] = s;
     }
-}
-// final pass: block (32 channels x 8 slab lanes), shared-memory tree over the lanes (deterministic)
-__global__ void k_col_final(const float* __restrict__ partial, int nslab, int C, float scale, float* __restrict__ out) {
-    __shared__ float sm[8][33];
-    int c = blockIdx.x * 32 + threadIdx.x;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const unsigned int t = atomicAdd(tickets + blockIdx.y, 1u);
+        last = (t == gridDim.x - 1);
+        if (last) tickets[blockIdx.y] = 0;      // ready for the next launch on this stream
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
     float s = 0.f;
     if (c < C)
-        for (int j = threadIdx.y; j < nslab; j += 8) s += partial[(int64_t)j * C + c];
+        for (int j = threadIdx.y; j < (int)gridDim.x; j += 8) s += __ldcg(partial + (int64_t)j * C + c);
     sm[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
@@ -397,22 +403,30 @@ __global__ void __launch_bounds__(256) k_crop_select(const uint64_t* __restrict_
 using namespace scn;
 
 static int col_reduce(const float* in, int ld, int n, int C, const float* mean, float scale, float* out, float* partial,
-                      int nslab, cudaStream_t st) {
-    dim3 grid(nslab, cdiv(C, 32)), block(32, 8);
+                      unsigned int* tickets, int nslab, cudaStream_t st) {
+    int slabs = cdiv(n, 64);
+    if (slabs > nslab) slabs = nslab;
+    if (slabs < 1) slabs = 1;
+    dim3 grid(slabs, cdiv(C, 32)), block(32, 8);
     if (mean)
-        k_col_partial<true><<<grid, block, 0, st>>>(in, ld, n, C, mean, partial);
+        k_col_reduce<true><<<grid, block, 0, st>>>(in, ld, n, C, mean, scale, partial, tickets, out);
     else
-        k_col_partial<false><<<grid, block, 0, st>>>(in, ld, n, C, nullptr, partial);
-    int rc = check_launch("col_partial");
-    if (rc) return rc;
-    k_col_final<<<cdiv(C, 32), dim3(32, 8), 0, st>>>(partial, nslab, C, scale, out);
-    return check_launch("col_final");
+        k_col_reduce<false><<<grid, block, 0, st>>>(in, ld, n, C, nullptr, scale, partial, tickets, out);
+    return check_launch("col_reduce");
 }
 
 // scratch for the two-stage column reductions: one persistent buffer per process/device
 static float* g_scratch = nullptr;
 static size_t g_scratch_bytes = 0;
+static unsigned int* g_tickets = nullptr;       // 64 self-resetting ticket counters (C <= 2048)
 static int ensure_scratch(size_t bytes) {
+    if (!g_tickets) {
+        if (cudaMalloc(&g_tickets, 64 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(g_tickets, 0, 64 * sizeof(unsigned int)) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("ticket alloc failed");
+            return SCN_ERR_CUDA;
+        }
+    }
     if (bytes <= g_scratch_bytes) return SCN_OK;
     if (g_scratch) cudaFree(g_scratch);
     g_scratch = nullptr;
@@ -460,15 +474,16 @@ int scn_col_sum(const float* in, int ld, int n, int C, float* out, scn_stream_t 
     SCN_REQUIRE(C > 0 && n >= 0, "col_sum: bad shape");
     int rc = ensure_scratch((size_t)NSLAB * 2 * C * sizeof(float));
     if (rc) return rc;
-    return col_reduce(in, ld, n, C, nullptr, 1.f, out, g_scratch, NSLAB, as_stream(stream));
+    SCN_REQUIRE(C <= 2048, "col_sum: C > 2048 not supported");
+    return col_reduce(in, ld, n, C, nullptr, 1.f, out, g_scratch, g_tickets, NSLAB, as_stream(stream));
 }
 int scn_bn_stats(const float* in, int n, int C, float* mean, float* var, scn_stream_t stream) {
     SCN_REQUIRE(C > 0 && n > 0, "bn_stats: needs at least one active row");
     int rc = ensure_scratch((size_t)NSLAB * 2 * C * sizeof(float));
     if (rc) return rc;
-    rc = col_reduce(in, C, n, C, nullptr, 1.f / n, mean, g_scratch, NSLAB, as_stream(stream));
+    rc = col_reduce(in, C, n, C, nullptr, 1.f / n, mean, g_scratch, g_tickets, NSLAB, as_stream(stream));
     if (rc) return rc;
-    return col_reduce(in, C, n, C, mean, 1.f / n, var, g_scratch, NSLAB, as_stream(stream));
+    return col_reduce(in, C, n, C, mean, 1.f / n, var, g_scratch + (size_t)NSLAB * C, g_tickets + 32, NSLAB, as_stream(stream));
 }
 int scn_bn_apply(const float* in, int n, int C, const float* mean, const float* var, const float* gamma,
                  const float* beta, float eps, float leak, float* out, scn_stream_t stream) {

@@ -169,38 +169,78 @@ def relu_round(x):
     return y
 
 
+def _image_buf(weight, K, cin, cout, key):
+    """Persistent packed-image buffer of a weight tensor (one per orientation) + whether it must be re-packed."""
+    bufs = getattr(weight, "_scn_imgbuf", None)
+    if bufs is None:
+        bufs = {}
+        try:
+            weight._scn_imgbuf = bufs
+        except AttributeError:
+            pass
+    ver = (weight._version, weight.data_ptr())
+    hit = bufs.get(key)
+    if hit is None:
+        nbytes = int(_lib.raw("scn_conv_weight_image_bytes")(K, cin, cout))
+        hit = [torch.empty(nbytes, dtype=torch.uint8, device=weight.device), None]
+        bufs[key] = hit
+    stale = hit[1] != ver
+    hit[1] = ver
+    return hit[0], stale
+
+
 class ResidualUnitFunction(Function):
     """y = x + conv2(relu(conv1(relu(x))))  -- the residual unit of the reference's sparse networks
-    (module_factory.py:127-183 with relu_first, identity shortcut) as TWO convolution launches plus one
-    elementwise pass: ReLU / residual add / TF32 rounding ride in the convolution epilogues
-    (SCN_EPI_RELU|ROUND on conv1, SCN_EPI_ADD on conv2; backward: SCN_EPI_MASK|ROUND and SCN_EPI_MASK|ADD)."""
+    (module_factory.py:127-183 with relu_first, identity shortcut).  ReLU / residual add / TF32 rounding ride in the
+    convolution epilogues (SCN_EPI_RELU|ROUND on conv1, SCN_EPI_ADD on conv2; backward: SCN_EPI_MASK|ROUND and
+    SCN_EPI_MASK|ADD), and each direction is ONE C-ABI call (scn_residual_unit_fwd / _bwd) because the step is
+    host bound."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, fmap, n):
         x = _check(x)
         K, c = w1.shape[0], w1.shape[-1]
-        r = relu_round(x)
-        h = conv_gemm(r, w1, K, c, c, fmap, n, b1, relu=True, round_out=True)
-        y = conv_gemm(h, w2, K, c, c, fmap, n, b2, residual=x)
+        tf32 = _state["precision"] == "tf32" and c <= 256
+        dev = x.device
+        r = torch.empty((n, c), dtype=torch.float32, device=dev)
+        h = torch.empty((n, c), dtype=torch.float32, device=dev)
+        y = torch.empty((n, c), dtype=torch.float32, device=dev)
+        if tf32:
+            i1, s1 = _image_buf(w1, K, c, c, "f")
+            i2, s2 = _image_buf(w2, K, c, c, "f")
+        else:
+            i1 = i2 = None
+            s1 = s2 = False
+        _lib.call("scn_residual_unit_fwd", _ptr(x), n, c, _ptr(fmap), K, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(i1),
+                  _ptr(i2), int(s1 or s2), _ptr(r), _ptr(h), _ptr(y), int(tf32), _stream())
         ctx.save_for_backward(r, h, w1, w2)
-        ctx.cfg = (fmap, n, K, c, b1 is not None, b2 is not None)
+        ctx.cfg = (fmap, n, K, c, b1 is not None, b2 is not None, tf32)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         r, h, w1, w2 = ctx.saved_tensors
-        fmap, n, K, c, has_b1, has_b2 = ctx.cfg
+        fmap, n, K, c, has_b1, has_b2, tf32 = ctx.cfg
         gy = _check(gy)
-        gyr = tf32_exact(gy) if _state["precision"] == "tf32" else gy
-        # d/dh' through conv2, masked by relu'(conv1 out) = (h > 0); rounded so it can feed the next MMA directly
-        gh = conv_gemm(gyr, w2, K, c, c, fmap, n, None, transpose=1, reverse=1, mask=h, round_out=True)
-        gw2 = _wgrad(h, fmap, gyr, K, c, c, n, w2) if ctx.needs_input_grad[3] else None
-        gb2 = _bgrad(gy, n, c) if has_b2 and ctx.needs_input_grad[4] else None
-        # d/dx = gy + relu'(x) * conv1^T(gh)
-        gx = conv_gemm(gh, w1, K, c, c, fmap, n, None, transpose=1, reverse=1, mask=r, residual=gy) \
-            if ctx.needs_input_grad[0] else None
-        gw1 = _wgrad(r, fmap, gh, K, c, c, n, w1) if ctx.needs_input_grad[1] else None
-        gb1 = _bgrad(gh, n, c) if has_b1 and ctx.needs_input_grad[2] else None
+        dev = gy.device
+        need = ctx.needs_input_grad
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        gyr = new(n, c) if tf32 else None
+        gh = new(n, c)
+        gx = new(n, c) if need[0] else None
+        gw1 = torch.empty_like(w1) if need[1] else None
+        gb1 = new(c) if (has_b1 and need[2]) else None
+        gw2 = torch.empty_like(w2) if need[3] else None
+        gb2 = new(c) if (has_b2 and need[4]) else None
+        if tf32:
+            i1, s1 = _image_buf(w1, K, c, c, "b")
+            i2, s2 = _image_buf(w2, K, c, c, "b")
+        else:
+            i1 = i2 = None
+            s1 = s2 = False
+        _lib.call("scn_residual_unit_bwd", _ptr(gy), _ptr(r), _ptr(h), n, c, _ptr(fmap), K, _ptr(w1), _ptr(w2), _ptr(i1),
+                  _ptr(i2), int(s1 or s2), _ptr(gyr), _ptr(gh), _ptr(gx), _ptr(gw1), _ptr(gb1), _ptr(gw2), _ptr(gb2),
+                  int(tf32), _stream())
         return gx, gw1, gb1, gw2, gb2, None, None
 
 
