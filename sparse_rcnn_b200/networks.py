@@ -193,6 +193,8 @@ class FeatureExtractor(nn.Module):
 
     def forward(self, data):
         scene_size, batch_size, x = self.input_stage(data)
+        if hasattr(x.metadata, "prebuild"):         # B200 backend: front-load the rulebook builder's host syncs
+            x.metadata.prebuild(len(self.channels) - 1)
         inter = self.main_network(x)
         extended = [x] + inter
         unet_out = self.unet(inter[-1], inter[:-1][::-1]) if self.include_unet else None
@@ -275,6 +277,8 @@ class ClassNetwork(nn.Module):
     def forward(self, feature_map, roi_bbox):
         x = self.input_conv_layer(feature_map)
         boxes, selection = self.roi_getter(x, roi_bbox)
+        if hasattr(boxes.metadata, "prebuild"):
+            boxes.metadata.prebuild(len(self.output_conv_layer))
         y = self.output_conv_layer(boxes)
         return self.linear_layer(self.vectorice_layer(y)), selection
 
@@ -321,5 +325,7 @@ class SparseMaskNetwork(nn.Module):
         boxes_tensor, selection = self.output_roi_cut(new_scene, roi_bbox)
         if boxes_tensor.features.shape[0] == 0:
             return combined.new_zeros((0, self.classes)), selection
+        if hasattr(boxes_tensor.metadata, "prebuild"):
+            boxes_tensor.metadata.prebuild(len(self.output_conv_layer.downsampling_layer) - 1)
         y = self.output_conv_layer(boxes_tensor)
         return self.linear_layer(self.final_point_layer(y)), selection

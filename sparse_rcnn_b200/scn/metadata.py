@@ -218,6 +218,26 @@ class Metadata:
             self.row_pts = torch.arange(self.n_points, dtype=torch.int32, device=dev)
         return self.row_ptr, self.row_pts
 
+    def prebuild(self, n_levels, filter_size=2, stride=2, subm_filter=3):
+        """Build `n_levels` strided levels below the input level (and the submanifold maps of every level) NOW.
+        Each new level costs one host sync (its active-row count sizes the buffers).  Done lazily, those syncs land
+        in the middle of the network and drain a full launch queue every time; done here, right after the input
+        layer, they cost ~30 us each and everything after runs asynchronously.  Purely an ordering change: the
+        same cached rulebooks are produced."""
+        size = self.input_size
+        for _ in range(n_levels + 1):
+            lvl = self.levels[size]
+            if subm_filter and lvl.n:
+                lvl.subm_map(subm_filter)
+            if _ == n_levels or any(s % 2 for s in size) or min(size) < 2:
+                break
+            try:
+                r = self.strided_rules(size, filter_size, stride)
+            except RuntimeError:
+                break
+            size = r.out_key
+        return self
+
     # ---------------------------------------------------------------- strided rulebooks
     def strided_rules(self, in_size, filter_size, stride):
         f, st = _triple(filter_size), _triple(stride)
