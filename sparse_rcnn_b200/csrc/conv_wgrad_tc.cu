@@ -7,11 +7,6 @@
 // row & 3) is the canonical MN-major SW128_32B layout with K = row.  One MMA (K=8) consumes two 4-row
 // swizzle atoms; M = 128 input channels (4 channel blocks 16 KB apart), N = up to 128 output channels.
 //
-// Offset packing: the M = 128 rows of one MMA hold P = 4 / ceil(Cin/32) kernel offsets side by side (4 offsets x 32
-// channels for Cin <= 32, 2 x 64 for Cin <= 64): the four 16 KB channel groups of the A stage are the gathered tiles
-// of P different offsets, so one 16-MMA sequence produces the weight gradients of P offsets and for C = 32 all 27
-// offsets' accumulators (7 groups x 32 columns) live in TMEM at once.
-//
 // Work split: grid = (row chunks) x (offset group, 128-wide Cin half, 128-wide Cout half).  A CTA keeps
 // the accumulators of ALL its offsets in TMEM across ALL its tiles and adds them to gw with one
 // round of atomics at the very end.  The grad-out tile is staged once per tile and reused by every
@@ -60,9 +55,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
     const int o0 = og * p.opg, nO = min(p.K, o0 + p.opg) - o0;
     if (nO <= 0) return;
     const int cin0 = mh * 128, cin_h = min(128, p.Cin - cin0), nblk_a = (cin_h + 31) / 32;
-    const int P = nblk_a == 1 ? 4 : (nblk_a == 2 ? 2 : 1);      // offsets packed into one MMA group
-    const int bpo = P == 1 ? nblk_a : 4 / P;                     // 16 KB channel blocks per offset
-    const int n_mg = (nO + P - 1) / P;                           // MMA groups (= pipeline units) per tile
     const int cout0 = nh * 128, cout_h = min(128, p.Cout - cout0), npad = (cout_h + 15) / 16 * 16;
     const int nblk_g = (npad + 31) / 32;
 
@@ -106,28 +98,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
         // ===================== producers =====================
         const int c = tid & 7, rbase = tid >> 3;        // rows rbase + 32 i
         const uint32_t dst_in_blk = swz_mn32b(rbase, c);      // (rbase + 32 i) & 3 == rbase & 3
-        // indices of the P offsets of a unit, fetched one unit ahead
-        auto load_idx = [&](int tile, int mg, int (&dst)[16]) {
+        auto load_idx = [&](int tile, int o, int (&dst)[4]) {
 #pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-                const int o = o0 + mg * P + pp;
-                const bool live = pp < P && o < o0 + nO && tile < t1;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = tile * TILE_M + rbase + 32 * i;
-                    int v = -1;
-                    if (live && r < p.n_out) v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
-                    dst[pp * 4 + i] = v;
-                }
+            for (int i = 0; i < 4; ++i) {
+                int r = tile * TILE_M + rbase + 32 * i;
+                int v = -1;
+                if (tile < t1 && r < p.n_out) v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
+                dst[i] = v;
             }
         };
-        int idx[16], idx_next[16];
-        load_idx(t0, 0, idx_next);
+        int idx[4], idx_next[4];
+        load_idx(t0, o0, idx_next);
         int sa = 0, sg = 0;
         uint32_t pha = 0, phg = 0;
-        const int cin_lim = min(p.Cin, cin0 + 128);
         for (int tile = t0; tile < t1; ++tile) {
-            // grad-out tile: staged once per tile, shared by every offset of the CTA
+            // grad-out tile: staged once per tile, shared by every offset of the group
             mbar_wait(g_empty(sg), phg ^ 1);
             {
                 const uint32_t gst = g_base + (uint32_t)sg * p.g_stage_bytes;
@@ -143,25 +128,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                 cp_async_mbar_arrive_noinc(g_full(sg));      // fires when this thread's copies have landed
                 if (++sg == GS) sg = 0, phg ^= 1;
             }
-            for (int mg = 0; mg < n_mg; ++mg) {
+            for (int oi = 0; oi < nO; ++oi) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) idx[i] = idx_next[i];
-                if (mg + 1 < n_mg) load_idx(tile, mg + 1, idx_next);
-                else load_idx(tile + 1, 0, idx_next);
+                for (int i = 0; i < 4; ++i) idx[i] = idx_next[i];
+                if (oi + 1 < nO) load_idx(tile, o0 + oi + 1, idx_next);
+                else load_idx(tile + 1, o0, idx_next);
                 mbar_wait(a_empty(sa), pha ^ 1);
                 const uint32_t ast = smem_base + (uint32_t)sa * p.a_stage_bytes;
+                for (int kb = 0; kb < nblk_a; ++kb) {
+                    const int col0 = cin0 + kb * KB + c * 4;
 #pragma unroll
-                for (int pp = 0; pp < 4; ++pp) {
-                    if (pp < P && o0 + mg * P + pp < o0 + nO) {
-                        for (int kb = 0; kb < bpo; ++kb) {
-                            const int col0 = cin0 + kb * KB + c * 4;
-                            if (col0 - c * 4 >= cin_lim) continue;        // whole block beyond Cin: never read as valid rows
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                wg_chunk<VEC>(ast + (uint32_t)(pp * bpo + kb) * A_STAGE_BYTES + dst_in_blk + (uint32_t)i * 4096u,
-                                              p.in, (int64_t)idx[pp * 4 + i] * p.ld_in, idx[pp * 4 + i] >= 0, col0, cin_lim);
-                        }
-                    }
+                    for (int i = 0; i < 4; ++i)
+                        wg_chunk<VEC>(ast + (uint32_t)kb * A_STAGE_BYTES + dst_in_blk + (uint32_t)i * 4096u, p.in,
+                                      (int64_t)idx[i] * p.ld_in, idx[i] >= 0, col0, min(p.Cin, cin0 + 128));
                 }
                 cp_async_mbar_arrive_noinc(a_full(sa));
                 if (++sa == AS) sa = 0, pha ^= 1;
@@ -182,11 +161,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
         for (int tile = t0; tile < t1; ++tile) {
             mbar_wait(g_full(sg), phg);
             const uint64_t db0 = make_desc_mn_sw128_32b(g_base + (uint32_t)sg * g_bytes, A_STAGE_BYTES, 512);
-            for (int mg = 0; mg < n_mg; ++mg) {
+            for (int oi = 0; oi < nO; ++oi) {
                 mbar_wait(a_full(sa), pha);
                 tc_fence_after();
                 const uint64_t da0 = make_desc_mn_sw128_32b(smem_base + (uint32_t)sa * a_bytes, A_STAGE_BYTES, 512);
-                const uint32_t tmem_d = tmem_base + (uint32_t)(mg * npad);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(oi * npad);
                 const uint32_t acc0 = tile != t0 ? 1u : 0u;
                 if (elect_one()) {
                     mma_tf32(tmem_d, da0, db0, idesc, acc0);
@@ -210,19 +189,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
         // ===================== epilogue: TMEM -> atomics into gw =====================
         mbar_wait<500>(done_bar, 0);
         tc_fence_after();
-        // accumulator row m = warp * 32 + lane  ->  (packed offset pp, channel ci)
-        const int blk = warp;                                   // 32 rows per warp = one 16 KB channel block
-        const int pp = blk / bpo;
-        const int ci = cin0 + (blk % bpo) * 32 + lane;
-        for (int mg = 0; mg < n_mg; ++mg) {
-            const int o = o0 + mg * P + pp;
-            const bool live = pp < P && o < o0 + nO && ci < min(p.Cin, cin0 + 128);
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mg * npad);
-            float* dst = p.gw + ((int64_t)o * p.Cin + ci) * p.Cout + cout0;
+        const int ci = cin0 + warp * 32 + lane;
+        for (int oi = 0; oi < nO; ++oi) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(oi * npad);
+            float* dst = p.gw + ((int64_t)(o0 + oi) * p.Cin + ci) * p.Cout + cout0;
             for (int c0 = 0; c0 < npad; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
-                if (live) {
+                if (ci < p.Cin) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (c0 + j < cout_h) atomicAdd(dst + c0 + j, v[j]);
@@ -265,29 +239,38 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
     const int n_nhalves = cdiv(Cout, 128);
     p.a_stage_bytes = cdiv(cin_h, 32) * A_STAGE_BYTES;
     p.g_stage_bytes = cdiv(npad, 32) * A_STAGE_BYTES;
-    // offset packing: P offsets share one MMA group (see the kernel header); a CTA keeps ceil(opg / P) groups of npad
-    // TMEM columns each, at most 512 columns
-    const int nblk_a = cdiv(cin_h, 32);
-    const int P = nblk_a == 1 ? 4 : (nblk_a == 2 ? 2 : 1);
-    int max_mg = 512 / npad;
-    if (max_mg < 1) max_mg = 1;
-    p.opg = max_mg * P;
+    // offsets per group: accumulators of one group must fit 256 TMEM columns (two CTAs per SM) when
+    // the tiles are narrow, 512 otherwise
+    int budget_cols = (p.a_stage_bytes + p.g_stage_bytes <= 32 * 1024) ? 256 : 512;
+    p.opg = budget_cols / npad;
     if (p.opg > K) p.opg = K;
+    if (p.opg < 1) p.opg = 1;
     p.n_ogroups = cdiv(K, p.opg);
-    p.opg = cdiv(cdiv(K, p.n_ogroups), P) * P;          // balance the groups, keep them multiples of P
-    p.n_ogroups = cdiv(K, p.opg);
+    p.opg = cdiv(K, p.n_ogroups);          // balance the groups
     int tc = 32;
-    while (tc < cdiv(p.opg, P) * npad) tc <<= 1;
+    while (tc < p.opg * npad) tc <<= 1;
     p.tmem_cols = tc;
-    // shared memory (one CTA per SM): A stage = four 16 KB channel blocks (P offsets x Cin/P channels), two stages;
-    // grad-out stage = ceil(npad / 32) blocks, two stages when they fit
-    p.a_stage_bytes = 4 * A_STAGE_BYTES;
-    p.a_stages = 2;
-    p.g_stages = (2 * p.a_stage_bytes + 2 * p.g_stage_bytes <= 222 * 1024) ? 2 : 1;
-    int smem = p.a_stages * p.a_stage_bytes + p.g_stages * p.g_stage_bytes;
-    const int ctas_per_sm = 1;
+    // shared memory: 2 grad-out stages if they fit, then as many A stages (<= 6) as fit.  M = 128 always
+    // reads a 64 KB window (4 channel blocks) from an A stage base, so the allocation must reach
+    // (a_stages - 1) * a_stage_bytes + 64 KB even when the stage itself is narrower.
+    int smem = 0;
+    p.a_stages = 0;
+    const int budgets[2] = {tc <= 256 ? 108 * 1024 : 0, 224 * 1024};      // two CTAs per SM first, else one
+    for (int b = 0; b < 2 && p.a_stages < 2; ++b)
+        for (int gs = 2; gs >= 1 && p.a_stages < 2; --gs)
+            for (int as = 6; as >= 2; --as) {
+                int total = as * p.a_stage_bytes + gs * p.g_stage_bytes;
+                int window_end = (as - 1) * p.a_stage_bytes + 4 * A_STAGE_BYTES;
+                if (total < window_end) total = window_end;
+                if (total <= budgets[b]) {
+                    p.a_stages = as, p.g_stages = gs, smem = total;
+                    break;
+                }
+            }
+    SCN_REQUIRE(p.a_stages >= 2, "conv_bwd_weight: tile does not fit in shared memory (Cin=%d Cout=%d)", Cin, Cout);
     smem += 1024 + 256;
     const int groups_y = p.n_ogroups * p.n_mhalves * n_nhalves;
+    const int ctas_per_sm = (tc <= 256 && smem <= 112 * 1024) ? 2 : 1;
     int n_chunks = (sm_count() * ctas_per_sm + groups_y - 1) / groups_y;
     // every CTA ends with opg x Cin x Cout atomics into gw: keep at least 4 tiles per chunk so that the final
     // reduction does not dominate small levels (profiles/r1_e_launches_fused.md)

@@ -60,15 +60,30 @@ __global__ void k_col_reduce(const float* __restrict__ in, int ld, int n, int C,
     const int c = blockIdx.y * 32 + threadIdx.x;
     float acc = 0.f;
     const float m = (SQ_DIFF && c < C) ? mean[c] : 0.f;
-    if (c < C)
-        for (int r = blockIdx.x * 8 + threadIdx.y; r < n; r += gridDim.x * 8) {
+    if (c < C) {
+        // four independent row streams per thread: four loads in flight instead of one (HBM-latency bound otherwise)
+        const int step = gridDim.x * 8;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int r = blockIdx.x * 8 + threadIdx.y;
+        for (; r + 3 * step < n; r += 4 * step) {
+            float v0 = in[(int64_t)r * ld + c], v1 = in[(int64_t)(r + step) * ld + c];
+            float v2 = in[(int64_t)(r + 2 * step) * ld + c], v3 = in[(int64_t)(r + 3 * step) * ld + c];
+            if (SQ_DIFF) {
+                v0 -= m, v1 -= m, v2 -= m, v3 -= m;
+                v0 *= v0, v1 *= v1, v2 *= v2, v3 *= v3;
+            }
+            a0 += v0, a1 += v1, a2 += v2, a3 += v3;
+        }
+        for (; r < n; r += step) {
             float v = in[(int64_t)r * ld + c];
             if (SQ_DIFF) {
                 v -= m;
                 v *= v;
             }
-            acc += v;
+            a0 += v;
         }
+        acc = (a0 + a1) + (a2 + a3);
+    }
     sm[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
