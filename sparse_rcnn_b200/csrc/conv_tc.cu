@@ -152,73 +152,125 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
         }
     } else if (!TMA && warp >= 4 && warp < 8) {
         // ===================== gather producers =====================
+        // Producer warp pw owns rows 32*pw .. 32*pw+31 of every tile.  Lane L reads the neighbour index of row
+        // 32*pw + L (one coalesced 128-byte map read per warp and unit) IDX_DEPTH units ahead; the copies fetch the
+        // index of their row with a shuffle: step i of the warp moves rows (lane >> 3) + 4 i, 8 lanes x 16 bytes each.
+        // The loop body is written for instruction count: the producers turned out to be ISSUE bound -- an earlier
+        // version spent ~390 SASS instructions per unit and warp (64-bit address arithmetic, an integer division per
+        // unit, predicate shuffling), which is the ~1350-cycle "per-CTA latency chain" of profiles/r1_d/r1_h.
+        constexpr int IDX_DEPTH = 4;
         const int pt = tid - 128;
-        const int c = pt & 7, rbase = pt >> 3;
-        const uint32_t dst_in_stage = (uint32_t)rbase * 128u + (uint32_t)((c ^ (rbase & 7)) << 4);
+        const int pw = warp - 4;
+        const int c = lane & 7, rsub = lane >> 3;
+        const uint32_t dst_even = (uint32_t)(32 * pw + rsub) * 128u + (uint32_t)((c ^ rsub) << 4);
+        const uint32_t dst_odd = (uint32_t)(32 * pw + rsub) * 128u + (uint32_t)((c ^ (rsub + 4)) << 4);
         int s = 0;
         uint32_t ph = 0;      // ring position / phase of this thread's unit stream
-        // neighbour indices are fetched one (tile, offset) ahead of the copies that depend on them, so
-        // the L2 latency of the map read overlaps the cp.async issue of the previous offset
-        auto load_idx = [&](int tile, int o, int (&dst)[8]) {
-            const int row0 = tile * TILE_M;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int r = row0 + rbase + 16 * i;
-                int v = -1;
-                if (tile < p.n_tiles && r < p.n_out) v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
-                dst[i] = v;
-            }
-        };
-        int idx[8], idx_next[8];
         const int n_work = p.n_tiles * p.osplit;
-        load_idx(blockIdx.x / p.osplit, (blockIdx.x % p.osplit) * p.opg, idx_next);
+        const int wstep = gridDim.x;
         const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int tile = w / p.osplit, o_lo = (w % p.osplit) * p.opg, o_hi = min(p.K, o_lo + p.opg);
-            for (int o = o_lo; o < o_hi; ++o) {
+        const uint32_t row_bytes = (uint32_t)p.ld_in * 4u;
+
+        // ---- index prefetch cursor (runs IDX_DEPTH units ahead of the copies)
+        int pf_w = blockIdx.x, pf_o, pf_ohi, pf_row = 0;
+        bool pf_ok = false;
+        const int32_t* pf_ptr = p.map;
+        auto pf_enter = [&]() {      // called when pf_w changes: a division per WORK ITEM, not per unit
+            const int tile = p.osplit > 1 ? pf_w / p.osplit : pf_w;
+            pf_o = p.osplit > 1 ? (pf_w - tile * p.osplit) * p.opg : 0;
+            pf_ohi = min(p.K, pf_o + p.opg);
+            pf_row = tile * TILE_M + 32 * pw + lane;
+            pf_ok = pf_w < n_work && pf_row < p.n_out;
+            if (p.map) pf_ptr = p.map + (int64_t)pf_o * p.n_out + pf_row;
+        };
+        auto pf_load = [&]() {
+            int v = -1;
+            if (pf_ok) v = p.map ? __ldg(pf_ptr) : pf_row;
+            if (++pf_o < pf_ohi) pf_ptr += p.n_out;
+            else {
+                pf_w += wstep;
+                pf_enter();
+            }
+            return v;
+        };
+        pf_enter();
+        int ring[IDX_DEPTH];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) idx[i] = idx_next[i];
-                if (o + 1 < o_hi) load_idx(tile, o + 1, idx_next);
-                else {
-                    const int wn = w + gridDim.x;
-                    load_idx(wn < n_work ? wn / p.osplit : p.n_tiles, (wn % p.osplit) * p.opg, idx_next);
-                }
+        for (int d = 0; d < IDX_DEPTH; ++d) ring[d] = pf_load();
+
+        // ---- copy cursor
+        int w = blockIdx.x, o = 0, o_hi = 0;
+        const uint8_t* wsrc = p.image;
+        auto enter = [&]() {
+            const int tile = p.osplit > 1 ? w / p.osplit : w;
+            o = p.osplit > 1 ? (w - tile * p.osplit) * p.opg : 0;
+            o_hi = min(p.K, o + p.opg);
+            wsrc = p.image + (size_t)o * p.n_kb * wbytes;
+        };
+        enter();
+        const char* in_c = reinterpret_cast<const char*>(p.in) + c * 16;
+        while (w < n_work) {
+#pragma unroll
+            for (int d = 0; d < IDX_DEPTH; ++d) {
+                if (w >= n_work) break;
+                const int my = ring[d];
+                ring[d] = pf_load();
+                int idx[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) idx[i] = __shfl_sync(0xffffffffu, my, rsub + 4 * i);
                 for (int kb = 0; kb < p.n_kb; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1);
                     const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
+                    const uint32_t fb = full_bar(s);
                     if (pt == 0) {
-                        mbar_arrive_expect_tx(full_bar(s), wbytes);
-                        bulk_g2s(a_stage + A_STAGE_BYTES, p.image + (size_t)(o * p.n_kb + kb) * wbytes, wbytes,
-                                 full_bar(s));
+                        mbar_arrive_expect_tx(fb, wbytes);
+                        bulk_g2s(a_stage + A_STAGE_BYTES, wsrc, wbytes, fb);
                     }
+                    wsrc += wbytes;
                     const int col0 = kb * KB + c * 4;
                     if (col0 < p.cin_pad8) {
                         if constexpr (VEC == 4) {
-                            // lean path: one IMAD.WIDE + one LDGSTS per 16-byte chunk; inactive rows (and the
-                            // all-padding chunk of a Cin that is not a multiple of 8) use src-size 0 = zero fill
-                            const float* colp = p.in + col0;
-                            const int full = col0 < p.Cin ? 16 : 0;
-                            const uint32_t dst = a_stage + dst_in_stage;
+                            // one VIMNMX + IMAD.WIDE + ISETP + LDGSTS per 16-byte chunk; inactive rows use the
+                            // ignore-src form (zero fill, no global access)
+                            const char* colp = in_c + kb * (KB * 4);
+                            const uint32_t de = a_stage + dst_even, dodd = a_stage + dst_odd;
+                            if (col0 < p.Cin) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int r = idx[i];
-                                const float* src = colp + (int64_t)max(r, 0) * p.ld_in;
-                                const int sz = r >= 0 ? full : 0;
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)i * 2048u),
-                                             "l"(src), "r"(sz)
-                                             : "memory");
+                                for (int i = 0; i < 8; ++i) {
+                                    const int r = idx[i];
+                                    const char* src = colp + (uint64_t)(uint32_t)max(r, 0) * row_bytes;
+                                    asm volatile(
+                                        "{\n\t"
+                                        ".reg .pred p;\n\t"
+                                        "setp.lt.s32 p, %2, 0;\n\t"
+                                        "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+                                        "}" ::"r"(((i & 1) ? dodd : de) + (uint32_t)i * 512u),
+                                        "l"(src), "r"(r)
+                                        : "memory");
+                                }
+                            } else {      // all-padding chunk of a Cin that is not a multiple of 8: zeros
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 0;" ::"r"(
+                                                     ((i & 1) ? dodd : de) + (uint32_t)i * 512u),
+                                                 "l"(colp)
+                                                 : "memory");
                             }
                         } else {
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                gather_chunk<VEC>(a_stage + dst_in_stage + (uint32_t)i * 2048u, p.in,
+                                gather_chunk<VEC>(a_stage + ((i & 1) ? dst_odd : dst_even) + (uint32_t)i * 512u, p.in,
                                                   (int64_t)idx[i] * p.ld_in, idx[i], col0, p.Cin);
                         }
                     }
                     // the stage's full barrier receives this thread's arrival when its copies have landed;
                     // up to S units are in flight per CTA and the producer only ever waits for a free slot
-                    cp_async_mbar_arrive_noinc(full_bar(s));
+                    cp_async_mbar_arrive_noinc(fb);
                     if (++s == S) s = 0, ph ^= 1;
+                }
+                if (++o >= o_hi) {
+                    w += wstep;
+                    enter();
                 }
             }
         }

@@ -37,21 +37,23 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.  After the first
-// failed probe the warp backs off with nanosleep so that waiting roles (epilogue, MMA issuer, producers
-// waiting for a free stage) do not steal issue slots from the warps doing the copies.
-template <int SLEEP_NS = 32>
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.  `mbarrier.try_wait` already
+// suspends the thread in hardware for a bounded time, so the loop is not a hot spin; roles that wait for a long time
+// (epilogue) add a nanosleep back-off.  The wall clock is only consulted every 4096 failed probes: reading
+// %globaltimer costs on the order of a microsecond, and taking a start stamp on the FIRST failed probe (as an earlier
+// version did) put that microsecond on the critical path of every pipeline unit.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    uint64_t t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    uint64_t t0 = 0;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(SLEEP_NS);
-        if ((++spins & 1023u) == 0) {
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        if ((++spins & 4095u) == 0) {
             uint64_t t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 4000000000ull) {
+            if (t0 == 0) t0 = t1;
+            else if (t1 - t0 > 4000000000ull) {
                 printf("scn_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
                        threadIdx.x, bar, parity);
                 __trap();
