@@ -11,7 +11,8 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "scn_b200.h")
-LIB_PATH = os.path.join(_HERE, "csrc", "libscn_b200.so")
+# SCN_B200_LIB: load another build of the same ABI (kernel experiments, scripts/build_variant.py); never a fallback
+LIB_PATH = os.environ.get("SCN_B200_LIB") or os.path.join(_HERE, "csrc", "libscn_b200.so")
 
 _PROTO = re.compile(r"^(const char\*|int64_t|int)\s+(scn_\w+)\s*\(([^;{]*)\)\s*;", re.M | re.S)
 

@@ -22,7 +22,6 @@
 
 namespace scn {
 
-constexpr int N_PRODUCERS = 128;
 constexpr int CONV_THREADS = 288;
 
 struct ConvTcParams {
@@ -83,7 +82,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), TMA ? 1 : N_PRODUCERS + 1);
+            mbar_init(full_bar(s), TMA ? 1 : 32 + 1);      // cp.async path: the 32 lanes of the owning warp + expect_tx
             mbar_init(empty_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -152,163 +151,201 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
         }
     } else if (!TMA && warp >= 4 && warp < 8) {
         // ===================== gather producers =====================
-        // Producer warp pw owns rows 32*pw .. 32*pw+31 of every tile.  Lane L reads the neighbour index of row
-        // 32*pw + L (one coalesced 128-byte map read per warp and unit) IDX_DEPTH units ahead; the copies fetch the
-        // index of their row with a shuffle: step i of the warp moves rows (lane >> 3) + 4 i, 8 lanes x 16 bytes each.
-        // The loop body is written for instruction count: the producers turned out to be ISSUE bound -- an earlier
-        // version spent ~390 SASS instructions per unit and warp (64-bit address arithmetic, an integer division per
-        // unit, predicate shuffling), which is the ~1350-cycle "per-CTA latency chain" of profiles/r1_d/r1_h.
-        constexpr int IDX_DEPTH = 4;
-        const int pt = tid - 128;
+        // Each producer warp OWNS every fourth unit of the CTA's flat unit stream (unit q = work item, offset, k-block in
+        // consumption order; warp pw fills q = pw, pw + 4, ...): all 128 rows of the stage, its weight block, and the
+        // only arrivals on its full barrier.  Why: the producers are bound by the LENGTH of their own serial
+        // instruction stream, not by memory (profiles/r1_h_issue_bound.md: with copies, MMAs, weight fetches and map
+        // reads all compiled out a unit still cost ~800 cycles per CTA).  When all four warps cooperate on every unit,
+        // each pays the per-unit overhead (barrier probe, ring bookkeeping, loop) for every unit; with owned units that
+        // chain is paid once per four units and four units are in production concurrently.
+        // Lane L reads the neighbour indices of rows L, L+32, L+64, L+96 (coalesced), one own unit (= four units)
+        // ahead; the copy of row (lane >> 3) + 4 i fetches its index with a shuffle, 8 lanes x 16 bytes per row.
+        // A warp that waits for "round k-1 of stage s consumed" can only tell it from parity, so round k-2 must already be
+        // known consumed when it looks: with G owner warps that holds iff S >= G (the warp's previous unit q-G needed unit
+        // q-G-S consumed, and q-2S <= q-G-S).  Hence G = min(4, S) owners; with S = 3 the fourth producer warp idles.
+        const int G = S < 4 ? S : 4;
         const int pw = warp - 4;
         const int c = lane & 7, rsub = lane >> 3;
-        const uint32_t dst_even = (uint32_t)(32 * pw + rsub) * 128u + (uint32_t)((c ^ rsub) << 4);
-        const uint32_t dst_odd = (uint32_t)(32 * pw + rsub) * 128u + (uint32_t)((c ^ (rsub + 4)) << 4);
-        int s = 0;
-        uint32_t ph = 0;      // ring position / phase of this thread's unit stream
+        const uint32_t dst_even = (uint32_t)rsub * 128u + (uint32_t)((c ^ rsub) << 4);
+        const uint32_t dst_odd = (uint32_t)rsub * 128u + (uint32_t)((c ^ (rsub + 4)) << 4);
         const int n_work = p.n_tiles * p.osplit;
         const int wstep = gridDim.x;
         const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
+        (void)wbytes;
         const uint32_t row_bytes = (uint32_t)p.ld_in * 4u;
-
-        // ---- index prefetch cursor (runs IDX_DEPTH units ahead of the copies)
-        int pf_w = blockIdx.x, pf_o, pf_ohi, pf_row = 0;
-        bool pf_ok = false;
-        const int32_t* pf_ptr = p.map;
-        auto pf_enter = [&]() {      // called when pf_w changes: a division per WORK ITEM, not per unit
-            const int tile = p.osplit > 1 ? pf_w / p.osplit : pf_w;
-            pf_o = p.osplit > 1 ? (pf_w - tile * p.osplit) * p.opg : 0;
-            pf_ohi = min(p.K, pf_o + p.opg);
-            pf_row = tile * TILE_M + 32 * pw + lane;
-            pf_ok = pf_w < n_work && pf_row < p.n_out;
-            if (p.map) pf_ptr = p.map + (int64_t)pf_o * p.n_out + pf_row;
-        };
-        auto pf_load = [&]() {
-            int v = -1;
-            if (pf_ok) v = p.map ? __ldg(pf_ptr) : pf_row;
-            if (++pf_o < pf_ohi) pf_ptr += p.n_out;
-            else {
-                pf_w += wstep;
-                pf_enter();
-            }
-            return v;
-        };
-        pf_enter();
-        int ring[IDX_DEPTH];
-#pragma unroll
-        for (int d = 0; d < IDX_DEPTH; ++d) ring[d] = pf_load();
-
-        // ---- copy cursor
-        int w = blockIdx.x, o = 0, o_hi = 0;
-        const uint8_t* wsrc = p.image;
-        auto enter = [&]() {
-            const int tile = p.osplit > 1 ? w / p.osplit : w;
-            o = p.osplit > 1 ? (w - tile * p.osplit) * p.opg : 0;
-            o_hi = min(p.K, o + p.opg);
-            wsrc = p.image + (size_t)o * p.n_kb * wbytes;
-        };
-        enter();
         const char* in_c = reinterpret_cast<const char*>(p.in) + c * 16;
-        while (w < n_work) {
+
+        struct Cursor {
+            int w, o, o_hi, kb, row0;      // row0 = first row of the tile
+        };
+        auto enter = [&](Cursor& q) {      // a division per WORK ITEM, not per unit
+            const int tile = p.osplit > 1 ? q.w / p.osplit : q.w;
+            q.o = p.osplit > 1 ? (q.w - tile * p.osplit) * p.opg : 0;
+            q.o_hi = min(p.K, q.o + p.opg);
+            q.row0 = tile * TILE_M;
+            q.kb = 0;
+        };
+        auto step = [&](Cursor& q) {
+            if (++q.kb == p.n_kb) {
+                q.kb = 0;
+                if (++q.o >= q.o_hi) {
+                    q.w += wstep;
+                    enter(q);
+                }
+            }
+        };
+        auto load_idx = [&](const Cursor& q, int (&dst)[4]) {
 #pragma unroll
-            for (int d = 0; d < IDX_DEPTH; ++d) {
-                if (w >= n_work) break;
-                const int my = ring[d];
-                ring[d] = pf_load();
-                int idx[8];
+            for (int j = 0; j < 4; ++j) dst[j] = -1;
+            if (q.w < n_work) {
+                const int r0 = q.row0 + lane;
+#ifdef SCN_EXP_NOIDX
+                const int32_t* mp = nullptr;
+#else
+                const int32_t* mp = p.map ? p.map + (int64_t)q.o * p.n_out + r0 : nullptr;
+#endif
 #pragma unroll
-                for (int i = 0; i < 8; ++i) idx[i] = __shfl_sync(0xffffffffu, my, rsub + 4 * i);
-                for (int kb = 0; kb < p.n_kb; ++kb) {
-                    mbar_wait(empty_bar(s), ph ^ 1);
-                    const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
-                    const uint32_t fb = full_bar(s);
-                    if (pt == 0) {
-                        mbar_arrive_expect_tx(fb, wbytes);
-                        bulk_g2s(a_stage + A_STAGE_BYTES, wsrc, wbytes, fb);
-                    }
-                    wsrc += wbytes;
-                    const int col0 = kb * KB + c * 4;
-                    if (col0 < p.cin_pad8) {
-                        if constexpr (VEC == 4) {
-                            // one VIMNMX + IMAD.WIDE + ISETP + LDGSTS per 16-byte chunk; inactive rows use the
-                            // ignore-src form (zero fill, no global access)
-                            const char* colp = in_c + kb * (KB * 4);
-                            const uint32_t de = a_stage + dst_even, dodd = a_stage + dst_odd;
-                            if (col0 < p.Cin) {
+                for (int j = 0; j < 4; ++j)
+                    if (r0 + 32 * j < p.n_out) dst[j] = mp ? __ldg(mp + 32 * j) : r0 + 32 * j;
+            }
+        };
+        Cursor cur, nxt;
+        cur.w = blockIdx.x;
+        enter(cur);
+        for (int j = 0; j < pw; ++j) step(cur);
+        nxt = cur;
+        for (int j = 0; j < G; ++j) step(nxt);
+        int s = pw;                                   // pw < G <= S
+        uint32_t ph = 0;
+        int idx[4], idx_next[4];
+        load_idx(cur, idx);
+        while (pw < G && cur.w < n_work) {
+            load_idx(nxt, idx_next);
+            mbar_wait(empty_bar(s), ph ^ 1);
+            const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
+            const uint32_t fb = full_bar(s);
+            if (elect_one()) {
+#ifdef SCN_EXP_NOWEIGHT
+                mbar_arrive(fb);
+#else
+                mbar_arrive_expect_tx(fb, wbytes);
+                bulk_g2s(a_stage + A_STAGE_BYTES, p.image + (size_t)(cur.o * p.n_kb + cur.kb) * wbytes, wbytes, fb);
+#endif
+            }
+            const int col0 = cur.kb * KB + c * 4;
+            // shuffles need the whole warp: lane-dependent conditions only predicate the copies
+            if constexpr (VEC == 4) {
+                // one ISETP + IMAD.WIDE + LDGSTS per 16-byte chunk; inactive rows use the ignore-src form
+                // (zero fill, the address is never dereferenced, so index -1 needs no clamp)
+                const char* colp = in_c + cur.kb * (KB * 4);
+                const uint32_t de = a_stage + dst_even, dodd = a_stage + dst_odd;
+                if (p.Cin - cur.kb * KB >= KB) {      // warp-uniform: a full 32-channel block
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int r = idx[i];
-                                    const char* src = colp + (uint64_t)(uint32_t)max(r, 0) * row_bytes;
-                                    asm volatile(
-                                        "{\n\t"
-                                        ".reg .pred p;\n\t"
-                                        "setp.lt.s32 p, %2, 0;\n\t"
-                                        "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
-                                        "}" ::"r"(((i & 1) ? dodd : de) + (uint32_t)i * 512u),
-                                        "l"(src), "r"(r)
-                                        : "memory");
-                                }
-                            } else {      // all-padding chunk of a Cin that is not a multiple of 8: zeros
+                    for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 0;" ::"r"(
-                                                     ((i & 1) ? dodd : de) + (uint32_t)i * 512u),
-                                                 "l"(colp)
-                                                 : "memory");
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                gather_chunk<VEC>(a_stage + ((i & 1) ? dst_odd : dst_even) + (uint32_t)i * 512u, p.in,
-                                                  (int64_t)idx[i] * p.ld_in, idx[i], col0, p.Cin);
+                        for (int i = 0; i < 8; ++i) {
+#ifdef SCN_EXP_NOCOPY
+                            if (p.n_out > 0) break;
+#endif
+                            const int r = __shfl_sync(0xffffffffu, idx[j], rsub + 4 * i);
+                            const char* src = colp + (uint64_t)(uint32_t)r * row_bytes;
+                            asm volatile(
+                                "{\n\t"
+                                ".reg .pred p;\n\t"
+                                "setp.lt.s32 p, %2, 0;\n\t"
+                                "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+                                "}" ::"r"(((i & 1) ? dodd : de) + (uint32_t)(32 * j + 4 * i) * 128u),
+                                "l"(src), "r"(r)
+                                : "memory");
                         }
                     }
-                    // the stage's full barrier receives this thread's arrival when its copies have landed;
-                    // up to S units are in flight per CTA and the producer only ever waits for a free slot
-                    cp_async_mbar_arrive_noinc(fb);
-                    if (++s == S) s = 0, ph ^= 1;
+                } else {      // last, partial block: chunks beyond cin_pad8 are not read by the MMA, chunks beyond Cin are zeros
+                    const bool wanted = col0 < p.cin_pad8, real = col0 < p.Cin;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            int r = __shfl_sync(0xffffffffu, idx[j], rsub + 4 * i);
+                            if (!real) r = -1;
+                            const char* src = colp + (uint64_t)(uint32_t)max(r, 0) * row_bytes;
+                            if (wanted)
+                                asm volatile(
+                                    "{\n\t"
+                                    ".reg .pred p;\n\t"
+                                    "setp.lt.s32 p, %2, 0;\n\t"
+                                    "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+                                    "}" ::"r"(((i & 1) ? dodd : de) + (uint32_t)(32 * j + 4 * i) * 128u),
+                                    "l"(src), "r"(r)
+                                    : "memory");
+                        }
+                    }
                 }
-                if (++o >= o_hi) {
-                    w += wstep;
-                    enter();
+            } else {
+                const bool wanted = col0 < p.cin_pad8;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = __shfl_sync(0xffffffffu, idx[j], rsub + 4 * i);
+                        if (wanted)
+                            gather_chunk<VEC>(a_stage + ((i & 1) ? dst_odd : dst_even) + (uint32_t)(32 * j + 4 * i) * 128u,
+                                              p.in, (int64_t)r * p.ld_in, r, col0, p.Cin);
+                    }
                 }
             }
+            // the stage's full barrier receives this thread's arrival when its copies have landed
+            cp_async_mbar_arrive_noinc(fb);
+            s += G;
+            if (s >= S) s -= S, ph ^= 1;
+            cur = nxt;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) idx[j] = idx_next[j];
+            for (int j = 0; j < G; ++j) step(nxt);
         }
         cp_async_wait<0>();
     } else if (warp == MMA_WARP) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TILE_M, p.cout_pad);
-            int s = 0, it = 0;
-            uint32_t ph = 0;
-            const int n_work = p.n_tiles * p.osplit;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-                const int o_lo = (w % p.osplit) * p.opg, o_hi = min(p.K, o_lo + p.opg);
-                const int b = it & 1;
-                mbar_wait(acce_bar(b), ((it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(b * p.cout_pad);
-                for (int o = o_lo; o < o_hi; ++o) {
-                    for (int kb = 0; kb < p.n_kb; ++kb) {
-                        mbar_wait(full_bar(s), ph);
-                        tc_fence_after();
-                        const uint32_t a_stage = smem_base + (uint32_t)s * stage_bytes;
-                        const uint64_t da = make_desc_sw128(a_stage);
-                        const uint64_t db = make_desc_sw128(a_stage + A_STAGE_BYTES);
+        // The whole warp stays converged and waits; one elected lane issues (cute::elect_one_sync pattern).  From a
+        // divergent `if (lane == 0)` region every UTCHMMA / UTCBAR is wrapped in an ELECT + BRA.U.ANY vote loop and the
+        // descriptors are rebuilt with ~20 uniform-datapath instructions per unit -- with owned producer units the
+        // issuing thread's serial instruction stream is what bounds the CTA (profiles/r1_h_issue_bound.md).
+        const uint32_t idesc = make_idesc_tf32(TILE_M, p.cout_pad);
+        const uint64_t desc0 = make_desc_sw128(smem_base);      // stage 0, A operand; the address field counts 16-byte units
+        const uint32_t stage_d = stage_bytes >> 4;
+        int s = 0, it = 0;
+        uint32_t ph = 0;
+        const int n_work = p.n_tiles * p.osplit;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int o_lo = (w % p.osplit) * p.opg, o_hi = min(p.K, o_lo + p.opg);
+            const int b = it & 1;
+            mbar_wait(acce_bar(b), ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(b * p.cout_pad);
+            uint32_t accum = 0;
+            for (int o = o_lo; o < o_hi; ++o) {
+                for (int kb = 0; kb < p.n_kb; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = desc0 + (uint64_t)((uint32_t)s * stage_d);
+                        const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
                         const int kcols = min(KB, p.cin_pad8 - kb * KB);
-                        for (int k = 0; k < kcols / 8; ++k) {
-                            // advance 32 bytes (8 tf32) inside the 128-byte swizzled row: +2 in the >>4 address field
-                            mma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                     ((o - o_lo) | kb | k) != 0 ? 1u : 0u);
-                        }
+#ifndef SCN_EXP_NOMMA
+                        // advance 32 bytes (8 tf32) inside the 128-byte swizzled row: +2 in the >>4 address field
+                        mma_tf32(tmem_d, da, db, idesc, accum);
+                        if (kcols > 8) mma_tf32(tmem_d, da + 2, db + 2, idesc, 1u);
+                        if (kcols > 16) mma_tf32(tmem_d, da + 4, db + 4, idesc, 1u);
+                        if (kcols > 24) mma_tf32(tmem_d, da + 6, db + 6, idesc, 1u);
+#endif
                         mma_commit(empty_bar(s));
-                        if (++s == S) s = 0, ph ^= 1;
                     }
+                    accum = 1u;
+                    if (++s == S) s = 0, ph ^= 1;
                 }
-                mma_commit(accf_bar(b));
             }
-            (void)units_per_tile;
+            if (elect_one()) mma_commit(accf_bar(b));
         }
+        (void)units_per_tile;
     } else if (warp < 4) {
         // ===================== epilogue warps 0..3 =====================
         int it = 0;
