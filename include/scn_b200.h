@@ -128,6 +128,10 @@ int64_t scn_conv_weight_image_bytes(int K, int Cin, int Cout);
  * submanifold convolution).  Values are rounded to TF32 (rna). */
 int scn_conv_pack_weights(const float* w, int K, int Cin, int Cout, int transpose, int reverse,
                           void* image, scn_stream_t stream);
+/* The same for n images in ONE launch (after optimizer.step() every layer needs both orientations re-packed:
+ * ~120 launches per training step otherwise).  table: device array of n rows of 7 int64
+ * {w pointer, image pointer, K, Cin, Cout, transpose, reverse}. */
+int scn_conv_pack_weights_multi(const int64_t* table, int n, scn_stream_t stream);
 /* TF32 tcgen05 implicit gather-GEMM (sm_100a).  Cin/Cout here are the GEMM's K/N widths, i.e.
  * after any transpose; n_in = rows of `in`.  residual (may be NULL) is [n_out, Cout] with leading
  * dimension ld_res.  When `in` and its row stride are 16-byte aligned the rows are gathered by TMA
@@ -156,13 +160,16 @@ int scn_residual_unit_fwd(const float* x, int n, int C, const int32_t* map, int 
                           const float* b1, const float* w2, const float* b2, void* img1, void* img2,
                           int repack, float* r, float* h, float* y, int use_tf32, scn_stream_t stream);
 /* backward of the unit: gx = gy + relu'(x) * conv1^T(relu'(h) * conv2^T(gy)); weight / bias gradients (any of the
- * g* outputs may be NULL).  gyr [n, C] is scratch (TF32-rounded gy), gh [n, C] receives d/dh. */
+ * g* outputs may be NULL).  gyr [n, C] is scratch (TF32-rounded gy), gh [n, C] receives d/dh.  accumulate != 0:
+ * gw* / gb* are ADDED to (the parameters' gradient buffers, training.py:458), otherwise they are overwritten. */
 int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n, int C, const int32_t* map,
                           int K, const float* w1, const float* w2, void* img1t, void* img2t, int repack,
                           float* gyr, float* gh, float* gx, float* gw1, float* gb1, float* gw2, float* gb2,
-                          int use_tf32, scn_stream_t stream);
+                          int accumulate, int use_tf32, scn_stream_t stream);
 /* out[c] = sum_r in[r][c]   (bias gradient) */
 int scn_col_sum(const float* in, int ld, int n, int C, float* out, scn_stream_t stream);
+/* out[c] += sum_r in[r][c]  (bias gradient accumulated straight into the parameter's .grad buffer) */
+int scn_col_sum_add(const float* in, int ld, int n, int C, float* out, scn_stream_t stream);
 
 /* ------------------------------------------------------------------ elementwise ------------
  * scn.ReLU module_factory.py:86-89; AddTable :51-57; BatchNorm(Leaky)ReLU :92-113. */

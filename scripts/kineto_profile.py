@@ -33,3 +33,17 @@ for s, e, n in ks:
     n = n.split("(")[0][:60]; agg[n][0] += 1; agg[n][1] += (e - s)
 for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:16]:
     print("%-62s n/step=%5.1f  %7.3f ms/step  avg %6.1f us" % (n, c / NS, t / NS / 1e3, t / c))
+# idle-gap analysis: where the GPU waits for the host (gap > 5 us), attributed to the kernel that follows the gap
+gaps = collections.defaultdict(lambda: [0, 0.0])
+end = ks[0][1]
+big = []
+for s, e, n in ks[1:]:
+    if s - end > 5:
+        nm = n.split("(")[0][:50]
+        gaps[nm][0] += 1; gaps[nm][1] += s - end
+        big.append((s - end, (s - t0) / 1e3, nm))
+    end = max(end, e)
+print("idle gaps > 5 us by following kernel (per step):")
+for n, (c, t) in sorted(gaps.items(), key=lambda x: -x[1][1])[:14]:
+    print("  %-52s n/step=%5.1f  %7.3f ms/step" % (n, c / NS, t / NS / 1e3))
+print("largest gaps (us @ ms since start): " + ", ".join("%.0f@%.1f %s" % (g, at, n[:24]) for g, at, n in sorted(big, reverse=True)[:15]))

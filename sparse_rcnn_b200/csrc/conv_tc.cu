@@ -477,6 +477,36 @@ __global__ void k_pack_weights(const float* __restrict__ w, int K, int A, int B,
     }
 }
 
+// one launch for many images: blockIdx.y = table row, blockIdx.x strides over the image
+__global__ void k_pack_weights_multi(const int64_t* __restrict__ table) {
+    const int64_t* e = table + (int64_t)blockIdx.y * 7;
+    const float* w = reinterpret_cast<const float*>(e[0]);
+    float* image = reinterpret_cast<float*>(e[1]);
+    const int K = (int)e[2], Cin = (int)e[3], Cout = (int)e[4], transpose = (int)e[5], reverse = (int)e[6];
+    const int A = transpose ? Cout : Cin, B = transpose ? Cin : Cout;
+    const int cout_pad = (Cout + 15) / 16 * 16, n_kb = (Cin + KB - 1) / KB;
+    const int64_t total = (int64_t)K * n_kb * cout_pad * KB;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int k = (int)(i % KB);
+        int n = (int)((i / KB) % cout_pad);
+        int kb = (int)((i / ((int64_t)KB * cout_pad)) % n_kb);
+        int o = (int)(i / ((int64_t)KB * cout_pad * n_kb));
+        int ci = kb * KB + k;
+        float v = 0.f;
+        if (ci < Cin && n < Cout) {
+            int oo = reverse ? K - 1 - o : o;
+            const float* pw = w + (int64_t)oo * A * B;
+            v = transpose ? pw[(int64_t)n * B + ci] : pw[(int64_t)ci * B + n];
+            uint32_t t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+            v = __uint_as_float(t);
+        }
+        int64_t blk = ((int64_t)o * n_kb + kb) * cout_pad * KB;
+        int off = n * KB + ((((k >> 2) ^ (n & 7)) << 2) | (k & 3));
+        image[blk + off] = v;
+    }
+}
+
 }  // namespace scn
 
 using namespace scn;
@@ -539,6 +569,15 @@ int scn_conv_pack_weights(const float* w, int K, int Cin, int Cout, int transpos
     k_pack_weights<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, K, A, B, transpose, reverse, Cin, Cout, pad16(Cout),
                                                                         n_kblocks(Cin), reinterpret_cast<float*>(image));
     return check_launch("pack_weights");
+}
+
+int scn_conv_pack_weights_multi(const int64_t* table, int n, scn_stream_t stream) {
+    SCN_REQUIRE(n >= 0 && (n == 0 || table), "pack_weights_multi: bad table");
+    if (n == 0) return SCN_OK;
+    // 24 blocks x 256 threads per image: the largest image of the shipped networks (27 x 112 x 112) is 1.4 M elements
+    dim3 grid(24, n);
+    k_pack_weights_multi<<<grid, 256, 0, as_stream(stream)>>>(table);
+    return check_launch("pack_weights_multi");
 }
 
 int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32_t* map, int n_out, int K, const void* image,

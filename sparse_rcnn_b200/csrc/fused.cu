@@ -37,17 +37,25 @@ int scn_residual_unit_fwd(const float* x, int n, int C, const int32_t* map, int 
 
 int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n, int C, const int32_t* map, int K,
                           const float* w1, const float* w2, void* img1t, void* img2t, int repack, float* gyr, float* gh,
-                          float* gx, float* gw1, float* gb1, float* gw2, float* gb2, int use_tf32, scn_stream_t stream) {
+                          float* gx, float* gw1, float* gb1, float* gw2, float* gb2, int accumulate, int use_tf32,
+                          scn_stream_t stream) {
     SCN_REQUIRE(n >= 0 && C > 0 && K > 0, "residual_unit_bwd: bad shape");
     cudaStream_t st = as_stream(stream);
     const size_t wbytes = (size_t)K * C * C * sizeof(float);
-    if (gw1) cudaMemsetAsync(gw1, 0, wbytes, st);
-    if (gw2) cudaMemsetAsync(gw2, 0, wbytes, st);
+    // accumulate != 0: gw* / gb* are the parameters' gradient buffers (already zeroed or holding earlier
+    // contributions); the weight-gradient kernel adds atomically anyway, so nothing is cleared and the bias sums add
+    if (!accumulate) {
+        if (gw1) cudaMemsetAsync(gw1, 0, wbytes, st);
+        if (gw2) cudaMemsetAsync(gw2, 0, wbytes, st);
+    }
     if (n == 0) {
-        if (gb1) cudaMemsetAsync(gb1, 0, C * sizeof(float), st);
-        if (gb2) cudaMemsetAsync(gb2, 0, C * sizeof(float), st);
+        if (!accumulate) {
+            if (gb1) cudaMemsetAsync(gb1, 0, C * sizeof(float), st);
+            if (gb2) cudaMemsetAsync(gb2, 0, C * sizeof(float), st);
+        }
         return check_launch("residual_unit_bwd(memset)");
     }
+    auto bias_sum = accumulate ? scn_col_sum_add : scn_col_sum;
     const int64_t total = (int64_t)n * C;
     const float* g_op = gy;      // operand of the transposed convolutions / weight gradients
     if (use_tf32) {
@@ -64,7 +72,7 @@ int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n
         SCN_TRY(scn_conv_fwd_fp32(g_op, C, C, map, n, K, w2, 1, 1, nullptr, nullptr, 0, h, C, gh, C, C, SCN_EPI_MASK, stream));
     }
     if (gw2) SCN_TRY(scn_conv_bwd_weight(h, C, C, map, n, K, g_op, C, C, gw2, use_tf32, stream));
-    if (gb2) SCN_TRY(scn_col_sum(gy, C, n, C, gb2, stream));
+    if (gb2) SCN_TRY(bias_sum(gy, C, n, C, gb2, stream));
     if (gx) {
         // d/dx = gy + relu'(x) * conv1^T(gh)
         if (use_tf32)
@@ -75,7 +83,7 @@ int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n
                                       stream));
     }
     if (gw1) SCN_TRY(scn_conv_bwd_weight(r, C, C, map, n, K, gh, C, C, gw1, use_tf32, stream));
-    if (gb1) SCN_TRY(scn_col_sum(gh, C, n, C, gb1, stream));
+    if (gb1) SCN_TRY(bias_sum(gh, C, n, C, gb1, stream));
     return SCN_OK;
 }
 

@@ -54,7 +54,7 @@ __global__ void k_add(const float* __restrict__ a, const float* __restrict__ b, 
 // partials in slab order.
 template <bool SQ_DIFF>
 __global__ void k_col_reduce(const float* __restrict__ in, int ld, int n, int C, const float* __restrict__ mean, float scale,
-                             float* __restrict__ partial, unsigned int* __restrict__ tickets, float* __restrict__ out) {
+                             float* __restrict__ partial, unsigned int* __restrict__ tickets, float* __restrict__ out, int accumulate) {
     __shared__ float sm[8][33];
     __shared__ bool last;
     const int c = blockIdx.y * 32 + threadIdx.x;
@@ -111,7 +111,7 @@ __global__ void k_col_reduce(const float* __restrict__ in, int ld, int n, int C,
         float t = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
-        out[c] = t * scale;
+        out[c] = accumulate ? out[c] + t * scale : t * scale;
     }
 }
 
@@ -418,15 +418,15 @@ __global__ void __launch_bounds__(256) k_crop_select(const uint64_t* __restrict_
 using namespace scn;
 
 static int col_reduce(const float* in, int ld, int n, int C, const float* mean, float scale, float* out, float* partial,
-                      unsigned int* tickets, int nslab, cudaStream_t st) {
+                      unsigned int* tickets, int nslab, cudaStream_t st, int accumulate = 0) {
     int slabs = cdiv(n, 64);
     if (slabs > nslab) slabs = nslab;
     if (slabs < 1) slabs = 1;
     dim3 grid(slabs, cdiv(C, 32)), block(32, 8);
     if (mean)
-        k_col_reduce<true><<<grid, block, 0, st>>>(in, ld, n, C, mean, scale, partial, tickets, out);
+        k_col_reduce<true><<<grid, block, 0, st>>>(in, ld, n, C, mean, scale, partial, tickets, out, accumulate);
     else
-        k_col_reduce<false><<<grid, block, 0, st>>>(in, ld, n, C, nullptr, scale, partial, tickets, out);
+        k_col_reduce<false><<<grid, block, 0, st>>>(in, ld, n, C, nullptr, scale, partial, tickets, out, accumulate);
     return check_launch("col_reduce");
 }
 
@@ -491,6 +491,14 @@ int scn_col_sum(const float* in, int ld, int n, int C, float* out, scn_stream_t 
     if (rc) return rc;
     SCN_REQUIRE(C <= 2048, "col_sum: C > 2048 not supported");
     return col_reduce(in, ld, n, C, nullptr, 1.f, out, g_scratch, g_tickets, NSLAB, as_stream(stream));
+}
+int scn_col_sum_add(const float* in, int ld, int n, int C, float* out, scn_stream_t stream) {
+    SCN_REQUIRE(C > 0 && n >= 0, "col_sum_add: bad shape");
+    if (n == 0) return SCN_OK;
+    int rc = ensure_scratch((size_t)NSLAB * 2 * C * sizeof(float));
+    if (rc) return rc;
+    SCN_REQUIRE(C <= 2048, "col_sum_add: C > 2048 not supported");
+    return col_reduce(in, ld, n, C, nullptr, 1.f, out, g_scratch, g_tickets, NSLAB, as_stream(stream), 1);
 }
 int scn_bn_stats(const float* in, int n, int C, float* mean, float* var, scn_stream_t stream) {
     SCN_REQUIRE(C > 0 && n > 0, "bn_stats: needs at least one active row");

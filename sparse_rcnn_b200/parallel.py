@@ -40,6 +40,7 @@ class GradientBuckets:
         if cur:
             self.buckets.append(cur)
         self.flats, self._pending, self._handles = [], [], []
+        self._fired = set()
         for bi, bucket in enumerate(self.buckets):
             n = sum(p.numel() for p in bucket)
             flat = torch.zeros(n, dtype=bucket[0].dtype, device=bucket[0].device)
@@ -47,15 +48,21 @@ class GradientBuckets:
             for p in bucket:
                 p.grad = flat[off:off + p.numel()].view_as(p)      # autograd accumulates in place
                 off += p.numel()
-                p.register_post_accumulate_grad_hook(self._make_hook(bi))
+                hook = self._make_hook(bi)
+                p.register_post_accumulate_grad_hook(hook)
+                # the scn autograd Functions accumulate parameter gradients straight into these views and call the hook
+                # themselves (no zero-fill + AccumulateGrad add per parameter); torch.autograd.grad() on such parameters
+                # is not supported while the buckets exist
+                p._scn_grad_hook = hook
             self.flats.append(flat)
             self._pending.append(len(bucket))
         self.enabled = True
 
     def _make_hook(self, bi):
         def hook(param):
-            if not self.enabled:
+            if not self.enabled or id(param) in self._fired:
                 return
+            self._fired.add(id(param))
             self._pending[bi] -= 1
             if self._pending[bi] == 0:
                 self._launch(bi)
@@ -72,6 +79,7 @@ class GradientBuckets:
             f.zero_()
         self._pending = [len(b) for b in self.buckets]
         self._handles = []
+        self._fired = set()
 
     def finish(self):
         """Call after backward, before optimizer.step(): launches buckets whose hooks did not all

@@ -32,12 +32,14 @@ class BackboneTrainer(nn.Module):
         self.buckets.enabled = True
         self.optimizer = torch.optim.Adam(self.parameters(), lr=lr, foreach=True)
         self.distributed = distributed
+        self._weights = [p for p in self.parameters() if p.dim() >= 2]
 
     def step(self, data, labels):
         """data: collate_fn 5-tuple, labels int64 [P] (host or device).  Returns the loss (device scalar)."""
         data = _to_device(data, self.device)
         labels = labels.to(self.device, non_blocking=True)
         self.buckets.zero()
+        scn.functions.pack_all(self._weights)      # one launch: every packed weight image the optimizer made stale
         out = self.backbone(data)
         logits = self.seg(out[5])
         loss = nn.functional.cross_entropy(logits, labels)

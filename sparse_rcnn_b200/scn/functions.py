@@ -34,8 +34,8 @@ def _check(x):
     return x.contiguous()
 
 
-def _image(weight, K, cin, cout, transpose, reverse):
-    """Packed (TF32-rounded, swizzled) weight image; cached on the tensor until it is modified."""
+def _image_entry(weight, K, cin, cout, transpose, reverse):
+    """Persistent packed-image buffer of a weight tensor (one per orientation): [image, packed version, meta]."""
     cache = getattr(weight, "_scn_img", None)
     if cache is None:
         cache = {}
@@ -44,15 +44,65 @@ def _image(weight, K, cin, cout, transpose, reverse):
         except AttributeError:
             pass
     key = (transpose, reverse)
-    ver = (weight._version, weight.data_ptr())
     hit = cache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    nbytes = int(_lib.raw("scn_conv_weight_image_bytes")(K, cin, cout))
-    img = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
-    _lib.call("scn_conv_pack_weights", _ptr(weight), K, cin, cout, transpose, reverse, _ptr(img), _stream())
-    cache[key] = (ver, img)
-    return img
+    if hit is None:
+        nbytes = int(_lib.raw("scn_conv_weight_image_bytes")(K, cin, cout))
+        hit = [torch.empty(nbytes, dtype=torch.uint8, device=weight.device), None, (K, cin, cout)]
+        cache[key] = hit
+    return hit
+
+
+def _image(weight, K, cin, cout, transpose, reverse):
+    """Packed (TF32-rounded, swizzled) weight image; re-packed when the tensor was modified since."""
+    hit = _image_entry(weight, K, cin, cout, transpose, reverse)
+    ver = (weight._version, weight.data_ptr())
+    if hit[1] != ver:
+        _lib.call("scn_conv_pack_weights", _ptr(weight), K, cin, cout, transpose, reverse, _ptr(hit[0]), _stream())
+        hit[1] = ver
+    return hit[0]
+
+
+_pack_tables = {}
+
+
+def pack_all(weights):
+    """Re-pack every stale image of the given weight tensors in ONE launch (call after optimizer.step(): each layer
+    otherwise re-packs both orientations lazily, ~120 launches per training step).  Images that were never used are
+    not created here."""
+    entries, rows = [], []
+    for w in weights:
+        cache = getattr(w, "_scn_img", None)
+        if not cache:
+            continue
+        ver = (w._version, w.data_ptr())
+        for (transpose, reverse), hit in cache.items():
+            if hit[1] != ver:
+                entries.append((hit, ver))
+                K, cin, cout = hit[2]
+                rows.append((w.data_ptr(), hit[0].data_ptr(), K, cin, cout, transpose, reverse))
+    if not rows:
+        return 0
+    key = tuple(r[:2] for r in rows)
+    dev = entries[0][0][0].device
+    table = _pack_tables.get(dev)
+    if table is None or table[0] != key:
+        table = (key, torch.tensor(rows, dtype=torch.int64).to(dev))
+        _pack_tables[dev] = table
+    _lib.call("scn_conv_pack_weights_multi", _ptr(table[1]), len(rows), _stream())
+    for hit, ver in entries:
+        hit[1] = ver
+    return len(rows)
+
+
+def _direct_grad(param):
+    """Gradient buffer to accumulate into directly (parallel.GradientBuckets keeps .grad as zeroed views of flat buckets and
+    registers `_scn_grad_hook`): saves a zero-fill and an AccumulateGrad add per parameter and step.  None -> regular path."""
+    if param is None or getattr(param, "_scn_grad_hook", None) is None:
+        return None
+    g = param.grad
+    if g is None or not g.is_contiguous() or g.dtype != torch.float32:
+        return None
+    return g
 
 
 def conv_gemm(x, weight, K, cin, cout, fmap, n_out, bias=None, transpose=0, reverse=0, residual=None, relu=False,
@@ -116,6 +166,7 @@ class ConvFunction(Function):
         ctx.save_for_backward(x, weight)
         ctx.maps = (fmap, bmap)
         ctx.dims = (K, cin, cout, n_out, x.shape[0], reverse_bwd, bias is not None)
+        ctx.bias_param = bias
         return conv_gemm(x, w, K, cin, cout, fmap, n_out, bias.detach() if bias is not None else None)
 
     @staticmethod
@@ -128,17 +179,30 @@ class ConvFunction(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = conv_gemm(go, w, K, cout, cin, bmap, n_in, None, transpose=1, reverse=reverse_bwd)
+        tf32 = 1 if _state["precision"] == "tf32" else 0
         if ctx.needs_input_grad[1]:
-            gw = torch.zeros_like(w)
+            direct = _direct_grad(w)
+            gw_buf = direct if direct is not None else torch.zeros_like(w)
             if n_out:
                 _lib.call("scn_conv_bwd_weight", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(go),
-                          go.stride(0), cout, _ptr(gw), 1 if _state["precision"] == "tf32" else 0, _stream())
-        if has_bias and ctx.needs_input_grad[2]:
-            gb = torch.empty(cout, dtype=torch.float32, device=go.device)
-            if n_out:
-                _lib.call("scn_col_sum", _ptr(go), go.stride(0), n_out, cout, _ptr(gb), _stream())
+                          go.stride(0), cout, _ptr(gw_buf), tf32, _stream())
+            if direct is not None:
+                w._scn_grad_hook(w)
             else:
-                gb.zero_()
+                gw = gw_buf
+        if has_bias and ctx.needs_input_grad[2]:
+            b = ctx.bias_param
+            direct = _direct_grad(b)
+            if direct is not None:
+                if n_out:
+                    _lib.call("scn_col_sum_add", _ptr(go), go.stride(0), n_out, cout, _ptr(direct), _stream())
+                b._scn_grad_hook(b)
+            else:
+                gb = torch.empty(cout, dtype=torch.float32, device=go.device)
+                if n_out:
+                    _lib.call("scn_col_sum", _ptr(go), go.stride(0), n_out, cout, _ptr(gb), _stream())
+                else:
+                    gb.zero_()
         return gx, gw, gb, None, None, None, None
 
 
@@ -170,20 +234,10 @@ def relu_round(x):
 
 
 def _image_buf(weight, K, cin, cout, key):
-    """Persistent packed-image buffer of a weight tensor (one per orientation) + whether it must be re-packed."""
-    bufs = getattr(weight, "_scn_imgbuf", None)
-    if bufs is None:
-        bufs = {}
-        try:
-            weight._scn_imgbuf = bufs
-        except AttributeError:
-            pass
+    """(packed-image buffer, must it be re-packed) for the fused unit: key 'f' = forward, 'b' = transposed + reversed."""
+    tr = 0 if key == "f" else 1
+    hit = _image_entry(weight, K, cin, cout, tr, tr)
     ver = (weight._version, weight.data_ptr())
-    hit = bufs.get(key)
-    if hit is None:
-        nbytes = int(_lib.raw("scn_conv_weight_image_bytes")(K, cin, cout))
-        hit = [torch.empty(nbytes, dtype=torch.uint8, device=weight.device), None]
-        bufs[key] = hit
     stale = hit[1] != ver
     hit[1] = ver
     return hit[0], stale
@@ -215,6 +269,7 @@ class ResidualUnitFunction(Function):
                   _ptr(i2), int(s1 or s2), _ptr(r), _ptr(h), _ptr(y), int(tf32), _stream())
         ctx.save_for_backward(r, h, w1, w2)
         ctx.cfg = (fmap, n, K, c, b1 is not None, b2 is not None, tf32)
+        ctx.biases = (b1, b2)
         return y
 
     @staticmethod
@@ -228,10 +283,16 @@ class ResidualUnitFunction(Function):
         gyr = new(n, c) if tf32 else None
         gh = new(n, c)
         gx = new(n, c) if need[0] else None
-        gw1 = torch.empty_like(w1) if need[1] else None
-        gb1 = new(c) if (has_b1 and need[2]) else None
-        gw2 = torch.empty_like(w2) if need[3] else None
-        gb2 = new(c) if (has_b2 and need[4]) else None
+        b1, b2 = ctx.biases
+        wanted = [(w1, need[1]), (b1, has_b1 and need[2]), (w2, need[3]), (b2, has_b2 and need[4])]
+        direct = [_direct_grad(p) if want else None for p, want in wanted]
+        # all-or-nothing: the C call either accumulates into every parameter gradient or overwrites fresh buffers
+        accumulate = all(d is not None for d, (p, want) in zip(direct, wanted) if want) and any(want for _, want in wanted)
+        if accumulate:
+            bufs = direct
+        else:
+            bufs = [(torch.empty_like(p) if want else None) for p, want in wanted]
+        gw1, gb1, gw2, gb2 = bufs
         if tf32:
             i1, s1 = _image_buf(w1, K, c, c, "b")
             i2, s2 = _image_buf(w2, K, c, c, "b")
@@ -240,7 +301,12 @@ class ResidualUnitFunction(Function):
             s1 = s2 = False
         _lib.call("scn_residual_unit_bwd", _ptr(gy), _ptr(r), _ptr(h), n, c, _ptr(fmap), K, _ptr(w1), _ptr(w2), _ptr(i1),
                   _ptr(i2), int(s1 or s2), _ptr(gyr), _ptr(gh), _ptr(gx), _ptr(gw1), _ptr(gb1), _ptr(gw2), _ptr(gb2),
-                  int(tf32), _stream())
+                  int(accumulate), int(tf32), _stream())
+        if accumulate:
+            for p, want in wanted:
+                if want:
+                    p._scn_grad_hook(p)
+            gw1 = gb1 = gw2 = gb2 = None
         return gx, gw1, gb1, gw2, gb2, None, None
 
 
