@@ -39,6 +39,8 @@ struct ConvTcParams {
     int ld_out, Cout, epi;
     int cout_pad, n_kb, cin_pad8, stages, tmem_cols, n_tiles;
     int osplit, opg;      // offsets of a tile are split over `osplit` work items of `opg` offsets each (small levels)
+    float* scratch;       // split mode: accumulation buffer [n_out][Cout], all-zero between launches
+    unsigned int* tickets;  // split mode: one self-resetting arrival counter per tile
 };
 
 // one 16-byte chunk of a gathered row, split into VEC-float cp.asyncs
@@ -368,6 +370,33 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             return x;
         };
         const int n_work = p.n_tiles * p.osplit;
+        __shared__ int s_last;
+        // bias / mask / residual / ReLU / rounding of 16 accumulator columns of one row, then the store
+        auto finish_store = [&](float (&v)[16], int row, int c0) {
+            float* orow = p.out + (int64_t)row * p.ld_out + c0;
+            const float* rrow = (epi & SCN_EPI_ADD) ? p.residual + (int64_t)row * p.ld_res + c0 : nullptr;
+            const float* mrow = (epi & SCN_EPI_MASK) ? p.mask + (int64_t)row * p.ld_mask + c0 : nullptr;
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.Cout) v[j] += __ldg(p.bias + c0 + j);
+            }
+            if (vec_ok && c0 + 16 <= p.Cout) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 r4 = rrow ? *reinterpret_cast<const float4*>(rrow + j) : make_float4(0, 0, 0, 0);
+                    float4 m4 = mrow ? *reinterpret_cast<const float4*>(mrow + j) : make_float4(1, 1, 1, 1);
+                    float4 x;
+                    x.x = finish(v[j], m4.x, r4.x), x.y = finish(v[j + 1], m4.y, r4.y);
+                    x.z = finish(v[j + 2], m4.z, r4.z), x.w = finish(v[j + 3], m4.w, r4.w);
+                    *reinterpret_cast<float4*>(orow + j) = x;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.Cout) orow[j] = finish(v[j], mrow ? mrow[j] : 1.f, rrow ? rrow[j] : 0.f);
+            }
+        };
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
             const int tile = w / p.osplit;
             const int b = it & 1;
@@ -375,46 +404,85 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             tc_fence_after();
             const int row = tile * TILE_M + warp * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * p.cout_pad);
-            for (int c0 = 0; c0 < p.cout_pad; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
-                if (p.osplit > 1) {
-                    // split-offset mode: this work item holds a PARTIAL sum; accumulate into the bias-prefilled output
-                    // (the epilogue flags are applied by k_conv_post once all partials have landed)
+            if (p.osplit == 1) {
+                for (int c0 = 0; c0 < p.cout_pad; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
+                    if (row < p.n_out && c0 < p.Cout) finish_store(v, row, c0);
+                }
+                tc_fence_before();
+                mbar_arrive(acce_bar(b));
+            } else {
+                // split-offset mode: this work item holds the PARTIAL sum of its offset group.  Partials are added with
+                // fp32 atomics into a library-owned accumulation buffer that is all-zero between launches; the last group
+                // of the tile to arrive (ticket counter) reads the complete sums, applies the epilogue, writes the output
+                // and zeroes the buffer again: one launch, no prefill / post-pass kernels.
+                float* arow = p.scratch + (int64_t)row * p.Cout;
+                const bool c4 = (p.Cout & 3) == 0;
+                for (int c0 = 0; c0 < p.cout_pad; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);      // warp-collective: every lane, also rows beyond n_out
                     if (row < p.n_out) {
-                        float* orow = p.out + (int64_t)row * p.ld_out + c0;
+                        if (c4) {      // 16-byte vector reductions: a quarter of the atomic operations
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < p.Cout) atomicAdd(orow + j, v[j]);
-                    }
-                } else if (row < p.n_out && c0 < p.Cout) {
-                    float* orow = p.out + (int64_t)row * p.ld_out + c0;
-                    const float* rrow = (epi & SCN_EPI_ADD) ? p.residual + (int64_t)row * p.ld_res + c0 : nullptr;
-                    const float* mrow = (epi & SCN_EPI_MASK) ? p.mask + (int64_t)row * p.ld_mask + c0 : nullptr;
-                    if (p.bias) {
+                            for (int j = 0; j < 16; j += 4)
+                                if (c0 + j < p.Cout)
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(arow + c0 + j),
+                                                 "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                                                 : "memory");
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < p.Cout) v[j] += __ldg(p.bias + c0 + j);
-                    }
-                    if (vec_ok && c0 + 16 <= p.Cout) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 r4 = rrow ? *reinterpret_cast<const float4*>(rrow + j) : make_float4(0, 0, 0, 0);
-                            float4 m4 = mrow ? *reinterpret_cast<const float4*>(mrow + j) : make_float4(1, 1, 1, 1);
-                            float4 x;
-                            x.x = finish(v[j], m4.x, r4.x), x.y = finish(v[j + 1], m4.y, r4.y);
-                            x.z = finish(v[j + 2], m4.z, r4.z), x.w = finish(v[j + 3], m4.w, r4.w);
-                            *reinterpret_cast<float4*>(orow + j) = x;
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < p.Cout) atomicAdd(arow + c0 + j, v[j]);
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < p.Cout) orow[j] = finish(v[j], mrow ? mrow[j] : 1.f, rrow ? rrow[j] : 0.f);
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(acce_bar(b));
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid == 0) {
+                    const unsigned int t = atomicAdd(p.tickets + tile, 1u);
+                    s_last = (t == (unsigned int)p.osplit - 1u);
+                    if (s_last) p.tickets[tile] = 0;      // ready for the next launch on this stream
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (s_last) {
+                    // final pass over the tile as a flat [rows x Cout] array: consecutive threads take consecutive
+                    // elements (coalesced; thread-per-row scalar accesses made this pass 20x slower)
+                    __threadfence();
+                    const int row0 = tile * TILE_M;
+                    const int rows = min(TILE_M, p.n_out - row0);
+                    float* abase = p.scratch + (int64_t)row0 * p.Cout;
+                    auto fin1 = [&](float x, int r, int c) {
+                        if (p.bias) x += __ldg(p.bias + c);
+                        const float m = (epi & SCN_EPI_MASK) ? p.mask[(int64_t)r * p.ld_mask + c] : 1.f;
+                        const float rs = (epi & SCN_EPI_ADD) ? p.residual[(int64_t)r * p.ld_res + c] : 0.f;
+                        return finish(x, m, rs);
+                    };
+                    if (c4 && vec_ok) {
+                        const int q = p.Cout >> 2, total = rows * q;
+                        for (int e = tid; e < total; e += 128) {
+                            const int r = e / q, c = (e - r * q) << 2;
+                            float4* ap = reinterpret_cast<float4*>(abase) + e;
+                            float4 x = __ldcg(ap);
+                            __stcg(ap, make_float4(0.f, 0.f, 0.f, 0.f));
+                            const int gr = row0 + r;
+                            x.x = fin1(x.x, gr, c), x.y = fin1(x.y, gr, c + 1), x.z = fin1(x.z, gr, c + 2), x.w = fin1(x.w, gr, c + 3);
+                            *reinterpret_cast<float4*>(p.out + (int64_t)gr * p.ld_out + c) = x;
+                        }
+                    } else {
+                        const int total = rows * p.Cout;
+                        for (int e = tid; e < total; e += 128) {
+                            const int r = e / p.Cout, c = e - r * p.Cout;
+                            const float x = __ldcg(abase + e);
+                            __stcg(abase + e, 0.f);
+                            p.out[(int64_t)(row0 + r) * p.ld_out + c] = fin1(x, row0 + r, c);
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // s_last is rewritten by the next work item
             }
-            tc_fence_before();
-            mbar_arrive(acce_bar(b));
         }
     }
 
@@ -422,32 +490,6 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
     __syncthreads();
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
-    }
-}
-
-// split-offset mode helpers: out = bias (before the partial sums are accumulated) / the epilogue flags afterwards
-__global__ void k_conv_prefill(float* __restrict__ out, int ld, const float* __restrict__ bias, int n, int C) {
-    int64_t total = (int64_t)n * C;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int r = (int)(i / C), c = (int)(i % C);
-        out[(int64_t)r * ld + c] = bias ? bias[c] : 0.f;
-    }
-}
-__global__ void k_conv_post(float* __restrict__ out, int ld, const float* __restrict__ mask, int ld_mask,
-                            const float* __restrict__ residual, int ld_res, int n, int C, int epi) {
-    int64_t total = (int64_t)n * C;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int r = (int)(i / C), c = (int)(i % C);
-        float x = out[(int64_t)r * ld + c];
-        if ((epi & SCN_EPI_MASK) && !(mask[(int64_t)r * ld_mask + c] > 0.f)) x = 0.f;
-        if (epi & SCN_EPI_ADD) x += residual[(int64_t)r * ld_res + c];
-        if (epi & SCN_EPI_RELU) x = fmaxf(x, 0.f);
-        if (epi & SCN_EPI_ROUND) {
-            uint32_t t;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
-            x = __uint_as_float(t);
-        }
-        out[(int64_t)r * ld + c] = x;
     }
 }
 
@@ -510,6 +552,50 @@ __global__ void k_pack_weights_multi(const int64_t* __restrict__ table) {
 }  // namespace scn
 
 using namespace scn;
+
+// Split-offset mode workspace: accumulation buffer (kept all-zero between launches by the kernel itself) + per-tile
+// ticket counters, owned by the library, grow-only (a
+// reallocation synchronises the device once; the sizes settle after the first training step).  One workspace per
+// process: split-mode convolutions must not run concurrently on two streams.
+namespace scn {
+static float* g_split_scratch = nullptr;
+static size_t g_split_bytes = 0;
+static unsigned int* g_split_tickets = nullptr;
+static int g_split_ntickets = 0;
+int split_workspace(size_t bytes, int n_tiles, float** scratch, unsigned int** tickets) {
+    if (bytes > g_split_bytes) {
+        if (g_split_scratch) {
+            cudaDeviceSynchronize();
+            cudaFree(g_split_scratch);
+        }
+        g_split_scratch = nullptr, g_split_bytes = 0;
+        size_t want = bytes + bytes / 4;
+        if (cudaMalloc(&g_split_scratch, want) != cudaSuccess || cudaMemset(g_split_scratch, 0, want) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("conv_fwd_tf32: split workspace of %zu bytes: allocation failed", want);
+            return SCN_ERR_CUDA;
+        }
+        g_split_bytes = want;
+    }
+    if (n_tiles > g_split_ntickets) {
+        if (g_split_tickets) {
+            cudaDeviceSynchronize();
+            cudaFree(g_split_tickets);
+        }
+        g_split_tickets = nullptr, g_split_ntickets = 0;
+        int want = n_tiles < 1024 ? 1024 : 2 * n_tiles;
+        if (cudaMalloc(&g_split_tickets, want * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemset(g_split_tickets, 0, want * sizeof(unsigned int)) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("conv_fwd_tf32: ticket allocation failed");
+            return SCN_ERR_CUDA;
+        }
+        g_split_ntickets = want;
+    }
+    *scratch = g_split_scratch, *tickets = g_split_tickets;
+    return SCN_OK;
+}
+}  // namespace scn
 
 // cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -665,11 +751,10 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     }
     const int n_work = p.n_tiles * p.osplit;
     int grid = n_work < slots ? n_work : slots;
+    p.scratch = nullptr, p.tickets = nullptr;
     if (p.osplit > 1) {
-        k_conv_prefill<<<grid_for((int64_t)n_out * Cout, 256), 256, 0, as_stream(stream)>>>(out, ld_out, bias, n_out, Cout);
-        int rc = check_launch("conv_prefill");
+        int rc = scn::split_workspace((size_t)n_out * Cout * sizeof(float), p.n_tiles, &p.scratch, &p.tickets);
         if (rc) return rc;
-        p.bias = nullptr;
     }
     cudaError_t e;
     auto launch = [&](auto kern, int threads) {
@@ -686,14 +771,7 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
         scn::set_error("conv_fwd_tf32: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
         return SCN_ERR_CUDA;
     }
-    int rc = check_launch("conv_fwd_tf32");
-    if (rc) return rc;
-    if (p.osplit > 1 && epi_flags) {
-        k_conv_post<<<grid_for((int64_t)n_out * Cout, 256), 256, 0, as_stream(stream)>>>(out, ld_out, mask, ld_mask, residual,
-                                                                                          ld_res, n_out, Cout, epi_flags);
-        rc = check_launch("conv_post");
-    }
-    return rc;
+    return check_launch("conv_fwd_tf32");
 }
 
 }  // extern "C"
