@@ -15,7 +15,6 @@
 
 namespace scn {
 
-constexpr int WG_PRODUCERS = 256;
 constexpr int WG_THREADS = 288;
 
 struct WgradParams {
@@ -73,11 +72,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < AS; ++s) {
-            mbar_init(a_full(s), WG_PRODUCERS);
+            mbar_init(a_full(s), 32);      // the 32 lanes of the owning producer warp
             mbar_init(a_empty(s), 1);
         }
         for (int s = 0; s < GS; ++s) {
-            mbar_init(g_full(s), WG_PRODUCERS);
+            mbar_init(g_full(s), 32);
             mbar_init(g_empty(s), 1);
         }
         mbar_init(done_bar, 1);
@@ -96,54 +95,103 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
 
     if (warp < 8) {
         // ===================== producers =====================
-        const int c = tid & 7, rbase = tid >> 3;        // rows rbase + 32 i
-        const uint32_t dst_in_blk = swz_mn32b(rbase, c);      // (rbase + 32 i) & 3 == rbase & 3
-        auto load_idx = [&](int tile, int o, int (&dst)[4]) {
+        // Owned units, as in conv_tc.cu: the CTA's A units (tile, offset) form a flat stream and warp w < NA fills every
+        // NA-th of them completely (128 rows x all channel blocks, the only arrivals on that stage's barrier); warps 6 and 7
+        // own the grad-out tiles (one per tile, shared by every offset of the group).  The per-unit chain (index read,
+        // barrier probe, ring bookkeeping) is paid once per NA units and NA + NG units are in production concurrently.
+        // Parity safety needs NA <= AS and NG <= GS (see conv_tc.cu).
+        const int NA = AS < 6 ? AS : 6, NG = GS < 2 ? GS : 2;
+        const int c = lane & 7, rsub = lane >> 3;
+        const uint32_t dst_lane = swz_mn32b(rsub, c);      // (32 j + rsub + 4 i) & 3 == rsub
+        if (warp < NA) {
+            const int n_units = (t1 - t0) * nO;
+            const uint32_t row_bytes = (uint32_t)p.ld_in * 4u;
+            const char* in_c = reinterpret_cast<const char*>(p.in + cin0) + c * 16;
+            const bool full_blocks = VEC == 4 && (cin_h & 31) == 0;
+            auto load_idx = [&](int u, int (&dst)[4]) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int r = tile * TILE_M + rbase + 32 * i;
-                int v = -1;
-                if (tile < t1 && r < p.n_out) v = p.map ? __ldg(p.map + (int64_t)o * p.n_out + r) : r;
-                dst[i] = v;
+                for (int j = 0; j < 4; ++j) dst[j] = -1;
+                if (u < n_units) {
+                    const int tl = u / nO, oi = u - tl * nO;
+                    const int r0 = (t0 + tl) * TILE_M + lane;
+                    const int32_t* mp = p.map ? p.map + (int64_t)(o0 + oi) * p.n_out + r0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (r0 + 32 * j < p.n_out) dst[j] = mp ? __ldg(mp + 32 * j) : r0 + 32 * j;
+                }
+            };
+            int idx[4], idx_next[4];
+            int sa = warp;                                   // warp < NA <= AS
+            uint32_t pha = 0;
+            load_idx(warp, idx);
+            for (int u = warp; u < n_units; u += NA) {
+                load_idx(u + NA, idx_next);
+                mbar_wait(a_empty(sa), pha ^ 1);
+                const uint32_t ast = smem_base + (uint32_t)sa * p.a_stage_bytes + dst_lane;
+                for (int kb = 0; kb < nblk_a; ++kb) {
+                    const uint32_t dst0 = ast + (uint32_t)kb * A_STAGE_BYTES;
+                    if (full_blocks) {
+                        // one ISETP + IMAD.WIDE + LDGSTS per 16-byte chunk; inactive rows: ignore-src form (zero fill)
+                        const char* colp = in_c + kb * (KB * 4);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int r = __shfl_sync(0xffffffffu, idx[j], rsub + 4 * i);
+                                const char* src = colp + (uint64_t)(uint32_t)r * row_bytes;
+                                asm volatile(
+                                    "{\n\t"
+                                    ".reg .pred p;\n\t"
+                                    "setp.lt.s32 p, %2, 0;\n\t"
+                                    "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+                                    "}" ::"r"(dst0 + (uint32_t)(32 * j + 4 * i) * 128u),
+                                    "l"(src), "r"(r)
+                                    : "memory");
+                            }
+                        }
+                    } else {
+                        const int col0 = cin0 + kb * KB + c * 4;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int r = __shfl_sync(0xffffffffu, idx[j], rsub + 4 * i);
+                                wg_chunk<VEC>(dst0 + (uint32_t)(32 * j + 4 * i) * 128u, p.in, (int64_t)r * p.ld_in, r >= 0, col0,
+                                              min(p.Cin, cin0 + 128));
+                            }
+                        }
+                    }
+                }
+                cp_async_mbar_arrive_noinc(a_full(sa));      // fires when this thread's copies have landed
+                sa += NA;
+                if (sa >= AS) sa -= AS, pha ^= 1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) idx[j] = idx_next[j];
             }
-        };
-        int idx[4], idx_next[4];
-        load_idx(t0, o0, idx_next);
-        int sa = 0, sg = 0;
-        uint32_t pha = 0, phg = 0;
-        for (int tile = t0; tile < t1; ++tile) {
-            // grad-out tile: staged once per tile, shared by every offset of the group
-            mbar_wait(g_empty(sg), phg ^ 1);
-            {
-                const uint32_t gst = g_base + (uint32_t)sg * p.g_stage_bytes;
+        } else if (warp >= 6 && warp - 6 < NG) {
+            // grad-out tiles: dense rows, staged once per tile
+            const int gw_i = warp - 6;
+            int sg = gw_i;                                   // gw_i < NG <= GS
+            uint32_t phg = 0;
+            const int cmax = min(p.Cout, cout0 + 128);
+            for (int tile = t0 + gw_i; tile < t1; tile += NG) {
+                mbar_wait(g_empty(sg), phg ^ 1);
+                const uint32_t gst = g_base + (uint32_t)sg * p.g_stage_bytes + dst_lane;
                 for (int blk = 0; blk < nblk_g; ++blk) {
                     const int col0 = cout0 + blk * KB + c * 4;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = tile * TILE_M + rbase + 32 * i;
-                        wg_chunk<VEC>(gst + (uint32_t)blk * A_STAGE_BYTES + dst_in_blk + (uint32_t)i * 4096u, p.go,
-                                      (int64_t)r * p.ld_go, r < p.n_out, col0, min(p.Cout, cout0 + 128));
+                    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = tile * TILE_M + 32 * j + rsub + 4 * i;
+                            wg_chunk<VEC>(gst + (uint32_t)blk * A_STAGE_BYTES + (uint32_t)(32 * j + 4 * i) * 128u, p.go,
+                                          (int64_t)r * p.ld_go, r < p.n_out, col0, cmax);
+                        }
                     }
                 }
-                cp_async_mbar_arrive_noinc(g_full(sg));      // fires when this thread's copies have landed
-                if (++sg == GS) sg = 0, phg ^= 1;
-            }
-            for (int oi = 0; oi < nO; ++oi) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) idx[i] = idx_next[i];
-                if (oi + 1 < nO) load_idx(tile, o0 + oi + 1, idx_next);
-                else load_idx(tile + 1, o0, idx_next);
-                mbar_wait(a_empty(sa), pha ^ 1);
-                const uint32_t ast = smem_base + (uint32_t)sa * p.a_stage_bytes;
-                for (int kb = 0; kb < nblk_a; ++kb) {
-                    const int col0 = cin0 + kb * KB + c * 4;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        wg_chunk<VEC>(ast + (uint32_t)kb * A_STAGE_BYTES + dst_in_blk + (uint32_t)i * 4096u, p.in,
-                                      (int64_t)idx[i] * p.ld_in, idx[i] >= 0, col0, min(p.Cin, cin0 + 128));
-                }
-                cp_async_mbar_arrive_noinc(a_full(sa));
-                if (++sa == AS) sa = 0, pha ^= 1;
+                cp_async_mbar_arrive_noinc(g_full(sg));
+                sg += NG;
+                if (sg >= GS) sg -= GS, phg ^= 1;
             }
         }
         cp_async_wait<0>();
@@ -190,6 +238,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
         mbar_wait<500>(done_bar, 0);
         tc_fence_after();
         const int ci = cin0 + warp * 32 + lane;
+        const bool vec_red = (p.Cout & 3) == 0 && (reinterpret_cast<uintptr_t>(p.gw) & 15) == 0;
         for (int oi = 0; oi < nO; ++oi) {
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(oi * npad);
             float* dst = p.gw + ((int64_t)(o0 + oi) * p.Cin + ci) * p.Cout + cout0;
@@ -197,9 +246,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                 float v[16];
                 tmem_ld16(taddr + c0, v);
                 if (ci < p.Cin) {
+                    if (vec_red) {      // 16-byte vector reductions: a quarter of the atomic operations
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < cout_h) atomicAdd(dst + c0 + j, v[j]);
+                        for (int j = 0; j < 16; j += 4)
+                            if (c0 + j < cout_h)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(v[j]),
+                                             "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                                             : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < cout_h) atomicAdd(dst + c0 + j, v[j]);
+                    }
                 }
             }
         }
