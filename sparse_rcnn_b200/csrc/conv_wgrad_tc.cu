@@ -7,6 +7,12 @@
 // row & 3) is the canonical MN-major SW128_32B layout with K = row.  One MMA (K=8) consumes two 4-row
 // swizzle atoms; M = 128 input channels (4 channel blocks 16 KB apart), N = up to 128 output channels.
 //
+// Offset packing: the M = 128 rows of one MMA hold P = 4 / ceil(Cin/32) kernel offsets side by side (4 offsets x 32
+// channels for Cin <= 32, 2 x 64 for Cin <= 64, else 1): the four 16 KB channel groups of an A stage are the gathered
+// tiles of P different offsets, so one 16-MMA sequence produces the weight gradients of P offsets.  An SS-mode MMA reads
+// all 128 M rows (4 KB per K step) from shared memory whether or not they hold channels, and that read is what bounds
+// the kernel (profiles/r1_h_issue_bound.md: 101 -> 46 us at C = 32 with the MMAs compiled out).
+//
 // Work split: grid = (row chunks) x (offset group, 128-wide Cin half, 128-wide Cout half).  A CTA keeps
 // the accumulators of ALL its offsets in TMEM across ALL its tiles and adds them to gw with one
 // round of atomics at the very end.  The grad-out tile is staged once per tile and reused by every
@@ -54,6 +60,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
     const int o0 = og * p.opg, nO = min(p.K, o0 + p.opg) - o0;
     if (nO <= 0) return;
     const int cin0 = mh * 128, cin_h = min(128, p.Cin - cin0), nblk_a = (cin_h + 31) / 32;
+    const int P = nblk_a == 1 ? 4 : (nblk_a == 2 ? 2 : 1);      // offsets packed into one MMA group
+    const int bpo = P == 1 ? nblk_a : 4 / P;                     // 16 KB channel blocks per offset
+    const int n_mg = (nO + P - 1) / P;                           // MMA groups (= pipeline units) per tile
     const int cout0 = nh * 128, cout_h = min(128, p.Cout - cout0), npad = (cout_h + 15) / 16 * 16;
     const int nblk_g = (npad + 31) / 32;
 
@@ -72,7 +81,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < AS; ++s) {
-            mbar_init(a_full(s), 32);      // the 32 lanes of the owning producer warp
+            mbar_init(a_full(s), 64);      // the two owning producer warps
             mbar_init(a_empty(s), 1);
         }
         for (int s = 0; s < GS; ++s) {
@@ -100,64 +109,84 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
         // own the grad-out tiles (one per tile, shared by every offset of the group).  The per-unit chain (index read,
         // barrier probe, ring bookkeeping) is paid once per NA units and NA + NG units are in production concurrently.
         // Parity safety needs NA <= AS and NG <= GS (see conv_tc.cu).
-        const int NA = AS < 6 ? AS : 6, NG = GS < 2 ? GS : 2;
+        // An A stage is 64 KB, so at most three fit: a PAIR of warps owns a unit (64 rows each, both arrive on the stage
+        // barrier) to keep six warps issuing copies -- one warp sustains only ~1 LDGSTS per 60 cycles.
+        const int NA = AS < 3 ? AS : 3, NG = GS < 2 ? GS : 2;
         const int c = lane & 7, rsub = lane >> 3;
         const uint32_t dst_lane = swz_mn32b(rsub, c);      // (32 j + rsub + 4 i) & 3 == rsub
-        if (warp < NA) {
-            const int n_units = (t1 - t0) * nO;
+        if (warp < 2 * NA) {
+            const int own = warp >> 1, half = warp & 1;      // rows 64 * half .. 64 * half + 63 of the unit
+            const int n_units = (t1 - t0) * n_mg;
             const uint32_t row_bytes = (uint32_t)p.ld_in * 4u;
+            const int cin_lim = min(p.Cin, cin0 + 128);
             const char* in_c = reinterpret_cast<const char*>(p.in + cin0) + c * 16;
-            const bool full_blocks = VEC == 4 && (cin_h & 31) == 0;
-            auto load_idx = [&](int u, int (&dst)[4]) {
+            // neighbour indices of the (up to four) offsets of unit u: lane L holds rows 64 half + L and + L + 32
+            auto load_idx = [&](int u, int (&dst)[8]) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = -1;
+                for (int q = 0; q < 8; ++q) dst[q] = -1;
                 if (u < n_units) {
-                    const int tl = u / nO, oi = u - tl * nO;
-                    const int r0 = (t0 + tl) * TILE_M + lane;
-                    const int32_t* mp = p.map ? p.map + (int64_t)(o0 + oi) * p.n_out + r0 : nullptr;
+                    const int tl = u / n_mg, mg = u - tl * n_mg;
+                    const int r0 = (t0 + tl) * TILE_M + 64 * half + lane;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (r0 + 32 * j < p.n_out) dst[j] = mp ? __ldg(mp + 32 * j) : r0 + 32 * j;
+                    for (int pp = 0; pp < 4; ++pp) {
+                        const int o = o0 + mg * P + pp;
+                        if (pp < P && o < o0 + nO) {
+                            const int32_t* mp = p.map ? p.map + (int64_t)o * p.n_out + r0 : nullptr;
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                                if (r0 + 32 * j < p.n_out) dst[pp * 2 + j] = mp ? __ldg(mp + 32 * j) : r0 + 32 * j;
+                        }
+                    }
                 }
             };
-            int idx[4], idx_next[4];
-            int sa = warp;                                   // warp < NA <= AS
+            int idx[8], idx_next[8];
+            int sa = own;                                    // own < NA <= AS
             uint32_t pha = 0;
-            load_idx(warp, idx);
-            for (int u = warp; u < n_units; u += NA) {
+            load_idx(own, idx);
+            for (int u = own; u < n_units; u += NA) {
                 load_idx(u + NA, idx_next);
+                const int mg = u % n_mg;
                 mbar_wait(a_empty(sa), pha ^ 1);
-                const uint32_t ast = smem_base + (uint32_t)sa * p.a_stage_bytes + dst_lane;
-                for (int kb = 0; kb < nblk_a; ++kb) {
-                    const uint32_t dst0 = ast + (uint32_t)kb * A_STAGE_BYTES;
-                    if (full_blocks) {
-                        // one ISETP + IMAD.WIDE + LDGSTS per 16-byte chunk; inactive rows: ignore-src form (zero fill)
-                        const char* colp = in_c + kb * (KB * 4);
+                const uint32_t ast = smem_base + (uint32_t)sa * p.a_stage_bytes + dst_lane + (uint32_t)(64 * half) * 128u;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                for (int pp = 0; pp < 4; ++pp) {
+                    if (pp >= P || mg * P + pp >= nO) continue;      // unused offset slot: its accumulator rows are never read
+                    for (int kb = 0; kb < bpo; ++kb) {
+                        const int cb = cin0 + kb * KB;               // first channel of this block
+                        if (cb >= cin_lim) continue;
+                        const uint32_t dst0 = ast + (uint32_t)(pp * bpo + kb) * A_STAGE_BYTES;
+                        if (VEC == 4 && cin_lim - cb >= KB) {
+                            // one ISETP + IMAD.WIDE + LDGSTS per 16-byte chunk; inactive rows: ignore-src form (zero fill)
+                            const char* colp = in_c + kb * (KB * 4);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int r = __shfl_sync(0xffffffffu, idx[j], rsub + 4 * i);
-                                const char* src = colp + (uint64_t)(uint32_t)r * row_bytes;
-                                asm volatile(
-                                    "{\n\t"
-                                    ".reg .pred p;\n\t"
-                                    "setp.lt.s32 p, %2, 0;\n\t"
-                                    "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
-                                    "}" ::"r"(dst0 + (uint32_t)(32 * j + 4 * i) * 128u),
-                                    "l"(src), "r"(r)
-                                    : "memory");
+                            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+#ifdef SCN_EXP_NOCOPY
+                                    if (p.n_out > 0) break;      // timing experiment: no gather copies
+#endif
+                                    const int r = __shfl_sync(0xffffffffu, idx[pp * 2 + j], rsub + 4 * i);
+                                    const char* src = colp + (uint64_t)(uint32_t)r * row_bytes;
+                                    asm volatile(
+                                        "{\n\t"
+                                        ".reg .pred p;\n\t"
+                                        "setp.lt.s32 p, %2, 0;\n\t"
+                                        "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+                                        "}" ::"r"(dst0 + (uint32_t)(32 * j + 4 * i) * 128u),
+                                        "l"(src), "r"(r)
+                                        : "memory");
+                                }
                             }
-                        }
-                    } else {
-                        const int col0 = cin0 + kb * KB + c * 4;
+                        } else {
+                            const int col0 = cb + c * 4;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                            for (int j = 0; j < 2; ++j) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int r = __shfl_sync(0xffffffffu, idx[j], rsub + 4 * i);
-                                wg_chunk<VEC>(dst0 + (uint32_t)(32 * j + 4 * i) * 128u, p.in, (int64_t)r * p.ld_in, r >= 0, col0,
-                                              min(p.Cin, cin0 + 128));
+                                for (int i = 0; i < 8; ++i) {
+                                    const int r = __shfl_sync(0xffffffffu, idx[pp * 2 + j], rsub + 4 * i);
+                                    wg_chunk<VEC>(dst0 + (uint32_t)(32 * j + 4 * i) * 128u, p.in, (int64_t)r * p.ld_in, r >= 0,
+                                                  col0, cin_lim);
+                                }
                             }
                         }
                     }
@@ -166,7 +195,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                 sa += NA;
                 if (sa >= AS) sa -= AS, pha ^= 1;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) idx[j] = idx_next[j];
+                for (int q = 0; q < 8; ++q) idx[q] = idx_next[q];
             }
         } else if (warp >= 6 && warp - 6 < NG) {
             // grad-out tiles: dense rows, staged once per tile
@@ -209,16 +238,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
         for (int tile = t0; tile < t1; ++tile) {
             mbar_wait(g_full(sg), phg);
             const uint64_t db0 = make_desc_mn_sw128_32b(g_base + (uint32_t)sg * g_bytes, A_STAGE_BYTES, 512);
-            for (int oi = 0; oi < nO; ++oi) {
+            for (int mg = 0; mg < n_mg; ++mg) {
                 mbar_wait(a_full(sa), pha);
                 tc_fence_after();
                 const uint64_t da0 = make_desc_mn_sw128_32b(smem_base + (uint32_t)sa * a_bytes, A_STAGE_BYTES, 512);
-                const uint32_t tmem_d = tmem_base + (uint32_t)(oi * npad);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(mg * npad);
                 const uint32_t acc0 = tile != t0 ? 1u : 0u;
                 if (elect_one()) {
+#ifndef SCN_EXP_NOMMA
                     mma_tf32(tmem_d, da0, db0, idesc, acc0);
+#endif
 #pragma unroll
-                    for (int j = 1; j < TILE_M / 8; ++j)      // one 8-row K step = 1024 bytes = +64 in the >>4 address field
+                    for (int j = 1; j < (
+#ifdef SCN_EXP_NOMMA
+                                            0 *
+#endif
+                                            TILE_M / 8);
+                         ++j)      // one 8-row K step = 1024 bytes = +64 in the >>4 address field
                         mma_tf32(tmem_d, da0 + (uint64_t)(64 * j), db0 + (uint64_t)(64 * j), idesc, 1u);
                     mma_commit(a_empty(sa));
                 }
@@ -237,15 +273,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
         // ===================== epilogue: TMEM -> atomics into gw =====================
         mbar_wait<500>(done_bar, 0);
         tc_fence_after();
-        const int ci = cin0 + warp * 32 + lane;
+        // accumulator row m = warp * 32 + lane  ->  (packed offset slot pp, channel ci)
+        const int pp = warp / bpo;                               // 32 rows per warp = one 16 KB channel block
+        const int ci = cin0 + (warp % bpo) * 32 + lane;
         const bool vec_red = (p.Cout & 3) == 0 && (reinterpret_cast<uintptr_t>(p.gw) & 15) == 0;
-        for (int oi = 0; oi < nO; ++oi) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(oi * npad);
-            float* dst = p.gw + ((int64_t)(o0 + oi) * p.Cin + ci) * p.Cout + cout0;
+        for (int mg = 0; mg < n_mg; ++mg) {
+            const int o = o0 + mg * P + pp;
+            const bool live = pp < P && o < o0 + nO && ci < min(p.Cin, cin0 + 128);
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mg * npad);
+            float* dst = p.gw + ((int64_t)o * p.Cin + ci) * p.Cout + cout0;
             for (int c0 = 0; c0 < npad; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
-                if (ci < p.Cin) {
+                if (live) {
                     if (vec_red) {      // 16-byte vector reductions: a quarter of the atomic operations
 #pragma unroll
                         for (int j = 0; j < 16; j += 4)
@@ -297,42 +337,48 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
     const int n_nhalves = cdiv(Cout, 128);
     p.a_stage_bytes = cdiv(cin_h, 32) * A_STAGE_BYTES;
     p.g_stage_bytes = cdiv(npad, 32) * A_STAGE_BYTES;
-    // offsets per group: accumulators of one group must fit 256 TMEM columns (two CTAs per SM) when
-    // the tiles are narrow, 512 otherwise
-    int budget_cols = (p.a_stage_bytes + p.g_stage_bytes <= 32 * 1024) ? 256 : 512;
-    p.opg = budget_cols / npad;
+    // offset packing: P offsets share one MMA group (see the header); a CTA keeps ceil(opg / P) groups of npad TMEM
+    // columns each, at most 512 columns
+    const int nblk_a = cdiv(cin_h, 32);
+    const int P = nblk_a == 1 ? 4 : (nblk_a == 2 ? 2 : 1);
+    int max_mg = 512 / npad;
+    if (max_mg < 1) max_mg = 1;
+    p.opg = max_mg * P;
     if (p.opg > K) p.opg = K;
-    if (p.opg < 1) p.opg = 1;
     p.n_ogroups = cdiv(K, p.opg);
-    p.opg = cdiv(K, p.n_ogroups);          // balance the groups
+    p.opg = cdiv(cdiv(K, p.n_ogroups), P) * P;          // balance the groups, keep them multiples of P
+    p.n_ogroups = cdiv(K, p.opg);
     int tc = 32;
-    while (tc < p.opg * npad) tc <<= 1;
+    while (tc < cdiv(p.opg, P) * npad) tc <<= 1;
     p.tmem_cols = tc;
-    // shared memory: 2 grad-out stages if they fit, then as many A stages (<= 6) as fit.  M = 128 always
-    // reads a 64 KB window (4 channel blocks) from an A stage base, so the allocation must reach
-    // (a_stages - 1) * a_stage_bytes + 64 KB even when the stage itself is narrower.
-    int smem = 0;
-    p.a_stages = 0;
-    const int budgets[2] = {tc <= 256 ? 108 * 1024 : 0, 224 * 1024};      // two CTAs per SM first, else one
-    for (int b = 0; b < 2 && p.a_stages < 2; ++b)
-        for (int gs = 2; gs >= 1 && p.a_stages < 2; --gs)
-            for (int as = 6; as >= 2; --as) {
-                int total = as * p.a_stage_bytes + gs * p.g_stage_bytes;
-                int window_end = (as - 1) * p.a_stage_bytes + 4 * A_STAGE_BYTES;
-                if (total < window_end) total = window_end;
-                if (total <= budgets[b]) {
-                    p.a_stages = as, p.g_stages = gs, smem = total;
-                    break;
-                }
-            }
+    // shared memory, one CTA per SM: an A stage is always the full 64 KB window an M = 128 MMA reads (four 16 KB channel
+    // blocks = P offsets x Cin/P channels); one or two grad-out stages; as many A stages as fit (one owner warp each)
+    p.a_stage_bytes = 4 * A_STAGE_BYTES;
+    p.g_stages = (2 * p.a_stage_bytes + 2 * p.g_stage_bytes <= 222 * 1024) ? 2 : 1;
+    p.a_stages = (222 * 1024 - p.g_stages * p.g_stage_bytes) / p.a_stage_bytes;
+    if (p.a_stages > 6) p.a_stages = 6;
     SCN_REQUIRE(p.a_stages >= 2, "conv_bwd_weight: tile does not fit in shared memory (Cin=%d Cout=%d)", Cin, Cout);
+    int smem = p.a_stages * p.a_stage_bytes + p.g_stages * p.g_stage_bytes;
+    const int ctas_per_sm = 1;
     smem += 1024 + 256;
-    const int groups_y = p.n_ogroups * p.n_mhalves * n_nhalves;
-    const int ctas_per_sm = (tc <= 256 && smem <= 112 * 1024) ? 2 : 1;
-    int n_chunks = (sm_count() * ctas_per_sm + groups_y - 1) / groups_y;
-    // every CTA ends with opg x Cin x Cout atomics into gw: keep at least 4 tiles per chunk so that the final
-    // reduction does not dominate small levels (profiles/r1_e_launches_fused.md)
+    // every CTA ends with opg x Cin x Cout reductions into gw: keep at least 4 tiles per chunk so that this does not
+    // dominate small levels, and when that leaves fewer chunks than SMs split the offsets over more groups instead
     const int max_chunks = p.n_tiles >= 8 ? p.n_tiles / 4 : (p.n_tiles >= 2 ? 2 : 1);
+    {
+        const int halves = p.n_mhalves * n_nhalves;
+        int want = cdiv(sm_count(), max_chunks * halves);
+        const int most = cdiv(K, P);
+        if (want > most) want = most;
+        if (want > p.n_ogroups) {
+            p.opg = cdiv(cdiv(K, want), P) * P;
+            p.n_ogroups = cdiv(K, p.opg);
+            tc = 32;
+            while (tc < cdiv(p.opg, P) * npad) tc <<= 1;
+            p.tmem_cols = tc;
+        }
+    }
+    const int groups_y = p.n_ogroups * p.n_mhalves * n_nhalves;
+    int n_chunks = (sm_count() * ctas_per_sm + groups_y - 1) / groups_y;
     if (n_chunks > max_chunks) n_chunks = max_chunks;
     if (n_chunks < 1) n_chunks = 1;
     p.tiles_per_chunk = cdiv(p.n_tiles, n_chunks);
