@@ -22,6 +22,24 @@
 
 namespace scn {
 
+#ifdef SCN_EXP_TRACE
+// timing experiment: globaltimer stamps of CTA 0 at fixed points (slot -> ns), read back with scn_debug_read_trace
+__device__ unsigned long long g_trace[32];
+__device__ unsigned long long g_cta_times[2 * 512];      // entry / exit stamp of every CTA (first 512)
+#define SCN_TRACE(slot)                                                   \
+    do {                                                                  \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                 \
+            unsigned long long t__;                                       \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));       \
+            g_trace[slot] = t__;                                          \
+        }                                                                 \
+    } while (0)
+#else
+#define SCN_TRACE(slot) \
+    do {                \
+    } while (0)
+#endif
+
 constexpr int CONV_THREADS = 288;
 
 struct ConvTcParams {
@@ -81,6 +99,14 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int units_per_tile = p.K * p.n_kb;
+    if (tid == 0) SCN_TRACE(0);
+#ifdef SCN_EXP_TRACE
+    if (tid == 0 && blockIdx.x < 512) {
+        unsigned long long t__;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
+        g_cta_times[2 * blockIdx.x] = t__;
+    }
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -103,6 +129,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (tid == 0) SCN_TRACE(1);
 
     if (TMA && warp == 4) {
         // ===================== TMA gather producer (one warp) =====================
@@ -221,6 +248,8 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
         uint32_t ph = 0;
         int idx[4], idx_next[4];
         load_idx(cur, idx);
+        if (pw == 0 && idx[0] == -12345) SCN_TRACE(31);
+        if (pw == 0) SCN_TRACE(2);
         while (pw < G && cur.w < n_work) {
             load_idx(nxt, idx_next);
             mbar_wait(empty_bar(s), ph ^ 1);
@@ -297,6 +326,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             }
             // the stage's full barrier receives this thread's arrival when its copies have landed
             cp_async_mbar_arrive_noinc(fb);
+            if (pw == 0) SCN_TRACE(3);
             s += G;
             if (s >= S) s -= S, ph ^= 1;
             cur = nxt;
@@ -328,6 +358,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                 for (int kb = 0; kb < p.n_kb; ++kb) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
+                    if (accum == 0) SCN_TRACE(4);
                     if (elect_one()) {
                         const uint64_t da = desc0 + (uint64_t)((uint32_t)s * stage_d);
                         const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
@@ -346,6 +377,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                 }
             }
             if (elect_one()) mma_commit(accf_bar(b));
+            SCN_TRACE(5);
         }
         (void)units_per_tile;
     } else if (warp < 4) {
@@ -402,6 +434,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             const int b = it & 1;
             mbar_wait<200>(accf_bar(b), (it >> 1) & 1);      // epilogue warps wait a whole tile: long back-off
             tc_fence_after();
+            if (warp == 0) SCN_TRACE(6);
             const int row = tile * TILE_M + warp * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * p.cout_pad);
             if (p.osplit == 1) {
@@ -447,6 +480,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                     if (s_last) p.tickets[tile] = 0;      // ready for the next launch on this stream
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 0) SCN_TRACE(9);
                 if (s_last) {
                     // final pass over the tile as a flat [rows x Cout] array: consecutive threads take consecutive
                     // elements (coalesced; thread-per-row scalar accesses made this pass 20x slower)
@@ -461,15 +495,28 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                         return finish(x, m, rs);
                     };
                     if (c4 && vec_ok) {
+                        // four 16-byte loads in flight per thread: the pass is a chain of L2 round trips otherwise
                         const int q = p.Cout >> 2, total = rows * q;
-                        for (int e = tid; e < total; e += 128) {
-                            const int r = e / q, c = (e - r * q) << 2;
-                            float4* ap = reinterpret_cast<float4*>(abase) + e;
-                            float4 x = __ldcg(ap);
-                            __stcg(ap, make_float4(0.f, 0.f, 0.f, 0.f));
-                            const int gr = row0 + r;
-                            x.x = fin1(x.x, gr, c), x.y = fin1(x.y, gr, c + 1), x.z = fin1(x.z, gr, c + 2), x.w = fin1(x.w, gr, c + 3);
-                            *reinterpret_cast<float4*>(p.out + (int64_t)gr * p.ld_out + c) = x;
+                        float4* ap = reinterpret_cast<float4*>(abase);
+                        for (int e0 = tid; e0 < total; e0 += 4 * 128) {
+                            float4 x[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (e0 + 128 * u < total) x[u] = __ldcg(ap + e0 + 128 * u);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (e0 + 128 * u < total) __stcg(ap + e0 + 128 * u, make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int e = e0 + 128 * u;
+                                if (e < total) {
+                                    const int r = e / q, c = (e - r * q) << 2, gr = row0 + r;
+                                    float4 y;
+                                    y.x = fin1(x[u].x, gr, c), y.y = fin1(x[u].y, gr, c + 1);
+                                    y.z = fin1(x[u].z, gr, c + 2), y.w = fin1(x[u].w, gr, c + 3);
+                                    *reinterpret_cast<float4*>(p.out + (int64_t)gr * p.ld_out + c) = y;
+                                }
+                            }
                         }
                     } else {
                         const int total = rows * p.Cout;
@@ -481,6 +528,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                         }
                     }
                 }
+                if (warp == 0) SCN_TRACE(10);
                 asm volatile("bar.sync 1, 128;" ::: "memory");      // s_last is rewritten by the next work item
             }
         }
@@ -488,6 +536,14 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
 
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) SCN_TRACE(11);
+#ifdef SCN_EXP_TRACE
+    if (tid == 0 && blockIdx.x < 512) {
+        unsigned long long t__;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
+        g_cta_times[2 * blockIdx.x + 1] = t__;
+    }
+#endif
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
@@ -657,6 +713,16 @@ int scn_conv_pack_weights(const float* w, int K, int Cin, int Cout, int transpos
     return check_launch("pack_weights");
 }
 
+#ifdef SCN_EXP_TRACE
+int scn_debug_read_trace(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, scn::g_trace, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : 1;
+}
+int scn_debug_read_cta_times(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, scn::g_cta_times, sizeof(unsigned long long) * 1024) == cudaSuccess ? 0 : 1;
+}
+#endif
 int scn_conv_pack_weights_multi(const int64_t* table, int n, scn_stream_t stream) {
     SCN_REQUIRE(n >= 0 && (n == 0 || table), "pack_weights_multi: bad table");
     if (n == 0) return SCN_OK;
