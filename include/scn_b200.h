@@ -215,6 +215,17 @@ int scn_sparse_to_dense_fwd(const float* in, int C, const uint64_t* tab_keys,
 int scn_sparse_to_dense_bwd(const float* grad_dense, const uint64_t* row_keys, int N, int C,
                             int X, int Y, int Z, float* grad_in, scn_stream_t stream);
 
+/* ------------------------------------------------------------------ point-wise loss ---------
+ * nn.CrossEntropyLoss(weight, ignore_index, reduction='mean') on the segmentation logits, ndsis/modules/loss.py:95-97:
+ * loss = sum_i w[y_i] * (lse_i - x_i[y_i]) / sum_i w[y_i] over rows with y_i != ignore_index.  fwd writes the per-row
+ * log-sum-exp (kept for the backward) and stats = {sum of weighted losses, sum of weights} (deterministic reduction);
+ * bwd writes dlogits = (*grad_loss) * w[y] / stats[1] * (softmax - onehot), zero for ignored rows.  weight may be NULL. */
+int scn_cross_entropy_fwd(const float* logits, int ld, int64_t n, int C, const int64_t* labels, const float* weight,
+                          int64_t ignore_index, float* lse, float* row_scratch, float* stats, scn_stream_t stream);
+int scn_cross_entropy_bwd(const float* logits, int ld, int64_t n, int C, const int64_t* labels, const float* weight,
+                          int64_t ignore_index, const float* lse, const float* stats, const float* grad_loss,
+                          float* dlogits, scn_stream_t stream);
+
 /* ------------------------------------------------------------------ pooling ----------------
  * MaxPooling / AveragePooling module_factory.py:315-354 (cmap from scn_strided_maps);
  * SparseGlobalPool custom_operations.py:42-59 (segment mean over batch-sorted rows). */

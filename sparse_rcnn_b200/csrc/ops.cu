@@ -417,6 +417,46 @@ __global__ void __launch_bounds__(256) k_crop_select(const uint64_t* __restrict_
 
 using namespace scn;
 
+// ---------------------------------------------------------------- point-wise cross entropy
+// one thread per row (C is the number of classes, ~20): max, log-sum-exp, weighted negative log-likelihood
+__global__ void k_ce_rows(const float* __restrict__ x, int ld, int64_t n, int C, const int64_t* __restrict__ y,
+                          const float* __restrict__ w, int64_t ignore, float* __restrict__ lse, float* __restrict__ rows) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float* xi = x + i * ld;
+        float m = -INFINITY;
+        for (int c = 0; c < C; ++c) m = fmaxf(m, xi[c]);
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += __expf(xi[c] - m);
+        const float l = m + __logf(sum);
+        lse[i] = l;
+        const int64_t yi = y[i];
+        float wi = 0.f, li = 0.f;
+        if (yi != ignore && yi >= 0 && yi < C) {
+            wi = w ? w[yi] : 1.f;
+            li = wi * (l - xi[yi]);
+        }
+        rows[2 * i] = li;
+        rows[2 * i + 1] = wi;
+    }
+}
+__global__ void k_ce_bwd(const float* __restrict__ x, int ld, int64_t n, int C, const int64_t* __restrict__ y,
+                         const float* __restrict__ w, int64_t ignore, const float* __restrict__ lse,
+                         const float* __restrict__ stats, const float* __restrict__ g, float* __restrict__ dx) {
+    const float scale = g[0] / stats[1];
+    const int64_t total = n * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / C;
+        const int c = (int)(e - i * C);
+        const int64_t yi = y[i];
+        float v = 0.f;
+        if (yi != ignore && yi >= 0 && yi < C) {
+            const float wi = w ? w[yi] : 1.f;
+            v = scale * wi * (__expf(x[i * ld + c] - lse[i]) - (c == yi ? 1.f : 0.f));
+        }
+        dx[e] = v;
+    }
+}
+
 static int col_reduce(const float* in, int ld, int n, int C, const float* mean, float scale, float* out, float* partial,
                       unsigned int* tickets, int nslab, cudaStream_t st, int accumulate = 0) {
     int slabs = cdiv(n, 64);
@@ -594,6 +634,25 @@ int scn_pool_bwd(const float* in, const float* out, const float* go, int C, cons
     k_pool_bwd<<<grid_for((int64_t)n_in * C, TB), TB, 0, as_stream(stream)>>>(in, out, go, C, parent_row, n_in, is_max,
                                                                               inv_volume, gi);
     return check_launch("pool_bwd");
+}
+int scn_cross_entropy_fwd(const float* logits, int ld, int64_t n, int C, const int64_t* labels, const float* weight,
+                          int64_t ignore_index, float* lse, float* row_scratch, float* stats, scn_stream_t stream) {
+    SCN_REQUIRE(n > 0 && C > 0 && ld >= C, "cross_entropy_fwd: bad shape");
+    SCN_REQUIRE(n < (int64_t)1 << 31, "cross_entropy_fwd: too many rows");
+    k_ce_rows<<<grid_for(n, TB), TB, 0, as_stream(stream)>>>(logits, ld, n, C, labels, weight, ignore_index, lse, row_scratch);
+    int rc = check_launch("cross_entropy_rows");
+    if (rc) return rc;
+    rc = ensure_scratch((size_t)NSLAB * 2 * 2 * sizeof(float));
+    if (rc) return rc;
+    return col_reduce(row_scratch, 2, (int)n, 2, nullptr, 1.f, stats, g_scratch, g_tickets, NSLAB, as_stream(stream));
+}
+int scn_cross_entropy_bwd(const float* logits, int ld, int64_t n, int C, const int64_t* labels, const float* weight,
+                          int64_t ignore_index, const float* lse, const float* stats, const float* grad_loss, float* dlogits,
+                          scn_stream_t stream) {
+    SCN_REQUIRE(n > 0 && C > 0 && ld >= C, "cross_entropy_bwd: bad shape");
+    k_ce_bwd<<<grid_for(n * C, TB), TB, 0, as_stream(stream)>>>(logits, ld, n, C, labels, weight, ignore_index, lse, stats,
+                                                               grad_loss, dlogits);
+    return check_launch("cross_entropy_bwd");
 }
 int scn_segment_mean_fwd(const float* in, int C, const int32_t* seg_ptr, int n_seg, float* out, scn_stream_t stream) {
     if (n_seg <= 0) return SCN_OK;

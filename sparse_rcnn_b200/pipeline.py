@@ -42,7 +42,7 @@ class BackboneTrainer(nn.Module):
         scn.functions.pack_all(self._weights)      # one launch: every packed weight image the optimizer made stale
         out = self.backbone(data)
         logits = self.seg(out[5])
-        loss = nn.functional.cross_entropy(logits, labels)
+        loss = scn.functions.cross_entropy(logits, labels)      # nn.CrossEntropyLoss semantics (loss.py:95-97)
         loss.backward()
         self.buckets.finish()
         self.optimizer.step()

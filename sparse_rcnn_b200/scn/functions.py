@@ -498,3 +498,42 @@ class BatchNormFunction(Function):
                   _ptr(weight.detach()) if affine else 0, eps, leak, int(training), _ptr(dx), _ptr(dg), _ptr(db),
                   _ptr(tmp), _stream())
         return dx, dg, db, None, None, None, None, None, None
+
+
+class CrossEntropyFunction(Function):
+    """nn.CrossEntropyLoss(weight, ignore_index, reduction='mean') of the segmentation head (ndsis/modules/loss.py:95-97)
+    as two passes over the logits (torch's log_softmax + nll_loss pair costs 0.7 ms per step on 273k points)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weight, ignore_index):
+        logits = _check(logits)
+        n, c = logits.shape
+        if labels.dtype != torch.int64 or labels.shape != (n,) or not labels.is_cuda:
+            raise RuntimeError("cross entropy expects int64 CUDA labels of shape [%d]" % n)
+        if n == 0:
+            raise RuntimeError("cross entropy needs at least one row")
+        dev = logits.device
+        lse = torch.empty(n, dtype=torch.float32, device=dev)
+        rows = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        stats = torch.empty(2, dtype=torch.float32, device=dev)
+        w = weight.contiguous() if weight is not None else None
+        _lib.call("scn_cross_entropy_fwd", _ptr(logits), logits.stride(0), n, c, _ptr(labels), _ptr(w), int(ignore_index),
+                  _ptr(lse), _ptr(rows), _ptr(stats), _stream())
+        ctx.save_for_backward(logits, labels, lse, stats)
+        ctx.cfg = (w, int(ignore_index))
+        return stats[0] / stats[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, lse, stats = ctx.saved_tensors
+        w, ignore_index = ctx.cfg
+        n, c = logits.shape
+        g = g.contiguous().float()
+        dx = torch.empty((n, c), dtype=torch.float32, device=logits.device)
+        _lib.call("scn_cross_entropy_bwd", _ptr(logits), logits.stride(0), n, c, _ptr(labels), _ptr(w), ignore_index,
+                  _ptr(lse), _ptr(stats), _ptr(g), _ptr(dx), _stream())
+        return dx, None, None, None
+
+
+def cross_entropy(logits, labels, weight=None, ignore_index=-100):
+    return CrossEntropyFunction.apply(logits, labels, weight, ignore_index)

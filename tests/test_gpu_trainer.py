@@ -75,3 +75,23 @@ def test_direct_gradients_equal_autograd_accumulation(cuda, precision):
         assert all(torch.isfinite(g).all() for g in grads[0])
     finally:
         scn.set_precision("tf32")
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_cross_entropy_matches_torch(cuda, weighted):
+    """fp32 op: tolerance 1e-5 relative against nn.functional.cross_entropy (ndsis/modules/loss.py:95-97 semantics)."""
+    from sparse_rcnn_b200.scn import functions as Fn
+    torch.manual_seed(1)
+    n, c = 10007, 20
+    x = (torch.randn(n, c, device=cuda) * 3).requires_grad_()
+    y = torch.randint(0, c, (n,), device=cuda)
+    y[::17] = -100                                                  # ignored rows
+    w = (torch.rand(c, device=cuda) + 0.5) if weighted else None
+    ref = torch.nn.functional.cross_entropy(x, y, weight=w, ignore_index=-100)
+    gref, = torch.autograd.grad(ref * 1.7, x)
+    x2 = x.detach().clone().requires_grad_()
+    out = Fn.cross_entropy(x2, y, w, -100)
+    (out * 1.7).backward()
+    assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert rel_err(x2.grad, gref) < 1e-5
+    assert float(x2.grad[::17].abs().max()) == 0.0
