@@ -147,10 +147,12 @@ int scn_conv_fwd_fp32(const float* in, int ld_in, int Cin, const int32_t* map, i
                       const float* w, int transpose, int reverse, const float* bias,
                       const float* residual, int ld_res, const float* mask, int ld_mask, float* out,
                       int ld_out, int Cout, int epi_flags, scn_stream_t stream);
-/* grad_w[o] (+)= in[map[o][:]]^T . grad_out   (fp32 accumulate; grad_w must be zeroed) */
+/* grad_w[o] += in[map[o][:]]^T . grad_out   (fp32 accumulate: grad_w must be zeroed or hold earlier contributions).
+ * grad_bias (may be NULL): grad_bias[c] += sum_r grad_out[r][c], computed from the grad-out tiles the kernel stages
+ * anyway (saves a pass over grad_out and a launch per layer). */
 int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const int32_t* map, int n_out,
                         int K, const float* grad_out, int ld_go, int Cout, float* grad_w,
-                        int use_tf32, scn_stream_t stream);
+                        float* grad_bias, int use_tf32, scn_stream_t stream);
 /* Residual unit  y = x + conv2(relu(conv1(relu(x))))  (module_factory.py:127-183, relu_first, identity shortcut;
  * both convolutions C -> C over the same map) as ONE call that enqueues all kernels (relu+round, two gather-GEMMs
  * with fused ReLU / residual-add epilogues); r = relu(x) and h = relu(conv1) are kept for the backward.  img1/img2:

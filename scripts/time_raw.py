@@ -39,10 +39,10 @@ for li, C in enumerate(chans):
         s = _stream()
         _lib.call("scn_conv_pack_weights", P(w), 27, C, C, 0, 0, P(img), s)
         x = Fn.tf32_exact(torch.randn(n, C, device=dev)); go = Fn.tf32_exact(torch.randn(n, C, device=dev))
-        out = torch.empty(n, C, device=dev); gw = torch.zeros(27, C, C, device=dev)
+        out = torch.empty(n, C, device=dev); gw = torch.zeros(27, C, C, device=dev); gb = torch.zeros(C, device=dev)
         tf = timed(lambda: _lib.call("scn_conv_fwd_tf32", P(x), C, C, n, P(fmap), n, 27, P(img), None, None, 0, None, 0,
                                      P(out), C, C, 0, s))
-        tw = timed(lambda: _lib.call("scn_conv_bwd_weight", P(x), C, C, P(fmap), n, 27, P(go), C, C, P(gw), 1, s))
+        tw = timed(lambda: _lib.call("scn_conv_bwd_weight", P(x), C, C, P(fmap), n, 27, P(go), C, C, P(gw), P(gb), 1, s))
         tot_f += tf; tot_w += tw
         print("L%d N=%d C=%d tiles=%d: fwd %.1f us  wgrad %.1f us" % (li, n, C, (n + 127) // 128, tf, tw), flush=True)
     cur = scn.SparseConvNetTensor(torch.randn(n, C, device=dev), md, cur.spatial_size)

@@ -31,6 +31,7 @@ struct WgradParams {
     const float* go;
     int ld_go, Cout;
     float* gw;
+    float* gb;      // optional: column sums of grad_out (bias gradient) are ADDED here
     int n_tiles, tiles_per_chunk;
     int opg, n_ogroups, n_mhalves;
     int a_stages, g_stages, a_stage_bytes, g_stage_bytes, tmem_cols;
@@ -203,6 +204,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
             int sg = gw_i;                                   // gw_i < NG <= GS
             uint32_t phg = 0;
             const int cmax = min(p.Cout, cout0 + 128);
+            const bool do_bias = p.gb != nullptr && og == 0 && mh == 0;      // one CTA per (row chunk, Cout half)
+            float bsum[4] = {0.f, 0.f, 0.f, 0.f};
             for (int tile = t0 + gw_i; tile < t1; tile += NG) {
                 mbar_wait(g_empty(sg), phg ^ 1);
                 const uint32_t gst = g_base + (uint32_t)sg * p.g_stage_bytes + dst_lane;
@@ -219,8 +222,34 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                     }
                 }
                 cp_async_mbar_arrive_noinc(g_full(sg));
+                if (do_bias) {
+                    // bias gradient = column sums of grad_out: the tile is in shared memory anyway and this warp has slack
+                    // (one tile per n_mg units).  Lane L owns columns L, L+32, ...; the stage is only read by the MMAs.
+                    cp_async_wait<0>();
+                    __syncwarp();
+                    const uint32_t cc = (uint32_t)lane >> 2, cw = ((uint32_t)lane & 3u) * 4u;
+                    const uint32_t gsb = g_base + (uint32_t)sg * p.g_stage_bytes;
+#pragma unroll 4
+                    for (int r = 0; r < TILE_M; ++r) {
+                        const uint32_t off = (uint32_t)r * 128u + (((((cc >> 1) ^ ((uint32_t)r & 3u)) << 1) | (cc & 1u)) << 4) + cw;
+#pragma unroll
+                        for (int blk = 0; blk < 4; ++blk)
+                            if (blk < nblk_g) {
+                                float v;
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(gsb + (uint32_t)blk * A_STAGE_BYTES + off));
+                                bsum[blk] += v;
+                            }
+                    }
+                }
                 sg += NG;
                 if (sg >= GS) sg -= GS, phg ^= 1;
+            }
+            if (do_bias) {
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk) {
+                    const int col = cout0 + blk * KB + lane;
+                    if (blk < nblk_g && col < cmax) atomicAdd(p.gb + col, bsum[blk]);
+                }
             }
         }
         cp_async_wait<0>();
@@ -316,20 +345,25 @@ using namespace scn;
 extern "C" int scn_conv_bwd_weight_fp32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K,
                                         const float* grad_out, int ld_go, int Cout, float* grad_w, scn_stream_t stream);
 
+extern "C" int scn_col_sum_add(const float* in, int ld, int n, int C, float* out, scn_stream_t stream);
+
 extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K,
-                                   const float* grad_out, int ld_go, int Cout, float* grad_w, int use_tf32,
-                                   scn_stream_t stream) {
+                                   const float* grad_out, int ld_go, int Cout, float* grad_w, float* grad_bias,
+                                   int use_tf32, scn_stream_t stream) {
     SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0, "conv_bwd_weight: bad shape");
     SCN_REQUIRE(map || K == 1, "conv_bwd_weight: identity map requires K == 1");
     if (n_out <= 0) return SCN_OK;
     static int is100 = -1;
     if (is100 < 0) is100 = scn_device_is_sm100();
-    if (!use_tf32 || !is100 || Cin > 512 || Cout > 512)
-        return scn_conv_bwd_weight_fp32(in, ld_in, Cin, map, n_out, K, grad_out, ld_go, Cout, grad_w, stream);
+    if (!use_tf32 || !is100 || Cin > 512 || Cout > 512) {
+        int rc = scn_conv_bwd_weight_fp32(in, ld_in, Cin, map, n_out, K, grad_out, ld_go, Cout, grad_w, stream);
+        if (rc || !grad_bias) return rc;
+        return scn_col_sum_add(grad_out, ld_go, n_out, Cout, grad_bias, stream);
+    }
 
     WgradParams p;
     p.in = in, p.ld_in = ld_in, p.Cin = Cin, p.map = map, p.n_out = n_out, p.K = K;
-    p.go = grad_out, p.ld_go = ld_go, p.Cout = Cout, p.gw = grad_w;
+    p.go = grad_out, p.ld_go = ld_go, p.Cout = Cout, p.gw = grad_w, p.gb = grad_bias;
     p.n_tiles = cdiv(n_out, TILE_M);
     const int cin_h = Cin < 128 ? Cin : 128, cout_h = Cout < 128 ? Cout : 128;
     const int npad = (cout_h + 15) / 16 * 16;

@@ -71,8 +71,13 @@ int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n
     } else {
         SCN_TRY(scn_conv_fwd_fp32(g_op, C, C, map, n, K, w2, 1, 1, nullptr, nullptr, 0, h, C, gh, C, C, SCN_EPI_MASK, stream));
     }
-    if (gw2) SCN_TRY(scn_conv_bwd_weight(h, C, C, map, n, K, g_op, C, C, gw2, use_tf32, stream));
-    if (gb2) SCN_TRY(bias_sum(gy, C, n, C, gb2, stream));
+    // bias gradients ride in the weight-gradient kernel (column sums of its grad-out tiles, added to gb)
+    if (!accumulate) {
+        if (gb1 && gw1) cudaMemsetAsync(gb1, 0, C * sizeof(float), st);
+        if (gb2 && gw2) cudaMemsetAsync(gb2, 0, C * sizeof(float), st);
+    }
+    if (gw2) SCN_TRY(scn_conv_bwd_weight(h, C, C, map, n, K, g_op, C, C, gw2, gb2, use_tf32, stream));
+    else if (gb2) SCN_TRY(bias_sum(gy, C, n, C, gb2, stream));
     if (gx) {
         // d/dx = gy + relu'(x) * conv1^T(gh)
         if (use_tf32)
@@ -82,8 +87,8 @@ int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n
             SCN_TRY(scn_conv_fwd_fp32(gh, C, C, map, n, K, w1, 1, 1, nullptr, gy, C, r, C, gx, C, C, SCN_EPI_MASK | SCN_EPI_ADD,
                                       stream));
     }
-    if (gw1) SCN_TRY(scn_conv_bwd_weight(r, C, C, map, n, K, gh, C, C, gw1, use_tf32, stream));
-    if (gb1) SCN_TRY(bias_sum(gh, C, n, C, gb1, stream));
+    if (gw1) SCN_TRY(scn_conv_bwd_weight(r, C, C, map, n, K, gh, C, C, gw1, gb1, use_tf32, stream));
+    else if (gb1) SCN_TRY(bias_sum(gh, C, n, C, gb1, stream));
     return SCN_OK;
 }
 

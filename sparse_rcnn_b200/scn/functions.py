@@ -180,29 +180,30 @@ class ConvFunction(Function):
         if ctx.needs_input_grad[0]:
             gx = conv_gemm(go, w, K, cout, cin, bmap, n_in, None, transpose=1, reverse=reverse_bwd)
         tf32 = 1 if _state["precision"] == "tf32" else 0
-        if ctx.needs_input_grad[1]:
+        want_w = ctx.needs_input_grad[1]
+        want_b = has_bias and ctx.needs_input_grad[2]
+        b = ctx.bias_param
+        db = _direct_grad(b) if want_b else None
+        gb_buf = None
+        if want_b:
+            gb_buf = db if db is not None else torch.zeros(cout, dtype=torch.float32, device=go.device)
+        if want_w:
             direct = _direct_grad(w)
             gw_buf = direct if direct is not None else torch.zeros_like(w)
-            if n_out:
+            if n_out:      # the bias gradient (column sums of go) rides in the weight-gradient kernel
                 _lib.call("scn_conv_bwd_weight", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(go),
-                          go.stride(0), cout, _ptr(gw_buf), tf32, _stream())
+                          go.stride(0), cout, _ptr(gw_buf), _ptr(gb_buf), tf32, _stream())
             if direct is not None:
                 w._scn_grad_hook(w)
             else:
                 gw = gw_buf
-        if has_bias and ctx.needs_input_grad[2]:
-            b = ctx.bias_param
-            direct = _direct_grad(b)
-            if direct is not None:
-                if n_out:
-                    _lib.call("scn_col_sum_add", _ptr(go), go.stride(0), n_out, cout, _ptr(direct), _stream())
+        elif want_b and n_out:
+            _lib.call("scn_col_sum_add", _ptr(go), go.stride(0), n_out, cout, _ptr(gb_buf), _stream())
+        if want_b:
+            if db is not None:
                 b._scn_grad_hook(b)
             else:
-                gb = torch.empty(cout, dtype=torch.float32, device=go.device)
-                if n_out:
-                    _lib.call("scn_col_sum", _ptr(go), go.stride(0), n_out, cout, _ptr(gb), _stream())
-                else:
-                    gb.zero_()
+                gb = gb_buf
         return gx, gw, gb, None, None, None, None
 
 
@@ -210,7 +211,7 @@ def _wgrad(x, fmap, go, K, cin, cout, n_out, like):
     gw = torch.zeros_like(like)
     if n_out:
         _lib.call("scn_conv_bwd_weight", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(go), go.stride(0), cout,
-                  _ptr(gw), 1 if _state["precision"] == "tf32" else 0, _stream())
+                  _ptr(gw), None, 1 if _state["precision"] == "tf32" else 0, _stream())
     return gw
 
 
