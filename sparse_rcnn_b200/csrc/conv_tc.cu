@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             for (int j = 0; j < 4; ++j) idx[j] = idx_next[j];
             for (int j = 0; j < G; ++j) step(nxt);
         }
-        cp_async_wait<0>();
+        cp_async_wait_all();
     } else if (warp == MMA_WARP) {
         // ===================== MMA issuer =====================
         // The whole warp stays converged and waits; one elected lane issues (cute::elect_one_sync pattern).  From a

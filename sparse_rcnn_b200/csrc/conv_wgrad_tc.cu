@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                 if (do_bias) {
                     // bias gradient = column sums of grad_out: the tile is in shared memory anyway and this warp has slack
                     // (one tile per n_mg units).  Lane L owns columns L, L+32, ...; the stage is only read by the MMAs.
-                    cp_async_wait<0>();
+                    cp_async_wait_all();      // the copies above are not in a committed group: wait_group would not cover them
                     __syncwarp();
                     const uint32_t cc = (uint32_t)lane >> 2, cw = ((uint32_t)lane & 3u) * 4u;
                     const uint32_t gsb = g_base + (uint32_t)sg * p.g_stage_bytes;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                 }
             }
         }
-        cp_async_wait<0>();
+        cp_async_wait_all();
     } else {
         // ===================== MMA issuer =====================
         // Whole warp 8 runs the loop (warp-uniform control flow); one elected lane issues the 16 MMAs of a unit

@@ -95,6 +95,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// all cp.async of this thread, committed to a group or not (wait_group only covers committed groups)
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // arrive on the mbarrier when all cp.async issued so far by this thread have landed (the arrival is one
 // of the barrier's expected arrivals: .noinc).  Same mechanism as CUTLASS' sm100 cp.async collective
 // (cutlass::arch::cpasync_barrier_arrive_noinc): the producer never blocks on its own copies.

@@ -30,7 +30,9 @@ class BackboneTrainer(nn.Module):
         self.to(device)
         self.buckets = GradientBuckets(list(self.parameters()), n_buckets=2)
         self.buckets.enabled = True
-        self.optimizer = torch.optim.Adam(self.parameters(), lr=lr, foreach=True)
+        # torch.optim.Adam as in the reference (ndsis/training/training.py:386); the fused implementation is the same
+        # update in one multi-tensor kernel (the foreach path costs ~1.2 ms of host time per step, and the step is host bound)
+        self.optimizer = torch.optim.Adam(self.parameters(), lr=lr, fused=True)
         self.distributed = distributed
         self._weights = [p for p in self.parameters() if p.dim() >= 2]
 
