@@ -59,6 +59,7 @@ struct ConvTcParams {
     int osplit, opg;      // offsets of a tile are split over `osplit` work items of `opg` offsets each (small levels)
     float* scratch;       // split mode: accumulation buffer [n_out][Cout], all-zero between launches
     unsigned int* tickets;  // split mode: one self-resetting arrival counter per tile
+    int cluster;          // > 1: the osplit work items of a tile are one thread-block cluster and reduce through DSMEM
 };
 
 // one 16-byte chunk of a gathered row, split into VEC-float cp.asyncs
@@ -389,6 +390,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                              ((p.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
                             (!(epi & SCN_EPI_MASK) ||
                              ((p.ld_mask % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+        const uint32_t part_pitch = (uint32_t)p.cout_pad * 4u + 16u;      // cluster mode: row pitch of the partial tile
         // order: bias, MASK (aux > 0 ? x : 0), ADD residual, RELU, ROUND (rna to TF32)
         auto finish = [&](float x, float m, float r) {
             if ((epi & SCN_EPI_MASK) && !(m > 0.f)) x = 0.f;
@@ -442,6 +444,21 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                     float v[16];
                     tmem_ld16(taddr + c0, v);
                     if (row < p.n_out && c0 < p.Cout) finish_store(v, row, c0);
+                }
+                tc_fence_before();
+                mbar_arrive(acce_bar(b));
+            } else if (p.cluster > 1) {
+                // cluster mode: the partial sum of this offset group goes to this CTA's own shared memory (the stage ring is
+                // free: every MMA of the work item has completed); the cluster reduces it through DSMEM below
+                const uint32_t prow = smem_base + (uint32_t)(warp * 32 + lane) * part_pitch;
+                for (int c0 = 0; c0 < p.cout_pad; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)(c0 + j) * 4u), "f"(v[j]),
+                                     "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                                     : "memory");
                 }
                 tc_fence_before();
                 mbar_arrive(acce_bar(b));
@@ -534,6 +551,72 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
         }
     }
 
+    if (p.cluster > 1) {
+        // ===================== cluster reduction through distributed shared memory =====================
+        // Work item w = tile * osplit + g is CTA g of cluster `tile`.  After the cluster barrier every CTA adds, for its
+        // slice of the tile's rows, the osplit partial tiles in rank order (deterministic, no global atomics, no scratch),
+        // applies the epilogue and writes the output rows.
+        cluster_sync_all();
+        if (warp < 4) {
+            const int cs = p.cluster;
+            const int tile = blockIdx.x / cs;
+            const int rank = (int)cluster_ctarank();
+            const int row0 = tile * TILE_M;
+            const int rows = min(TILE_M, p.n_out - row0);
+            const int per = (TILE_M + cs - 1) / cs;
+            const int r_lo = rank * per, r_hi = min(rows, r_lo + per);
+            const uint32_t part_pitch = (uint32_t)p.cout_pad * 4u + 16u;
+            const int epi = p.epi;
+            uint32_t rbase[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) rbase[rr] = mapa_shared(smem_base, (uint32_t)(rr < cs ? rr : 0));
+            auto fin1 = [&](float x, int r, int c) {
+                if (p.bias) x += __ldg(p.bias + c);
+                if ((epi & SCN_EPI_MASK) && !(p.mask[(int64_t)r * p.ld_mask + c] > 0.f)) x = 0.f;
+                if (epi & SCN_EPI_ADD) x += p.residual[(int64_t)r * p.ld_res + c];
+                if (epi & SCN_EPI_RELU) x = fmaxf(x, 0.f);
+                if (epi & SCN_EPI_ROUND) {
+                    uint32_t t;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+                    x = __uint_as_float(t);
+                }
+                return x;
+            };
+            if (r_hi > r_lo) {
+                const bool v4 = (p.Cout & 3) == 0 && (p.ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+                if (v4) {
+                    const int q = p.Cout >> 2, total = (r_hi - r_lo) * q;
+                    for (int e = tid; e < total; e += 128) {
+                        const int r = r_lo + e / q, c = (e % q) << 2;
+                        const uint32_t off = (uint32_t)r * part_pitch + (uint32_t)c * 4u;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr)
+                            if (rr < cs) {
+                                const float4 v = ld_dsmem_v4(rbase[rr] + off);
+                                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+                            }
+                        const int gr = row0 + r;
+                        acc.x = fin1(acc.x, gr, c), acc.y = fin1(acc.y, gr, c + 1), acc.z = fin1(acc.z, gr, c + 2);
+                        acc.w = fin1(acc.w, gr, c + 3);
+                        *reinterpret_cast<float4*>(p.out + (int64_t)gr * p.ld_out + c) = acc;
+                    }
+                } else {
+                    const int total = (r_hi - r_lo) * p.Cout;
+                    for (int e = tid; e < total; e += 128) {
+                        const int r = r_lo + e / p.Cout, c = e % p.Cout;
+                        const uint32_t off = (uint32_t)r * part_pitch + (uint32_t)c * 4u;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr)
+                            if (rr < cs) acc += ld_dsmem_f32(rbase[rr] + off);
+                        p.out[(int64_t)(row0 + r) * p.ld_out + c] = fin1(acc, row0 + r, c);
+                    }
+                }
+            }
+        }
+        cluster_sync_all();      // nobody leaves while its shared memory is still being read
+    }
     tc_fence_before();
     __syncthreads();
     if (tid == 0) SCN_TRACE(11);
@@ -812,13 +895,24 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     if (!no_split && K > 1 && p.n_tiles * 2 <= slots) {
         int g = slots / p.n_tiles;
         if (g > K) g = K;
+        if (g > 8) g = 8;      // one cluster per tile (portable cluster size limit)
         p.opg = cdiv(K, g);
         p.osplit = cdiv(K, p.opg);
     }
     const int n_work = p.n_tiles * p.osplit;
     int grid = n_work < slots ? n_work : slots;
-    p.scratch = nullptr, p.tickets = nullptr;
-    if (p.osplit > 1) {
+    p.scratch = nullptr, p.tickets = nullptr, p.cluster = 0;
+    // split mode as a thread-block cluster (<= 8 CTAs, the portable limit) reducing through DSMEM when the partial tile
+    // (128 rows x (cout_pad + 4) floats) fits in the stage ring; otherwise atomics into the library workspace
+    static int no_cluster = -1;
+    if (no_cluster < 0) {
+        const char* ev = getenv("SCN_CONV_NOCLUSTER");
+        no_cluster = (ev && ev[0] == '1') ? 1 : 0;
+    }
+    if (p.osplit > 1 && p.osplit <= 8 && !no_cluster && !use_tma && grid == n_work &&
+        TILE_M * (p.cout_pad * 4 + 16) <= stages * stage_bytes)
+        p.cluster = p.osplit;
+    if (p.osplit > 1 && !p.cluster) {
         int rc = scn::split_workspace((size_t)n_out * Cout * sizeof(float), p.n_tiles, &p.scratch, &p.tickets);
         if (rc) return rc;
     }
@@ -826,7 +920,18 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     auto launch = [&](auto kern, int threads) {
         e = (cudaError_t)scn::ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
         if (e != cudaSuccess) return;
-        kern<<<grid, threads, smem, as_stream(stream)>>>(tmap, p);
+        if (p.cluster > 1) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(grid), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = as_stream(stream);
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = p.cluster, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr, cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, kern, tmap, p);
+        } else {
+            kern<<<grid, threads, smem, as_stream(stream)>>>(tmap, p);
+        }
     };
     if (use_tma) launch(k_conv_tc<4, true>, 192);
     else if (vec == 4) launch(k_conv_tc<4, false>, CONV_THREADS);
