@@ -187,6 +187,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--prefetch", action="store_true",
+                    help="build each step's rulebooks one step ahead on a side stream (scn.GeometryPrefetcher).  Off by "
+                         "default: measured neutral (7.8 vs 7.8 ms) to harmful here, the worker thread shares the GIL with "
+                         "an already host-bound training thread (profiles/r1_i_host_bound.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -221,15 +225,18 @@ def main():
         torch.cuda.synchronize()
 
     def timed(inputs, read_loss):
+        # --prefetch: the following batch is known (as with a DataLoader), so its rulebooks are built on a side stream
+        # while this step runs; every step's geometry is still built inside the loop, one step ahead
+        nxt = (lambda i: inputs[(i + 1) % n_distinct][0]) if args.prefetch else (lambda i: None)
         for i in range(W):
-            trainer.step(*inputs[i % n_distinct])
+            trainer.step(*inputs[i % n_distinct], next_data=nxt(i))
         barrier()
         launches0 = _lib.raw("scn_launch_count")()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         voxels, t0 = 0, time.perf_counter()
         e0.record()
         for i in range(K):
-            loss = trainer.step(*inputs[i % n_distinct])
+            loss = trainer.step(*inputs[i % n_distinct], next_data=nxt(i))
             if read_loss:
                 float(loss.item())                      # D2H read of the step's result
             voxels += trainer.last_active

@@ -6,6 +6,7 @@
 // HBM/L2-latency bound integer work: one thread per point / row, coalesced streaming of the
 // key arrays, random probes into a table sized at load factor <= 0.5 that lives in the 126 MB L2.
 #include <stdarg.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace scn {
@@ -17,7 +18,7 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-static int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};      // launches come from two host threads when geometry is prefetched
 int check_launch(const char* what) {
     ++g_launches;
     cudaError_t e = cudaGetLastError();
@@ -316,7 +317,7 @@ extern "C" {
 
 const char* scn_last_error(void) { return g_err; }
 int scn_version(void) { return 100; }
-int64_t scn_launch_count(void) { return g_launches; }
+int64_t scn_launch_count(void) { return g_launches.load(); }
 int scn_device_sm_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {

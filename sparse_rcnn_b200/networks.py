@@ -145,14 +145,18 @@ class InputStage(nn.Module):
     def __init__(self, scn, mode=4):
         super().__init__()
         self.scn, self.mode = scn, mode
+        self.prefetcher = None      # optional scn.GeometryPrefetcher (B200 backend): geometry of this batch built ahead
 
     def forward(self, data):
         coords, feats, spatial_size, batch_size = data[:4]
         spatial_size = torch.as_tensor(spatial_size, dtype=torch.long)
         if not len(coords):
             return spatial_size, batch_size, None
-        md = self.scn.Metadata(3)
-        f = self.scn.ioLayers.InputLayerFunction.apply(3, md, spatial_size, coords.long(), feats, batch_size, self.mode)
+        coords = coords.long()      # int64 already in the reference contract (data.py:95-98): the same tensor object
+        md = self.prefetcher.take(coords) if self.prefetcher is not None else None
+        if md is None:
+            md = self.scn.Metadata(3)
+        f = self.scn.ioLayers.InputLayerFunction.apply(3, md, spatial_size, coords, feats, batch_size, self.mode)
         t = self.scn.SparseConvNetTensor(features=f, metadata=md, spatial_size=spatial_size)
         return spatial_size, t.batch_size(), t
 

@@ -35,9 +35,22 @@ class BackboneTrainer(nn.Module):
         self.optimizer = torch.optim.Adam(self.parameters(), lr=lr, fused=True)
         self.distributed = distributed
         self._weights = [p for p in self.parameters() if p.dim() >= 2]
+        self.prefetcher = None
 
-    def step(self, data, labels):
-        """data: collate_fn 5-tuple, labels int64 [P] (host or device).  Returns the loss (device scalar)."""
+    def prefetch(self, data):
+        """Start building the geometry (voxel hash, level pyramid, neighbour maps) of an upcoming batch on a side stream;
+        the step() that later receives the same coords tensor picks it up (scn.GeometryPrefetcher)."""
+        if self.prefetcher is None:
+            self.prefetcher = scn.GeometryPrefetcher(self.device, n_levels=len(self.backbone.channels) - 1)
+            self.backbone.input_stage.prefetcher = self.prefetcher
+        coords, _, size, bs = data[:4]
+        self.prefetcher.submit(coords.long(), torch.as_tensor(size, dtype=torch.long), bs)
+
+    def step(self, data, labels, next_data=None):
+        """data: collate_fn 5-tuple, labels int64 [P] (host or device).  next_data: the batch of the following step, if
+        already known (its rulebooks are then built while this step runs).  Returns the loss (device scalar)."""
+        if next_data is not None:
+            self.prefetch(next_data)
         data = _to_device(data, self.device)
         labels = labels.to(self.device, non_blocking=True)
         self.buckets.zero()

@@ -10,7 +10,7 @@ from .layers import (AddTable, AveragePooling, BatchNormalization, BatchNormLeak
                      Convolution, Deconvolution, Identity, InputLayer, JoinTable, MaxPooling, NetworkInNetwork,
                      OutputLayer, ReLU, Sequential, SparseConvNetTensor, SparseToDense, SubmanifoldConvolution,
                      ValidConvolution)
-from .metadata import Metadata
+from .metadata import GeometryPrefetcher, Metadata
 
 ioLayers = types.SimpleNamespace(
     InputLayerFunction=InputLayerFunction, OutputLayerFunction=OutputLayerFunction,

@@ -156,11 +156,17 @@ class Metadata:
         self.n_samples = 0
         self.mode = None
         self.input_size = None
+        self._prebuilt_for = None
 
     # ---------------------------------------------------------------- input layer rule
     def set_input(self, spatial_size, coords, batch_size, mode, device):
         """coords: int64 [P, 3|4] on CPU or device, or already-packed keys (int64 [P], device) when
         `coords.dim() == 1` (device-side crop path).  Returns the number of active rows."""
+        if self._prebuilt_for is not None:
+            # geometry built ahead of time by a GeometryPrefetcher for exactly this coords tensor
+            if self._prebuilt_for is not coords or mode != self.mode or size_key(spatial_size) != self.input_size:
+                raise RuntimeError("prefetched Metadata used with a different input than it was built for")
+            return self.levels[self.input_size].n
         s = _stream()
         if coords.dim() == 1:
             keys = coords
@@ -271,3 +277,72 @@ class Metadata:
         r = Strided(out_size, cmap, dmap, parent_row, K)
         self.strided[key] = r
         return r
+
+
+def _walk_tensors(obj, seen):
+    """Every torch tensor reachable from a Metadata (levels, maps, rules, caches)."""
+    if id(obj) in seen:
+        return
+    seen.add(id(obj))
+    if isinstance(obj, torch.Tensor):
+        yield obj
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            yield from _walk_tensors(v, seen)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            yield from _walk_tensors(v, seen)
+    elif isinstance(obj, (Level, Strided, Metadata)):
+        yield from _walk_tensors(vars(obj), seen)
+
+
+class GeometryPrefetcher:
+    """Builds the geometry of the NEXT batch (voxel hash, every level of the pyramid, neighbour maps) while the current
+    step runs: a worker thread issues the rulebook kernels on a high-priority side stream and takes their host round
+    trips (one active-row count per level), so the training thread never waits for the GPU.  Same kernels, same results;
+    only WHEN they run changes -- the role a DataLoader worker plays for the reference's CPU-side preprocessing
+    (ndsis/data/data.py:88-115).  Without it the step has a bubble at its start: the host waits for the previous step
+    to drain before it can read the first count, then the GPU waits for the host (profiles/r1_i_host_bound.md)."""
+
+    def __init__(self, device, n_levels, mode=4, dimension=3):
+        import concurrent.futures
+        self.device = torch.device(device)
+        self.n_levels, self.mode, self.dimension = n_levels, mode, dimension
+        self.stream = torch.cuda.Stream(self.device, priority=-1)
+        self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="scn-geometry")
+        self.pending = {}
+
+    def _build(self, coords, spatial_size, batch_size):
+        torch.cuda.set_device(self.device)
+        with torch.cuda.stream(self.stream):
+            md = Metadata(self.dimension)
+            md.set_input(spatial_size, coords, batch_size, self.mode, self.device)
+            md.prebuild(self.n_levels)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        md._prebuilt_for = coords
+        md._ready = ev
+        return md
+
+    def submit(self, coords, spatial_size, batch_size):
+        """Start building the geometry of `coords` (a later InputLayer call with this very tensor picks it up)."""
+        if id(coords) in self.pending or not len(coords):
+            return
+        self.pending[id(coords)] = (self.pool.submit(self._build, coords, spatial_size, batch_size), coords)
+
+    def take(self, coords):
+        """The prefetched Metadata for `coords`, ordered after its build on the current stream; None if not submitted."""
+        item = self.pending.pop(id(coords), None)
+        if item is None:
+            return None
+        md = item[0].result()
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(md._ready)
+        for t in _walk_tensors(md, set()):
+            if t.is_cuda:
+                t.record_stream(cur)      # allocated on the side stream, used (and later freed) under the training stream
+        return md
+
+    def shutdown(self):
+        self.pool.shutdown(wait=True)
+        self.pending.clear()

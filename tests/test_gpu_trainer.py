@@ -95,3 +95,31 @@ def test_cross_entropy_matches_torch(cuda, weighted):
     assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref))
     assert rel_err(x2.grad, gref) < 1e-5
     assert float(x2.grad[::17].abs().max()) == 0.0
+
+
+def test_prefetched_geometry_equals_inline(cuda):
+    """Rulebooks built one step ahead on the side stream (scn.GeometryPrefetcher) give the same losses as building them
+    inside the step; a mismatching input is refused."""
+    from sparse_rcnn_b200 import pipeline, scn
+    import bench
+    scn.set_precision("fp32")
+    try:
+        batches = [bench.make_inputs(s, scene_kw=bench.CPU_SAMPLE) for s in (0, 1, 2)]
+        losses = []
+        for prefetch in (False, True):
+            tr = pipeline.BackboneTrainer(cuda, seed=5)
+            out = []
+            for i, (d, l) in enumerate(batches):
+                nxt = batches[i + 1][0] if prefetch and i + 1 < len(batches) else None
+                out.append(float(tr.step(d, l, next_data=nxt)))
+            losses.append(out)
+            if prefetch:
+                assert tr.prefetcher is not None and not tr.prefetcher.pending
+                tr.prefetcher.shutdown()
+        assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-5, losses
+        md = scn.Metadata(3)
+        md._prebuilt_for = batches[0][0][0]
+        with pytest.raises(RuntimeError):
+            md.set_input(batches[1][0][2], batches[1][0][0], 1, 4, cuda)
+    finally:
+        scn.set_precision("tf32")
