@@ -279,8 +279,8 @@ def main():
                 "achieved": achieved, "peak": peak, "peak_source": "measured" if peaks else "fallback",
                 "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this layer from the ncu --set full
-                # capture summarised in profiles/r1_b_ncu_full_conv_c32.md (39.62 MB + 0.49 MB; the output stays in L2)
-                "traffic": 40.11e6,
+                # capture summarised in profiles/r1_j_ncu_full_conv_owned_units.md (39.66 MB + 0.24 MB; the output stays in L2)
+                "traffic": 39.90e6,
                 "ms_per_launch": kms, "algorithmic_bytes": alg_bytes,
                 "tflops_useful": flops / (kms * 1e-3) / 1e12, "l2": "flushed between launches"}
 
