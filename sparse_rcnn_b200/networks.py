@@ -112,8 +112,8 @@ def _fused_class(scn):
                 inner = self[0]._modules["1"]
                 c1, c2 = inner[1], inner[3]
                 lvl = x.metadata.level(x.spatial_size)
-                f = ResidualUnitFunction.apply(x.features, c1.weight, c1.bias, c2.weight, c2.bias,
-                                               lvl.subm_map(c1.filter_size), lvl.n)
+                f = ResidualUnitFunction.apply(x.features, lvl.subm_map(c1.filter_size), lvl.n,
+                                               c1.weight, c1.bias, c2.weight, c2.bias)
                 return scn.SparseConvNetTensor(f, x.metadata, x.spatial_size)
 
         _FUSED_CLASSES[scn] = FusedResidualUnit
@@ -121,7 +121,38 @@ def _fused_class(scn):
 
 
 def unit_stage(scn, channels, num_units):
-    return scn.Sequential(*[residual_unit(scn, channels, channels) for _ in range(num_units)])
+    stage = scn.Sequential(*[residual_unit(scn, channels, channels) for _ in range(num_units)])
+    if getattr(scn, "BACKEND", "") == "b200-cuda":
+        stage.__class__ = _fused_stage_class(scn)
+    return stage
+
+
+_FUSED_STAGES = {}
+
+
+def _fused_stage_class(scn):
+    """Same module tree as the reference's stack of residual units; forward runs the whole stack as ONE autograd node."""
+    if scn not in _FUSED_STAGES:
+        from .scn.functions import ResidualUnitFunction
+        fused_unit = _fused_class(scn)
+
+        class FusedUnitStage(scn.Sequential):
+            def forward(self, x):
+                units = list(self._modules.values())
+                if not FUSE["residual"] or not units or not all(type(u) is fused_unit for u in units):
+                    return super().forward(x)
+                params, fs = [], None
+                for u in units:
+                    inner = u[0]._modules["1"]
+                    c1, c2 = inner[1], inner[3]
+                    fs = c1.filter_size
+                    params += [c1.weight, c1.bias, c2.weight, c2.bias]
+                lvl = x.metadata.level(x.spatial_size)
+                f = ResidualUnitFunction.apply(x.features, lvl.subm_map(fs), lvl.n, *params)
+                return scn.SparseConvNetTensor(f, x.metadata, x.spatial_size)
+
+        _FUSED_STAGES[scn] = FusedUnitStage
+    return _FUSED_STAGES[scn]
 
 
 def encoder_level(scn, cin, cout, stride, num_units):

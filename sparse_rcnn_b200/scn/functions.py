@@ -244,71 +244,93 @@ def _image_buf(weight, K, cin, cout, key):
     return hit[0], stale
 
 
+def _unit_forward(x, w1, b1, w2, b2, fmap, n, tf32):
+    """One residual unit forward (one C-ABI call): returns (r = relu(x), h = relu(conv1(r)), y = x + conv2(h))."""
+    K, c = w1.shape[0], w1.shape[-1]
+    dev = x.device
+    r = torch.empty((n, c), dtype=torch.float32, device=dev)
+    h = torch.empty((n, c), dtype=torch.float32, device=dev)
+    y = torch.empty((n, c), dtype=torch.float32, device=dev)
+    if tf32:
+        i1, s1 = _image_buf(w1, K, c, c, "f")
+        i2, s2 = _image_buf(w2, K, c, c, "f")
+    else:
+        i1 = i2 = None
+        s1 = s2 = False
+    _lib.call("scn_residual_unit_fwd", _ptr(x), n, c, _ptr(fmap), K, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(i1),
+              _ptr(i2), int(s1 or s2), _ptr(r), _ptr(h), _ptr(y), int(tf32), _stream())
+    return r, h, y
+
+
+def _unit_backward(gy, r, h, w1, b1, w2, b2, fmap, n, tf32, need_x, need_p):
+    """One residual unit backward (one C-ABI call).  need_p: (w1, b1, w2, b2) wanted.  Returns (gx, [gw1, gb1, gw2, gb2]);
+    gradients that went straight into the parameters' buckets come back as None."""
+    K, c = w1.shape[0], w1.shape[-1]
+    dev = gy.device
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    gyr = new(n, c) if tf32 else None
+    gh = new(n, c)
+    gx = new(n, c) if need_x else None
+    wanted = [(w1, need_p[0]), (b1, b1 is not None and need_p[1]), (w2, need_p[2]), (b2, b2 is not None and need_p[3])]
+    direct = [_direct_grad(p) if want else None for p, want in wanted]
+    # all-or-nothing: the C call either accumulates into every parameter gradient or overwrites fresh buffers
+    accumulate = all(d is not None for d, (p, want) in zip(direct, wanted) if want) and any(want for _, want in wanted)
+    bufs = direct if accumulate else [(torch.empty_like(p) if want else None) for p, want in wanted]
+    if tf32:
+        i1, s1 = _image_buf(w1, K, c, c, "b")
+        i2, s2 = _image_buf(w2, K, c, c, "b")
+    else:
+        i1 = i2 = None
+        s1 = s2 = False
+    _lib.call("scn_residual_unit_bwd", _ptr(gy), _ptr(r), _ptr(h), n, c, _ptr(fmap), K, _ptr(w1), _ptr(w2), _ptr(i1),
+              _ptr(i2), int(s1 or s2), _ptr(gyr), _ptr(gh), _ptr(gx), _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]),
+              _ptr(bufs[3]), int(accumulate), int(tf32), _stream())
+    if accumulate:
+        for p, want in wanted:
+            if want:
+                p._scn_grad_hook(p)
+        bufs = [None, None, None, None]
+    return gx, bufs
+
+
 class ResidualUnitFunction(Function):
-    """y = x + conv2(relu(conv1(relu(x))))  -- the residual unit of the reference's sparse networks
-    (module_factory.py:127-183 with relu_first, identity shortcut).  ReLU / residual add / TF32 rounding ride in the
-    convolution epilogues (SCN_EPI_RELU|ROUND on conv1, SCN_EPI_ADD on conv2; backward: SCN_EPI_MASK|ROUND and
-    SCN_EPI_MASK|ADD), and each direction is ONE C-ABI call (scn_residual_unit_fwd / _bwd) because the step is
-    host bound."""
+    """A chain of U residual units  y = x + conv2(relu(conv1(relu(x))))  over one neighbour map -- the `unit_stage` of the
+    reference's sparse networks (module_factory.py:127-183 with relu_first, identity shortcut; :438-578 stacks num_units
+    of them per level).  ReLU / residual add / TF32 rounding ride in the convolution epilogues (SCN_EPI_RELU|ROUND on conv1,
+    SCN_EPI_ADD on conv2; backward: SCN_EPI_MASK|ROUND and SCN_EPI_MASK|ADD); each unit and direction is ONE C-ABI call and
+    the whole chain is ONE autograd node, because the step is host bound (~45 us of Python per node and direction).
+    apply(x, fmap, n, w1, b1, w2, b2[, w1', b1', w2', b2' ...])."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, fmap, n):
+    def forward(ctx, x, fmap, n, *params):
         x = _check(x)
-        K, c = w1.shape[0], w1.shape[-1]
+        units = [params[i:i + 4] for i in range(0, len(params), 4)]
+        c = units[0][0].shape[-1]
         tf32 = _state["precision"] == "tf32" and c <= 256
-        dev = x.device
-        r = torch.empty((n, c), dtype=torch.float32, device=dev)
-        h = torch.empty((n, c), dtype=torch.float32, device=dev)
-        y = torch.empty((n, c), dtype=torch.float32, device=dev)
-        if tf32:
-            i1, s1 = _image_buf(w1, K, c, c, "f")
-            i2, s2 = _image_buf(w2, K, c, c, "f")
-        else:
-            i1 = i2 = None
-            s1 = s2 = False
-        _lib.call("scn_residual_unit_fwd", _ptr(x), n, c, _ptr(fmap), K, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(i1),
-                  _ptr(i2), int(s1 or s2), _ptr(r), _ptr(h), _ptr(y), int(tf32), _stream())
-        ctx.save_for_backward(r, h, w1, w2)
-        ctx.cfg = (fmap, n, K, c, b1 is not None, b2 is not None, tf32)
-        ctx.biases = (b1, b2)
-        return y
+        saved = []
+        for w1, b1, w2, b2 in units:
+            r, h, x = _unit_forward(x, w1, b1, w2, b2, fmap, n, tf32)
+            saved += [r, h]
+        ctx.save_for_backward(*saved, *[u[0] for u in units], *[u[2] for u in units])
+        ctx.cfg = (fmap, n, tf32, len(units))
+        ctx.biases = [(u[1], u[3]) for u in units]
+        return x
 
     @staticmethod
     def backward(ctx, gy):
-        r, h, w1, w2 = ctx.saved_tensors
-        fmap, n, K, c, has_b1, has_b2, tf32 = ctx.cfg
-        gy = _check(gy)
-        dev = gy.device
+        fmap, n, tf32, U = ctx.cfg
+        t = ctx.saved_tensors
+        rh, w1s, w2s = t[:2 * U], t[2 * U:3 * U], t[3 * U:]
         need = ctx.needs_input_grad
-        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
-        gyr = new(n, c) if tf32 else None
-        gh = new(n, c)
-        gx = new(n, c) if need[0] else None
-        b1, b2 = ctx.biases
-        wanted = [(w1, need[1]), (b1, has_b1 and need[2]), (w2, need[3]), (b2, has_b2 and need[4])]
-        direct = [_direct_grad(p) if want else None for p, want in wanted]
-        # all-or-nothing: the C call either accumulates into every parameter gradient or overwrites fresh buffers
-        accumulate = all(d is not None for d, (p, want) in zip(direct, wanted) if want) and any(want for _, want in wanted)
-        if accumulate:
-            bufs = direct
-        else:
-            bufs = [(torch.empty_like(p) if want else None) for p, want in wanted]
-        gw1, gb1, gw2, gb2 = bufs
-        if tf32:
-            i1, s1 = _image_buf(w1, K, c, c, "b")
-            i2, s2 = _image_buf(w2, K, c, c, "b")
-        else:
-            i1 = i2 = None
-            s1 = s2 = False
-        _lib.call("scn_residual_unit_bwd", _ptr(gy), _ptr(r), _ptr(h), n, c, _ptr(fmap), K, _ptr(w1), _ptr(w2), _ptr(i1),
-                  _ptr(i2), int(s1 or s2), _ptr(gyr), _ptr(gh), _ptr(gx), _ptr(gw1), _ptr(gb1), _ptr(gw2), _ptr(gb2),
-                  int(accumulate), int(tf32), _stream())
-        if accumulate:
-            for p, want in wanted:
-                if want:
-                    p._scn_grad_hook(p)
-            gw1 = gb1 = gw2 = gb2 = None
-        return gx, gw1, gb1, gw2, gb2, None, None
+        g = _check(gy)
+        grads = [None] * (4 * U)
+        for u in range(U - 1, -1, -1):
+            b1, b2 = ctx.biases[u]
+            need_x = need[0] if u == 0 else True
+            g, gp = _unit_backward(g, rh[2 * u], rh[2 * u + 1], w1s[u], b1, w2s[u], b2, fmap, n, tf32, need_x,
+                                   need[3 + 4 * u:7 + 4 * u])
+            grads[4 * u:4 * u + 4] = gp
+        return (g, None, None, *grads)
 
 
 class ReLUFunction(Function):
