@@ -228,6 +228,15 @@ int scn_cross_entropy_bwd(const float* logits, int ld, int64_t n, int C, const i
                           int64_t ignore_index, const float* lse, const float* stats, const float* grad_loss,
                           float* dlogits, scn_stream_t stream);
 
+/* ------------------------------------------------------------------ proposal selection ---
+ * ProposalSelector.forward ndsis/modules/proposal_selector.py:60-89 + non_maximum_supression ndsis/utils/bbox.py:713-759
+ * (IoU as bbox_overlap_unsqueezed_area_start_end :235-240).  boxes: [B, n, 2, 3] fp32 (start, stop), every sample sorted
+ * by DESCENDING score; n <= 4096.  keep [B, n]: 1 where the reference's is_maximum is True; keep_idx [B, max_keep]: the
+ * first min(kept, max_keep) survivors in score order, counts [B] their number.  workspace: scn_nms3d_workspace_bytes. */
+int64_t scn_nms3d_workspace_bytes(int B, int n);
+int scn_nms3d(const float* boxes, int B, int n, float thresh, int max_keep, void* workspace, uint8_t* keep,
+              int32_t* keep_idx, int32_t* counts, scn_stream_t stream);
+
 /* ------------------------------------------------------------------ pooling ----------------
  * MaxPooling / AveragePooling module_factory.py:315-354 (cmap from scn_strided_maps);
  * SparseGlobalPool custom_operations.py:42-59 (segment mean over batch-sorted rows). */

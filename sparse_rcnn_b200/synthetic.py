@@ -114,3 +114,23 @@ def make_boxes(coords, n_boxes=256, seed=0, spatial_size=(256, 256, 128)):
         box = np.clip(box, 0, np.asarray(spatial_size, float)[None, None])
         out.append(torch.from_numpy(box.astype(np.float32)))
     return out
+
+
+def make_proposals(seed, B, A, scene=(256.0, 256.0, 128.0), clustered=True):
+    """RPN-like proposals: A boxes per sample clustered around a few object centres (heavy overlaps) + scores in (0, 1).
+    -> (score [B, A] fp32, boxes [B, A, 2, 3] fp32 (start, stop)).  CPU tensors, torch.Generator seeded."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    n_obj = 12
+    centres = torch.rand(B, n_obj, 3, generator=g) * torch.tensor(scene)
+    which = torch.randint(0, n_obj, (B, A), generator=g)
+    c = torch.gather(centres, 1, which[..., None].expand(B, A, 3))
+    if clustered:
+        c = c + torch.randn(B, A, 3, generator=g) * 6.0
+    else:
+        c = torch.rand(B, A, 3, generator=g) * torch.tensor(scene)
+    size = 8.0 + torch.rand(B, A, 3, generator=g) * 40.0
+    boxes = torch.stack([c - size / 2, c + size / 2], dim=2)
+    # unique scores per sample (a permutation), so that the descending order is the same on every device / library
+    score = torch.stack([(torch.randperm(A, generator=g).float() + 0.5) / A for _ in range(B)])
+    return score, boxes

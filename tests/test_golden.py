@@ -100,3 +100,26 @@ def test_reference_graph_live_when_available():
                                                                  os.path.join(root, "oracle", "make_golden.py"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK 120" in r.stdout, r.stdout + r.stderr
+
+
+# ----------------------------------------------------------------------------- proposal selection
+def test_nms_oracle_matches_reference():
+    """oracle/scn_oracle/nms_ref.py == the unmodified reference's ProposalSelector / non_maximum_supression
+    (tests/golden/nms.pt, oracle/make_golden_nms.py), bit for bit."""
+    import os
+    import torch
+    from scn_oracle import nms_ref
+    from sparse_rcnn_b200.synthetic import make_proposals
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "nms.pt"))
+    for c in gold["cases"]:
+        score, boxes = make_proposals(c["seed"], c["B"], c["A"], clustered=c["clustered"])
+        s, b, i = nms_ref.select(score, boxes, c["pre"], c["post"], c["thresh"])
+        for k in range(c["B"]):
+            assert torch.equal(i[k], c["indices"][k])
+            assert torch.equal(s[k], c["scores"][k])
+        if c["pre"] > 0:
+            _, order = torch.topk(score, c["pre"], dim=1, sorted=True)
+        else:
+            _, order = torch.sort(score, dim=1, descending=True)
+        for k in range(c["B"]):
+            assert torch.equal(nms_ref.nms(boxes[k][order[k]], c["thresh"]), c["keep"][k])

@@ -1,0 +1,98 @@
+"""Proposal selection on the GPU: bit-exact against the unmodified reference's outputs
+(tests/golden/nms.pt) and against the pinned CPU restatement (oracle/scn_oracle/nms_ref.py)."""
+import os
+
+import pytest
+import torch
+
+from scn_oracle import nms_ref
+from sparse_rcnn_b200.synthetic import make_proposals
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def test_selector_matches_reference_goldens(cuda):
+    from sparse_rcnn_b200 import proposal
+    gold = torch.load(os.path.join(G, "nms.pt"))
+    for c in gold["cases"]:
+        score, boxes = make_proposals(c["seed"], c["B"], c["A"], clustered=c["clustered"])
+        sel = proposal.ProposalSelector(c["pre"], c["post"], c["thresh"])
+        s, b, i = sel(score.to(cuda), boxes.to(cuda))
+        assert len(s) == len(b) == len(i) == c["B"]
+        for k in range(c["B"]):
+            assert not i[k].is_cuda and i[k].dtype == torch.int64          # reference returns CPU indices
+            assert torch.equal(i[k], c["indices"][k])
+            assert torch.equal(s[k].cpu(), c["scores"][k])
+            assert torch.equal(b[k].cpu(), boxes[k][c["indices"][k]])
+        # the raw NMS indicator on the reference's sorted order
+        if c["pre"] > 0:
+            _, order = torch.topk(score, c["pre"], dim=1, sorted=True)
+        else:
+            _, order = torch.sort(score, dim=1, descending=True)
+        sorted_boxes = boxes[torch.arange(c["B"])[:, None], order]
+        keep, keep_idx, counts = proposal.nms3d(sorted_boxes.to(cuda), c["thresh"], c["post"])
+        assert torch.equal(keep.cpu(), c["keep"])
+        assert counts.cpu().tolist() == [min(n, c["post"]) for n in c["n_kept"]]
+
+
+@pytest.mark.parametrize("B,n,thr", [(1, 1, 0.5), (2, 31, 0.2), (1, 32, 0.2), (3, 33, 0.4), (1, 2000, 0.3), (2, 4096, 0.5)])
+def test_nms_vs_restatement_edge_sizes(cuda, B, n, thr):
+    """word boundaries, a single box, the global-memory path (n > 1264) and the maximum size"""
+    from sparse_rcnn_b200 import proposal
+    score, boxes = make_proposals(100 + n, B, n)
+    order = torch.sort(score, dim=1, descending=True)[1]
+    sb = boxes[torch.arange(B)[:, None], order]
+    keep, keep_idx, counts = proposal.nms3d(sb.to(cuda), thr, n)
+    for k in range(B):
+        ref = nms_ref.nms(sb[k], thr)
+        assert torch.equal(keep[k].cpu(), ref)
+        cnt = int(counts[k])
+        assert cnt == int(ref.sum())
+        assert torch.equal(keep_idx[k, :cnt].cpu().long(), torch.nonzero(ref).flatten())
+
+
+def test_nms_degenerate_and_empty(cuda):
+    from sparse_rcnn_b200 import proposal
+    # zero-volume boxes: IoU is NaN (0/0) in the reference arithmetic, never above the threshold -> all kept
+    z = torch.zeros(1, 5, 2, 3)
+    keep, _, counts = proposal.nms3d(z.to(cuda), 0.5, 5)
+    assert keep.all() and int(counts[0]) == 5 and nms_ref.nms(z[0], 0.5).all()
+    # identical boxes: only the first survives
+    one = torch.tensor([[[0., 0, 0], [4, 4, 4]]]).repeat(7, 1, 1)[None]
+    keep, keep_idx, counts = proposal.nms3d(one.to(cuda), 0.5, 7)
+    assert keep[0].tolist() == [True] + [False] * 6 and int(counts[0]) == 1 and int(keep_idx[0, 0]) == 0
+    # no proposals at all
+    keep, keep_idx, counts = proposal.nms3d(torch.zeros(2, 0, 2, 3, device=cuda), 0.5, 4)
+    assert keep.shape == (2, 0) and counts.tolist() == [0, 0]
+    with pytest.raises(RuntimeError):
+        proposal.nms3d(torch.zeros(1, 4, 2, 3), 0.5)                       # CPU tensor: no fallback
+
+
+def test_nms_full_size_properties(cuda):
+    """BASELINE size (8 samples x 1024 proposals): no two survivors overlap above the threshold, every suppressed box
+    overlaps a better survivor, and NMS is idempotent on its own output."""
+    from sparse_rcnn_b200 import proposal
+    B, n, thr = 8, 1024, 0.5
+    score, boxes = make_proposals(7, B, n)
+    order = torch.sort(score, dim=1, descending=True)[1]
+    sb = boxes[torch.arange(B)[:, None], order].to(cuda)
+    keep, keep_idx, counts = proposal.nms3d(sb, thr, n)
+    for k in range(B):
+        iou = nms_ref.iou_matrix(sb[k].cpu())
+        kk = keep[k].cpu()
+        sub = iou[kk][:, kk]
+        sub.fill_diagonal_(0)
+        assert float(sub.max()) <= thr
+        dead = torch.nonzero(~kk).flatten()
+        better = torch.tril(iou > thr, diagonal=-1)                        # [i, j]: j better than i and overlapping
+        assert bool((better[dead][:, kk].any(dim=1)).all())
+        again, _, c2 = proposal.nms3d(sb[k][kk.to(cuda)][None], thr, n)
+        assert bool(again.all()) and int(c2[0]) == int(kk.sum())
