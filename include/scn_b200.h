@@ -228,6 +228,16 @@ int scn_cross_entropy_bwd(const float* logits, int ld, int64_t n, int C, const i
                           int64_t ignore_index, const float* lse, const float* stats, const float* grad_loss,
                           float* dlogits, scn_stream_t stream);
 
+/* ------------------------------------------------------------------ per-box mask loss ---
+ * MaskLoss._single_sample_loss + the per-box loop of MaskLoss.forward, ndsis/modules/loss.py:284-300:
+ * mean_out[s] = mean over the segment's elements of binary_cross_entropy_with_logits(x_i, t_i)   (NaN for an empty
+ * segment, as torch's mean of an empty tensor); segments are the boxes' (box, point) rows, seg_ptr [n_seg + 1].
+ * bwd: grad_logits_i = grad_mean[s] / count_s * (sigmoid(x_i) - t_i). */
+int scn_segment_bce_fwd(const float* logits, const uint8_t* targets, const int32_t* seg_ptr, int n_seg,
+                        float* mean_out, scn_stream_t stream);
+int scn_segment_bce_bwd(const float* logits, const uint8_t* targets, const int32_t* seg_ptr, int n_seg,
+                        const float* grad_mean, float* grad_logits, scn_stream_t stream);
+
 /* ------------------------------------------------------------------ proposal selection ---
  * ProposalSelector.forward ndsis/modules/proposal_selector.py:60-89 + non_maximum_supression ndsis/utils/bbox.py:713-759
  * (IoU as bbox_overlap_unsqueezed_area_start_end :235-240).  boxes: [B, n, 2, 3] fp32 (start, stop), every sample sorted

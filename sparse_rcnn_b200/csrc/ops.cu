@@ -417,6 +417,38 @@ __global__ void __launch_bounds__(256) k_crop_select(const uint64_t* __restrict_
 
 using namespace scn;
 
+// ---------------------------------------------------------------- per-box (segment) BCE with logits
+// torch's formulation (aten binary_cross_entropy_with_logits): (1 - t) x + m + log(exp(-m) + exp(-x - m)), m = max(-x, 0)
+__device__ __forceinline__ float bce_logits(float x, float t) {
+    const float m = fmaxf(-x, 0.f);
+    return (1.f - t) * x + m + logf(expf(-m) + expf(-x - m));
+}
+// one block per segment; fixed-shape tree reduction => deterministic
+__global__ void k_segment_bce_fwd(const float* __restrict__ x, const uint8_t* __restrict__ t, const int32_t* __restrict__ ptr,
+                                  float* __restrict__ out) {
+    __shared__ float sm[256];
+    const int s = blockIdx.x, lo = ptr[s], hi = ptr[s + 1];
+    float acc = 0.f;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += bce_logits(x[i], t[i] ? 1.f : 0.f);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if (threadIdx.x < d) sm[threadIdx.x] += sm[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[s] = sm[0] / (float)(hi - lo);      // 0/0 = NaN for an empty box, like torch.mean
+}
+__global__ void k_segment_bce_bwd(const float* __restrict__ x, const uint8_t* __restrict__ t, const int32_t* __restrict__ ptr,
+                                  const float* __restrict__ g, float* __restrict__ gx) {
+    const int s = blockIdx.x, lo = ptr[s], hi = ptr[s + 1];
+    if (hi <= lo) return;
+    const float scale = g[s] / (float)(hi - lo);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float sig = 1.f / (1.f + expf(-x[i]));
+        gx[i] = scale * (sig - (t[i] ? 1.f : 0.f));
+    }
+}
+
 // ---------------------------------------------------------------- point-wise cross entropy
 // one thread per row (C is the number of classes, ~20): max, log-sum-exp, weighted negative log-likelihood
 __global__ void k_ce_rows(const float* __restrict__ x, int ld, int64_t n, int C, const int64_t* __restrict__ y,
@@ -634,6 +666,20 @@ int scn_pool_bwd(const float* in, const float* out, const float* go, int C, cons
     k_pool_bwd<<<grid_for((int64_t)n_in * C, TB), TB, 0, as_stream(stream)>>>(in, out, go, C, parent_row, n_in, is_max,
                                                                               inv_volume, gi);
     return check_launch("pool_bwd");
+}
+int scn_segment_bce_fwd(const float* logits, const uint8_t* targets, const int32_t* seg_ptr, int n_seg, float* mean_out,
+                        scn_stream_t stream) {
+    SCN_REQUIRE(n_seg >= 0, "segment_bce_fwd: bad shape");
+    if (n_seg == 0) return SCN_OK;
+    k_segment_bce_fwd<<<n_seg, 256, 0, as_stream(stream)>>>(logits, targets, seg_ptr, mean_out);
+    return check_launch("segment_bce_fwd");
+}
+int scn_segment_bce_bwd(const float* logits, const uint8_t* targets, const int32_t* seg_ptr, int n_seg,
+                        const float* grad_mean, float* grad_logits, scn_stream_t stream) {
+    SCN_REQUIRE(n_seg >= 0, "segment_bce_bwd: bad shape");
+    if (n_seg == 0) return SCN_OK;
+    k_segment_bce_bwd<<<n_seg, 256, 0, as_stream(stream)>>>(logits, targets, seg_ptr, grad_mean, grad_logits);
+    return check_launch("segment_bce_bwd");
 }
 int scn_cross_entropy_fwd(const float* logits, int ld, int64_t n, int C, const int64_t* labels, const float* weight,
                           int64_t ignore_index, float* lse, float* row_scratch, float* stats, scn_stream_t stream) {

@@ -134,3 +134,22 @@ def make_proposals(seed, B, A, scene=(256.0, 256.0, 128.0), clustered=True):
     # unique scores per sample (a permutation), so that the descending order is the same on every device / library
     score = torch.stack([(torch.randperm(A, generator=g).float() + 0.5) / A for _ in range(B)])
     return score, boxes
+
+
+def make_mask_loss_case(seed, boxes_per_sample, max_points=400, num_classes=18, empty_every=5):
+    """Inputs of the reference's MaskLoss.forward: (masks_output, mask_target, class_target) = lists over samples of lists
+    over boxes of [n_b] logits / bool targets, and int64 class ids per box.  Every `empty_every`-th box has no points."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    outs, tgts, cls = [], [], []
+    k = 0
+    for nb in boxes_per_sample:
+        so, st = [], []
+        for _ in range(nb):
+            k += 1
+            n = 0 if (empty_every and k % empty_every == 0) else int(torch.randint(1, max_points, (1,), generator=g))
+            so.append(torch.randn(n, generator=g) * 4.0)
+            st.append(torch.rand(n, generator=g) > 0.6)
+        outs.append(so), tgts.append(st)
+        cls.append(torch.randint(0, num_classes, (nb,), generator=g))
+    return outs, tgts, cls

@@ -123,3 +123,18 @@ def test_nms_oracle_matches_reference():
             _, order = torch.sort(score, dim=1, descending=True)
         for k in range(c["B"]):
             assert torch.equal(nms_ref.nms(boxes[k][order[k]], c["thresh"]), c["keep"][k])
+
+
+# ----------------------------------------------------------------------------- per-box mask loss
+def test_maskloss_oracle_matches_reference():
+    """oracle/scn_oracle/maskloss_ref.py (fp64) vs the unmodified reference's MaskLoss (fp32): 1e-6 relative."""
+    import os
+    import torch
+    from scn_oracle import maskloss_ref
+    from sparse_rcnn_b200.synthetic import make_mask_loss_case
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "maskloss.pt"))
+    for c in gold["cases"]:
+        outs, tgts, cls = make_mask_loss_case(c["seed"], c["boxes_per_sample"], empty_every=c["empty_every"])
+        w = (torch.arange(18, dtype=torch.float32) % 5 + 0.5) if c["weighted"] else None
+        got = maskloss_ref.mask_loss(outs, tgts, cls, w)
+        assert abs(got - c["loss"]) <= 1e-6 * max(abs(c["loss"]), 1.0), (got, c["loss"])

@@ -96,3 +96,55 @@ def test_nms_full_size_properties(cuda):
         assert bool((better[dead][:, kk].any(dim=1)).all())
         again, _, c2 = proposal.nms3d(sb[k][kk.to(cuda)][None], thr, n)
         assert bool(again.all()) and int(c2[0]) == int(kk.sum())
+
+
+# ----------------------------------------------------------------------------- per-box mask loss
+def test_mask_loss_matches_reference_goldens(cuda):
+    """floating-point kernel: 1e-5 relative on the loss and on the gradients, against the unmodified reference's MaskLoss
+    (tests/golden/maskloss.pt) incl. empty boxes, all-empty and no-box cases, with and without class weights."""
+    from sparse_rcnn_b200 import losses
+    from sparse_rcnn_b200.synthetic import make_mask_loss_case
+    from tests.util import rel_err
+    gold = torch.load(os.path.join(G, "maskloss.pt"))
+    for c in gold["cases"]:
+        outs, tgts, cls = make_mask_loss_case(c["seed"], c["boxes_per_sample"], empty_every=c["empty_every"])
+        outs = [[m.to(cuda).requires_grad_() for m in s] for s in outs]
+        tgts = [[m.to(cuda) for m in s] for s in tgts]
+        cls = [t.to(cuda) for t in cls]
+        w = (torch.arange(18, dtype=torch.float32) % 5 + 0.5).to(cuda) if c["weighted"] else None
+        ml = losses.MaskLoss(class_weights=w).to(cuda)
+        loss = ml(outs, tgts, cls) if c["boxes_per_sample"] else ml([], [], [torch.zeros(0, dtype=torch.long, device=cuda)])
+        assert abs(float(loss) - c["loss"]) <= 1e-5 * max(abs(c["loss"]), 1.0), (float(loss), c["loss"])
+        if c["grads"]:
+            loss.backward()
+            flat = [m for s in outs for m in s]
+            for m, g in zip(flat, c["grads"]):
+                got = m.grad if m.grad is not None else torch.zeros_like(m)
+                assert got.shape == g.shape
+                if len(g):
+                    assert rel_err(got, g) < 1e-5
+
+
+def test_segment_bce_full_size(cuda):
+    """BASELINE size: 256 boxes, 615k (box, point) rows: equals torch's elementwise op reduced per box (1e-5), and the sum of
+    the gradients of a box equals mean(sigmoid(x) - t) (linearity of the backward)."""
+    from sparse_rcnn_b200 import losses
+    g = torch.Generator().manual_seed(3)
+    counts = torch.randint(0, 4800, (256,), generator=g).tolist()
+    counts[10] = counts[200] = 0
+    M = sum(counts)
+    x = (torch.randn(M, generator=g) * 3).to(cuda).requires_grad_()
+    t = (torch.rand(M, generator=g) > 0.5).to(cuda)
+    means = losses.segment_bce_with_logits(x, t, counts)
+    el = torch.nn.functional.binary_cross_entropy_with_logits(x.detach(), t.float(), reduction="none").double()
+    ptr = torch.tensor([0] + counts).cumsum(0)
+    ref = torch.stack([el[a:b].mean() if b > a else torch.tensor(float("nan"), device=cuda, dtype=torch.float64)
+                       for a, b in zip(ptr[:-1].tolist(), ptr[1:].tolist())])
+    ok = ~torch.isnan(ref)
+    assert torch.equal(torch.isnan(means), ~ok)
+    assert float(((means.double() - ref)[ok].abs() / ref[ok]).max()) < 1e-5
+    torch.nan_to_num(means, nan=0.0).sum().backward()
+    sg = (torch.sigmoid(x.detach().double()) - t.double())
+    for a, b in list(zip(ptr[:-1].tolist(), ptr[1:].tolist()))[:40]:
+        if b > a:
+            assert abs(float(x.grad[a:b].double().sum()) - float(sg[a:b].mean())) < 1e-5
