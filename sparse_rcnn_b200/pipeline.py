@@ -10,11 +10,17 @@ import torch.nn as nn
 
 from . import networks, roi, scn
 from .parallel import GradientBuckets
+from .scn.metadata import stage_to_device, take_staged
+
+
+def _dev(t, device):
+    d = take_staged(t)
+    return d if d is not None else t.to(device, non_blocking=True)
 
 
 def _to_device(data, device):
     coords, feats, size, bs, splits = data
-    return coords, feats.to(device, non_blocking=True), size, bs, splits
+    return coords, _dev(feats, device), size, bs, splits
 
 
 class BackboneTrainer(nn.Module):
@@ -46,13 +52,22 @@ class BackboneTrainer(nn.Module):
         coords, _, size, bs = data[:4]
         self.prefetcher.submit(coords.long(), torch.as_tensor(size, dtype=torch.long), bs)
 
-    def step(self, data, labels, next_data=None):
-        """data: collate_fn 5-tuple, labels int64 [P] (host or device).  next_data: the batch of the following step, if
-        already known (its rulebooks are then built while this step runs).  Returns the loss (device scalar)."""
+    def stage(self, data, labels=None):
+        """Start the host->device copies (coords, features, labels; pinned host tensors) of an upcoming batch on the copy
+        stream; the step() that later receives the same tensor objects uses the staged copies."""
+        stage_to_device([data[0], data[1], labels], self.device)
+
+    def step(self, data, labels, next_data=None, next_batch=None):
+        """data: collate_fn 5-tuple, labels int64 [P] (host or device).  Returns the loss (device scalar).
+        next_batch = (data, labels) of the following step, if already known (as from a DataLoader): its host->device copies
+        are issued now on a side stream and overlap this step.  next_data: additionally build its rulebooks ahead
+        (scn.GeometryPrefetcher, opt-in)."""
         if next_data is not None:
             self.prefetch(next_data)
         data = _to_device(data, self.device)
-        labels = labels.to(self.device, non_blocking=True)
+        labels = _dev(labels, self.device)
+        if next_batch is not None:
+            self.stage(*next_batch)
         self.buckets.zero()
         scn.functions.pack_all(self._weights)      # one launch: every packed weight image the optimizer made stale
         out = self.backbone(data)

@@ -181,7 +181,10 @@ class Metadata:
             max_b = 0
             if ncol == 4 and P:
                 max_b = int(coords[:, 3].max())          # CPU in the reference contract => no device sync
-            cdev = coords.to(device, non_blocking=True).contiguous()
+            cdev = take_staged(coords)             # uploaded ahead of time on the copy stream (stage_to_device)?
+            if cdev is None:
+                cdev = coords.to(device, non_blocking=True)
+            cdev = cdev.contiguous()
             keys = torch.empty(P, dtype=torch.int64, device=device)
             err = torch.zeros(1, dtype=torch.int32, device=device)
             _lib.call("scn_pack_coords", _ptr(cdev), P, ncol, _ptr(keys), _ptr(err), s)
@@ -277,6 +280,42 @@ class Metadata:
         r = Strided(out_size, cmap, dmap, parent_row, K)
         self.strided[key] = r
         return r
+
+
+# ---------------------------------------------------------------- host -> device staging one step ahead
+_copy_streams = {}
+_staged = {}
+
+
+def stage_to_device(tensors, device):
+    """Start the host->device copies of an UPCOMING batch's tensors (pinned host memory) on a side stream, so that they
+    overlap the current step instead of sitting at the head of the next one.  Plain asynchronous copies issued by the
+    calling thread: no worker thread, no host synchronisation.  `take_staged(t)` later returns the device copy."""
+    device = torch.device(device)
+    cs = _copy_streams.get(device)
+    if cs is None:
+        cs = _copy_streams[device] = torch.cuda.Stream(device)
+    todo = [t for t in tensors if isinstance(t, torch.Tensor) and not t.is_cuda and id(t) not in _staged]
+    if not todo:
+        return
+    with torch.cuda.stream(cs):
+        for t in todo:
+            d = t.to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            _staged[id(t)] = (t, d, ev)
+
+
+def take_staged(t):
+    """Device copy of host tensor `t` if it was staged (ordered after the copy on the current stream), else None."""
+    item = _staged.pop(id(t), None) if isinstance(t, torch.Tensor) else None
+    if item is None or item[0] is not t:
+        return None
+    _, d, ev = item
+    cur = torch.cuda.current_stream(d.device)
+    cur.wait_event(ev)
+    d.record_stream(cur)
+    return d
 
 
 def _walk_tensors(obj, seen):

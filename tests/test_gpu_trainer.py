@@ -123,3 +123,26 @@ def test_prefetched_geometry_equals_inline(cuda):
             md.set_input(batches[1][0][2], batches[1][0][0], 1, 4, cuda)
     finally:
         scn.set_precision("tf32")
+
+
+def test_staged_uploads_equal_inline(cuda):
+    """Host->device copies issued one step ahead on the copy stream (BackboneTrainer.stage / next_batch) change nothing."""
+    from sparse_rcnn_b200 import pipeline, scn
+    from sparse_rcnn_b200.scn import metadata
+    import bench
+    scn.set_precision("fp32")
+    try:
+        host = [bench.make_inputs(s, scene_kw=bench.CPU_SAMPLE) for s in (0, 1, 2)]
+        batches = [((d[0].pin_memory(), d[1].pin_memory(), d[2], d[3], d[4]), l.pin_memory()) for d, l in host]
+        losses = []
+        for stage in (False, True):
+            tr = pipeline.BackboneTrainer(cuda, seed=5)
+            out = []
+            for i, (d, l) in enumerate(batches):
+                nb = batches[i + 1] if stage and i + 1 < len(batches) else None
+                out.append(float(tr.step(d, l, next_batch=nb)))
+            losses.append(out)
+        assert not metadata._staged                                  # every staged tensor was picked up
+        assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-6, losses
+    finally:
+        scn.set_precision("tf32")
