@@ -112,7 +112,7 @@ def _fused_class(scn):
                 inner = self[0]._modules["1"]
                 c1, c2 = inner[1], inner[3]
                 lvl = x.metadata.level(x.spatial_size)
-                f = ResidualUnitFunction.apply(x.features, lvl.subm_map(c1.filter_size), lvl.n,
+                f = ResidualUnitFunction.run(x.features, lvl.subm_map(c1.filter_size), lvl.n,
                                                c1.weight, c1.bias, c2.weight, c2.bias)
                 return scn.SparseConvNetTensor(f, x.metadata, x.spatial_size)
 
@@ -148,7 +148,7 @@ def _fused_stage_class(scn):
                     fs = c1.filter_size
                     params += [c1.weight, c1.bias, c2.weight, c2.bias]
                 lvl = x.metadata.level(x.spatial_size)
-                f = ResidualUnitFunction.apply(x.features, lvl.subm_map(fs), lvl.n, *params)
+                f = ResidualUnitFunction.run(x.features, lvl.subm_map(fs), lvl.n, *params)
                 return scn.SparseConvNetTensor(f, x.metadata, x.spatial_size)
 
         _FUSED_STAGES[scn] = FusedUnitStage
@@ -187,7 +187,8 @@ class InputStage(nn.Module):
         md = self.prefetcher.take(coords) if self.prefetcher is not None else None
         if md is None:
             md = self.scn.Metadata(3)
-        f = self.scn.ioLayers.InputLayerFunction.apply(3, md, spatial_size, coords, feats, batch_size, self.mode)
+        fn = self.scn.ioLayers.InputLayerFunction
+        f = getattr(fn, "run", fn.apply)(3, md, spatial_size, coords, feats, batch_size, self.mode)
         t = self.scn.SparseConvNetTensor(features=f, metadata=md, spatial_size=spatial_size)
         return spatial_size, t.batch_size(), t
 
@@ -269,7 +270,7 @@ class SparseGlobalPool(nn.Module):
             md = x.metadata
             n_seg = md.n_samples
             ptr = md.level(x.spatial_size).batch_ptr(n_seg)
-            return SegmentMeanFunction.apply(x.features, ptr, n_seg)
+            return SegmentMeanFunction.run(x.features, ptr, n_seg)
         # generic namespace (e.g. the CPU oracle in tests): reference algorithm
         b = x.get_spatial_locations()[:, -1]
         n = x.batch_size()

@@ -20,9 +20,9 @@ import weakref
 
 import torch
 import torch.nn as nn
-from torch.autograd import Function
 
 from . import _lib
+from .scn.functions import Function
 from .scn.metadata import _ptr, _stream, exclusive_scan, size_key
 
 CROP_CHUNK = 2048      # SCN_CROP_CHUNK
@@ -208,7 +208,7 @@ class SparseRoiCut(nn.Module):
         boxes, counts, assoc = self.bbox_transformer(bbox_batch, spatial_size)
         sel_pt, new_keys, box_ptr, total, inside = crop(keys, ptr, max_len, boxes, assoc)
         sel = CropSelection(sel_pt, new_keys, box_ptr, boxes.shape[0], keys.numel(), inside, counts, splits)
-        new_feats = GatherRowsFunction.apply(feats, sel_pt)
+        new_feats = GatherRowsFunction.run(feats, sel_pt)
         out = combine_crop(self.scn, self.combine, new_keys, new_feats, spatial_size, boxes.shape[0],
                            mode=4 if self.raw_scene else 0)
         return out, sel
@@ -221,7 +221,8 @@ def combine_crop(scn, how, new_keys, new_feats, spatial_size, n_boxes, mode):
         return new_keys, new_feats, spatial_size, n_boxes
     md = scn.Metadata(3)
     size = torch.as_tensor(spatial_size, dtype=torch.long)
-    f = scn.ioLayers.InputLayerFunction.apply(3, md, size, new_keys, new_feats, n_boxes, mode)
+    fn = scn.ioLayers.InputLayerFunction
+    f = getattr(fn, "run", fn.apply)(3, md, size, new_keys, new_feats, n_boxes, mode)
     return scn.SparseConvNetTensor(features=f, metadata=md, spatial_size=size)
 
 
@@ -231,7 +232,7 @@ class SparseRoiExtraCut(nn.Module):
 
     def forward(self, feature_map, selection):
         feats = feature_map[1]
-        return GatherRowsFunction.apply(feats, selection.sel_pt)
+        return GatherRowsFunction.run(feats, selection.sel_pt)
 
 
 class SparseMaskPredictor(nn.Module):

@@ -85,7 +85,7 @@ class AddTable(nn.Module):
     def forward(self, xs):
         f = xs[0].features
         for x in xs[1:]:
-            f = F.AddFunction.apply(f, x.features)
+            f = F.AddFunction.run(f, x.features)
         return _like(xs[0], f)
 
 
@@ -96,7 +96,7 @@ class JoinTable(nn.Module):
 
 class ReLU(nn.Module):
     def forward(self, x):
-        return _like(x, F._mark(F.ReLUFunction.apply(x.features)))
+        return _like(x, F._mark(F.ReLUFunction.run(x.features)))
 
     def input_spatial_size(self, out_size):
         return out_size
@@ -116,7 +116,7 @@ class BatchNormalization(nn.Module):
             self.register_parameter("bias", None)
 
     def forward(self, x):
-        f = F.BatchNormFunction.apply(x.features, self.weight, self.bias, self.running_mean, self.running_var,
+        f = F.BatchNormFunction.run(x.features, self.weight, self.bias, self.running_mean, self.running_var,
                                       self.eps, self.momentum, float(self.leakiness), self.training)
         return _like(x, f)
 
@@ -156,7 +156,7 @@ class SubmanifoldConvolution(nn.Module):
     def forward(self, x):
         lvl = x.metadata.level(x.spatial_size)
         m = lvl.subm_map(self.filter_size)
-        f = F.ConvFunction.apply(x.features, self.weight, self.bias, m, m, lvl.n, 1)
+        f = F.ConvFunction.run(x.features, self.weight, self.bias, m, m, lvl.n, 1)
         return _like(x, f)
 
     def input_spatial_size(self, out_size):
@@ -180,7 +180,7 @@ class Convolution(nn.Module):
         md = x.metadata
         r = md.strided_rules(x.spatial_size, self.filter_size, self.filter_stride)
         n_out = md.levels[r.out_key].n
-        f = F.ConvFunction.apply(x.features, self.weight, self.bias, r.cmap, r.dmap, n_out, 0)
+        f = F.ConvFunction.run(x.features, self.weight, self.bias, r.cmap, r.dmap, n_out, 0)
         return SparseConvNetTensor(f, md, r.out_size)
 
     def input_spatial_size(self, out_size):
@@ -208,7 +208,7 @@ class Deconvolution(nn.Module):
         lvl = md.levels[out_size]
         if getattr(lvl, "size_tensor", None) is None:
             lvl.size_tensor = torch.tensor(out_size, dtype=torch.long)
-        f = F.ConvFunction.apply(x.features, self.weight, self.bias, r.dmap, r.cmap, lvl.n, 0)
+        f = F.ConvFunction.run(x.features, self.weight, self.bias, r.dmap, r.cmap, lvl.n, 0)
         return SparseConvNetTensor(f, md, lvl.size_tensor)
 
 
@@ -222,7 +222,7 @@ class NetworkInNetwork(nn.Module):
         self.bias = nn.Parameter(torch.zeros(nOut)) if bias else None
 
     def forward(self, x):
-        f = F.ConvFunction.apply(x.features, self.weight, self.bias, None, None, x.features.shape[0], 0)
+        f = F.ConvFunction.run(x.features, self.weight, self.bias, None, None, x.features.shape[0], 0)
         return _like(x, f)
 
     def input_spatial_size(self, out_size):
@@ -241,7 +241,7 @@ class _Pooling(nn.Module):
         r = md.strided_rules(x.spatial_size, self.pool_size, self.pool_stride)
         n_out = md.levels[r.out_key].n
         vol = self.pool_size[0] * self.pool_size[1] * self.pool_size[2]
-        f = F.PoolFunction.apply(x.features, r, n_out, self.IS_MAX, 1.0 / vol)
+        f = F.PoolFunction.run(x.features, r, n_out, self.IS_MAX, 1.0 / vol)
         return SparseConvNetTensor(f, md, r.out_size)
 
 
@@ -264,7 +264,7 @@ class SparseToDense(nn.Module):
 
     def forward(self, x):
         md = x.metadata
-        return F.SparseToDenseFunction.apply(x.features, md.level(x.spatial_size), md.n_samples,
+        return F.SparseToDenseFunction.run(x.features, md.level(x.spatial_size), md.n_samples,
                                              size_key(x.spatial_size))
 
 
@@ -274,7 +274,7 @@ class OutputLayer(nn.Module):
         self.dimension = dimension
 
     def forward(self, x):
-        return F.OutputLayerFunction.apply(self.dimension, x.metadata, x.features)
+        return F.OutputLayerFunction.run(self.dimension, x.metadata, x.features)
 
 
 class InputLayer(nn.Module):
@@ -287,5 +287,5 @@ class InputLayer(nn.Module):
         coords, feats = inp[0], inp[1]
         bs = inp[2] if len(inp) > 2 else 0
         md = Metadata(self.dimension)
-        f = F.InputLayerFunction.apply(self.dimension, md, self.spatial_size, coords, feats, bs, self.mode)
+        f = F.InputLayerFunction.run(self.dimension, md, self.spatial_size, coords, feats, bs, self.mode)
         return SparseConvNetTensor(f, md, self.spatial_size)
