@@ -904,11 +904,8 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     p.scratch = nullptr, p.tickets = nullptr, p.cluster = 0;
     // split mode as a thread-block cluster (<= 8 CTAs, the portable limit) reducing through DSMEM when the partial tile
     // (128 rows x (cout_pad + 4) floats) fits in the stage ring; otherwise atomics into the library workspace
-    static int no_cluster = -1;
-    if (no_cluster < 0) {
-        const char* ev = getenv("SCN_CONV_NOCLUSTER");
-        no_cluster = (ev && ev[0] == '1') ? 1 : 0;
-    }
+    const char* ev_nc = getenv("SCN_CONV_NOCLUSTER");      // read per call: the fallback path is exercised by a test
+    const int no_cluster = (ev_nc && ev_nc[0] == '1') ? 1 : 0;
     if (p.osplit > 1 && p.osplit <= 8 && !no_cluster && !use_tma && grid == n_work &&
         TILE_M * (p.cout_pad * 4 + 16) <= stages * stage_bytes)
         p.cluster = p.osplit;

@@ -109,3 +109,29 @@ def test_large_layer_linearity(cuda, precision):
         scn.set_precision("fp32")
         ref = conv(T(x)).features
         assert rel_err(cx, ref) <= TOL[precision]
+
+
+def test_split_mode_fallback_equals_cluster_mode(cuda, monkeypatch):
+    """Small levels: the cluster/DSMEM reduction (default) and the atomics fallback (SCN_CONV_NOCLUSTER=1: self-cleaning
+    accumulation buffer + last-arriver epilogue) give the same result; the fallback leaves its buffer zeroed (second call)."""
+    from sparse_rcnn_b200 import scn
+    from sparse_rcnn_b200.synthetic import make_batch
+    scn.set_precision("tf32")
+    torch.manual_seed(0)
+    coords, feats, size, bs, _ = make_batch(1, 3, spatial_size=(64, 64, 32), room=(40, 40, 20), room_offset=(8, 8, 4),
+                                            n_furniture=3)
+    md = scn.Metadata(3)
+    f = scn.ioLayers.InputLayerFunction.apply(3, md, size, coords, feats.to(cuda), bs, 4)
+    n = f.shape[0]
+    assert n // 128 < 148                                            # few tiles => split-offset mode
+    conv = scn.SubmanifoldConvolution(3, 48, 48, 3, True).to(cuda)
+    x = scn.SparseConvNetTensor(torch.randn(n, 48, device=cuda), md, size)
+    with torch.no_grad():
+        a = conv(x).features.clone()
+        monkeypatch.setenv("SCN_CONV_NOCLUSTER", "1")
+        b1 = conv(x).features.clone()
+        b2 = conv(x).features.clone()
+        monkeypatch.delenv("SCN_CONV_NOCLUSTER")
+        a2 = conv(x).features
+    assert torch.equal(a, a2)                                        # cluster mode is deterministic
+    assert rel_err(b1, a) < 1e-5 and rel_err(b2, a) < 1e-5           # fallback: same sums, atomics order differs
