@@ -187,6 +187,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--build-ahead", action="store_true",
+                    help="build each step's rulebooks between the previous step's forward and backward (the next batch is "
+                         "known one step ahead, as with a DataLoader).  Off by default: measured 7.89 vs 7.80 ms -- the "
+                         "host is busy, not blocked, so moving its synchronisation points buys nothing")
     ap.add_argument("--stage", action="store_true",
                     help="upload each batch one step ahead on a copy stream (BackboneTrainer.stage).  Off by default: measured "
                          "e2e 9.49 vs 8.86 ms -- the inline upload already overlaps the host's issue of the rulebook kernels, "
@@ -232,9 +236,11 @@ def main():
         # --prefetch: the following batch is known (as with a DataLoader), so its rulebooks are built on a side stream
         # while this step runs; every step's geometry is still built inside the loop, one step ahead
         nxt = (lambda i: inputs[(i + 1) % n_distinct][0]) if args.prefetch else (lambda i: None)
-        # the following batch is known (DataLoader): its host->device copies are issued one step ahead on a copy stream;
-        # every step still uploads exactly one batch inside the loop (h2d_bytes_per_step)
-        nb = (lambda i: inputs[(i + 1) % n_distinct]) if args.stage else (lambda i: None)
+        # the following batch is known (DataLoader): its rulebooks are built between this step's forward and backward
+        # (--no-build-ahead: at the head of its own step); every step still builds exactly one geometry and uploads exactly
+        # one batch inside the loop (h2d_bytes_per_step)
+        trainer.stage_uploads, trainer.build_ahead = args.stage, args.build_ahead
+        nb = (lambda i: inputs[(i + 1) % n_distinct]) if (args.stage or args.build_ahead) else (lambda i: None)
         for i in range(W):
             trainer.step(*inputs[i % n_distinct], next_data=nxt(i), next_batch=nb(i))
         barrier()

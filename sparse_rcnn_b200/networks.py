@@ -177,6 +177,22 @@ class InputStage(nn.Module):
         super().__init__()
         self.scn, self.mode = scn, mode
         self.prefetcher = None      # optional scn.GeometryPrefetcher (B200 backend): geometry of this batch built ahead
+        self.ready = {}             # id(coords) -> Metadata built by build_ahead()
+
+    def build_ahead(self, data, n_levels, device):
+        """Build the geometry (voxel hash, level pyramid, neighbour maps) of an UPCOMING batch now, on the current stream.
+        Called between the forward and the backward of the current step, the builder's host round trips wait for the
+        forward's kernels to drain (the GPU is busy) instead of idling the GPU at the head of the next step, and the next
+        forward is issued without any synchronisation.  Same kernels, same order of results."""
+        coords, _, spatial_size, batch_size = data[:4]
+        coords = coords.long()
+        if not len(coords) or id(coords) in self.ready or getattr(self.scn, "BACKEND", "") != "b200-cuda":
+            return
+        md = self.scn.Metadata(3)
+        md.set_input(torch.as_tensor(spatial_size, dtype=torch.long), coords, batch_size, self.mode, device)
+        md.prebuild(n_levels)
+        md._prebuilt_for = coords
+        self.ready[id(coords)] = md
 
     def forward(self, data):
         coords, feats, spatial_size, batch_size = data[:4]
@@ -184,7 +200,9 @@ class InputStage(nn.Module):
         if not len(coords):
             return spatial_size, batch_size, None
         coords = coords.long()      # int64 already in the reference contract (data.py:95-98): the same tensor object
-        md = self.prefetcher.take(coords) if self.prefetcher is not None else None
+        md = self.ready.pop(id(coords), None)       # geometry built ahead of time for exactly this tensor (build_ahead)
+        if md is None and self.prefetcher is not None:
+            md = self.prefetcher.take(coords)
         if md is None:
             md = self.scn.Metadata(3)
         fn = self.scn.ioLayers.InputLayerFunction

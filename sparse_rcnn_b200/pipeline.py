@@ -42,6 +42,8 @@ class BackboneTrainer(nn.Module):
         self.distributed = distributed
         self._weights = [p for p in self.parameters() if p.dim() >= 2]
         self.prefetcher = None
+        self.build_ahead = False       # next_batch: build its rulebooks between this step's forward and backward (no gain)
+        self.stage_uploads = False     # next_batch: also issue its host->device copies now (measured: no gain)
 
     def prefetch(self, data):
         """Start building the geometry (voxel hash, level pyramid, neighbour maps) of an upcoming batch on a side stream;
@@ -59,20 +61,24 @@ class BackboneTrainer(nn.Module):
 
     def step(self, data, labels, next_data=None, next_batch=None):
         """data: collate_fn 5-tuple, labels int64 [P] (host or device).  Returns the loss (device scalar).
-        next_batch = (data, labels) of the following step, if already known (as from a DataLoader): its host->device copies
-        are issued now on a side stream and overlap this step.  next_data: additionally build its rulebooks ahead
-        (scn.GeometryPrefetcher, opt-in)."""
+        next_batch = (data, labels) of the following step, if already known (as from a DataLoader): its rulebooks are built
+        between this step's forward and backward (`build_ahead`), optionally its host->device copies are issued now
+        (`stage_uploads`).  next_data: build its rulebooks in a worker thread instead (scn.GeometryPrefetcher, opt-in)."""
         if next_data is not None:
             self.prefetch(next_data)
         data = _to_device(data, self.device)
         labels = _dev(labels, self.device)
-        if next_batch is not None:
+        if next_batch is not None and self.stage_uploads:
             self.stage(*next_batch)
         self.buckets.zero()
         scn.functions.pack_all(self._weights)      # one launch: every packed weight image the optimizer made stale
         out = self.backbone(data)
         logits = self.seg(out[5])
         loss = scn.functions.cross_entropy(logits, labels)      # nn.CrossEntropyLoss semantics (loss.py:95-97)
+        if next_batch is not None and self.build_ahead:
+            # the following batch's rulebooks, between this step's forward and backward: their host round trips wait
+            # while the GPU drains the forward instead of idling it at the head of the next step
+            self.backbone.input_stage.build_ahead(next_batch[0], len(self.backbone.channels) - 1, self.device)
         loss.backward()
         self.buckets.finish()
         self.optimizer.step()

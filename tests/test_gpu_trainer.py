@@ -137,12 +137,36 @@ def test_staged_uploads_equal_inline(cuda):
         losses = []
         for stage in (False, True):
             tr = pipeline.BackboneTrainer(cuda, seed=5)
+            tr.stage_uploads = True
             out = []
             for i, (d, l) in enumerate(batches):
                 nb = batches[i + 1] if stage and i + 1 < len(batches) else None
                 out.append(float(tr.step(d, l, next_batch=nb)))
             losses.append(out)
         assert not metadata._staged                                  # every staged tensor was picked up
+        assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-6, losses
+    finally:
+        scn.set_precision("tf32")
+
+
+def test_geometry_built_ahead_equals_inline(cuda):
+    """next_batch: rulebooks built between the previous step's forward and backward (InputStage.build_ahead) give the same
+    losses as building them at the head of the step."""
+    from sparse_rcnn_b200 import pipeline, scn
+    import bench
+    scn.set_precision("fp32")
+    try:
+        batches = [bench.make_inputs(s, scene_kw=bench.CPU_SAMPLE) for s in (0, 1, 2)]
+        losses = []
+        for ahead in (False, True):
+            tr = pipeline.BackboneTrainer(cuda, seed=5)
+            tr.build_ahead = ahead
+            out = []
+            for i, (d, l) in enumerate(batches):
+                nb = batches[i + 1] if i + 1 < len(batches) else None
+                out.append(float(tr.step(d, l, next_batch=nb)))
+                assert len(tr.backbone.input_stage.ready) == (1 if ahead and nb is not None else 0)
+            losses.append(out)
         assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-6, losses
     finally:
         scn.set_precision("tf32")
