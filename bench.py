@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--sync-loss", action="store_true",
+                    help="e2e: read every step's loss with a blocking .item() right after the step instead of one step late")
     ap.add_argument("--build-ahead", action="store_true",
                     help="build each step's rulebooks between the previous step's forward and backward (the next batch is "
                          "known one step ahead, as with a DataLoader).  Off by default: measured 7.89 vs 7.80 ms -- the "
@@ -248,11 +250,30 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         voxels, t0 = 0, time.perf_counter()
         e0.record()
+        # e2e: every step's loss is copied device->host (4 bytes, pinned) and read by the host.  Like a training loop that
+        # logs its loss, the host reads step i's value after it has queued step i+1 (--sync-loss: right away, which stalls
+        # the host until the whole step has drained and leaves the GPU idle while the next step is being issued)
+        slots = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        evs = [torch.cuda.Event() for _ in range(2)]
+        pending, loss_sum = None, 0.0
         for i in range(K):
             loss = trainer.step(*inputs[i % n_distinct], next_data=nxt(i), next_batch=nb(i))
             if read_loss:
-                float(loss.item())                      # D2H read of the step's result
+                if args.sync_loss:
+                    loss_sum += float(loss.item())
+                else:
+                    slots[i & 1].copy_(loss.reshape(1), non_blocking=True)
+                    evs[i & 1].record()
+                    if pending is not None:
+                        evs[pending].synchronize()
+                        loss_sum += float(slots[pending][0])
+                    pending = i & 1
             voxels += trainer.last_active
+        if read_loss and pending is not None:
+            evs[pending].synchronize()
+            loss_sum += float(slots[pending][0])
+        if read_loss and not (loss_sum == loss_sum):
+            raise RuntimeError("non-finite loss in the timed region")
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -343,6 +364,8 @@ def main():
                        "l2": "a different scene every step (4 distinct, inputs+activations > L2 over a step)",
                        "precision": args.precision},
             "e2e": {"value": vox_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "loss_read": "blocking .item() per step" if args.sync_loss else
+                    "every step, async copy into pinned memory, read by the host one step late",
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "inference": inference,
         }
