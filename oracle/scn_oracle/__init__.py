@@ -457,6 +457,24 @@ class AveragePooling(nn.Module):
         return SparseConvNetTensor(f, x.metadata, torch.tensor(out_key, dtype=torch.long))
 
 
+class UnPooling(nn.Module):
+    """Inverse site map of the poolings: every active fine site gets its coarse parent's row (SparseConvNet UnPooling)."""
+
+    def __init__(self, dimension, pool_size, pool_stride, nFeaturesToDrop=0):
+        super().__init__()
+        self.pool_size, self.pool_stride = _triple(pool_size), _triple(pool_stride)
+
+    def forward(self, x):
+        md = x.metadata
+        coarse = torch.as_tensor(x.spatial_size)
+        fine = (coarse - 1) * torch.tensor(self.pool_stride) + torch.tensor(self.pool_size)
+        if md._key(fine) not in md.grids:
+            raise RuntimeError("UnPooling needs the finer grid to exist in the Metadata")
+        out_key, _, parent, _ = md.conv_rules(fine, self.pool_size, self.pool_stride)
+        assert tuple(out_key) == tuple(int(v) for v in coarse)
+        return SparseConvNetTensor(x.features[_idx(parent)], md, fine)
+
+
 class SparseToDense(nn.Module):
     def __init__(self, dimension, nPlanes):
         super().__init__()

@@ -9,7 +9,7 @@ from .functions import (InputLayerFunction, OutputLayerFunction, get_precision, 
 from .layers import (AddTable, AveragePooling, BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, ConcatTable,
                      Convolution, Deconvolution, Identity, InputLayer, JoinTable, MaxPooling, NetworkInNetwork,
                      OutputLayer, ReLU, Sequential, SparseConvNetTensor, SparseToDense, SubmanifoldConvolution,
-                     ValidConvolution)
+                     UnPooling, ValidConvolution)
 from .metadata import GeometryPrefetcher, Metadata
 
 ioLayers = types.SimpleNamespace(

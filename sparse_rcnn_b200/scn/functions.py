@@ -579,3 +579,24 @@ class CrossEntropyFunction(Function):
 
 def cross_entropy(logits, labels, weight=None, ignore_index=-100):
     return CrossEntropyFunction.run(logits, labels, weight, ignore_index)
+
+
+class UnPoolFunction(Function):
+    """Transpose of sum-pooling: every fine row receives its coarse parent's row; backward sums the children."""
+
+    @staticmethod
+    def forward(ctx, x, parent_row, n_coarse):
+        x = _check(x)
+        n, C = parent_row.numel(), x.shape[1]
+        out = torch.empty((n, C), dtype=torch.float32, device=x.device)
+        _lib.call("scn_gather_rows", _ptr(x), x.stride(0), _ptr(parent_row), n, C, _ptr(out), C, _stream())
+        ctx.parent_row, ctx.shape = parent_row, (n_coarse, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        go = _check(go)
+        gi = torch.zeros(ctx.shape, dtype=torch.float32, device=go.device)
+        _lib.call("scn_scatter_add_rows", _ptr(go), _ptr(ctx.parent_row), ctx.parent_row.numel(), ctx.shape[1], _ptr(gi),
+                  _stream())
+        return gi, None, None

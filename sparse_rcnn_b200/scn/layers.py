@@ -255,6 +255,28 @@ class AveragePooling(_Pooling):
     IS_MAX = False
 
 
+class UnPooling(nn.Module):
+    """SparseConvNet UnPooling(dimension, pool_size, pool_stride): the inverse site map of MaxPooling/AveragePooling --
+    every active site of the FINER level (which must already exist in the Metadata, as for Deconvolution) receives the
+    feature row of its coarse parent.  Not used by the shipped ndsis configurations; named by the build's north star."""
+
+    def __init__(self, dimension, pool_size, pool_stride, nFeaturesToDrop=0):
+        super().__init__()
+        self.pool_size, self.pool_stride = _triple(pool_size), _triple(pool_stride)
+
+    def forward(self, x):
+        md = x.metadata
+        ck = size_key(x.spatial_size)
+        fine = tuple((o - 1) * s + f for o, f, s in zip(ck, self.pool_size, self.pool_stride))
+        if fine not in md.levels:
+            raise RuntimeError("UnPooling needs the finer grid to exist in the Metadata")
+        r = md.strided_rules(fine, self.pool_size, self.pool_stride)
+        if r.out_key != ck:
+            raise RuntimeError("UnPooling: spatial size %s is not the pooled size of %s" % (ck, fine))
+        f = F.UnPoolFunction.run(x.features, r.parent_row, md.levels[ck].n)
+        return SparseConvNetTensor(f, md, torch.tensor(fine, dtype=torch.long))
+
+
 class SparseToDense(nn.Module):
     """module_factory.py:429-435 -> [B, C, X, Y, Z]."""
 

@@ -63,6 +63,22 @@ def test_pooling_fwd_bwd(cuda, kind):
         lambda v: pg(scn.SparseConvNetTensor(v, tg.metadata, size)).features, to.features, tg.features)
 
 
+def test_unpooling_fwd_bwd(cuda):
+    """scn.UnPooling (named by the north star; transpose of sum pooling) against the oracle, forward and backward, and the
+    error when the finer level does not exist."""
+    scn = _scn()
+    coords, feats, size = random_scene(41, channels=8)
+    to, tg = make_pair(scn, coords, feats, size, cuda)
+    po, pg = O.AveragePooling(3, 2, 2)(to), scn.AveragePooling(3, 2, 2)(tg)
+    _fb(lambda v: O.UnPooling(3, 2, 2)(O.SparseConvNetTensor(v, to.metadata, po.spatial_size)).features,
+        lambda v: scn.UnPooling(3, 2, 2)(scn.SparseConvNetTensor(v, tg.metadata, pg.spatial_size)).features,
+        po.features.detach(), pg.features.detach())
+    up = scn.UnPooling(3, 2, 2)(pg)
+    assert torch.equal(up.get_spatial_locations(), tg.get_spatial_locations())
+    with pytest.raises(RuntimeError):
+        scn.UnPooling(3, 2, 2)(tg)                     # nothing finer than the input level
+
+
 def test_sparse_to_dense_fwd_bwd(cuda):
     scn = _scn()
     coords, feats, size = random_scene(50, channels=7, n_samples=3)

@@ -69,6 +69,20 @@ def test_pooling_equals_dense():
     assert torch.allclose(_at(F.avg_pool3d(d, 2), ap.get_spatial_locations()), ap.features, atol=1e-6)
 
 
+def test_unpooling_equals_masked_nearest_upsample():
+    """UnPooling(pool(x)) puts the pooled value on every ACTIVE site of the finer level: the dense equivalent is a nearest
+    upsample masked to the active set; it is also the transpose of sum pooling (<unpool(c), y> == <c, 8 * avgpool(y)>)."""
+    t, _, _ = _tensor(5, 4)
+    ap = O.AveragePooling(3, 2, 2)(t)
+    up = O.UnPooling(3, 2, 2)(ap)
+    assert torch.equal(up.get_spatial_locations(), t.get_spatial_locations())
+    dense = F.interpolate(O.SparseToDense(3, 4)(ap), scale_factor=2, mode="nearest")
+    assert torch.allclose(_at(dense, t.get_spatial_locations()), up.features)
+    c = torch.randn_like(ap.features)
+    lhs = (O.UnPooling(3, 2, 2)(O.SparseConvNetTensor(c, ap.metadata, ap.spatial_size)).features * t.features).sum()
+    assert torch.allclose(lhs, (c * ap.features * 8).sum(), rtol=1e-5)
+
+
 def test_input_layer_mode4_is_unique_mean_in_first_appearance_order():
     t, coords, feats = _tensor(4, 6)
     keys = R.pack_keys(coords.numpy())
