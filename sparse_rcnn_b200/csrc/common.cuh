@@ -33,6 +33,39 @@ static inline int grid_for(int64_t work_items, int block, int ctas_per_sm = 8) {
     return (int)(need < cap ? need : cap);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Kernels that are launched back to back on one stream inside a C-ABI call (a residual unit = 3 launches forward, 6
+// backward) pay ~3 us of launch latency + prologue each, serialised behind the previous kernel's drain.  With the
+// programmatic-stream-serialization launch attribute the next kernel's CTAs may start (barrier init, TMEM allocation,
+// index arithmetic) as soon as every CTA of the previous kernel has executed `pdl_trigger()` or exited and resources are
+// free; `pdl_wait()` then blocks until the previous grid has COMPLETED and its memory is visible.  Rule kept by every
+// kernel that uses it: no global-memory access before pdl_wait().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// SCN_PDL=0 turns the launch attribute off (the device-side instructions are then no-ops)
+bool pdl_enabled();
+// launch config with the PDL attribute (and an optional cluster dimension); attrs must outlive the launch call
+struct PdlLaunch {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attrs[2];
+    PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster = 0) {
+        cfg = cudaLaunchConfig_t{};
+        cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+        int n = 0;
+        if (pdl_enabled()) {
+            attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attrs[n].val.programmaticStreamSerializationAllowed = 1;
+            ++n;
+        }
+        if (cluster > 1) {
+            attrs[n].id = cudaLaunchAttributeClusterDimension;
+            attrs[n].val.clusterDim.x = cluster, attrs[n].val.clusterDim.y = 1, attrs[n].val.clusterDim.z = 1;
+            ++n;
+        }
+        cfg.attrs = attrs, cfg.numAttrs = n;
+    }
+};
+
 // ---------------------------------------------------------------- packed voxel keys
 __host__ __device__ __forceinline__ uint64_t make_key(uint32_t x, uint32_t y, uint32_t z, uint32_t b) {
     return ((uint64_t)b << 48) | ((uint64_t)x << 32) | ((uint64_t)y << 16) | (uint64_t)z;

@@ -131,6 +131,10 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (tid == 0) SCN_TRACE(1);
+    // PDL: everything above touched only shared memory / TMEM / parameters; the next kernel on the stream may start its
+    // own prologue now, and we wait here for the previous kernel's results
+    pdl_trigger();
+    pdl_wait();
 
     if (TMA && warp == 4) {
         // ===================== TMA gather producer (one warp) =====================
@@ -917,18 +921,8 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     auto launch = [&](auto kern, int threads) {
         e = (cudaError_t)scn::ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
         if (e != cudaSuccess) return;
-        if (p.cluster > 1) {
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof(cfg));
-            cfg.gridDim = dim3(grid), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = as_stream(stream);
-            cudaLaunchAttribute attr;
-            attr.id = cudaLaunchAttributeClusterDimension;
-            attr.val.clusterDim.x = p.cluster, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
-            cfg.attrs = &attr, cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, kern, tmap, p);
-        } else {
-            kern<<<grid, threads, smem, as_stream(stream)>>>(tmap, p);
-        }
+        scn::PdlLaunch L(dim3(grid), dim3(threads), smem, as_stream(stream), p.cluster);
+        e = cudaLaunchKernelEx(&L.cfg, kern, tmap, p);
     };
     if (use_tma) launch(k_conv_tc<4, true>, 192);
     else if (vec == 4) launch(k_conv_tc<4, false>, CONV_THREADS);

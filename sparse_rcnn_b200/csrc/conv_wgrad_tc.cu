@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_trigger();      // PDL (common.cuh): only shared memory / TMEM / parameters were touched so far
+    pdl_wait();
 
     if (warp < 8) {
         // ===================== producers =====================
@@ -426,7 +428,8 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
     auto launch = [&](auto kern) {
         e = (cudaError_t)scn::ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
         if (e != cudaSuccess) return;
-        kern<<<grid, WG_THREADS, smem, as_stream(stream)>>>(p);
+        scn::PdlLaunch L(grid, dim3(WG_THREADS), smem, as_stream(stream));
+        e = cudaLaunchKernelEx(&L.cfg, kern, p);
     };
     if (vec == 4) launch(k_conv_wgrad_tc<4>);
     else if (vec == 2) launch(k_conv_wgrad_tc<2>);

@@ -7,6 +7,7 @@
 // key arrays, random probes into a table sized at load factor <= 0.5 that lives in the 126 MB L2.
 #include <stdarg.h>
 #include <atomic>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace scn {
@@ -28,6 +29,15 @@ int check_launch(const char* what) {
     }
     return SCN_OK;
 }
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("SCN_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 int sm_count() {
     static int n = -1;
     if (n < 0) {

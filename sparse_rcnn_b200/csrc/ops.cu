@@ -23,6 +23,8 @@ __device__ __forceinline__ float ew(float v) {
 }
 template <int MODE>
 __global__ void k_relu_fwd(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
+    pdl_trigger();      // PDL (common.cuh): let the convolution that follows start its prologue
+    pdl_wait();
     int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
@@ -38,6 +40,8 @@ __global__ void k_relu_fwd(const float* __restrict__ in, float* __restrict__ out
 }
 template <bool ROUND>
 __global__ void k_relu_bwd(const float* __restrict__ y, const float* __restrict__ go, float* __restrict__ gi, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float g = y[i] > 0.f ? go[i] : 0.f;
@@ -534,22 +538,37 @@ extern "C" {
 int scn_relu_fwd(const float* in, float* out, int64_t n, int round_tf32, scn_stream_t stream) {
     if (n <= 0) return SCN_OK;
     if (round_tf32)
-        k_relu_fwd<1><<<grid_for((n + 3) / 4, TB), TB, 0, as_stream(stream)>>>(in, out, n);
+        {
+            PdlLaunch L(dim3(grid_for((n + 3) / 4, TB)), dim3(TB), 0, as_stream(stream));
+            cudaLaunchKernelEx(&L.cfg, k_relu_fwd<1>, in, out, n);
+        }
     else
-        k_relu_fwd<0><<<grid_for((n + 3) / 4, TB), TB, 0, as_stream(stream)>>>(in, out, n);
+        {
+            PdlLaunch L(dim3(grid_for((n + 3) / 4, TB)), dim3(TB), 0, as_stream(stream));
+            cudaLaunchKernelEx(&L.cfg, k_relu_fwd<0>, in, out, n);
+        }
     return check_launch("relu_fwd");
 }
 int scn_relu_bwd(const float* y, const float* go, float* gi, int64_t n, int round_tf32, scn_stream_t stream) {
     if (n <= 0) return SCN_OK;
     if (round_tf32)
-        k_relu_bwd<true><<<grid_for(n, TB), TB, 0, as_stream(stream)>>>(y, go, gi, n);
+        {
+            PdlLaunch L(dim3(grid_for(n, TB)), dim3(TB), 0, as_stream(stream));
+            cudaLaunchKernelEx(&L.cfg, k_relu_bwd<true>, y, go, gi, n);
+        }
     else
-        k_relu_bwd<false><<<grid_for(n, TB), TB, 0, as_stream(stream)>>>(y, go, gi, n);
+        {
+            PdlLaunch L(dim3(grid_for(n, TB)), dim3(TB), 0, as_stream(stream));
+            cudaLaunchKernelEx(&L.cfg, k_relu_bwd<false>, y, go, gi, n);
+        }
     return check_launch("relu_bwd");
 }
 int scn_round_tf32(const float* in, float* out, int64_t n, scn_stream_t stream) {
     if (n <= 0) return SCN_OK;
-    k_relu_fwd<2><<<grid_for((n + 3) / 4, TB), TB, 0, as_stream(stream)>>>(in, out, n);
+    {
+        PdlLaunch L(dim3(grid_for((n + 3) / 4, TB)), dim3(TB), 0, as_stream(stream));
+        cudaLaunchKernelEx(&L.cfg, k_relu_fwd<2>, in, out, n);
+    }
     return check_launch("round_tf32");
 }
 int scn_add(const float* a, const float* b, float* out, int64_t n, scn_stream_t stream) {
