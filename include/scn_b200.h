@@ -88,6 +88,13 @@ int scn_hash_assign_rows(const uint64_t* keys, int P, const uint64_t* tab_keys,
 /* tab_vals[s] = rank[tab_vals[s]] for occupied slots: the table now maps key -> row */
 int scn_hash_finalize(const uint64_t* tab_keys, int32_t* tab_vals, uint32_t cap,
                       const int32_t* rank, scn_stream_t stream);
+/* One level around its single host round trip, as two calls: scn_level_count = clear + insert_first + first_flags +
+ * exclusive scan (rank [P + 1]; rank[P] is the number of active rows the host reads back), scn_level_finish =
+ * assign_rows + finalize.  Same kernels as the separate entry points above. */
+int scn_level_count(const uint64_t* keys, int P, uint64_t* tab_keys, int32_t* tab_vals, uint32_t cap,
+                    int32_t* first, int32_t* rank, int32_t* scan_tmp, scn_stream_t stream);
+int scn_level_finish(const uint64_t* keys, int P, uint64_t* tab_keys, int32_t* tab_vals, uint32_t cap,
+                     const int32_t* rank, int32_t* point_row, uint64_t* row_keys, scn_stream_t stream);
 /* rows[i] = lookup(keys[i]) or -1 */
 int scn_hash_lookup(const uint64_t* keys, int n, const uint64_t* tab_keys,
                     const int32_t* tab_vals, uint32_t cap, int32_t* rows, scn_stream_t stream);
@@ -99,6 +106,10 @@ int scn_rule_count(const int32_t* point_row, int P, int32_t* row_cnt, scn_stream
 int scn_rule_fill(const int32_t* point_row, int P, const int32_t* row_ptr, int32_t* cursor,
                   int32_t* row_pts, scn_stream_t stream);
 int scn_rule_sort(const int32_t* row_ptr, int N, int32_t* row_pts, scn_stream_t stream);
+/* count + exclusive scan + fill + sort as ONE call (same kernels): row_ptr [N + 1], row_pts [P]; cursor: N int32 and
+ * scan_tmp: scn_scan_tmp_elems(N) int32 of scratch. */
+int scn_input_rule(const int32_t* point_row, int P, int N, int32_t* cursor, int32_t* row_ptr,
+                   int32_t* row_pts, int32_t* scan_tmp, scn_stream_t stream);
 
 /* submanifold neighbour map for an (fx,fy,fz) filter (odd sizes): map [fx*fy*fz, N].
  * SubmanifoldConvolution call sites module_factory.py:377-414. */

@@ -397,6 +397,22 @@ int scn_hash_assign_rows(const uint64_t* keys, int P, const uint64_t* tk, const 
     k_hash_assign_rows<<<grid_for(P, TB), TB, 0, as_stream(stream)>>>(keys, P, tk, tv, cap - 1, rank, point_row, row_keys);
     return check_launch("hash_assign_rows");
 }
+// The two halves of building one level around its single host round trip (the active-row count), each as ONE call: the
+// training step is host bound and a level otherwise costs six Python -> C round trips.
+int scn_level_count(const uint64_t* keys, int P, uint64_t* tk, int32_t* tv, uint32_t cap, int32_t* first, int32_t* rank,
+                    int32_t* scan_tmp, scn_stream_t stream) {
+    int rc = scn_hash_clear(tk, tv, cap, stream);
+    if (rc) return rc;
+    if ((rc = scn_hash_insert_first(keys, P, tk, tv, cap, stream))) return rc;
+    if ((rc = scn_hash_first_flags(keys, P, tk, tv, cap, first, stream))) return rc;
+    return scn_exclusive_scan(first, rank, P, scan_tmp, stream);
+}
+int scn_level_finish(const uint64_t* keys, int P, uint64_t* tk, int32_t* tv, uint32_t cap, const int32_t* rank,
+                     int32_t* point_row, uint64_t* row_keys, scn_stream_t stream) {
+    int rc = scn_hash_assign_rows(keys, P, tk, tv, cap, rank, point_row, row_keys, stream);
+    if (rc) return rc;
+    return scn_hash_finalize(tk, tv, cap, rank, stream);
+}
 int scn_hash_finalize(const uint64_t* tk, int32_t* tv, uint32_t cap, const int32_t* rank, scn_stream_t stream) {
     k_hash_finalize<<<grid_for(cap, TB), TB, 0, as_stream(stream)>>>(tk, tv, cap, rank);
     return check_launch("hash_finalize");
@@ -423,6 +439,19 @@ int scn_rule_sort(const int32_t* row_ptr, int N, int32_t* row_pts, scn_stream_t 
     if (N <= 0) return SCN_OK;
     k_rule_sort<<<grid_for(N, TB), TB, 0, as_stream(stream)>>>(row_ptr, N, row_pts);
     return check_launch("rule_sort");
+}
+// input rule CSR in one call: count -> exclusive scan -> fill -> per-row sort (cursor: N int32 of scratch)
+int scn_input_rule(const int32_t* point_row, int P, int N, int32_t* cursor, int32_t* row_ptr, int32_t* row_pts,
+                   int32_t* scan_tmp, scn_stream_t stream) {
+    SCN_REQUIRE(P >= 0 && N >= 0, "input_rule: bad shape");
+    cudaStream_t st = as_stream(stream);
+    if (N > 0) cudaMemsetAsync(cursor, 0, sizeof(int32_t) * N, st);
+    int rc = scn_rule_count(point_row, P, cursor, stream);
+    if (rc) return rc;
+    if ((rc = scn_exclusive_scan(cursor, row_ptr, N, scan_tmp, stream))) return rc;
+    if (N > 0) cudaMemsetAsync(cursor, 0, sizeof(int32_t) * N, st);
+    if ((rc = scn_rule_fill(point_row, P, row_ptr, cursor, row_pts, stream))) return rc;
+    return scn_rule_sort(row_ptr, N, row_pts, stream);
 }
 int scn_subm_map(const uint64_t* row_keys, int N, const uint64_t* tk, const int32_t* tv, uint32_t cap, int fx, int fy,
                  int fz, int32_t* map, scn_stream_t stream) {

@@ -119,17 +119,15 @@ def build_level(keys):
     tab_keys = torch.empty(cap, dtype=torch.int64, device=dev)
     tab_vals = torch.empty(cap, dtype=torch.int32, device=dev)
     s = _stream()
-    _lib.call("scn_hash_clear", _ptr(tab_keys), _ptr(tab_vals), cap, s)
-    _lib.call("scn_hash_insert_first", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, s)
     first = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
-    _lib.call("scn_hash_first_flags", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(first), s)
-    rank = exclusive_scan(first[:P])
+    rank = torch.empty(P + 1, dtype=torch.int32, device=dev)
+    tmp = torch.empty(int(_lib.raw("scn_scan_tmp_elems")(P)), dtype=torch.int32, device=dev)
+    _lib.call("scn_level_count", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(first), _ptr(rank), _ptr(tmp), s)
     n = int(rank[P].item())
     point_row = torch.empty(P, dtype=torch.int32, device=dev)
     row_keys = torch.empty(n, dtype=torch.int64, device=dev)
-    _lib.call("scn_hash_assign_rows", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(rank),
-              _ptr(point_row), _ptr(row_keys), s)
-    _lib.call("scn_hash_finalize", _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(rank), s)
+    _lib.call("scn_level_finish", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(rank), _ptr(point_row),
+              _ptr(row_keys), s)
     return Level(row_keys, tab_keys, tab_vals, cap, n), point_row
 
 
@@ -204,13 +202,11 @@ class Metadata:
         self.n_samples = max(int(batch_size), max_b + 1, 1)
         if mode != 0:
             n = level.n
-            cnt = torch.zeros(n, dtype=torch.int32, device=device)
-            _lib.call("scn_rule_count", _ptr(point_row), P, _ptr(cnt), s)
-            self.row_ptr = exclusive_scan(cnt)
-            cnt.zero_()
+            cnt = torch.empty(max(n, 1), dtype=torch.int32, device=device)
+            self.row_ptr = torch.empty(n + 1, dtype=torch.int32, device=device)
             self.row_pts = torch.empty(P, dtype=torch.int32, device=device)
-            _lib.call("scn_rule_fill", _ptr(point_row), P, _ptr(self.row_ptr), _ptr(cnt), _ptr(self.row_pts), s)
-            _lib.call("scn_rule_sort", _ptr(self.row_ptr), n, _ptr(self.row_pts), s)
+            tmp = torch.empty(int(_lib.raw("scn_scan_tmp_elems")(n)), dtype=torch.int32, device=device)
+            _lib.call("scn_input_rule", _ptr(point_row), P, n, _ptr(cnt), _ptr(self.row_ptr), _ptr(self.row_pts), _ptr(tmp), s)
         return level.n
 
     def level(self, spatial_size):
