@@ -125,6 +125,16 @@ int scn_stride_keys(const uint64_t* row_keys, int N, int sx, int sy, int sz,
  * dmap [K, n_in]: dmap[o][i] = (o == offs[i]) ? parent_row[i] : -1 */
 int scn_strided_maps(const int32_t* parent_row, const int32_t* offs, int n_in, int n_out, int K,
                      int32_t* cmap, int32_t* dmap, scn_stream_t stream);
+/* A strided level as two calls around its host round trip (same kernels as scn_stride_keys, scn_level_count /
+ * scn_level_finish and scn_strided_maps; cmap [K, n_out] is cleared to -1 by the second call). */
+int scn_strided_level_count(const uint64_t* fine_keys, int n_in, int sx, int sy, int sz,
+                            uint64_t* parent_keys, int32_t* offs, uint64_t* tab_keys, int32_t* tab_vals,
+                            uint32_t cap, int32_t* first, int32_t* rank, int32_t* scan_tmp,
+                            scn_stream_t stream);
+int scn_strided_level_finish(const uint64_t* parent_keys, const int32_t* offs, int n_in, uint64_t* tab_keys,
+                             int32_t* tab_vals, uint32_t cap, const int32_t* rank, int32_t* parent_row,
+                             uint64_t* row_keys, int n_out, int K, int32_t* cmap, int32_t* dmap,
+                             scn_stream_t stream);
 
 /* ------------------------------------------------------------------ convolution family -----
  * out[r] = bias + sum_o  in[map[o][r]] . W[o]      (SubmanifoldConvolution, Convolution,

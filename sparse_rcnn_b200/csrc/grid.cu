@@ -475,6 +475,23 @@ int scn_strided_maps(const int32_t* parent_row, const int32_t* offs, int n_in, i
     k_strided_maps<<<grid_for(n_in, TB), TB, 0, as_stream(stream)>>>(parent_row, offs, n_in, n_out, K, cmap, dmap);
     return check_launch("strided_maps");
 }
+// A strided level around its host round trip: parent keys + the coarse level's count half, then its finish half + the
+// child / parent maps (cmap is cleared to -1 here).
+int scn_strided_level_count(const uint64_t* fine_keys, int n_in, int sx, int sy, int sz, uint64_t* parent_keys, int32_t* offs,
+                            uint64_t* tk, int32_t* tv, uint32_t cap, int32_t* first, int32_t* rank, int32_t* scan_tmp,
+                            scn_stream_t stream) {
+    int rc = scn_stride_keys(fine_keys, n_in, sx, sy, sz, parent_keys, offs, stream);
+    if (rc) return rc;
+    return scn_level_count(parent_keys, n_in, tk, tv, cap, first, rank, scan_tmp, stream);
+}
+int scn_strided_level_finish(const uint64_t* parent_keys, const int32_t* offs, int n_in, uint64_t* tk, int32_t* tv,
+                             uint32_t cap, const int32_t* rank, int32_t* parent_row, uint64_t* row_keys, int n_out, int K,
+                             int32_t* cmap, int32_t* dmap, scn_stream_t stream) {
+    int rc = scn_level_finish(parent_keys, n_in, tk, tv, cap, rank, parent_row, row_keys, stream);
+    if (rc) return rc;
+    if (n_out > 0 && K > 0) cudaMemsetAsync(cmap, 0xFF, sizeof(int32_t) * (size_t)K * n_out, as_stream(stream));
+    return scn_strided_maps(parent_row, offs, n_in, n_out, K, cmap, dmap, stream);
+}
 int scn_batch_offsets(const uint64_t* row_keys, int N, int n_seg, int32_t* seg_ptr, scn_stream_t stream) {
     SCN_REQUIRE(n_seg >= 1, "batch_offsets: n_seg must be >= 1");
     k_batch_offsets<<<grid_for(N + 1, TB), TB, 0, as_stream(stream)>>>(row_keys, N, n_seg, seg_ptr);

@@ -261,18 +261,37 @@ class Metadata:
         K = f[0] * f[1] * f[2]
         pkeys = torch.empty(lin.n, dtype=torch.int64, device=dev)
         offs = torch.empty(lin.n, dtype=torch.int32, device=dev)
-        _lib.call("scn_stride_keys", _ptr(lin.keys), lin.n, st[0], st[1], st[2], _ptr(pkeys), _ptr(offs), s)
         if out_size in self.levels:
+            _lib.call("scn_stride_keys", _ptr(lin.keys), lin.n, st[0], st[1], st[2], _ptr(pkeys), _ptr(offs), s)
             lout = self.levels[out_size]
             parent_row = torch.empty(lin.n, dtype=torch.int32, device=dev)
             _lib.call("scn_hash_lookup", _ptr(pkeys), lin.n, _ptr(lout.tab_keys), _ptr(lout.tab_vals), lout.cap,
                       _ptr(parent_row), s)
+            cmap = torch.full((K, lout.n), -1, dtype=torch.int32, device=dev)
+            dmap = torch.empty((K, lin.n), dtype=torch.int32, device=dev)
+            _lib.call("scn_strided_maps", _ptr(parent_row), _ptr(offs), lin.n, lout.n, K, _ptr(cmap), _ptr(dmap), s)
         else:
-            lout, parent_row = build_level(pkeys)
+            # new coarse level: two C calls around the one host round trip (its active-row count)
+            P = lin.n
+            cap = 64
+            while cap < 2 * P:
+                cap <<= 1
+            tab_keys = torch.empty(cap, dtype=torch.int64, device=dev)
+            tab_vals = torch.empty(cap, dtype=torch.int32, device=dev)
+            first = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+            rank = torch.empty(P + 1, dtype=torch.int32, device=dev)
+            tmp = torch.empty(int(_lib.raw("scn_scan_tmp_elems")(P)), dtype=torch.int32, device=dev)
+            _lib.call("scn_strided_level_count", _ptr(lin.keys), P, st[0], st[1], st[2], _ptr(pkeys), _ptr(offs),
+                      _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(first), _ptr(rank), _ptr(tmp), s)
+            n = int(rank[P].item())
+            parent_row = torch.empty(P, dtype=torch.int32, device=dev)
+            row_keys = torch.empty(n, dtype=torch.int64, device=dev)
+            cmap = torch.empty((K, n), dtype=torch.int32, device=dev)
+            dmap = torch.empty((K, P), dtype=torch.int32, device=dev)
+            _lib.call("scn_strided_level_finish", _ptr(pkeys), _ptr(offs), P, _ptr(tab_keys), _ptr(tab_vals), cap,
+                      _ptr(rank), _ptr(parent_row), _ptr(row_keys), n, K, _ptr(cmap), _ptr(dmap), s)
+            lout = Level(row_keys, tab_keys, tab_vals, cap, n)
             self.levels[out_size] = lout
-        cmap = torch.full((K, lout.n), -1, dtype=torch.int32, device=dev)
-        dmap = torch.empty((K, lin.n), dtype=torch.int32, device=dev)
-        _lib.call("scn_strided_maps", _ptr(parent_row), _ptr(offs), lin.n, lout.n, K, _ptr(cmap), _ptr(dmap), s)
         r = Strided(out_size, cmap, dmap, parent_row, K)
         self.strided[key] = r
         return r
