@@ -189,6 +189,18 @@ int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n
                           int K, const float* w1, const float* w2, void* img1t, void* img2t, int repack,
                           float* gyr, float* gh, float* gx, float* gw1, float* gb1, float* gw2, float* gb2,
                           int accumulate, int use_tf32, scn_stream_t stream);
+/* One convolution layer (SubmanifoldConvolution / Convolution / Deconvolution / NetworkInNetwork, module_factory.py:221-414)
+ * per direction as ONE call that enqueues: TF32 rounding of the gathered operand unless *_exact (scratch x_round / go_round),
+ * weight packing when repack != 0, the gather-GEMM(s), and the weight + bias gradient (gw, gb are ADDED to: zeroed buffers
+ * or the parameters' gradient buckets).  bwd: fmap [K, n_out] is the forward map, bmap [K, n_in] the map of the input
+ * gradient, reverse_bwd = 1 for submanifold layers (bmap == fmap, offsets reversed); any of gx / gw / gb may be NULL. */
+int scn_conv_layer_fwd(const float* x, int ld_x, int n_in, int Cin, int x_exact, float* x_round,
+                       const int32_t* map, int n_out, int K, const float* w, void* image, int repack,
+                       const float* bias, float* out, int Cout, int use_tf32, scn_stream_t stream);
+int scn_conv_layer_bwd(const float* go, int n_out, int Cout, int go_exact, float* go_round, const float* x,
+                       int ld_x, int n_in, int Cin, const int32_t* fmap, const int32_t* bmap, int K,
+                       const float* w, void* image_t, int repack, int reverse_bwd, float* gx, float* gw,
+                       float* gb, int use_tf32, scn_stream_t stream);
 /* out[c] = sum_r in[r][c]   (bias gradient) */
 int scn_col_sum(const float* in, int ld, int n, int C, float* out, scn_stream_t stream);
 /* out[c] += sum_r in[r][c]  (bias gradient accumulated straight into the parameter's .grad buffer) */

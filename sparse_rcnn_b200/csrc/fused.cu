@@ -92,4 +92,54 @@ int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n
     return SCN_OK;
 }
 
+// One convolution layer (SubM / strided / transposed / 1x1) per direction as ONE call: operand rounding, weight packing
+// when stale, the gather-GEMM(s) and the weight + bias gradient.  Same kernels as the separate entry points.
+int scn_conv_layer_fwd(const float* x, int ld_x, int n_in, int Cin, int x_exact, float* x_round, const int32_t* map, int n_out,
+                       int K, const float* w, void* image, int repack, const float* bias, float* out, int Cout, int use_tf32,
+                       scn_stream_t stream) {
+    SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0 && n_in >= 0 && n_out >= 0, "conv_layer_fwd: bad shape");
+    if (n_out == 0) return SCN_OK;
+    if (!use_tf32)
+        return scn_conv_fwd_fp32(x, ld_x, Cin, map, n_out, K, w, 0, 0, bias, nullptr, 0, nullptr, 0, out, Cout, Cout, 0, stream);
+    const float* xin = x;
+    int ld = ld_x;
+    if (!x_exact) {      // tcgen05 truncates fp32 operands: round the gathered operand to nearest once
+        SCN_REQUIRE(x_round && ld_x == Cin, "conv_layer_fwd: rounding needs a scratch buffer and a dense input");
+        SCN_TRY(scn_round_tf32(x, x_round, (int64_t)n_in * Cin, stream));
+        xin = x_round, ld = Cin;
+    }
+    if (repack) SCN_TRY(scn_conv_pack_weights(w, K, Cin, Cout, 0, 0, image, stream));
+    return scn_conv_fwd_tf32(xin, ld, Cin, n_in, map, n_out, K, image, bias, nullptr, 0, nullptr, 0, out, Cout, Cout, 0, stream);
+}
+
+int scn_conv_layer_bwd(const float* go, int n_out, int Cout, int go_exact, float* go_round, const float* x, int ld_x, int n_in,
+                       int Cin, const int32_t* fmap, const int32_t* bmap, int K, const float* w, void* image_t, int repack,
+                       int reverse_bwd, float* gx, float* gw, float* gb, int use_tf32, scn_stream_t stream) {
+    SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0 && n_in >= 0 && n_out >= 0, "conv_layer_bwd: bad shape");
+    if (n_out == 0) {
+        if (gx && n_in > 0) cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)n_in * Cin, as_stream(stream));
+        return check_launch("conv_layer_bwd(memset)");
+    }
+    const float* g = go;
+    if (use_tf32 && !go_exact && (gx || gw)) {
+        SCN_REQUIRE(go_round, "conv_layer_bwd: rounding needs a scratch buffer");
+        SCN_TRY(scn_round_tf32(go, go_round, (int64_t)n_out * Cout, stream));
+        g = go_round;
+    }
+    if (gx && n_in > 0) {
+        // d/dx: the transposed (and, for submanifold layers, offset-reversed) weights over the backward map
+        if (use_tf32) {
+            if (repack) SCN_TRY(scn_conv_pack_weights(w, K, Cout, Cin, 1, reverse_bwd, image_t, stream));
+            SCN_TRY(scn_conv_fwd_tf32(g, Cout, Cout, n_out, bmap, n_in, K, image_t, nullptr, nullptr, 0, nullptr, 0, gx, Cin, Cin,
+                                      0, stream));
+        } else {
+            SCN_TRY(scn_conv_fwd_fp32(g, Cout, Cout, bmap, n_in, K, w, 1, reverse_bwd, nullptr, nullptr, 0, nullptr, 0, gx, Cin,
+                                      Cin, 0, stream));
+        }
+    }
+    if (gw) SCN_TRY(scn_conv_bwd_weight(x, ld_x, Cin, fmap, n_out, K, g, Cout, Cout, gw, gb, use_tf32, stream));
+    else if (gb) SCN_TRY(scn_col_sum_add(go, Cout, n_out, Cout, gb, stream));
+    return SCN_OK;
+}
+
 }  // extern "C"

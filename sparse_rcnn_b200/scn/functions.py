@@ -169,8 +169,18 @@ def _mark(t):
     return t
 
 
+def _image_state(weight, K, cin, cout, transpose, reverse):
+    """(packed-image buffer, must it be re-packed); marks it packed (the C call that follows does the packing)."""
+    hit = _image_entry(weight, K, cin, cout, transpose, reverse)
+    ver = (weight._version, weight.data_ptr())
+    stale = hit[1] != ver
+    hit[1] = ver
+    return hit[0], stale
+
+
 class ConvFunction(Function):
-    """Shared by SubmanifoldConvolution / Convolution / Deconvolution / NetworkInNetwork.
+    """Shared by SubmanifoldConvolution / Convolution / Deconvolution / NetworkInNetwork; each direction is ONE C-ABI call
+    (scn_conv_layer_fwd / _bwd: operand rounding, stale-image packing, gather-GEMM(s), weight + bias gradient).
 
     fmap [K, n_out]: forward map; bmap [K, n_in]: map of the input gradient (for a submanifold
     conv bmap is fmap with the offsets reversed, expressed through `reverse_bwd`)."""
@@ -186,7 +196,20 @@ class ConvFunction(Function):
         ctx.maps = (fmap, bmap)
         ctx.dims = (K, cin, cout, n_out, x.shape[0], reverse_bwd, bias is not None)
         ctx.bias_param = bias
-        return conv_gemm(x, w, K, cin, cout, fmap, n_out, bias.detach() if bias is not None else None)
+        tf32 = _state["precision"] == "tf32" and cout <= 256
+        out = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
+        if n_out == 0:
+            return out
+        img = xr = None
+        stale, exact = False, True
+        if tf32:
+            img, stale = _image_state(w, K, cin, cout, 0, 0)
+            exact = bool(getattr(x, "_scn_tf32", False))
+            if not exact:
+                xr = torch.empty_like(x)
+        _lib.call("scn_conv_layer_fwd", _ptr(x), x.stride(0), x.shape[0], cin, int(exact), _ptr(xr), _ptr(fmap), n_out, K,
+                  _ptr(w), _ptr(img), int(stale), _ptr(bias), _ptr(out), cout, int(tf32), _stream())
+        return out
 
     @staticmethod
     def backward(ctx, go):
@@ -196,28 +219,34 @@ class ConvFunction(Function):
         go = _check(go)
         w = weight
         gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = conv_gemm(go, w, K, cout, cin, bmap, n_in, None, transpose=1, reverse=reverse_bwd)
-        tf32 = 1 if _state["precision"] == "tf32" else 0
+        tf32 = _state["precision"] == "tf32" and cin <= 256
+        want_x = ctx.needs_input_grad[0]
         want_w = ctx.needs_input_grad[1]
         want_b = has_bias and ctx.needs_input_grad[2]
+        dev = go.device
+        if want_x:
+            gx = torch.empty((n_in, cin), dtype=torch.float32, device=dev)
         b = ctx.bias_param
+        dw = _direct_grad(w) if want_w else None
         db = _direct_grad(b) if want_b else None
-        gb_buf = None
-        if want_b:
-            gb_buf = db if db is not None else torch.zeros(cout, dtype=torch.float32, device=go.device)
+        gw_buf = (dw if dw is not None else torch.zeros_like(w)) if want_w else None
+        gb_buf = (db if db is not None else torch.zeros(cout, dtype=torch.float32, device=dev)) if want_b else None
+        img = gr = None
+        stale, exact = False, True
+        if tf32:
+            exact = bool(getattr(go, "_scn_tf32", False))
+            if not exact and (want_x or want_w) and n_out:
+                gr = torch.empty_like(go)
+            if want_x:
+                img, stale = _image_state(w, K, cout, cin, 1, reverse_bwd)
+        _lib.call("scn_conv_layer_bwd", _ptr(go), n_out, cout, int(exact), _ptr(gr), _ptr(x), x.stride(0), n_in, cin,
+                  _ptr(fmap), _ptr(bmap), K, _ptr(w), _ptr(img), int(stale), int(reverse_bwd), _ptr(gx), _ptr(gw_buf),
+                  _ptr(gb_buf), int(tf32), _stream())
         if want_w:
-            direct = _direct_grad(w)
-            gw_buf = direct if direct is not None else torch.zeros_like(w)
-            if n_out:      # the bias gradient (column sums of go) rides in the weight-gradient kernel
-                _lib.call("scn_conv_bwd_weight", _ptr(x), x.stride(0), cin, _ptr(fmap), n_out, K, _ptr(go),
-                          go.stride(0), cout, _ptr(gw_buf), _ptr(gb_buf), tf32, _stream())
-            if direct is not None:
+            if dw is not None:
                 w._scn_grad_hook(w)
             else:
                 gw = gw_buf
-        elif want_b and n_out:
-            _lib.call("scn_col_sum_add", _ptr(go), go.stride(0), n_out, cout, _ptr(gb_buf), _stream())
         if want_b:
             if db is not None:
                 b._scn_grad_hook(b)
