@@ -41,13 +41,17 @@ class GradientBuckets:
             self.buckets.append(cur)
         self.flats, self._pending, self._handles = [], [], []
         self._fired = set()
+        self.offsets = []
         for bi, bucket in enumerate(self.buckets):
-            n = sum(p.numel() for p in bucket)
-            flat = torch.zeros(n, dtype=bucket[0].dtype, device=bucket[0].device)
-            off = 0
+            # every view starts on a 16-byte boundary (vector reductions / loads in the kernels); the pad elements stay 0
+            offs, n = [], 0
             for p in bucket:
+                offs.append(n)
+                n += (p.numel() + 3) // 4 * 4
+            self.offsets.append(offs)
+            flat = torch.zeros(n, dtype=bucket[0].dtype, device=bucket[0].device)
+            for p, off in zip(bucket, offs):
                 p.grad = flat[off:off + p.numel()].view_as(p)      # autograd accumulates in place
-                off += p.numel()
                 hook = self._make_hook(bi)
                 p.register_post_accumulate_grad_hook(hook)
                 # the scn autograd Functions accumulate parameter gradients straight into these views and call the hook
@@ -71,6 +75,24 @@ class GradientBuckets:
     def _launch(self, bi):
         if self.world > 1:
             self._handles.append(dist.all_reduce(self.flats[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def flatten_parameters(self):
+        """Make every parameter a view of one flat buffer per bucket (same order as its gradient view) and return the flat
+        buffers as leaf Parameters whose .grad are the gradient buckets.  An optimizer over THESE (two tensors instead of
+        ~150) does the same element-wise update with none of the per-parameter host work, which matters because the step is
+        host bound.  Modules keep their Parameter objects; `p.data` now aliases the flat storage."""
+        flat_params = []
+        for bucket, offs, gflat in zip(self.buckets, self.offsets, self.flats):
+            data = torch.zeros(gflat.numel(), dtype=bucket[0].dtype, device=bucket[0].device)
+            for p, off in zip(bucket, offs):
+                view = data[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+            fp = torch.nn.Parameter(data)
+            fp.grad = gflat
+            flat_params.append(fp)
+        self.flat_params = flat_params
+        return flat_params
 
     def zero(self):
         """Zero the flat buckets (instead of optimizer.zero_grad(set_to_none=True), which would

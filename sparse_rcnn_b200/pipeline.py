@@ -38,7 +38,9 @@ class BackboneTrainer(nn.Module):
         self.buckets.enabled = True
         # torch.optim.Adam as in the reference (ndsis/training/training.py:386); the fused implementation is the same
         # update in one multi-tensor kernel (the foreach path costs ~1.2 ms of host time per step, and the step is host bound)
-        self.optimizer = torch.optim.Adam(self.parameters(), lr=lr, fused=True)
+        # ... over the two flat parameter buffers (every parameter is a view into them): same element-wise update, no
+        # per-parameter host work (torch's Adam spends ~0.4 ms per step walking 150 parameters)
+        self.optimizer = torch.optim.Adam(self.buckets.flatten_parameters(), lr=lr, fused=True)
         self.distributed = distributed
         self._weights = [p for p in self.parameters() if p.dim() >= 2]
         self.prefetcher = None

@@ -79,3 +79,38 @@ def test_scene_sharding_is_a_partition():
         shards = [shard_scenes(19, r, world) for r in range(world)]
         assert sorted(sum(shards, [])) == list(range(19))
         assert max(map(len, shards)) - min(map(len, shards)) <= 1
+
+
+def test_flat_parameter_adam_equals_per_parameter_adam():
+    """GradientBuckets.flatten_parameters: Adam over the flat buffers is the same element-wise update as Adam over the
+    individual parameters (run.py:1441-1449), the modules' parameters stay live views of the flat storage, every view
+    starts on a 16-byte boundary and the pad elements never move."""
+    def make():
+        torch.manual_seed(3)
+        return nn.Sequential(nn.Linear(5, 7), nn.ReLU(), nn.Linear(7, 9), nn.ReLU(), nn.Linear(9, 3))     # odd sizes: padding
+    a, b = make(), make()
+    buckets = GradientBuckets(list(b.parameters()), n_buckets=2)
+    flat = buckets.flatten_parameters()
+    assert len(flat) == len(buckets.buckets) == 2
+    for bucket, offs, fp in zip(buckets.buckets, buckets.offsets, flat):
+        assert all(o % 4 == 0 for o in offs)
+        for p, o in zip(bucket, offs):
+            assert p.data_ptr() == fp.data_ptr() + 4 * o and p.grad.data_ptr() == fp.grad.data_ptr() + 4 * o
+    opt_a = torch.optim.Adam(a.parameters(), lr=1e-2)
+    opt_b = torch.optim.Adam(flat, lr=1e-2)
+    g = torch.Generator().manual_seed(5)
+    for step in range(4):
+        x, y = torch.randn(8, 5, generator=g), torch.randn(8, 3, generator=g)
+        opt_a.zero_grad()
+        ((a(x) - y) ** 2).mean().backward()
+        opt_a.step()
+        buckets.zero()
+        ((b(x) - y) ** 2).mean().backward()
+        buckets.finish()
+        opt_b.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, atol=1e-7, rtol=1e-6)
+    used = torch.zeros(flat[0].numel(), dtype=torch.bool)
+    for p, o in zip(buckets.buckets[0], buckets.offsets[0]):
+        used[o:o + p.numel()] = True
+    assert (flat[0].detach()[~used] == 0).all()
