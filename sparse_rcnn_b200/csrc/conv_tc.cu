@@ -60,6 +60,7 @@ struct ConvTcParams {
     float* scratch;       // split mode: accumulation buffer [n_out][Cout], all-zero between launches
     unsigned int* tickets;  // split mode: one self-resetting arrival counter per tile
     int cluster;          // > 1: the osplit work items of a tile are one thread-block cluster and reduce through DSMEM
+    int skip;             // 1: producers skip rows that are inactive now and were inactive in the stage's previous use
 };
 
 // one 16-byte chunk of a gathered row, split into VEC-float cp.asyncs
@@ -252,6 +253,13 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
         int s = pw;                                   // pw < G <= S
         uint32_t ph = 0;
         int idx[4], idx_next[4];
+        // Row skipping (profiles/r1_j: the shared-memory fill path is the unit closest to its ceiling and 63 % of the rows
+        // it writes are zero fill): with S == G an owner warp always refills the SAME stage, so lane L knows from its
+        // previous unit whether rows L + 32 j of that stage already hold zeros.  Bit j of `dirty` = "row may be
+        // non-zero"; an inactive row over a clean row needs no copy at all (code -2: the cp.async is predicated off),
+        // an inactive row over a dirty row is zero-filled (code -1, ignore-src), an active row is copied.
+        const bool skipping = p.skip && G == S;
+        uint32_t dirty = 0xFu;                       // shared memory starts undefined
         load_idx(cur, idx);
         if (pw == 0 && idx[0] == -12345) SCN_TRACE(31);
         if (pw == 0) SCN_TRACE(2);
@@ -276,45 +284,62 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                 const char* colp = in_c + cur.kb * (KB * 4);
                 const uint32_t de = a_stage + dst_even, dodd = a_stage + dst_odd;
                 if (p.Cin - cur.kb * KB >= KB) {      // warp-uniform: a full 32-channel block
+                    uint32_t now = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        const int code = idx[j] >= 0 ? idx[j] : (((dirty >> j) & 1u) ? -1 : -2);
+                        now |= (idx[j] >= 0 ? 1u : 0u) << j;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
 #ifdef SCN_EXP_NOCOPY
                             if (p.n_out > 0) break;
 #endif
-                            const int r = __shfl_sync(0xffffffffu, idx[j], rsub + 4 * i);
+                            const int r = __shfl_sync(0xffffffffu, code, rsub + 4 * i);
                             const char* src = colp + (uint64_t)(uint32_t)r * row_bytes;
                             asm volatile(
                                 "{\n\t"
-                                ".reg .pred p;\n\t"
+                                ".reg .pred p, q;\n\t"
                                 "setp.lt.s32 p, %2, 0;\n\t"
-                                "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+                                "setp.ne.s32 q, %2, -2;\n\t"
+                                "@q cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
                                 "}" ::"r"(((i & 1) ? dodd : de) + (uint32_t)(32 * j + 4 * i) * 128u),
                                 "l"(src), "r"(r)
                                 : "memory");
                         }
                     }
-                } else {      // last, partial block: chunks beyond cin_pad8 are not read by the MMA, chunks beyond Cin are zeros
+                    if (skipping) dirty = now;
+                } else {
+                    // last, partial block: the MMA reads chunks below cin_pad8 ("wanted"), chunks at or beyond Cin must be
+                    // zeros.  Row skipping here: the dirty bit travels in bit 30 of an active row's index; a lane of a
+                    // chunk the MMA does not read only has to clear it when the row turns clean (inactive over dirty), so
+                    // that "clean" keeps meaning "all 128 bytes are zero" for a later full block in the same stage.
                     const bool wanted = col0 < p.cin_pad8, real = col0 < p.Cin;
+                    uint32_t now = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        const uint32_t d = (dirty >> j) & 1u;
+                        const int code = idx[j] >= 0 ? (int)((uint32_t)idx[j] | (d << 30)) : (d ? -1 : -2);
+                        now |= (idx[j] >= 0 ? 1u : 0u) << j;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            int r = __shfl_sync(0xffffffffu, idx[j], rsub + 4 * i);
-                            if (!real) r = -1;
-                            const char* src = colp + (uint64_t)(uint32_t)max(r, 0) * row_bytes;
-                            if (wanted)
+                            const int r = __shfl_sync(0xffffffffu, code, rsub + 4 * i);
+                            const bool active = r >= 0;
+                            const bool was_dirty = active ? ((r >> 30) & 1) != 0 : r == -1;
+                            const bool do_copy = active && real;
+                            const bool do_zero = was_dirty && (real ? !active : (wanted ? true : (skipping && !active)));
+                            const char* src = colp + (uint64_t)((uint32_t)r & 0x3FFFFFFFu) * row_bytes;
+                            if (do_copy || do_zero)
                                 asm volatile(
                                     "{\n\t"
                                     ".reg .pred p;\n\t"
-                                    "setp.lt.s32 p, %2, 0;\n\t"
+                                    "setp.eq.s32 p, %2, 0;\n\t"
                                     "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
                                     "}" ::"r"(((i & 1) ? dodd : de) + (uint32_t)(32 * j + 4 * i) * 128u),
-                                    "l"(src), "r"(r)
+                                    "l"(src), "r"((int)do_copy)
                                     : "memory");
                         }
                     }
+                    if (skipping) dirty = now;
                 }
             } else {
                 const bool wanted = col0 < p.cin_pad8;
@@ -906,6 +931,7 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     const int n_work = p.n_tiles * p.osplit;
     int grid = n_work < slots ? n_work : slots;
     p.scratch = nullptr, p.tickets = nullptr, p.cluster = 0;
+    p.skip = scn::conv_row_skipping();
     // split mode as a thread-block cluster (<= 8 CTAs, the portable limit) reducing through DSMEM when the partial tile
     // (128 rows x (cout_pad + 4) floats) fits in the stage ring; otherwise atomics into the library workspace
     const char* ev_nc = getenv("SCN_CONV_NOCLUSTER");      // read per call: the fallback path is exercised by a test

@@ -17,6 +17,7 @@
 // the accumulators of ALL its offsets in TMEM across ALL its tiles and adds them to gw with one
 // round of atomics at the very end.  The grad-out tile is staged once per tile and reused by every
 // offset of the group.  8 producer warps (cp.async gather, zero fill for inactive rows) + 1 MMA warp.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace scn {
@@ -35,6 +36,7 @@ struct WgradParams {
     int n_tiles, tiles_per_chunk;
     int opg, n_ogroups, n_mhalves;
     int a_stages, g_stages, a_stage_bytes, g_stage_bytes, tmem_cols;
+    int skip;      // 1: producers skip rows that are inactive now and were inactive in the stage's previous use
 };
 
 template <int VEC>
@@ -145,6 +147,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
             int idx[8], idx_next[8];
             int sa = own;                                    // own < NA <= AS
             uint32_t pha = 0;
+            // Row skipping as in conv_tc.cu: with NA == AS a warp pair always refills the same stage, so bit pp * 2 + j of
+            // `dirty` remembers whether rows lane + 32 j of offset slot pp may hold non-zero bytes there (every path below
+            // writes all eight chunks of a row, and all channel blocks of a slot see the same rows).  An inactive row over
+            // a clean row is not written at all: the fill shares the shared-memory pipe with the MMAs' operand reads.
+            const bool skipping = p.skip && NA == AS;
+            uint32_t dirty = 0xFFu;                          // shared memory starts undefined
             load_idx(own, idx);
             for (int u = own; u < n_units; u += NA) {
                 load_idx(u + NA, idx_next);
@@ -154,6 +162,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
 #pragma unroll
                 for (int pp = 0; pp < 4; ++pp) {
                     if (pp >= P || mg * P + pp >= nO) continue;      // unused offset slot: its accumulator rows are never read
+                    int code[2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int q = pp * 2 + j;
+                        code[j] = idx[q] >= 0 ? idx[q] : (((dirty >> q) & 1u) ? -1 : -2);
+                        if (skipping) dirty = (dirty & ~(1u << q)) | ((idx[q] >= 0 ? 1u : 0u) << q);
+                    }
                     for (int kb = 0; kb < bpo; ++kb) {
                         const int cb = cin0 + kb * KB;               // first channel of this block
                         if (cb >= cin_lim) continue;
@@ -168,13 +183,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
 #ifdef SCN_EXP_NOCOPY
                                     if (p.n_out > 0) break;      // timing experiment: no gather copies
 #endif
-                                    const int r = __shfl_sync(0xffffffffu, idx[pp * 2 + j], rsub + 4 * i);
+                                    const int r = __shfl_sync(0xffffffffu, code[j], rsub + 4 * i);
                                     const char* src = colp + (uint64_t)(uint32_t)r * row_bytes;
                                     asm volatile(
                                         "{\n\t"
-                                        ".reg .pred p;\n\t"
+                                        ".reg .pred p, q;\n\t"
                                         "setp.lt.s32 p, %2, 0;\n\t"
-                                        "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+                                        "setp.ne.s32 q, %2, -2;\n\t"
+                                        "@q cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
                                         "}" ::"r"(dst0 + (uint32_t)(32 * j + 4 * i) * 128u),
                                         "l"(src), "r"(r)
                                         : "memory");
@@ -186,9 +202,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                             for (int j = 0; j < 2; ++j) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const int r = __shfl_sync(0xffffffffu, idx[pp * 2 + j], rsub + 4 * i);
-                                    wg_chunk<VEC>(dst0 + (uint32_t)(32 * j + 4 * i) * 128u, p.in, (int64_t)r * p.ld_in, r >= 0,
-                                                  col0, cin_lim);
+                                    const int r = __shfl_sync(0xffffffffu, code[j], rsub + 4 * i);
+                                    if (r != -2)
+                                        wg_chunk<VEC>(dst0 + (uint32_t)(32 * j + 4 * i) * 128u, p.in, (int64_t)r * p.ld_in,
+                                                      r >= 0, col0, cin_lim);
                                 }
                             }
                         }
@@ -367,6 +384,7 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
     p.in = in, p.ld_in = ld_in, p.Cin = Cin, p.map = map, p.n_out = n_out, p.K = K;
     p.go = grad_out, p.ld_go = ld_go, p.Cout = Cout, p.gw = grad_w, p.gb = grad_bias;
     p.n_tiles = cdiv(n_out, TILE_M);
+    p.skip = scn::conv_row_skipping();
     const int cin_h = Cin < 128 ? Cin : 128, cout_h = Cout < 128 ? Cout : 128;
     const int npad = (cout_h + 15) / 16 * 16;
     p.n_mhalves = cdiv(Cin, 128);

@@ -2,6 +2,7 @@
 // tcgen05.mma / commit / ld.  Bit layouts follow cute/arch/mma_sm100_desc.hpp (CUTLASS), which is
 // only consulted as documentation -- nothing here includes CUTLASS.
 #pragma once
+#include <stdlib.h>
 #include <cuda.h>
 #include "common.cuh"
 
@@ -191,6 +192,17 @@ __device__ __forceinline__ uint32_t swz_mn32b(int r, int c) {
 // kind::tf32 instruction descriptor with both operands MN-major (bits 15 and 16 set)
 __device__ __forceinline__ uint32_t make_idesc_tf32_mn(int M, int N) {
     return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);
+}
+
+// Row skipping in the gather producers of both tensor-core kernels (conv_tc.cu, conv_wgrad_tc.cu).  SCN_CONV_SKIP=0 / 1
+// overrides the default; read per call (a test runs both settings in one process).
+#ifndef SCN_CONV_SKIP_DEFAULT
+#define SCN_CONV_SKIP_DEFAULT 0
+#endif
+static inline int conv_row_skipping() {
+    const char* e = getenv("SCN_CONV_SKIP");
+    if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+    return SCN_CONV_SKIP_DEFAULT;
 }
 
 }  // namespace scn

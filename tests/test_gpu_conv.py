@@ -135,3 +135,45 @@ def test_split_mode_fallback_equals_cluster_mode(cuda, monkeypatch):
         a2 = conv(x).features
     assert torch.equal(a, a2)                                        # cluster mode is deterministic
     assert rel_err(b1, a) < 1e-5 and rel_err(b2, a) < 1e-5           # fallback: same sums, atomics order differs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels", [32, 64, 48, 128])
+def test_row_skipping_is_bit_exact(cuda, monkeypatch, channels):
+    """Producers skip a gathered row that is inactive now and was inactive in the stage's previous use (conv_tc.cu);
+    SCN_CONV_SKIP=0 fills every row as before.  Same arithmetic on the same operands => identical bits, on a level with
+    many tiles per CTA (stages are reused hundreds of times) and with full (32, 64, 128) and partial (48) channel blocks."""
+    from sparse_rcnn_b200 import scn
+    from sparse_rcnn_b200.synthetic import make_batch
+    scn.set_precision("tf32")
+    torch.manual_seed(1)
+    coords, feats, size, bs, _ = make_batch(1, 5, spatial_size=(256, 256, 128))
+    md = scn.Metadata(3)
+    f = scn.ioLayers.InputLayerFunction.apply(3, md, size, coords, feats.to(cuda), bs, 4)
+    n = f.shape[0]
+    assert n // 128 > 3 * 148                                        # several tiles per persistent CTA
+    conv = scn.SubmanifoldConvolution(3, channels, channels, 3, True).to(cuda)
+    x = scn.SparseConvNetTensor(torch.randn(n, channels, device=cuda), md, size)
+    with torch.no_grad():
+        monkeypatch.setenv("SCN_CONV_SKIP", "1")
+        a = conv(x).features.clone()
+        monkeypatch.setenv("SCN_CONV_SKIP", "0")
+        b = conv(x).features.clone()
+        monkeypatch.setenv("SCN_CONV_SKIP", "1")
+        a2 = conv(x).features
+    assert torch.equal(a, b) and torch.equal(a, a2)
+    # backward: the input gradient runs the same kernel (bit-exact); the weight-gradient kernel skips rows the same way
+    # but ends with atomics into gw, so its two runs agree to fp32 summation order
+    go = torch.randn(n, channels, device=cuda)
+
+    def grads():
+        xin = x.features.clone().requires_grad_(True)
+        conv.zero_grad()
+        conv(scn.SparseConvNetTensor(xin, md, size)).features.backward(go)
+        return xin.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone()
+    gx_a, gw_a, gb_a = grads()
+    monkeypatch.setenv("SCN_CONV_SKIP", "0")
+    gx_b, gw_b, gb_b = grads()
+    monkeypatch.delenv("SCN_CONV_SKIP")
+    assert torch.equal(gx_a, gx_b)
+    assert rel_err(gw_a, gw_b) < 1e-5 and rel_err(gb_a, gb_b) < 1e-5
