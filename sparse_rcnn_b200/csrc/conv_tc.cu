@@ -342,17 +342,24 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                     if (skipping) dirty = now;
                 }
             } else {
+                // 8- and 4-byte copies (row stride not a multiple of 16 bytes): a written chunk is always written whole
+                // (gather_chunk zero-fills columns at or beyond Cin), so the same row skipping applies; lanes of chunks the
+                // MMA does not read clear theirs when the row turns clean
                 const bool wanted = col0 < p.cin_pad8;
+                uint32_t now = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
+                    const int code = idx[j] >= 0 ? idx[j] : (((dirty >> j) & 1u) ? -1 : -2);
+                    now |= (idx[j] >= 0 ? 1u : 0u) << j;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int r = __shfl_sync(0xffffffffu, idx[j], rsub + 4 * i);
-                        if (wanted)
+                        const int r = __shfl_sync(0xffffffffu, code, rsub + 4 * i);
+                        if (wanted ? r != -2 : (skipping && r == -1))
                             gather_chunk<VEC>(a_stage + ((i & 1) ? dst_odd : dst_even) + (uint32_t)(32 * j + 4 * i) * 128u,
                                               p.in, (int64_t)r * p.ld_in, r, col0, p.Cin);
                     }
                 }
+                if (skipping) dirty = now;
             }
             // the stage's full barrier receives this thread's arrival when its copies have landed
             cp_async_mbar_arrive_noinc(fb);
@@ -921,6 +928,11 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
         const char* e = getenv("SCN_CONV_NOSPLIT");
         no_split = (e && e[0] == '1') ? 1 : 0;
     }
+    // split mode as a thread-block cluster (<= 8 CTAs, the portable limit) reducing through DSMEM when the partial tile
+    // (128 rows x (cout_pad + 4) floats) fits in the stage ring; otherwise atomics into the library workspace
+    const char* ev_nc = getenv("SCN_CONV_NOCLUSTER");      // read per call: the fallback path is exercised by a test
+    const int no_cluster = (ev_nc && ev_nc[0] == '1') ? 1 : 0;
+    const bool cluster_ok = !no_cluster && !use_tma && TILE_M * (p.cout_pad * 4 + 16) <= stages * stage_bytes;
     if (!no_split && K > 1 && p.n_tiles * 2 <= slots) {
         int g = slots / p.n_tiles;
         if (g > K) g = K;
@@ -928,17 +940,15 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
         p.opg = cdiv(K, g);
         p.osplit = cdiv(K, p.opg);
     }
+    // (Measured and dropped, profiles/r1_m_row_skipping.md: the same cluster split for mid-size levels -- 0.5 .. 3 tiles per
+    // slot, where the persistent grid's last wave is mostly empty -- with one work item per CTA and a grid larger than the
+    // resident slots.  A non-persistent work item pays its prologue and the cluster reduction every time: level 1 of the
+    // bench scene 82.6 -> 82.9 / 85.6 / 90.4 us at cluster size 2 / 3 / 4.)
     const int n_work = p.n_tiles * p.osplit;
     int grid = n_work < slots ? n_work : slots;
     p.scratch = nullptr, p.tickets = nullptr, p.cluster = 0;
     p.skip = scn::conv_row_skipping();
-    // split mode as a thread-block cluster (<= 8 CTAs, the portable limit) reducing through DSMEM when the partial tile
-    // (128 rows x (cout_pad + 4) floats) fits in the stage ring; otherwise atomics into the library workspace
-    const char* ev_nc = getenv("SCN_CONV_NOCLUSTER");      // read per call: the fallback path is exercised by a test
-    const int no_cluster = (ev_nc && ev_nc[0] == '1') ? 1 : 0;
-    if (p.osplit > 1 && p.osplit <= 8 && !no_cluster && !use_tma && grid == n_work &&
-        TILE_M * (p.cout_pad * 4 + 16) <= stages * stage_bytes)
-        p.cluster = p.osplit;
+    if (p.osplit > 1 && p.osplit <= 8 && cluster_ok && grid == n_work) p.cluster = p.osplit;
     if (p.osplit > 1 && !p.cluster) {
         int rc = scn::split_workspace((size_t)n_out * Cout * sizeof(float), p.n_tiles, &p.scratch, &p.tickets);
         if (rc) return rc;

@@ -197,7 +197,7 @@ __device__ __forceinline__ uint32_t make_idesc_tf32_mn(int M, int N) {
 // Row skipping in the gather producers of both tensor-core kernels (conv_tc.cu, conv_wgrad_tc.cu).  SCN_CONV_SKIP=0 / 1
 // overrides the default; read per call (a test runs both settings in one process).
 #ifndef SCN_CONV_SKIP_DEFAULT
-#define SCN_CONV_SKIP_DEFAULT 0
+#define SCN_CONV_SKIP_DEFAULT 1
 #endif
 static inline int conv_row_skipping() {
     const char* e = getenv("SCN_CONV_SKIP");

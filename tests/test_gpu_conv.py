@@ -138,11 +138,11 @@ def test_split_mode_fallback_equals_cluster_mode(cuda, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("channels", [32, 64, 48, 128])
+@pytest.mark.parametrize("channels", [32, 64, 48, 128, 22, 7])
 def test_row_skipping_is_bit_exact(cuda, monkeypatch, channels):
     """Producers skip a gathered row that is inactive now and was inactive in the stage's previous use (conv_tc.cu);
     SCN_CONV_SKIP=0 fills every row as before.  Same arithmetic on the same operands => identical bits, on a level with
-    many tiles per CTA (stages are reused hundreds of times) and with full (32, 64, 128) and partial (48) channel blocks."""
+    many tiles per CTA (stages are reused hundreds of times) with full (32, 64, 128) and partial (48) channel blocks and the 8- / 4-byte copy paths (22, 7)."""
     from sparse_rcnn_b200 import scn
     from sparse_rcnn_b200.synthetic import make_batch
     scn.set_precision("tf32")
