@@ -41,6 +41,9 @@ __device__ unsigned long long g_cta_times[2 * 512];      // entry / exit stamp o
 #endif
 
 constexpr int CONV_THREADS = 288;
+#ifndef SCN_CONV_TAILSPLIT_DEFAULT
+#define SCN_CONV_TAILSPLIT_DEFAULT 0
+#endif
 
 struct ConvTcParams {
     const float* in;
@@ -61,7 +64,20 @@ struct ConvTcParams {
     unsigned int* tickets;  // split mode: one self-resetting arrival counter per tile
     int cluster;          // > 1: the osplit work items of a tile are one thread-block cluster and reduce through DSMEM
     int skip;             // 1: producers skip rows that are inactive now and were inactive in the stage's previous use
+    int n_whole, n_work;  // work items [0, n_whole) are whole tiles (all K offsets, direct epilogue); items beyond are the
+                          // offset groups of tiles n_whole, n_whole + 1, ... (osplit per tile).  n_whole = 0: every tile is
+                          // split; n_whole = n_tiles: none is; in between: only the tail tiles of the last wave are
 };
+
+// work item -> (tile, offset range)
+__device__ __forceinline__ void decode_item(const ConvTcParams& p, int w, int& tile, int& o_lo, int& o_hi) {
+    if (w < p.n_whole) {
+        tile = w, o_lo = 0, o_hi = p.K;
+    } else {
+        const int v = w - p.n_whole, t = v / p.osplit;
+        tile = p.n_whole + t, o_lo = (v - t * p.osplit) * p.opg, o_hi = min(p.K, o_lo + p.opg);
+    }
+}
 
 // one 16-byte chunk of a gathered row, split into VEC-float cp.asyncs
 template <int VEC>
@@ -153,18 +169,25 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                 }
             };
             int idx[4], idx_next[4];
-            const int n_work = p.n_tiles * p.osplit;
-            load_idx(blockIdx.x / p.osplit, (blockIdx.x % p.osplit) * p.opg, idx_next);
+            const int n_work = p.n_work;
+            {
+                int t0_, lo0_, hi0_;
+                decode_item(p, blockIdx.x, t0_, lo0_, hi0_);
+                load_idx(t0_, lo0_, idx_next);
+            }
             const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int tile = w / p.osplit, o_lo = (w % p.osplit) * p.opg, o_hi = min(p.K, o_lo + p.opg);
+                int tile, o_lo, o_hi;
+                decode_item(p, w, tile, o_lo, o_hi);
                 for (int o = o_lo; o < o_hi; ++o) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) idx[i] = idx_next[i];
                     if (o + 1 < o_hi) load_idx(tile, o + 1, idx_next);
                     else {
                         const int wn = w + gridDim.x;
-                        load_idx(wn < n_work ? wn / p.osplit : p.n_tiles, (wn % p.osplit) * p.opg, idx_next);
+                        int tn = p.n_tiles, lon = 0, hin = 0;
+                        if (wn < n_work) decode_item(p, wn, tn, lon, hin);
+                        load_idx(tn, lon, idx_next);
                     }
                     for (int kb = 0; kb < p.n_kb; ++kb) {
                         mbar_wait(empty_bar(s), ph ^ 1);
@@ -203,7 +226,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
         const int c = lane & 7, rsub = lane >> 3;
         const uint32_t dst_even = (uint32_t)rsub * 128u + (uint32_t)((c ^ rsub) << 4);
         const uint32_t dst_odd = (uint32_t)rsub * 128u + (uint32_t)((c ^ (rsub + 4)) << 4);
-        const int n_work = p.n_tiles * p.osplit;
+        const int n_work = p.n_work;
         const int wstep = gridDim.x;
         const uint32_t wbytes = (uint32_t)p.cout_pad * 128u;
         (void)wbytes;
@@ -214,9 +237,8 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             int w, o, o_hi, kb, row0;      // row0 = first row of the tile
         };
         auto enter = [&](Cursor& q) {      // a division per WORK ITEM, not per unit
-            const int tile = p.osplit > 1 ? q.w / p.osplit : q.w;
-            q.o = p.osplit > 1 ? (q.w - tile * p.osplit) * p.opg : 0;
-            q.o_hi = min(p.K, q.o + p.opg);
+            int tile;
+            decode_item(p, q.w, tile, q.o, q.o_hi);
             q.row0 = tile * TILE_M;
             q.kb = 0;
         };
@@ -383,9 +405,10 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
         const uint32_t stage_d = stage_bytes >> 4;
         int s = 0, it = 0;
         uint32_t ph = 0;
-        const int n_work = p.n_tiles * p.osplit;
+        const int n_work = p.n_work;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-            const int o_lo = (w % p.osplit) * p.opg, o_hi = min(p.K, o_lo + p.opg);
+            int tile_, o_lo, o_hi;
+            decode_item(p, w, tile_, o_lo, o_hi);
             const int b = it & 1;
             mbar_wait(acce_bar(b), ((it >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -439,7 +462,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             }
             return x;
         };
-        const int n_work = p.n_tiles * p.osplit;
+        const int n_work = p.n_work;
         __shared__ int s_last;
         // bias / mask / residual / ReLU / rounding of 16 accumulator columns of one row, then the store
         auto finish_store = [&](float (&v)[16], int row, int c0) {
@@ -468,14 +491,15 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
             }
         };
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-            const int tile = w / p.osplit;
+            int tile, o_lo_, o_hi_;
+            decode_item(p, w, tile, o_lo_, o_hi_);
             const int b = it & 1;
             mbar_wait<200>(accf_bar(b), (it >> 1) & 1);      // epilogue warps wait a whole tile: long back-off
             tc_fence_after();
             if (warp == 0) SCN_TRACE(6);
             const int row = tile * TILE_M + warp * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * p.cout_pad);
-            if (p.osplit == 1) {
+            if (w < p.n_whole) {
                 for (int c0 = 0; c0 < p.cout_pad; c0 += 16) {
                     float v[16];
                     tmem_ld16(taddr + c0, v);
@@ -944,11 +968,32 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     // slot, where the persistent grid's last wave is mostly empty -- with one work item per CTA and a grid larger than the
     // resident slots.  A non-persistent work item pays its prologue and the cluster reduction every time: level 1 of the
     // bench scene 82.6 -> 82.9 / 85.6 / 90.4 us at cluster size 2 / 3 / 4.)
-    const int n_work = p.n_tiles * p.osplit;
+    p.n_whole = p.osplit > 1 ? 0 : p.n_tiles;
+    // Tail split: a persistent grid walks whole tiles round robin, so a level with slots < tiles costs ceil(tiles / slots)
+    // tile times even when the last wave is nearly empty (level 1 of the bench scene: 503 tiles on 444 slots = two tile
+    // times, 83 us against 52 us for level 0 with 2.6x the rows; profiles/r1_m_row_skipping.md).  The `rem` tiles of the
+    // last wave are split into offset groups instead, one group per otherwise idle CTA, and use the atomics + last-arriver
+    // epilogue of split mode (the cluster reduction needs one work item per CTA).  SCN_CONV_TAILSPLIT=0/1 overrides.
+    {
+        const char* ev_ts = getenv("SCN_CONV_TAILSPLIT");
+        const int tail_on = ev_ts ? (ev_ts[0] == '1') : SCN_CONV_TAILSPLIT_DEFAULT;
+        const int rem = p.n_tiles % slots;
+        if (tail_on && !no_split && !use_tma && K > 1 && p.osplit == 1 && p.n_tiles > slots && rem > 0 && rem * 2 <= slots) {
+            int g = slots / rem;
+            if (g > K) g = K;
+            if (g > 8) g = 8;      // depth of the same-address reduction chain
+            p.opg = cdiv(K, g);
+            p.osplit = cdiv(K, p.opg);
+            if (p.osplit > 1) p.n_whole = p.n_tiles - rem;
+            else p.opg = K;
+        }
+    }
+    const int n_work = p.n_whole + (p.n_tiles - p.n_whole) * p.osplit;
+    p.n_work = n_work;
     int grid = n_work < slots ? n_work : slots;
     p.scratch = nullptr, p.tickets = nullptr, p.cluster = 0;
     p.skip = scn::conv_row_skipping();
-    if (p.osplit > 1 && p.osplit <= 8 && cluster_ok && grid == n_work) p.cluster = p.osplit;
+    if (p.osplit > 1 && p.n_whole == 0 && p.osplit <= 8 && cluster_ok && grid == n_work) p.cluster = p.osplit;
     if (p.osplit > 1 && !p.cluster) {
         int rc = scn::split_workspace((size_t)n_out * Cout * sizeof(float), p.n_tiles, &p.scratch, &p.tickets);
         if (rc) return rc;

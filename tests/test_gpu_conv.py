@@ -177,3 +177,41 @@ def test_row_skipping_is_bit_exact(cuda, monkeypatch, channels):
     monkeypatch.delenv("SCN_CONV_SKIP")
     assert torch.equal(gx_a, gx_b)
     assert rel_err(gw_a, gw_b) < 1e-5 and rel_err(gb_a, gb_b) < 1e-5
+
+
+@pytest.mark.parametrize("channels", [32, 48, 128])
+def test_tail_split_equals_persistent_grid(cuda, monkeypatch, channels):
+    """Levels whose last wave of tiles is less than half full: the tail tiles are split into offset groups handed to the
+    otherwise idle CTAs (conv_tc.cu, SCN_CONV_TAILSPLIT) and reduced with atomics + a last-arriver epilogue.  Same sums as
+    whole tiles up to fp32 summation order; the accumulation buffer is left clean (second and third call)."""
+    from sparse_rcnn_b200 import scn
+    from sparse_rcnn_b200.synthetic import make_batch
+    scn.set_precision("tf32")
+    torch.manual_seed(2)
+    coords, feats, size, bs, _ = make_batch(1, 5, spatial_size=(192, 192, 96), room=(128, 128, 64), room_offset=(32, 32, 8),
+                                            n_furniture=12)
+    md = scn.Metadata(3)
+    f = scn.ioLayers.InputLayerFunction.apply(3, md, size, coords, feats.to(cuda), bs, 4)
+    n = f.shape[0]
+    tiles = (n + 127) // 128
+    assert 0 < tiles % (148 * 3) <= 148 * 3 // 2 and 0 < tiles % (148 * 2) <= 148 and tiles > 148 * 3
+    conv = scn.SubmanifoldConvolution(3, channels, channels, 3, True).to(cuda)
+    x = scn.SparseConvNetTensor(torch.randn(n, channels, device=cuda), md, size)
+    res = x.features.clone()
+    with torch.no_grad():
+        monkeypatch.setenv("SCN_CONV_TAILSPLIT", "0")
+        ref = conv(x).features.clone()
+        monkeypatch.setenv("SCN_CONV_TAILSPLIT", "1")
+        for _ in range(3):
+            a = conv(x).features
+            assert rel_err(a, ref) < 1e-5, rel_err(a, ref)
+            assert (a[-128 * 40:] - ref[-128 * 40:]).abs().max() < 1e-4 * ref.abs().max()      # the tail tiles themselves
+    # backward through the same kernel (input gradient) with the switch on
+    xin = res.requires_grad_(True)
+    go = torch.randn(n, channels, device=cuda)
+    conv(scn.SparseConvNetTensor(xin, md, size)).features.backward(go)
+    g_on = xin.grad.clone()
+    monkeypatch.setenv("SCN_CONV_TAILSPLIT", "0")
+    xin.grad = None
+    conv(scn.SparseConvNetTensor(xin, md, size)).features.backward(go)
+    assert rel_err(g_on, xin.grad) < 1e-5
