@@ -42,7 +42,7 @@ __device__ unsigned long long g_cta_times[2 * 512];      // entry / exit stamp o
 
 constexpr int CONV_THREADS = 288;
 #ifndef SCN_CONV_TAILSPLIT_DEFAULT
-#define SCN_CONV_TAILSPLIT_DEFAULT 0
+#define SCN_CONV_TAILSPLIT_DEFAULT 1
 #endif
 
 struct ConvTcParams {

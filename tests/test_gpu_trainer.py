@@ -144,7 +144,7 @@ def test_staged_uploads_equal_inline(cuda):
                 out.append(float(tr.step(d, l, next_batch=nb)))
             losses.append(out)
         assert not metadata._staged                                  # every staged tensor was picked up
-        assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-6, losses
+        assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-5, losses      # sums contain fp32 atomics
     finally:
         scn.set_precision("tf32")
 
@@ -167,6 +167,6 @@ def test_geometry_built_ahead_equals_inline(cuda):
                 out.append(float(tr.step(d, l, next_batch=nb)))
                 assert len(tr.backbone.input_stage.ready) == (1 if ahead and nb is not None else 0)
             losses.append(out)
-        assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-6, losses
+        assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-5, losses      # sums contain fp32 atomics
     finally:
         scn.set_precision("tf32")
