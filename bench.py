@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--infer-workers", type=int, default=2,
+                    help="host threads (one CUDA stream each) of the sparse inference measurement; 1 = one scene at a time")
     ap.add_argument("--sync-loss", action="store_true",
                     help="e2e: read every step's loss with a blocking .item() right after the step instead of one step late")
     ap.add_argument("--build-ahead", action="store_true",
@@ -328,29 +330,41 @@ def main():
     infer = pipeline.SparseInference(dev)
     boxes = [make_boxes(d[0], 256, 7 + i) for i, (d, _) in enumerate(host)]
     n_inf = max(K, 8)
+    n_inf += n_inf % 2
+    workers = max(1, args.infer_workers)
+    consume = lambda i, res: (int(res["mpn_mask"].shape[0]), res["mpn_class"].argmax(1).cpu())   # D2H of the class decision
+    seq = lambda n: ([pinned[i % n_distinct][0] for i in range(n)], [boxes[i % n_distinct] for i in range(n)])
     for i in range(max(W, 2 * n_distinct)):              # every distinct scene twice: the caching allocator has to settle
                                                          # on the inference pass's tensor sizes (a cudaMalloc costs ~10 ms)
         infer(pinned[i % n_distinct][0], boxes[i % n_distinct])
-    barrier()
-    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = _lib.raw("scn_launch_count")()
-    i0.record()
-    mask_pts = 0
-    for i in range(n_inf):
-        res = infer(pinned[i % n_distinct][0], boxes[i % n_distinct])
-        mask_pts += int(res["mpn_mask"].shape[0])
-        res["mpn_class"].argmax(1).cpu()                   # D2H of the per-box class decision
-    i1.record()
-    barrier()
-    inf_ms = i0.elapsed_time(i1)
-    inf_launches = _lib.raw("scn_launch_count")() - l0
-    if world > 1:
-        tmax = torch.tensor([inf_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        inf_ms = float(tmax[0])
+
+    def timed_inference(nw):
+        sc, bx = seq(n_inf)
+        for _ in range(2 if nw > 1 else 0):              # the allocator pools are per stream: settle the workers' too
+            infer.run_many(sc, bx, workers=nw, consume=consume)
+        barrier()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.raw("scn_launch_count")()
+        i0.record()
+        out = infer.run_many(sc, bx, workers=nw, consume=consume)
+        i1.record()
+        barrier()
+        ms = i0.elapsed_time(i1)
+        if world > 1:
+            tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms = float(tmax[0])
+        return ms, sum(o[0] for o in out), _lib.raw("scn_launch_count")() - l0
+
+    ser_ms, mask_pts, inf_launches = timed_inference(1)
+    inf_ms = ser_ms
+    if workers > 1:
+        inf_ms, mask_pts, inf_launches = timed_inference(workers)
     inference = {"scenes_per_sec": world * n_inf / (inf_ms * 1e-3), "ms_per_scene": inf_ms / n_inf, "boxes_per_scene": 256,
                  "mask_points_per_scene": mask_pts // n_inf, "scn_launches_per_scene": int(inf_launches // n_inf),
-                 "scope": "sparse path only: backbone+seg+class net+mask net on given boxes (dense RPN/NMS out of scope)"}
+                 "host_threads": workers, "ms_per_scene_one_thread": ser_ms / n_inf,
+                 "scope": "sparse path only: backbone+seg+class net+mask net on given boxes (dense RPN/NMS out of scope); "
+                          "scenes are independent, each host thread drives its own stream (SparseInference.run_many)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -753,45 +753,68 @@ __global__ void k_pack_weights_multi(const int64_t* __restrict__ table) {
 using namespace scn;
 
 // Split-offset mode workspace: accumulation buffer (kept all-zero between launches by the kernel itself) + per-tile
-// ticket counters, owned by the library, grow-only (a
-// reallocation synchronises the device once; the sizes settle after the first training step).  One workspace per
-// process: split-mode convolutions must not run concurrently on two streams.
+// ticket counters, owned by the library, grow-only (a reallocation synchronises the device once; the sizes settle after
+// the first step).  One workspace PER STREAM (kernels of one stream are serialised, also under programmatic dependent
+// launch: `pdl_wait()` returns only when the previous grid has completed), so split-mode convolutions may run concurrently
+// on different streams (pipeline.SparseInference.run_many drives one stream per host thread).
+#include <mutex>
 namespace scn {
-static float* g_split_scratch = nullptr;
-static size_t g_split_bytes = 0;
-static unsigned int* g_split_tickets = nullptr;
-static int g_split_ntickets = 0;
-int split_workspace(size_t bytes, int n_tiles, float** scratch, unsigned int** tickets) {
-    if (bytes > g_split_bytes) {
-        if (g_split_scratch) {
+struct SplitWs {
+    cudaStream_t stream;
+    float* scratch;
+    size_t bytes;
+    unsigned int* tickets;
+    int ntickets;
+    bool used;
+};
+static SplitWs g_ws[16];
+static std::mutex g_ws_mutex;
+int split_workspace(cudaStream_t stream, size_t bytes, int n_tiles, float** scratch, unsigned int** tickets) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    SplitWs* w = nullptr;
+    for (auto& e : g_ws)
+        if (e.used && e.stream == stream) w = &e;
+    if (!w)
+        for (auto& e : g_ws)
+            if (!e.used) {
+                w = &e;
+                *w = SplitWs{stream, nullptr, 0, nullptr, 0, true};
+                break;
+            }
+    if (!w) {
+        set_error("conv_fwd_tf32: split-mode convolutions on more than 16 streams");
+        return SCN_ERR_INVALID;
+    }
+    if (bytes > w->bytes) {
+        if (w->scratch) {
             cudaDeviceSynchronize();
-            cudaFree(g_split_scratch);
+            cudaFree(w->scratch);
         }
-        g_split_scratch = nullptr, g_split_bytes = 0;
+        w->scratch = nullptr, w->bytes = 0;
         size_t want = bytes + bytes / 4;
-        if (cudaMalloc(&g_split_scratch, want) != cudaSuccess || cudaMemset(g_split_scratch, 0, want) != cudaSuccess) {
+        if (cudaMalloc(&w->scratch, want) != cudaSuccess || cudaMemsetAsync(w->scratch, 0, want, stream) != cudaSuccess) {
             cudaGetLastError();
             set_error("conv_fwd_tf32: split workspace of %zu bytes: allocation failed", want);
             return SCN_ERR_CUDA;
         }
-        g_split_bytes = want;
+        w->bytes = want;
     }
-    if (n_tiles > g_split_ntickets) {
-        if (g_split_tickets) {
+    if (n_tiles > w->ntickets) {
+        if (w->tickets) {
             cudaDeviceSynchronize();
-            cudaFree(g_split_tickets);
+            cudaFree(w->tickets);
         }
-        g_split_tickets = nullptr, g_split_ntickets = 0;
+        w->tickets = nullptr, w->ntickets = 0;
         int want = n_tiles < 1024 ? 1024 : 2 * n_tiles;
-        if (cudaMalloc(&g_split_tickets, want * sizeof(unsigned int)) != cudaSuccess ||
-            cudaMemset(g_split_tickets, 0, want * sizeof(unsigned int)) != cudaSuccess) {
+        if (cudaMalloc(&w->tickets, want * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemsetAsync(w->tickets, 0, want * sizeof(unsigned int), stream) != cudaSuccess) {
             cudaGetLastError();
             set_error("conv_fwd_tf32: ticket allocation failed");
             return SCN_ERR_CUDA;
         }
-        g_split_ntickets = want;
+        w->ntickets = want;
     }
-    *scratch = g_split_scratch, *tickets = g_split_tickets;
+    *scratch = w->scratch, *tickets = w->tickets;
     return SCN_OK;
 }
 }  // namespace scn
@@ -995,7 +1018,7 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     p.skip = scn::conv_row_skipping();
     if (p.osplit > 1 && p.n_whole == 0 && p.osplit <= 8 && cluster_ok && grid == n_work) p.cluster = p.osplit;
     if (p.osplit > 1 && !p.cluster) {
-        int rc = scn::split_workspace((size_t)n_out * Cout * sizeof(float), p.n_tiles, &p.scratch, &p.tickets);
+        int rc = scn::split_workspace(as_stream(stream), (size_t)n_out * Cout * sizeof(float), p.n_tiles, &p.scratch, &p.tickets);
         if (rc) return rc;
     }
     cudaError_t e;

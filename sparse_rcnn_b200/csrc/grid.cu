@@ -7,6 +7,7 @@
 // key arrays, random probes into a table sized at load factor <= 0.5 that lives in the 126 MB L2.
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -56,6 +57,8 @@ int ensure_dynamic_smem(const void* kernel, int bytes) {
     static const void* fns[32];
     static int vals[32];
     static int n = 0;
+    static std::mutex mu;      // launches may come from several host threads (one stream each)
+    std::lock_guard<std::mutex> lock(mu);
     int i = 0;
     for (; i < n; ++i)
         if (fns[i] == kernel) break;

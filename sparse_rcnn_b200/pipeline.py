@@ -117,3 +117,65 @@ class SparseInference(nn.Module):
         mask, mask_sel = self.mask_network(data, unet, boxes)
         return dict(segmentation=seg, mpn_class=cls, mpn_mask=mask, class_selection=cls_sel, mask_selection=mask_sel,
                     n_active=inter[0].features.shape[0])
+
+    def run_many(self, scenes, boxes, workers=2, consume=None):
+        """Inference over independent scenes from `workers` host threads, one CUDA stream each (scene i -> worker
+        i mod workers).  Why: one scene's pass is a ping-pong between host and GPU -- 16 host reads of row counts (every
+        level of three pyramids and two crops) during which the host waits for the GPU, each followed by a stretch in which
+        the GPU waits for the host to issue again (`scripts/host_profile_infer.py`: ~3 of 11 ms per scene blocked in
+        `.item()`).  Those reads release the GIL, so a second thread issues its scene's kernels meanwhile.  Scenes are
+        independent (no collective), the library keeps its split-mode workspace per stream, crop key caches are
+        per thread, packed weight images are read-only here.
+        `consume(i, result)` runs on the worker's stream right after scene i (e.g. the device->host read of a decision) and
+        its return value replaces the result; returned tensors are `record_stream`-ed for the caller's stream."""
+        import threading
+        n = len(scenes)
+        if workers <= 1 or n <= 1:
+            out = []
+            for i in range(n):
+                r = self(scenes[i], boxes[i])
+                out.append(consume(i, r) if consume is not None else r)
+            return out
+        workers = min(workers, n)
+        streams = getattr(self, "_streams", None)
+        if streams is None or len(streams) < workers:
+            streams = self._streams = [torch.cuda.Stream(device=self.device) for _ in range(workers)]
+        caller = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(caller)
+        done = [torch.cuda.Event() for _ in range(workers)]
+        results, errors = [None] * n, []
+
+        def work(k):
+            try:
+                torch.cuda.set_device(self.device)
+                with torch.cuda.stream(streams[k]):
+                    streams[k].wait_event(ready)      # weights / packed images written on the caller's stream
+                    for i in range(k, n, workers):
+                        r = self(scenes[i], boxes[i])
+                        results[i] = consume(i, r) if consume is not None else r
+                    done[k].record(streams[k])
+            except BaseException as e:      # surfaced in the calling thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(k,), name="scn-infer-%d" % k) for k in range(workers)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        for d in done:
+            caller.wait_event(d)
+
+        def mark(o):
+            if isinstance(o, torch.Tensor) and o.is_cuda:
+                o.record_stream(caller)
+            elif isinstance(o, dict):
+                for v in o.values():
+                    mark(v)
+            elif isinstance(o, (list, tuple)):
+                for v in o:
+                    mark(v)
+        mark(results)
+        return results

@@ -16,6 +16,7 @@ the selection is compacted on the device (count -> scan -> ordered select) and t
 the device hash builder directly; `is_inside` is produced on the device (optionally copied to the
 CPU to keep the reference's return format).
 """
+import threading
 import weakref
 
 import torch
@@ -58,13 +59,21 @@ class BBoxTransformerSlice(nn.Module):
 
 
 # ------------------------------------------------------------------------------- key cache
-_KEY_CACHE = {}
+_TLS = threading.local()      # per host thread: SparseInference.run_many drives one scene stream per thread
+
+
+def _key_cache():
+    c = getattr(_TLS, "keys", None)
+    if c is None:
+        c = _TLS.keys = {}
+    return c
 
 
 def _packed_keys(coords, device):
     """Packed device keys of a raw [P,4] coordinate tensor (cached per tensor object)."""
+    cache = _key_cache()
     k = id(coords)
-    hit = _KEY_CACHE.get(k)
+    hit = cache.get(k)
     if hit is not None and hit[0]() is coords:
         return hit[1]
     P, ncol = coords.shape
@@ -72,21 +81,22 @@ def _packed_keys(coords, device):
     keys = torch.empty(P, dtype=torch.int64, device=device)
     err = torch.zeros(1, dtype=torch.int32, device=device)
     _lib.call("scn_pack_coords", _ptr(cdev), P, ncol, _ptr(keys), _ptr(err), _stream())
-    if len(_KEY_CACHE) > 64:
-        _KEY_CACHE.clear()
-    _KEY_CACHE[k] = (weakref.ref(coords), keys)
+    if len(cache) > 64:
+        cache.clear()
+    cache[k] = (weakref.ref(coords), keys)
     return keys
 
 
 def register_keys(coords, keys):
     """Let a crop reuse the keys the input layer already packed for the same coords tensor."""
-    if len(_KEY_CACHE) > 64:
-        _KEY_CACHE.clear()
-    _KEY_CACHE[id(coords)] = (weakref.ref(coords), keys)
+    cache = _key_cache()
+    if len(cache) > 64:
+        cache.clear()
+    cache[id(coords)] = (weakref.ref(coords), keys)
 
 
 def clear_key_cache():
-    _KEY_CACHE.clear()
+    _key_cache().clear()
 
 
 class GatherRowsFunction(Function):

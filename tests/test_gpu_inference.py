@@ -1,0 +1,61 @@
+"""GPU: SparseInference.run_many (independent scenes from several host threads, one CUDA stream each; SURVEY 8e: scenes
+shard with no collective) must return exactly what one scene at a time returns."""
+import pytest
+import torch
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 2e-4)])
+def test_run_many_equals_one_scene_at_a_time(cuda, precision, tol):
+    """fp32 verification mode: equal up to fp32 summation order (1e-5) -- this is the check that would catch a race between
+    the streams.  TF32 mode: a one-ulp fp32 difference upstream of a TF32 rounding point (order of atomics in a split
+    reduction) can flip that rounding; measured 2e-5 on the mask logits between the one-stream and the two-stream run; bar
+    2e-4, a tenth of the TF32 parity tolerance."""
+    from sparse_rcnn_b200 import pipeline, scn
+    from sparse_rcnn_b200.synthetic import make_batch, make_boxes
+    scn.set_precision(precision)
+    size = (64, 64, 32)
+    scenes, boxes = [], []
+    for i in range(6):                                               # ragged: different scenes, different box counts
+        d = make_batch(1, 10 + i, spatial_size=size, room=(40 + 2 * (i % 3), 44, 22), room_offset=(8, 8, 2), n_furniture=3)
+        scenes.append(d)
+        boxes.append(make_boxes(d[0], 8 + 4 * i, i, size))
+    inf = pipeline.SparseInference(cuda)
+    keys = ("segmentation", "mpn_class", "mpn_mask")
+    ref = [{k: v.clone() for k, v in inf(s, b).items() if k in keys} for s, b in zip(scenes, boxes)]
+    for workers in (2, 3):
+        for _ in range(2):                                           # second round: stream-local allocator pools are warm
+            got = inf.run_many(scenes, boxes, workers=workers)
+            torch.cuda.synchronize()
+            assert len(got) == len(ref)
+            for g, r in zip(got, ref):
+                for k in keys:
+                    assert g[k].shape == r[k].shape, k
+                    assert rel_err(g[k], r[k]) < tol, (workers, k, rel_err(g[k], r[k]))
+    # consume runs on the worker's stream and replaces the result; order is the scene order
+    out = inf.run_many(scenes, boxes, workers=2, consume=lambda i, res: (i, res["mpn_class"].argmax(1).cpu()))
+    assert [o[0] for o in out] == list(range(6))
+    for (i, cls), r in zip(out, ref):
+        top2 = r["mpn_class"].topk(2, dim=1).values
+        clear = ((top2[:, 0] - top2[:, 1]) > 1e-3).cpu()             # ties within rounding noise may flip
+        assert torch.equal(cls[clear], r["mpn_class"].argmax(1).cpu()[clear])
+    scn.set_precision("tf32")
+
+
+def test_run_many_surfaces_worker_errors(cuda):
+    from sparse_rcnn_b200 import pipeline, scn
+    from sparse_rcnn_b200.synthetic import make_batch, make_boxes
+    scn.set_precision("tf32")
+    size = (64, 64, 32)
+    d = make_batch(1, 3, spatial_size=size, room=(44, 44, 22), room_offset=(8, 8, 2), n_furniture=3)
+    b = make_boxes(d[0], 8, 0, size)
+    bad = (d[0].clone(), d[1], d[2], d[3], d[4])
+    bad[0][0, 0] = 70000                                             # coordinate out of the packable range
+    inf = pipeline.SparseInference(cuda)
+    with pytest.raises(RuntimeError):
+        inf.run_many([d, bad, d], [b, b, b], workers=2)
+    res = inf.run_many([d, d], [b, b], workers=2)                    # the pipeline is usable afterwards
+    assert res[0]["mpn_class"].shape == res[1]["mpn_class"].shape
