@@ -332,42 +332,44 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                     if (skipping) dirty = now;
                 } else {
                     // last, partial block: the MMA reads chunks below cin_pad8 ("wanted"), chunks at or beyond Cin must be
-                    // zeros.  Row skipping here: the dirty bit travels in bit 30 of an active row's index; a lane of a
-                    // chunk the MMA does not read only has to clear it when the row turns clean (inactive over dirty), so
-                    // that "clean" keeps meaning "all 128 bytes are zero" for a later full block in the same stage.
-                    const bool wanted = col0 < p.cin_pad8, real = col0 < p.Cin;
+                    // zeros, lanes of the other chunks do nothing.  Row skipping must not lengthen this loop (an earlier
+                    // version carried the dirty bit of active rows through the shuffle and let the idle lanes clear their
+                    // chunks: C = 16 layers ran 1.8x slower, profiles/r1_p): same three-way code as a full block; the price
+                    // is that a partial unit cannot make a row CLEAN for a later full block in the same stage (chunks the
+                    // MMA does not read keep stale bytes), so it only ever sets dirty bits -- unless every unit of the
+                    // layer is this block (n_kb == 1), where those chunks are never read at all.
+                    // One lane-constant clamp instead of branches around the copy (an `if (wanted)` around inline PTX that
+                    // carries its own guard predicate compiles to a divergent branch + BSSY/BSYNC per copy): a real chunk
+                    // keeps its code, a zero-padding chunk (Cin <= column < cin_pad8) is zero-filled unless the row is
+                    // clean (-1), a chunk the MMA does not read is always skipped (-2).
+                    const int clamp = col0 < p.cin_pad8 ? (col0 < p.Cin ? 0x7fffffff : -1) : -2;
                     uint32_t now = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t d = (dirty >> j) & 1u;
-                        const int code = idx[j] >= 0 ? (int)((uint32_t)idx[j] | (d << 30)) : (d ? -1 : -2);
+                        const int code = idx[j] >= 0 ? idx[j] : (((dirty >> j) & 1u) ? -1 : -2);
                         now |= (idx[j] >= 0 ? 1u : 0u) << j;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int r = __shfl_sync(0xffffffffu, code, rsub + 4 * i);
-                            const bool active = r >= 0;
-                            const bool was_dirty = active ? ((r >> 30) & 1) != 0 : r == -1;
-                            const bool do_copy = active && real;
-                            const bool do_zero = was_dirty && (real ? !active : (wanted ? true : (skipping && !active)));
-                            const char* src = colp + (uint64_t)((uint32_t)r & 0x3FFFFFFFu) * row_bytes;
-                            if (do_copy || do_zero)
-                                asm volatile(
-                                    "{\n\t"
-                                    ".reg .pred p;\n\t"
-                                    "setp.eq.s32 p, %2, 0;\n\t"
-                                    "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
-                                    "}" ::"r"(((i & 1) ? dodd : de) + (uint32_t)(32 * j + 4 * i) * 128u),
-                                    "l"(src), "r"((int)do_copy)
-                                    : "memory");
+                            const int r = min(__shfl_sync(0xffffffffu, code, rsub + 4 * i), clamp);
+                            const char* src = colp + (uint64_t)(uint32_t)r * row_bytes;
+                            asm volatile(
+                                "{\n\t"
+                                ".reg .pred p, q;\n\t"
+                                "setp.lt.s32 p, %2, 0;\n\t"
+                                "setp.ne.s32 q, %2, -2;\n\t"
+                                "@q cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+                                "}" ::"r"(((i & 1) ? dodd : de) + (uint32_t)(32 * j + 4 * i) * 128u),
+                                "l"(src), "r"(r)
+                                : "memory");
                         }
                     }
-                    if (skipping) dirty = now;
+                    if (skipping) dirty = p.n_kb == 1 ? now : (dirty | now);
                 }
             } else {
                 // 8- and 4-byte copies (row stride not a multiple of 16 bytes): a written chunk is always written whole
-                // (gather_chunk zero-fills columns at or beyond Cin), so the same row skipping applies; lanes of chunks the
-                // MMA does not read clear theirs when the row turns clean
+                // (gather_chunk zero-fills columns at or beyond Cin); same rules as the partial block above
                 const bool wanted = col0 < p.cin_pad8;
+                const bool clears = p.n_kb == 1 || p.cin_pad8 - cur.kb * KB >= KB;      // a full block rewrites every chunk
                 uint32_t now = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -376,12 +378,12 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = __shfl_sync(0xffffffffu, code, rsub + 4 * i);
-                        if (wanted ? r != -2 : (skipping && r == -1))
+                        if (wanted && r != -2)
                             gather_chunk<VEC>(a_stage + ((i & 1) ? dst_odd : dst_even) + (uint32_t)(32 * j + 4 * i) * 128u,
                                               p.in, (int64_t)r * p.ld_in, r, col0, p.Cin);
                     }
                 }
-                if (skipping) dirty = now;
+                if (skipping) dirty = clears ? now : (dirty | now);
             }
             // the stage's full barrier receives this thread's arrival when its copies have landed
             cp_async_mbar_arrive_noinc(fb);
