@@ -79,20 +79,6 @@ __device__ __forceinline__ void decode_item(const ConvTcParams& p, int w, int& t
     }
 }
 
-// one 16-byte chunk of a gathered row, split into VEC-float cp.asyncs
-template <int VEC>
-__device__ __forceinline__ void gather_chunk(uint32_t dst, const float* __restrict__ in, int64_t row_off, int src_row,
-                                             int col0, int Cin) {
-    constexpr int BYTES = VEC * 4;
-#pragma unroll
-    for (int j = 0; j < 4 / VEC; ++j) {
-        int col = col0 + j * VEC;
-        bool valid = src_row >= 0 && col < Cin;
-        const float* src = valid ? in + row_off + col : in;
-        cp_async<BYTES>(dst + j * BYTES, src, valid);
-    }
-}
-
 // TMA = true : the A stage is filled by ONE producer warp with `cp.async.bulk.tensor.2d ... tile::gather4`
 //              (SASS UTMALDG): lane L gathers rows 4L..4L+3 of the tile by index, the hardware applies the
 //              128B swizzle, zero-fills index -1 / out-of-range columns, rounds fp32 -> TF32 (to nearest)
@@ -366,10 +352,18 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                     if (skipping) dirty = p.n_kb == 1 ? now : (dirty | now);
                 }
             } else {
-                // 8- and 4-byte copies (row stride not a multiple of 16 bytes): a written chunk is always written whole
-                // (gather_chunk zero-fills columns at or beyond Cin); same rules as the partial block above
-                const bool wanted = col0 < p.cin_pad8;
+                // 8- and 4-byte copies (row stride not a multiple of 16 bytes): each 16-byte chunk is 4 / VEC sub-copies,
+                // every one the same guarded copy as above behind its own lane-constant clamp (real column: the row's
+                // code; zero padding inside a chunk the MMA reads: zero fill unless the row is clean; chunk the MMA does not
+                // read: skip).  Branch-free: the mask network's 22-channel layers run here.
+                constexpr int NSUB = 4 / VEC;
+                int clamp[NSUB];
+#pragma unroll
+                for (int u = 0; u < NSUB; ++u)
+                    clamp[u] = col0 + u * VEC < p.Cin ? 0x7fffffff : (col0 < p.cin_pad8 ? -1 : -2);
                 const bool clears = p.n_kb == 1 || p.cin_pad8 - cur.kb * KB >= KB;      // a full block rewrites every chunk
+                const char* colp = in_c + cur.kb * (KB * 4);
+                const uint32_t de = a_stage + dst_even, dodd = a_stage + dst_odd;
                 uint32_t now = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -377,10 +371,33 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                     now |= (idx[j] >= 0 ? 1u : 0u) << j;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int r = __shfl_sync(0xffffffffu, code, rsub + 4 * i);
-                        if (wanted && r != -2)
-                            gather_chunk<VEC>(a_stage + ((i & 1) ? dst_odd : dst_even) + (uint32_t)(32 * j + 4 * i) * 128u,
-                                              p.in, (int64_t)r * p.ld_in, r, col0, p.Cin);
+                        const int r0 = __shfl_sync(0xffffffffu, code, rsub + 4 * i);
+                        const char* src = colp + (uint64_t)(uint32_t)r0 * row_bytes;
+                        const uint32_t dst = ((i & 1) ? dodd : de) + (uint32_t)(32 * j + 4 * i) * 128u;
+#pragma unroll
+                        for (int u = 0; u < NSUB; ++u) {
+                            const int r = min(r0, clamp[u]);
+                            if constexpr (VEC == 2)
+                                asm volatile(
+                                    "{\n\t"
+                                    ".reg .pred p, q;\n\t"
+                                    "setp.lt.s32 p, %2, 0;\n\t"
+                                    "setp.ne.s32 q, %2, -2;\n\t"
+                                    "@q cp.async.ca.shared.global [%0], [%1], 8, p;\n\t"
+                                    "}" ::"r"(dst + (uint32_t)u * 8u),
+                                    "l"(src + u * 8), "r"(r)
+                                    : "memory");
+                            else
+                                asm volatile(
+                                    "{\n\t"
+                                    ".reg .pred p, q;\n\t"
+                                    "setp.lt.s32 p, %2, 0;\n\t"
+                                    "setp.ne.s32 q, %2, -2;\n\t"
+                                    "@q cp.async.ca.shared.global [%0], [%1], 4, p;\n\t"
+                                    "}" ::"r"(dst + (uint32_t)u * 4u),
+                                    "l"(src + u * 4), "r"(r)
+                                    : "memory");
+                        }
                     }
                 }
                 if (skipping) dirty = clears ? now : (dirty | now);

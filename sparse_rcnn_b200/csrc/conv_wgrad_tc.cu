@@ -196,6 +196,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
                                         : "memory");
                                 }
                             }
+                        } else if (VEC == 4) {
+                            // partial channel block, 16-byte copies: the same copy as above behind one lane-constant clamp
+                            // (chunks at or beyond the channel limit are zero-filled unless the row is skipped) instead of
+                            // per-chunk validity arithmetic (14 -> 6 instructions per copy; conv_tc.cu, profiles/r1_p)
+                            const int clamp = cb + c * 4 < cin_lim ? 0x7fffffff : -1;
+                            const char* colp = in_c + kb * (KB * 4);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int r = min(__shfl_sync(0xffffffffu, code[j], rsub + 4 * i), clamp);
+                                    const char* src = colp + (uint64_t)(uint32_t)r * row_bytes;
+                                    asm volatile(
+                                        "{\n\t"
+                                        ".reg .pred p, q;\n\t"
+                                        "setp.lt.s32 p, %2, 0;\n\t"
+                                        "setp.ne.s32 q, %2, -2;\n\t"
+                                        "@q cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+                                        "}" ::"r"(dst0 + (uint32_t)(32 * j + 4 * i) * 128u),
+                                        "l"(src), "r"(r)
+                                        : "memory");
+                                }
+                            }
                         } else {
                             const int col0 = cb + c * 4;
 #pragma unroll
