@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
     auto acce_bar = [&](int b) { return bars + 8u * (2 * S + 2 + b); };
     const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle from lane 0: the compiler then knows it is warp-uniform (uniform registers for the ring
+    // bookkeeping and barrier addresses, no vote loops around barrier instructions; cutlass::canonical_warp_idx_sync)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int units_per_tile = p.K * p.n_kb;
     if (tid == 0) SCN_TRACE(0);
 #ifdef SCN_EXP_TRACE

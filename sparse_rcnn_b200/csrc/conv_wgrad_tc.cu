@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_tc(const WgradPara
     const uint32_t done_bar = bars + 8u * (2 * AS + 2 * GS);
     const uint32_t tmem_slot = done_bar + 8u;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // warp-uniform for the compiler (conv_tc.cu)
     if (tid == 0) {
         for (int s = 0; s < AS; ++s) {
             mbar_init(a_full(s), 64);      // the two owning producer warps
