@@ -319,8 +319,8 @@ def main():
                 "achieved": achieved, "peak": peak, "peak_source": "measured" if peaks else "fallback",
                 "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this layer from the ncu --set full
-                # capture summarised in profiles/r1_n_final_ncu_and_bench.md (40.18 MB + 0.44 MB; the output stays in L2)
-                "traffic": 40.62e6,
+                # capture summarised in profiles/r1_p_final_state.md section 7 (39.66 MB + 0.53 MB; the output stays in L2)
+                "traffic": 40.19e6,
                 "ms_per_launch": kms, "algorithmic_bytes": alg_bytes,
                 "tflops_useful": flops / (kms * 1e-3) / 1e12, "l2": "flushed between launches"}
 
