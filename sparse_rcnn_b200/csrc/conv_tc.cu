@@ -330,8 +330,36 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                     // carries its own guard predicate compiles to a divergent branch + BSSY/BSYNC per copy): a real chunk
                     // keeps its code, a zero-padding chunk (Cin <= column < cin_pad8) is zero-filled unless the row is
                     // clean (-1), a chunk the MMA does not read is always skipped (-2).
-                    const int clamp = col0 < p.cin_pad8 ? (col0 < p.Cin ? 0x7fffffff : -1) : -2;
                     uint32_t now = 0;
+                    if (p.cin_pad8 - cur.kb * KB <= 16) {
+                        // at most four chunks of a row are read (C = 16, 48, 80, 112: the last 16 channels): four lanes per
+                        // row, EIGHT rows per copy instruction -- 16 copies per unit instead of 32 with half the lanes idle
+                        const int c4 = lane & 3, r8 = lane >> 2;
+                        const int col4 = cur.kb * KB + c4 * 4;
+                        const int clamp4 = col4 < p.cin_pad8 ? (col4 < p.Cin ? 0x7fffffff : -1) : -2;
+                        const char* colp4 = reinterpret_cast<const char*>(p.in) + cur.kb * (KB * 4) + c4 * 16;
+                        const uint32_t d8 = a_stage + (uint32_t)r8 * 128u + (uint32_t)((c4 ^ r8) << 4);      // row & 7 == r8
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int code = idx[j] >= 0 ? idx[j] : (((dirty >> j) & 1u) ? -1 : -2);
+                            now |= (idx[j] >= 0 ? 1u : 0u) << j;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = min(__shfl_sync(0xffffffffu, code, r8 + 8 * i), clamp4);
+                                const char* src = colp4 + (uint64_t)(uint32_t)r * row_bytes;
+                                asm volatile(
+                                    "{\n\t"
+                                    ".reg .pred p, q;\n\t"
+                                    "setp.lt.s32 p, %2, 0;\n\t"
+                                    "setp.ne.s32 q, %2, -2;\n\t"
+                                    "@q cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+                                    "}" ::"r"(d8 + (uint32_t)(32 * j + 8 * i) * 128u),
+                                    "l"(src), "r"(r)
+                                    : "memory");
+                            }
+                        }
+                    } else {
+                    const int clamp = col0 < p.cin_pad8 ? (col0 < p.Cin ? 0x7fffffff : -1) : -2;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int code = idx[j] >= 0 ? idx[j] : (((dirty >> j) & 1u) ? -1 : -2);
@@ -350,6 +378,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                                 "l"(src), "r"(r)
                                 : "memory");
                         }
+                    }
                     }
                     if (skipping) dirty = p.n_kb == 1 ? now : (dirty | now);
                 }
