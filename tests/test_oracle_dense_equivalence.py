@@ -127,3 +127,39 @@ def test_rules_to_map_roundtrip_and_offset_order():
     r = np.nonzero(m[22] >= 0)[0]   # +1 in x
     assert (loc[m[22][r], 0] - loc[r, 0] == 1).all()
     assert (m[13] == np.arange(m.shape[1])).all()
+
+
+def test_ragged_batch_with_an_empty_sample_and_forced_batch_size():
+    """Edge cases the reference relies on (roi_select_sparse.py:75-84,113-122: one sample per box, empty boxes allowed, the
+    batch_size argument forces the sample count): a batch whose middle sample has no points keeps batch-sorted rows, the
+    forced batch size is reported, and a submanifold convolution never mixes samples (same answer as per-sample runs)."""
+    coords, feats, size = random_scene(9, size=(10, 8, 6), n_samples=3, density=0.2, channels=4)
+    keep = coords[:, 3] != 1                                          # sample 1 becomes empty
+    coords, feats = coords[keep], feats[keep]
+    md = O.Metadata(3)
+    f = O.ioLayers.InputLayerFunction.apply(3, md, size, coords, feats, 5, 4)       # 5 samples forced, 3 and 4 empty too
+    t = O.SparseConvNetTensor(f, md, size)
+    loc = t.get_spatial_locations()
+    assert t.batch_size() == 5
+    assert bool((loc[1:, 3] >= loc[:-1, 3]).all()) and set(loc[:, 3].tolist()) == {0, 2}
+    torch.manual_seed(0)
+    conv = O.SubmanifoldConvolution(3, 4, 5, 3, True)
+    whole = conv(t).features
+    for b in (0, 2):
+        sel = coords[:, 3] == b
+        mdb = O.Metadata(3)
+        cb = coords[sel].clone()
+        cb[:, 3] = 0
+        fb = O.ioLayers.InputLayerFunction.apply(3, mdb, size, cb, feats[sel], 0, 4)
+        part = conv(O.SparseConvNetTensor(fb, mdb, size)).features
+        assert torch.allclose(whole[loc[:, 3] == b], part, atol=1e-6)
+
+
+def test_strided_convolution_rejects_odd_sizes():
+    """SparseConvNet asserts (out - 1) * stride + filter == in per dimension: an odd grid must raise, not
+    silently drop a border."""
+    coords, feats, size = random_scene(2, size=(9, 8, 6), n_samples=1, density=0.2, channels=3)
+    md = O.Metadata(3)
+    f = O.ioLayers.InputLayerFunction.apply(3, md, size, coords, feats, 0, 4)
+    with pytest.raises(Exception):
+        O.Convolution(3, 3, 4, 2, 2, False)(O.SparseConvNetTensor(f, md, size))
