@@ -17,14 +17,16 @@ int scn_residual_unit_fwd(const float* x, int n, int C, const int32_t* map, int 
                           const float* w2, const float* b2, void* img1, void* img2, int repack, float* r, float* h, float* y,
                           int use_tf32, scn_stream_t stream) {
     SCN_REQUIRE(n >= 0 && C > 0 && K > 0, "residual_unit_fwd: bad shape");
+    // the caller has already recorded the images as packed for the current weight version: pack BEFORE any early return
+    // (an empty crop would otherwise leave an unpacked image marked fresh for the next, non-empty call)
+    if (use_tf32 && repack) {
+        SCN_TRY(scn_conv_pack_weights(w1, K, C, C, 0, 0, img1, stream));
+        SCN_TRY(scn_conv_pack_weights(w2, K, C, C, 0, 0, img2, stream));
+    }
     if (n == 0) return SCN_OK;
     const int64_t total = (int64_t)n * C;
     SCN_TRY(scn_relu_fwd(x, r, total, use_tf32 ? 1 : 0, stream));
     if (use_tf32) {
-        if (repack) {
-            SCN_TRY(scn_conv_pack_weights(w1, K, C, C, 0, 0, img1, stream));
-            SCN_TRY(scn_conv_pack_weights(w2, K, C, C, 0, 0, img2, stream));
-        }
         SCN_TRY(scn_conv_fwd_tf32(r, C, C, n, map, n, K, img1, b1, nullptr, 0, nullptr, 0, h, C, C, SCN_EPI_RELU | SCN_EPI_ROUND,
                                   stream));
         SCN_TRY(scn_conv_fwd_tf32(h, C, C, n, map, n, K, img2, b2, x, C, nullptr, 0, y, C, C, SCN_EPI_ADD, stream));
@@ -48,6 +50,10 @@ int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n
         if (gw1) cudaMemsetAsync(gw1, 0, wbytes, st);
         if (gw2) cudaMemsetAsync(gw2, 0, wbytes, st);
     }
+    if (use_tf32 && repack) {      // before any early return: the caller has marked the images packed
+        SCN_TRY(scn_conv_pack_weights(w1, K, C, C, 1, 1, img1t, stream));
+        SCN_TRY(scn_conv_pack_weights(w2, K, C, C, 1, 1, img2t, stream));
+    }
     if (n == 0) {
         if (!accumulate) {
             if (gb1) cudaMemsetAsync(gb1, 0, C * sizeof(float), st);
@@ -61,10 +67,6 @@ int scn_residual_unit_bwd(const float* gy, const float* r, const float* h, int n
     if (use_tf32) {
         SCN_TRY(scn_round_tf32(gy, gyr, total, stream));
         g_op = gyr;
-        if (repack) {
-            SCN_TRY(scn_conv_pack_weights(w1, K, C, C, 1, 1, img1t, stream));
-            SCN_TRY(scn_conv_pack_weights(w2, K, C, C, 1, 1, img2t, stream));
-        }
         // d/dh through conv2, masked by relu'(h), rounded so that it feeds the next MMAs directly
         SCN_TRY(scn_conv_fwd_tf32(g_op, C, C, n, map, n, K, img2t, nullptr, nullptr, 0, h, C, gh, C, C,
                                   SCN_EPI_MASK | SCN_EPI_ROUND, stream));
@@ -98,6 +100,7 @@ int scn_conv_layer_fwd(const float* x, int ld_x, int n_in, int Cin, int x_exact,
                        int K, const float* w, void* image, int repack, const float* bias, float* out, int Cout, int use_tf32,
                        scn_stream_t stream) {
     SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0 && n_in >= 0 && n_out >= 0, "conv_layer_fwd: bad shape");
+    if (use_tf32 && repack) SCN_TRY(scn_conv_pack_weights(w, K, Cin, Cout, 0, 0, image, stream));      // before any early return
     if (n_out == 0) return SCN_OK;
     if (!use_tf32)
         return scn_conv_fwd_fp32(x, ld_x, Cin, map, n_out, K, w, 0, 0, bias, nullptr, 0, nullptr, 0, out, Cout, Cout, 0, stream);
@@ -108,7 +111,6 @@ int scn_conv_layer_fwd(const float* x, int ld_x, int n_in, int Cin, int x_exact,
         SCN_TRY(scn_round_tf32(x, x_round, (int64_t)n_in * Cin, stream));
         xin = x_round, ld = Cin;
     }
-    if (repack) SCN_TRY(scn_conv_pack_weights(w, K, Cin, Cout, 0, 0, image, stream));
     return scn_conv_fwd_tf32(xin, ld, Cin, n_in, map, n_out, K, image, bias, nullptr, 0, nullptr, 0, out, Cout, Cout, 0, stream);
 }
 
@@ -116,6 +118,8 @@ int scn_conv_layer_bwd(const float* go, int n_out, int Cout, int go_exact, float
                        int Cin, const int32_t* fmap, const int32_t* bmap, int K, const float* w, void* image_t, int repack,
                        int reverse_bwd, float* gx, float* gw, float* gb, int use_tf32, scn_stream_t stream) {
     SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0 && n_in >= 0 && n_out >= 0, "conv_layer_bwd: bad shape");
+    // the caller has marked the transposed image packed: pack it before any early return (empty crops)
+    if (use_tf32 && repack && image_t && gx) SCN_TRY(scn_conv_pack_weights(w, K, Cout, Cin, 1, reverse_bwd, image_t, stream));
     if (n_out == 0) {
         if (gx && n_in > 0) cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)n_in * Cin, as_stream(stream));
         return check_launch("conv_layer_bwd(memset)");
@@ -129,7 +133,6 @@ int scn_conv_layer_bwd(const float* go, int n_out, int Cout, int go_exact, float
     if (gx && n_in > 0) {
         // d/dx: the transposed (and, for submanifold layers, offset-reversed) weights over the backward map
         if (use_tf32) {
-            if (repack) SCN_TRY(scn_conv_pack_weights(w, K, Cout, Cin, 1, reverse_bwd, image_t, stream));
             SCN_TRY(scn_conv_fwd_tf32(g, Cout, Cout, n_out, bmap, n_in, K, image_t, nullptr, nullptr, 0, nullptr, 0, gx, Cin, Cin,
                                       0, stream));
         } else {

@@ -60,8 +60,14 @@ class MaskLoss(nn.Module):
         tgts = [m for sample in mask_target for m in sample]
         if not outs:
             return self.default_loss
-        class_target_cat = torch.cat(class_target)
-        maskwise_loss = segment_bce_with_logits(torch.cat(outs), torch.cat(tgts), [len(m) for m in outs])
+        return self.forward_flat(torch.cat(outs), torch.cat(tgts), [len(m) for m in outs], torch.cat(class_target))
+
+    def forward_flat(self, logits, targets, counts, class_target_cat):
+        """Same loss from the concatenated (box, point) layout `roi.SparseMaskLossSelector.flat` holds: logits [M], targets
+        [M], per-box lengths (host ints), labels [boxes] -- no per-box Python, no list concatenation."""
+        if not len(counts):
+            return self.default_loss
+        maskwise_loss = segment_bce_with_logits(logits, targets, counts)
         valid = ~torch.isnan(maskwise_loss)
         if self.class_weights is not None:
             w = self.class_weights[class_target_cat] * valid

@@ -5,7 +5,7 @@
 (scannet_config/run.py:515-815) are restated here, parameterised by the `scn` namespace
 (the B200 backend `sparse_rcnn_b200.scn`, or any other object exposing the same names --
 tests pass the CPU oracle).  Module nesting and attribute names follow the reference tree so
-that `state_dict()` keys are identical (tests/test_reference_graph.py checks this against the
+that `state_dict()` keys are identical (tests/test_golden.py::test_graph_mirror_has_reference_state_dict checks this against the
 unmodified reference when it is available).
 
 Graph facts restated (with the reference line that produces them):

@@ -41,6 +41,7 @@ class GradientBuckets:
             self.buckets.append(cur)
         self.flats, self._pending, self._handles = [], [], []
         self._fired = set()
+        self._launched = []
         self.offsets = []
         for bi, bucket in enumerate(self.buckets):
             # every view starts on a 16-byte boundary (vector reductions / loads in the kernels); the pad elements stay 0
@@ -60,6 +61,7 @@ class GradientBuckets:
                 p._scn_grad_hook = hook
             self.flats.append(flat)
             self._pending.append(len(bucket))
+            self._launched.append(False)
         self.enabled = True
 
     def _make_hook(self, bi):
@@ -69,10 +71,22 @@ class GradientBuckets:
             self._fired.add(id(param))
             self._pending[bi] -= 1
             if self._pending[bi] == 0:
-                self._launch(bi)
+                self._launch_ready()
         return hook
 
+    def _launch_ready(self):
+        """Collectives are issued in FIXED bucket order on every rank (bucket i only after buckets 0..i-1), whatever the
+        order in which the buckets complete locally: a rank whose class / mask head saw no RoI completes its buckets in a
+        different order than its peers, and mismatched all_reduce sequences hang or corrupt (same rule as torch DDP)."""
+        for bi in range(len(self.buckets)):
+            if self._launched[bi]:
+                continue
+            if self._pending[bi] > 0:
+                break
+            self._launch(bi)
+
     def _launch(self, bi):
+        self._launched[bi] = True
         if self.world > 1:
             self._handles.append(dist.all_reduce(self.flats[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
@@ -89,6 +103,10 @@ class GradientBuckets:
                 view.copy_(p.data)
                 p.data = view
             fp = torch.nn.Parameter(data)
+            for p in bucket:
+                # the optimizer mutates `fp`, so fp's version counter is what tells a cached derivative of p (the packed
+                # tensor-core weight images, scn/functions.py:_wver) that p has changed; p._version itself never moves
+                p._scn_flat = fp
             fp.grad = gflat
             flat_params.append(fp)
         self.flat_params = flat_params
@@ -100,15 +118,16 @@ class GradientBuckets:
         for f in self.flats:
             f.zero_()
         self._pending = [len(b) for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
         self._handles = []
         self._fired = set()
 
     def finish(self):
         """Call after backward, before optimizer.step(): launches buckets whose hooks did not all
         fire (unused parameters), waits for the collectives and turns the sums into means."""
-        for bi, left in enumerate(self._pending):
-            if left > 0:
-                self._pending[bi] = 0
+        for bi in range(len(self.buckets)):      # unused parameters: whatever is left, still in bucket order
+            self._pending[bi] = 0
+            if not self._launched[bi]:
                 self._launch(bi)
         for h in self._handles:
             h.wait()

@@ -141,6 +141,8 @@ class SparseInference(nn.Module):
         if streams is None or len(streams) < workers:
             streams = self._streams = [torch.cuda.Stream(device=self.device) for _ in range(workers)]
         caller = torch.cuda.current_stream(self.device)
+        # every forward weight image exists and is packed on the caller's stream before a worker can look at it
+        scn.functions.prepack_forward(self)
         ready = torch.cuda.Event()
         ready.record(caller)
         done = [torch.cuda.Event() for _ in range(workers)]

@@ -283,3 +283,111 @@ class SparseMaskPredictor(nn.Module):
             b0 += nb
             p0 += npts
         return out
+
+
+# ------------------------------------------------------------------------------- loss-side consumers of the selection
+def split_select_nd(tensor, splits_dims, dims=None):
+    """Diagonal blocks of `tensor` cut by a table of splits (reference utils/basic_functions.py:177-216): column j of the
+    table gives, per listed dimension, the length of block j; returns [tensor[block_j along every listed dim] for j]."""
+    table = splits_dims if isinstance(splits_dims, torch.Tensor) else torch.stack(list(splits_dims))
+    if table.dim() != 2:
+        raise ValueError("splits must form a [n_dims, n_blocks] table")
+    dims = list(range(table.shape[0])) if dims is None else list(dims)
+    if len(dims) != table.shape[0]:
+        raise ValueError("one row of splits per dimension")
+    stops = table.cumsum(1)
+    for d, row in zip(dims, stops):
+        if tensor.shape[d] != (int(row[-1]) if row.numel() else 0):
+            raise ValueError("splits of dimension %d do not sum to its length" % d)
+    starts = (stops - table).tolist()
+    stops = stops.tolist()
+    out = []
+    for j in range(table.shape[1]):
+        index = [slice(None)] * tensor.dim()
+        for k, d in enumerate(dims):
+            index[d] = slice(starts[k][j], stops[k][j])
+        out.append(tensor[tuple(index)])
+    return out
+
+
+class LossFilter(nn.Module):
+    """reference LossFilter (model.py:1017-1032): keep boxes whose best overlap reaches the positive threshold (or falls
+    below the negative one: those are associated with -1)."""
+
+    def __init__(self, positive_threshold, negative_threshold=0):
+        super().__init__()
+        self.positive_threshold, self.negative_threshold = positive_threshold, negative_threshold
+
+    def forward(self, max_overlap, argmax_overlap):
+        keep = max_overlap >= self.positive_threshold
+        assoc = argmax_overlap
+        if self.negative_threshold:
+            negative = max_overlap < self.negative_threshold
+            keep = keep | negative
+            assoc = torch.where(negative, torch.full_like(assoc, -1), assoc)
+        return keep, assoc[keep]
+
+
+def _nest(flat_list, counts):
+    out, i = [], 0
+    for c in counts:
+        out.append(list(flat_list[i:i + c]))
+        i += c
+    return out
+
+
+class SparseMaskLossSelector(nn.Module):
+    """reference SparseMaskLossSelector (model.py:1152-1227): for every kept box the logit column of its ground-truth label
+    at the box's points, and the ground-truth mask of its associated instance at the same points.  The reference splits the
+    dense [BB, P] `is_inside` block-diagonally on the CPU and indexes per box in Python; here the (box, point) CSR of the
+    crop (`CropSelection.box_ptr / sel_pt`) yields both as ONE gather each on the device.  Returns the reference's nested
+    lists (views of the flat tensors); the flat form is kept in `.flat` = (logits [M], targets [M], per-box lengths,
+    labels [boxes]) for `losses.MaskLoss.forward_flat`."""
+
+    def __init__(self, positive_threshold):
+        super().__init__()
+        self.loss_filter = LossFilter(positive_threshold, 0)
+        self.flat = None
+
+    def forward(self, mask_scores, selection, class_selector_description_list, pred_gt_max_argmax_tuple_list,
+                gt_labels_list, gt_masks_list):
+        dev = mask_scores.device
+        counts = [int(c) for c in selection.bbox_sample_count]
+        splits = [int(v) for v in selection.batch_splits]
+        if class_selector_description_list is None:
+            kept = [self.loss_filter(mx, am) for _, _, mx, am in pred_gt_max_argmax_tuple_list]
+            keep_list, assoc_list = [k for k, _ in kept], [a for _, a in kept]
+        else:
+            keep_list = [torch.ones(c, dtype=torch.bool) for c in counts]
+            assoc_list = [d.gt_association for d in class_selector_description_list]
+        selected_labels = [gl[a.to(gl.device)] for gl, a in zip(gt_labels_list, assoc_list)]
+        kept_per_sample = [int(k.sum()) for k in keep_list]
+        keep = torch.cat([k.to(dev) for k in keep_list]) if keep_list else torch.zeros(0, dtype=torch.bool, device=dev)
+        if keep.numel() != sum(counts):
+            raise RuntimeError("one overlap entry per box expected")
+        box_ptr = selection.box_ptr.to(dev).long()
+        boxes = keep.nonzero().squeeze(1)
+        lens = (box_ptr[1:] - box_ptr[:-1])[boxes]
+        lens_host = lens.tolist()
+        nk, M = len(lens_host), sum(lens_host)
+        seg = torch.repeat_interleave(torch.arange(nk, device=dev), lens, output_size=M)
+        first = torch.cumsum(lens, 0) - lens
+        rows = box_ptr[:-1][boxes][seg] + (torch.arange(M, device=dev) - first[seg])
+        labels = torch.cat([l.to(dev) for l in selected_labels]).long() if selected_labels else boxes
+        logits = mask_scores[rows, labels[seg]]
+        # ground truth: sample of every kept box, its instance, the point's index inside the sample
+        n_s = len(counts)
+        sample_of_box = torch.repeat_interleave(torch.arange(n_s), torch.tensor(counts, dtype=torch.long)).to(dev)[boxes]
+        p0 = torch.tensor([0] + splits[:-1], dtype=torch.long).cumsum(0).to(dev)
+        psize = torch.tensor(splits, dtype=torch.long, device=dev)
+        gsz = [int(m.shape[0]) * int(m.shape[1]) for m in gt_masks_list]
+        gbase = torch.tensor([0] + gsz[:-1], dtype=torch.long).cumsum(0).to(dev)
+        gflat = torch.cat([m.to(dev).reshape(-1) for m in gt_masks_list]) if gt_masks_list else keep[:0]
+        assoc = torch.cat([a.to(dev) for a in assoc_list]).long() if assoc_list else boxes
+        sb = sample_of_box[seg]
+        local_pt = selection.sel_pt.to(dev).long()[rows] - p0[sb]
+        targets = gflat[gbase[sb] + assoc[seg] * psize[sb] + local_pt]
+        self.flat = (logits, targets, lens_host, labels)
+        pred = _nest(torch.split(logits, lens_host), kept_per_sample)
+        gt = _nest(torch.split(targets, lens_host), kept_per_sample)
+        return pred, gt, selected_labels

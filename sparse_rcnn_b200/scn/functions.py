@@ -53,6 +53,14 @@ def _check(x):
     return x.contiguous()
 
 
+def _wver(weight):
+    """Staleness key of a weight tensor.  `parallel.GradientBuckets.flatten_parameters` makes every Parameter a view of a
+    flat buffer (`p._scn_flat`) and the optimizer updates THAT tensor: the module Parameter's own version counter never
+    moves, so the flat buffer's version is part of the key."""
+    flat = getattr(weight, "_scn_flat", None)
+    return (weight._version, weight.data_ptr(), -1 if flat is None else flat._version)
+
+
 def _image_entry(weight, K, cin, cout, transpose, reverse):
     """Persistent packed-image buffer of a weight tensor (one per orientation): [image, packed version, meta]."""
     cache = getattr(weight, "_scn_img", None)
@@ -74,7 +82,7 @@ def _image_entry(weight, K, cin, cout, transpose, reverse):
 def _image(weight, K, cin, cout, transpose, reverse):
     """Packed (TF32-rounded, swizzled) weight image; re-packed when the tensor was modified since."""
     hit = _image_entry(weight, K, cin, cout, transpose, reverse)
-    ver = (weight._version, weight.data_ptr())
+    ver = _wver(weight)
     if hit[1] != ver:
         _lib.call("scn_conv_pack_weights", _ptr(weight), K, cin, cout, transpose, reverse, _ptr(hit[0]), _stream())
         hit[1] = ver
@@ -93,7 +101,7 @@ def pack_all(weights):
         cache = getattr(w, "_scn_img", None)
         if not cache:
             continue
-        ver = (w._version, w.data_ptr())
+        ver = _wver(w)
         for (transpose, reverse), hit in cache.items():
             if hit[1] != ver:
                 entries.append((hit, ver))
@@ -111,6 +119,26 @@ def pack_all(weights):
     for hit, ver in entries:
         hit[1] = ver
     return len(rows)
+
+
+def prepack_forward(module):
+    """Create and pack the FORWARD weight image of every convolution parameter under `module` on the current stream
+    (one launch).  Inference from several host threads / streams (pipeline.SparseInference.run_many) calls this on the
+    caller's stream first and makes the workers wait for it: a lazily created image is marked packed by the first thread
+    that touches it BEFORE its pack kernel has run on that thread's stream, so a second stream could read it unpacked."""
+    if _state["precision"] != "tf32":
+        return 0
+    weights = []
+    for m in module.modules():
+        w = getattr(m, "weight", None)
+        if w is None or not w.is_cuda or not hasattr(m, "nOut") or not hasattr(m, "nIn"):
+            continue
+        K = w.shape[0] if w.dim() > 2 else 1
+        cin, cout = w.shape[-2], w.shape[-1]
+        if cout <= 256:
+            _image_entry(w, K, cin, cout, 0, 0)
+            weights.append(w)
+    return pack_all(weights)
 
 
 def _direct_grad(param):
@@ -170,9 +198,10 @@ def _mark(t):
 
 
 def _image_state(weight, K, cin, cout, transpose, reverse):
-    """(packed-image buffer, must it be re-packed); marks it packed (the C call that follows does the packing)."""
+    """(packed-image buffer, must it be re-packed); marks it packed (the C call that follows does the packing --
+    callers only ask when that call really runs its kernels, i.e. not for empty inputs)."""
     hit = _image_entry(weight, K, cin, cout, transpose, reverse)
-    ver = (weight._version, weight.data_ptr())
+    ver = _wver(weight)
     stale = hit[1] != ver
     hit[1] = ver
     return hit[0], stale
@@ -285,11 +314,7 @@ def relu_round(x):
 def _image_buf(weight, K, cin, cout, key):
     """(packed-image buffer, must it be re-packed) for the fused unit: key 'f' = forward, 'b' = transposed + reversed."""
     tr = 0 if key == "f" else 1
-    hit = _image_entry(weight, K, cin, cout, tr, tr)
-    ver = (weight._version, weight.data_ptr())
-    stale = hit[1] != ver
-    hit[1] = ver
-    return hit[0], stale
+    return _image_state(weight, K, cin, cout, tr, tr)
 
 
 def _unit_forward(x, w1, b1, w2, b2, fmap, n, tf32):
@@ -366,9 +391,12 @@ class ResidualUnitFunction(Function):
 
     @staticmethod
     def backward(ctx, gy):
-        fmap, n, tf32, U = ctx.cfg
+        fmap, n, _, U = ctx.cfg
         t = ctx.saved_tensors
         rh, w1s, w2s = t[:2 * U], t[2 * U:3 * U], t[3 * U:]
+        # precision is read when the backward runs (like ConvFunction.backward): tests isolate the backward kernels'
+        # arithmetic from ReLU-mask flips by running an fp32 forward and a tf32 backward over the same saved activations
+        tf32 = _state["precision"] == "tf32" and w1s[0].shape[-1] <= 256
         need = ctx.needs_input_grad
         g = _check(gy)
         grads = [None] * (4 * U)

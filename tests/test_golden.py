@@ -138,3 +138,65 @@ def test_maskloss_oracle_matches_reference():
         w = (torch.arange(18, dtype=torch.float32) % 5 + 0.5) if c["weighted"] else None
         got = maskloss_ref.mask_loss(outs, tgts, cls, w)
         assert abs(got - c["loss"]) <= 1e-6 * max(abs(c["loss"]), 1.0), (got, c["loss"])
+
+
+# ------------------------------------------------------------------ consumers of the crop selection
+def _consumer_case():
+    import types
+    from sparse_rcnn_b200 import roi
+    g = torch.load(os.path.join(G, "consumers.pt"), weights_only=False)
+    inside = torch.from_numpy(np.unpackbits(g["inside_packed"], axis=1)[:, :g["inside_shape"][1]].astype(bool))
+    box, pt = inside.nonzero(as_tuple=True)                       # row-major = (box, point) order of the crop
+    box_ptr = torch.zeros(inside.shape[0] + 1, dtype=torch.int32)
+    box_ptr[1:] = inside.sum(1).cumsum(0).to(torch.int32)
+    sel = roi.CropSelection(pt.to(torch.int32), None, box_ptr, inside.shape[0], inside.shape[1],
+                            inside.to(torch.uint8).reshape(-1), g["counts"], g["splits"])
+    return g, inside, sel, types
+
+
+def test_split_select_nd_matches_reference():
+    from sparse_rcnn_b200 import roi
+    g, inside, sel, _ = _consumer_case()
+    blocks = roi.split_select_nd(inside, torch.tensor([g["counts"], g["splits"]]))
+    assert [tuple(b.shape) for b in blocks] == g["blocks_shape"]
+    assert [int(b.sum()) for b in blocks] == g["blocks_sum"]
+    with pytest.raises(ValueError):
+        roi.split_select_nd(inside, torch.tensor([g["counts"], [1, 2, 3]]))
+
+
+@pytest.mark.parametrize("num_valid,cls_key", [(0, "cls"), (18, "cls_hi")])
+def test_mask_predictor_matches_reference_golden(num_valid, cls_key):
+    """Golden from the UNMODIFIED reference SparseMaskPredictor (model.py:826-882, oracle/make_golden_consumers.py)."""
+    from sparse_rcnn_b200 import roi
+    g, inside, sel, _ = _consumer_case()
+    got = roi.SparseMaskPredictor(num_valid)(g["scores"], sel, g[cls_key])
+    ref = g["predictor_%d" % num_valid]
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape and torch.allclose(a, b, atol=1e-7)
+
+
+@pytest.mark.parametrize("branch", ["loss_by_overlap", "loss_by_description"])
+def test_mask_loss_selector_matches_reference_golden(branch):
+    """Golden from the UNMODIFIED reference SparseMaskLossSelector (model.py:1152-1227), both branches; the flat form feeds
+    losses.MaskLoss.forward_flat."""
+    from sparse_rcnn_b200 import roi
+    g, inside, sel, types = _consumer_case()
+    selector = roi.SparseMaskLossSelector(0.5)
+    if branch == "loss_by_overlap":
+        descr, tuples = None, [(None, None, m, a) for m, a in zip(g["max_ov"], g["arg_ov"])]
+    else:
+        descr, tuples = [types.SimpleNamespace(gt_association=a) for a in g["assoc_given"]], None
+    pred, gt, labels = selector(g["scores"], sel, descr, tuples, g["gt_labels"], g["gt_masks"])
+    ref = g[branch]
+    assert [len(s) for s in pred] == [len(s) for s in ref["pred"]]
+    for sa, sb in zip(pred, ref["pred"]):
+        for a, b in zip(sa, sb):
+            assert torch.equal(a, b)
+    for sa, sb in zip(gt, ref["gt"]):
+        for a, b in zip(sa, sb):
+            assert torch.equal(a.bool(), b.bool())
+    for a, b in zip(labels, ref["labels"]):
+        assert torch.equal(a, b)
+    logits, targets, lens, lab = selector.flat
+    assert logits.numel() == sum(lens) == targets.numel() and lab.numel() == len(lens)

@@ -170,3 +170,78 @@ def test_geometry_built_ahead_equals_inline(cuda):
         assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-5, losses      # sums contain fp32 atomics
     finally:
         scn.set_precision("tf32")
+
+
+def test_tf32_weight_images_follow_the_optimizer(cuda):
+    """the optimizer updates the FLAT parameter buffers, so the packed TF32 weight images must be keyed on
+    the flat buffers' version.  After two Adam steps with lr > 0 every cached image must equal a fresh pack of the current
+    weights, and the TF32 losses must track the fp32 ones (they did not move off the initial weights before the fix)."""
+    from sparse_rcnn_b200 import _lib, pipeline, scn
+    from sparse_rcnn_b200.scn import functions as Fn
+    from sparse_rcnn_b200.scn.metadata import _stream
+    import bench
+    data, labels = bench.make_inputs(0, scene_kw=bench.CPU_SAMPLE)
+    losses = {}
+    try:
+        for precision in ("fp32", "tf32"):
+            scn.set_precision(precision)
+            tr = pipeline.BackboneTrainer(cuda, seed=3, lr=3e-3)
+            losses[precision] = [float(tr.step(data, labels)) for _ in range(4)]
+        Fn.pack_all(tr._weights)                                       # what the next step starts with
+        checked = 0
+        for w in tr._weights:
+            for (transpose, reverse), hit in getattr(w, "_scn_img", {}).items():
+                K, cin, cout = hit[2]
+                fresh = torch.zeros_like(hit[0])
+                _lib.call("scn_conv_pack_weights", w.data_ptr(), K, cin, cout, transpose, reverse, fresh.data_ptr(), _stream())
+                assert torch.equal(fresh, hit[0]), (tuple(w.shape), transpose, reverse)
+                checked += 1
+        assert checked > 100
+        a, b = losses["fp32"], losses["tf32"]
+        assert a[-1] < 0.9 * a[0]                                      # the scene is being fitted
+        assert max(abs(x - y) / abs(x) for x, y in zip(a, b)) < 2e-2, (a, b)
+    finally:
+        scn.set_precision("tf32")
+
+
+def test_empty_input_does_not_leave_an_unpacked_image_marked_fresh(cuda):
+    """an empty crop / batch runs no kernel; the packed image it would have used must not stay marked as
+    packed for the current weight version.  Empty call first, then a real one, against untouched copies of the weights."""
+    from sparse_rcnn_b200 import scn
+    from sparse_rcnn_b200.scn.functions import ConvFunction, ResidualUnitFunction
+    from tests.util import make_pair, random_scene
+    scn.set_precision("tf32")
+    torch.manual_seed(0)
+    coords, feats, size = random_scene(3, channels=32, size=(28, 24, 16))
+    _, tg = make_pair(scn, coords, feats, size, cuda)
+    lvl = tg.metadata.level(size)
+    m, n = lvl.subm_map(3), lvl.n
+    ps = [torch.randn(27, 1, 32, 32, device=cuda) * 0.05, torch.randn(32, device=cuda),
+          torch.randn(27, 1, 32, 32, device=cuda) * 0.05, torch.randn(32, device=cuda)]
+    ps = [p.requires_grad_(True) for p in ps]
+    x = tg.features.detach()
+    go = torch.randn(n, 32, device=cuda)
+
+    def run(params, xin):
+        xin = xin.clone().requires_grad_(True)
+        y = ResidualUnitFunction.apply(xin, m, xin.shape[0], *params)
+        y.backward(go[: xin.shape[0]])
+        return y.detach(), xin.grad
+
+    run(ps, x[:0])                                                     # empty first: forward and backward
+    y, gx = run(ps, x)
+    y_ref, gx_ref = run([p.detach().clone().requires_grad_(True) for p in ps], x)
+    assert torch.equal(y, y_ref) and torch.equal(gx, gx_ref)
+    # plain convolution layer: an empty backward first (forward returns before touching the image)
+    w, b = ps[0], ps[1]
+
+    def conv(wt, bt, xin, n_out):
+        xin = xin.clone().requires_grad_(True)
+        y = ConvFunction.apply(xin, wt, bt, m, m, n_out, 1)
+        y.backward(go[:n_out])
+        return xin.grad
+    w2, b2 = (torch.randn_like(w) * 0.05).requires_grad_(True), b.detach().clone().requires_grad_(True)
+    conv(w2, b2, x[:0], 0)
+    g1 = conv(w2, b2, x, n)
+    g2 = conv(w2.detach().clone().requires_grad_(True), b2.detach().clone().requires_grad_(True), x, n)
+    assert torch.equal(g1, g2)

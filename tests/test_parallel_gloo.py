@@ -114,3 +114,65 @@ def test_flat_parameter_adam_equals_per_parameter_adam():
     for p, o in zip(buckets.buckets[0], buckets.offsets[0]):
         used[o:o + p.numel()] = True
     assert (flat[0].detach()[~used] == 0).all()
+
+
+def _worker_unused(rank, world, port, q):
+    """Rank 1 never touches the parameters of the first-registered head, so its buckets COMPLETE in a different order than
+    rank 0's; collectives must still be issued in the same (bucket) order on both ranks."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    trunk, head_a, head_b = nn.Linear(4, 8), nn.Linear(8, 8), nn.Linear(8, 2)
+    params = list(trunk.parameters()) + list(head_a.parameters()) + list(head_b.parameters())
+    buckets = GradientBuckets(params, n_buckets=3)
+    order = []
+    orig = buckets._launch
+    buckets._launch = lambda bi: (order.append(bi), orig(bi))[1]
+    g = torch.Generator().manual_seed(7 + rank)
+    x = torch.randn(5, 4, generator=g)
+    buckets.zero()
+    h = trunk(x)
+    if rank == 0:
+        loss = head_b(head_a(h)).sum()
+    else:
+        loss = head_a(h).sum()                      # head_b (the bucket that finishes first on rank 0) gets no gradient here
+    loss.backward()
+    buckets.finish()
+    flat = torch.cat([f.reshape(-1) for f in buckets.flats])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    q.put((rank, order, float((gathered[0] - gathered[1]).abs().max()), len(buckets.buckets)))
+    dist.destroy_process_group()
+
+
+def test_bucket_collectives_keep_a_fixed_order_with_unused_parameters():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_unused, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, order, diff, nb in res:
+        assert nb >= 2 and order == list(range(nb)), (rank, order)
+        assert diff == 0.0
+
+
+def test_flat_parameters_expose_the_optimizers_version_counter():
+    """Adam over the flat buffers never bumps the module Parameters' version counters; the packed
+    tensor-core weight images key their staleness on `_wver`, which must change with every optimizer step."""
+    from sparse_rcnn_b200.scn.functions import _wver
+    net = nn.Sequential(nn.Linear(4, 4), nn.Linear(4, 2))
+    buckets = GradientBuckets(list(net.parameters()), n_buckets=2)
+    opt = torch.optim.Adam(buckets.flatten_parameters(), lr=1e-2)
+    w = net[0].weight
+    before = _wver(w)
+    buckets.zero()
+    net(torch.randn(3, 4)).sum().backward()
+    buckets.finish()
+    opt.step()
+    assert _wver(w) != before
+    assert w._version == before[0]                  # the very reason the flat version is part of the key
