@@ -88,6 +88,17 @@ int scn_hash_assign_rows(const uint64_t* keys, int P, const uint64_t* tab_keys,
 /* tab_vals[s] = rank[tab_vals[s]] for occupied slots: the table now maps key -> row */
 int scn_hash_finalize(const uint64_t* tab_keys, int32_t* tab_vals, uint32_t cap,
                       const int32_t* rank, scn_stream_t stream);
+/* Spatially coherent row order (round 2, csrc/sort.cu; no reference counterpart: SparseConvNet numbers level-0 rows by first
+ * appearance, Metadata/InputLayer.h, and SURVEY 8c admits any batch-sorted order).  Stable radix sort of the points by
+ * (b, Morton(x, y, z)): perm[i] = index of the i-th point in sorted order, sorted_keys[i] = keys[perm[i]].  Only digits
+ * that can be non-zero are sorted: coord_bits = bits of the largest coordinate (from the spatial size), batch_bits likewise
+ * for the sample index.  ws: scn_morton_order_ws_bytes(P) bytes of scratch.  The level builder then runs over
+ * sorted_keys (first appearance over the sorted list = Morton order of the voxels) and scn_scatter_i32 returns its
+ * point_row to the original point order: dst[perm[i]] = src[i]. */
+int64_t scn_morton_order_ws_bytes(int P);
+int scn_morton_order(const uint64_t* keys, int P, int coord_bits, int batch_bits, int32_t* perm,
+                     uint64_t* sorted_keys, void* ws, scn_stream_t stream);
+int scn_scatter_i32(const int32_t* src, const int32_t* perm, int n, int32_t* dst, scn_stream_t stream);
 /* One level around its single host round trip, as two calls: scn_level_count = clear + insert_first + first_flags +
  * exclusive scan (rank [P + 1]; rank[P] is the number of active rows the host reads back), scn_level_finish =
  * assign_rows + finalize.  Same kernels as the separate entry points above. */

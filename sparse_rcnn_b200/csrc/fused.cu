@@ -119,7 +119,7 @@ int scn_conv_layer_bwd(const float* go, int n_out, int Cout, int go_exact, float
                        int reverse_bwd, float* gx, float* gw, float* gb, int use_tf32, scn_stream_t stream) {
     SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0 && n_in >= 0 && n_out >= 0, "conv_layer_bwd: bad shape");
     // the caller has marked the transposed image packed: pack it before any early return (empty crops)
-    if (use_tf32 && repack && image_t && gx) SCN_TRY(scn_conv_pack_weights(w, K, Cout, Cin, 1, reverse_bwd, image_t, stream));
+    if (use_tf32 && repack && image_t) SCN_TRY(scn_conv_pack_weights(w, K, Cout, Cin, 1, reverse_bwd, image_t, stream));
     if (n_out == 0) {
         if (gx && n_in > 0) cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)n_in * Cin, as_stream(stream));
         return check_launch("conv_layer_bwd(memset)");

@@ -84,6 +84,7 @@ class BackboneTrainer(nn.Module):
         loss.backward()
         self.buckets.finish()
         self.optimizer.step()
+        scn.functions.weights_changed()            # packed TF32 weight images are stale now (re-packed by the next pack_all)
         self.last_active = out[4][0].features.shape[0]
         return loss.detach()
 

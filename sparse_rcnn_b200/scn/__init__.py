@@ -10,7 +10,7 @@ from .layers import (AddTable, AveragePooling, BatchNormalization, BatchNormLeak
                      Convolution, Deconvolution, Identity, InputLayer, JoinTable, MaxPooling, NetworkInNetwork,
                      OutputLayer, ReLU, Sequential, SparseConvNetTensor, SparseToDense, SubmanifoldConvolution,
                      UnPooling, ValidConvolution)
-from .metadata import GeometryPrefetcher, Metadata
+from .metadata import GeometryPrefetcher, Metadata, get_row_order, set_row_order
 
 ioLayers = types.SimpleNamespace(
     InputLayerFunction=InputLayerFunction, OutputLayerFunction=OutputLayerFunction,

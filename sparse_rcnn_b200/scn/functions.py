@@ -53,12 +53,27 @@ def _check(x):
     return x.contiguous()
 
 
+def weights_changed():
+    """Mark every cached packed weight image stale.  Called from a global optimizer step post-hook (below), so any
+    `optimizer.step()` in the process is followed by a re-pack: version counters alone are not enough -- measured on
+    torch 2.11, `Adam(fused=True)` updates parameters without touching `_version`, and an optimizer over the flat buffers of
+    `parallel.GradientBuckets.flatten_parameters` never touches the module Parameters at all."""
+    _state["generation"] += 1
+
+
+_state["generation"] = 0
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook
+    _register_step_hook(lambda optimizer, args, kwargs: weights_changed())
+except ImportError:      # older torch: trainers call weights_changed() themselves (pipeline.BackboneTrainer does anyway)
+    pass
+
+
 def _wver(weight):
-    """Staleness key of a weight tensor.  `parallel.GradientBuckets.flatten_parameters` makes every Parameter a view of a
-    flat buffer (`p._scn_flat`) and the optimizer updates THAT tensor: the module Parameter's own version counter never
-    moves, so the flat buffer's version is part of the key."""
+    """Staleness key of a weight tensor: its own version counter and storage (load_state_dict, `.data =`), the version of
+    the flat buffer it is a view of, and the global optimizer-step generation."""
     flat = getattr(weight, "_scn_flat", None)
-    return (weight._version, weight.data_ptr(), -1 if flat is None else flat._version)
+    return (weight._version, weight.data_ptr(), -1 if flat is None else flat._version, _state["generation"])
 
 
 def _image_entry(weight, K, cin, cout, transpose, reverse):

@@ -31,6 +31,23 @@ def _ptr(t):
 
 _KEY_ATTR = "_scn_size_key"
 
+_order = {"rows": "morton"}
+
+
+def set_row_order(order):
+    """'morton' (default): rows of every level follow the Morton curve of (b, x, y, z) -- spatially coherent tiles, the
+    layout the tile-local convolution kernel needs (csrc/sort.cu, conv_ts.cu).  'first': SparseConvNet's numbering, level-0
+    rows in order of first appearance in the point list (Metadata/InputLayer.h).  Either way rows are grouped by ascending
+    sample index (roi_select_sparse.py:106-107) and every result is identical after the canonical (b, x, y, z) sort
+    (SURVEY 8c).  Mode-0 input layers (rows = input order by contract) are never reordered."""
+    if order not in ("morton", "first"):
+        raise ValueError("row order must be 'morton' or 'first'")
+    _order["rows"] = order
+
+
+def get_row_order():
+    return _order["rows"]
+
 
 def size_key(size):
     """Hashable key of a spatial size; cached on the tensor object (the same size tensor travels through a level)."""
@@ -108,11 +125,20 @@ class Level:
         return self.subm[f]
 
 
-def build_level(keys):
-    """keys int64[P] (packed) -> (Level, point_row int32 [P]).  Rows are numbered by first
-    appearance (SparseConvNet InputLayer.h).  One host sync (the active count)."""
+def build_level(keys, morton_bits=None):
+    """keys int64[P] (packed) -> (Level, point_row int32 [P]).  Rows are numbered by first appearance (SparseConvNet
+    InputLayer.h) over the point list -- or, with morton_bits = (coordinate bits, batch bits), over the point list
+    sorted by (b, Morton(x, y, z)), i.e. in Morton order of the voxels.  One host sync (the active count)."""
     dev = keys.device
     P = keys.numel()
+    perm = None
+    if morton_bits is not None and P > 1:
+        ws = torch.empty(int(_lib.raw("scn_morton_order_ws_bytes")(P)), dtype=torch.uint8, device=dev)
+        perm = torch.empty(P, dtype=torch.int32, device=dev)
+        skeys = torch.empty(P, dtype=torch.int64, device=dev)
+        _lib.call("scn_morton_order", _ptr(keys), P, int(morton_bits[0]), int(morton_bits[1]), _ptr(perm), _ptr(skeys),
+                  _ptr(ws), _stream())
+        keys = skeys
     cap = 64
     while cap < 2 * P:
         cap <<= 1
@@ -128,6 +154,9 @@ def build_level(keys):
     row_keys = torch.empty(n, dtype=torch.int64, device=dev)
     _lib.call("scn_level_finish", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(rank), _ptr(point_row),
               _ptr(row_keys), s)
+    if perm is not None:      # back to the caller's point order
+        sorted_rows, point_row = point_row, torch.empty(P, dtype=torch.int32, device=dev)
+        _lib.call("scn_scatter_i32", _ptr(sorted_rows), _ptr(perm), P, _ptr(point_row), s)
     return Level(row_keys, tab_keys, tab_vals, cap, n), point_row
 
 
@@ -187,7 +216,13 @@ class Metadata:
             err = torch.zeros(1, dtype=torch.int32, device=device)
             _lib.call("scn_pack_coords", _ptr(cdev), P, ncol, _ptr(keys), _ptr(err), s)
             self._err = err
-        level, point_row = build_level(keys)
+        morton_bits = None
+        if mode != 0 and _order["rows"] == "morton":
+            smax = max(size_key(spatial_size))
+            nb = max(int(batch_size) - 1, max_b if max_b is not None else 65535, 0)      # unknown sample count: all 16 bits
+            morton_bits = (min(max(int(smax) - 1, 1).bit_length(), 16), nb.bit_length())
+        level, point_row = build_level(keys, morton_bits)
+        self.row_order = "morton" if morton_bits is not None else "first"
         if coords.dim() != 1 and int(self._err.item()):
             raise RuntimeError("InputLayer: coordinate outside [0, 65534]")
         if max_b is None:

@@ -19,3 +19,15 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture
+def first_rows():
+    """Row numbering of SparseConvNet (first appearance in the point list) for tests that compare rows with the oracle
+    one to one; the product default is Morton order, compared through the canonical sort (test_gpu_baseline_size.py,
+    test_gpu_morton.py)."""
+    from sparse_rcnn_b200 import scn
+    prev = scn.get_row_order()
+    scn.set_row_order("first")
+    yield
+    scn.set_row_order(prev)

@@ -18,7 +18,7 @@ def frac_above(a, b, tol):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float(((a - b).abs() > tol * b.abs().max()).double().mean())
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("first_rows")]
 
 
 def _small_batch(n_scenes=2):

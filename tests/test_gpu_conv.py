@@ -6,7 +6,7 @@ import torch
 import scn_oracle as O
 from tests.util import copy_params, make_pair, random_scene, rel_err
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("first_rows")]
 TOL = {"fp32": 1e-5, "tf32": 2e-3}
 
 

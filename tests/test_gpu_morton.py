@@ -1,0 +1,128 @@
+"""GPU parity of the DEFAULT row order (Morton, csrc/sort.cu) against the oracle through the canonical sort: the sort itself
+(bit-exact against numpy), the input rule, the rulebooks of ragged multi-sample batches incl. empty samples, and one
+convolution layer forward + backward."""
+import numpy as np
+import pytest
+import torch
+
+import scn_oracle as O
+from scn_oracle import rules as R
+from tests.util import make_pair, random_scene, rel_err
+from tests.test_gpu_baseline_size import batch_sorted, canon, canon_map
+
+pytestmark = pytest.mark.gpu
+
+
+def _morton_np(c):
+    def spread(v):
+        v = v.astype(np.uint64) & np.uint64(0xFFFF)
+        for sh, m in ((32, 0x1f00000000ffff), (16, 0x1f0000ff0000ff), (8, 0x100f00f00f00f00f), (4, 0x10c30c30c30c30c3),
+                      (2, 0x1249249249249249)):
+            v = (v | (v << np.uint64(sh))) & np.uint64(m)
+        return v
+    return (c[:, 3].astype(np.uint64) << np.uint64(48)) | (spread(c[:, 0]) << np.uint64(2)) | \
+           (spread(c[:, 1]) << np.uint64(1)) | spread(c[:, 2])
+
+
+@pytest.mark.parametrize("P,size,B", [(1, 8, 1), (2049, 64, 1), (70001, 256, 3), (300000, 300, 255), (50000, 65535, 40000)])
+def test_morton_order_is_the_stable_sort(cuda, P, size, B):
+    from sparse_rcnn_b200 import _lib
+    from sparse_rcnn_b200.scn.metadata import _stream
+    rng = np.random.default_rng(P)
+    c = np.stack([rng.integers(0, size, P), rng.integers(0, size, P), rng.integers(0, max(size // 2, 1), P),
+                  np.sort(rng.integers(0, B, P))], 1).astype(np.int64)
+    c[P // 3:P // 3 + 50] = c[P // 3]                                 # duplicates: stability matters
+    keys = torch.from_numpy(R.pack_keys(c).view(np.int64)).to(cuda)
+    ws = torch.empty(int(_lib.raw("scn_morton_order_ws_bytes")(P)), dtype=torch.uint8, device=cuda)
+    perm = torch.empty(P, dtype=torch.int32, device=cuda)
+    skeys = torch.empty(P, dtype=torch.int64, device=cuda)
+    cb, bb = max(size - 1, 1).bit_length(), (B - 1).bit_length()
+    _lib.call("scn_morton_order", keys.data_ptr(), P, cb, bb, perm.data_ptr(), skeys.data_ptr(), ws.data_ptr(), _stream())
+    ref = np.argsort(_morton_np(c), kind="stable")
+    assert np.array_equal(perm.cpu().numpy(), ref)
+    assert np.array_equal(skeys.cpu().numpy(), R.pack_keys(c).view(np.int64)[ref])
+
+
+@pytest.mark.parametrize("seed,mode", [(0, 4), (1, 3), (2, 1), (3, 2)])
+def test_rulebooks_in_morton_order(cuda, seed, mode):
+    from sparse_rcnn_b200 import scn
+    assert scn.get_row_order() == "morton"
+    coords, feats, size = random_scene(seed, size=(32, 32, 16), n_samples=4, density=0.05, dup=1.7)
+    coords = coords[coords[:, 3] != 1]                                # an empty sample in the middle
+    feats = feats[: len(coords)]
+    to, tg = make_pair(scn, coords, feats, size, cuda, mode=mode, batch_size=6)
+    assert tg.metadata.row_order == "morton" and tg.batch_size() == to.batch_size() == 6
+    loc = tg.get_spatial_locations()
+    assert batch_sorted(loc)
+    mk = _morton_np(loc.numpy())
+    assert (mk[:-1] < mk[1:]).all()                                   # strictly increasing Morton keys
+    kg, og, ig = canon(loc)
+    ko, oo, io = canon(to.get_spatial_locations())
+    assert np.array_equal(kg, ko)
+    assert np.array_equal(ig[tg.metadata.point_row.cpu().numpy()], io[to.metadata.point_row])
+    assert rel_err(tg.features.cpu()[torch.from_numpy(og)], to.features[torch.from_numpy(oo)]) <= 1e-6
+    # input-rule CSR: ascending point indices per row
+    md = tg.metadata
+    ptr, pts, pr = md.row_ptr.cpu().numpy(), md.row_pts.cpu().numpy(), md.point_row.cpu().numpy()
+    for r in range(0, len(ptr) - 1, 5):
+        seg = pts[ptr[r]:ptr[r + 1]]
+        assert len(seg) and (np.diff(seg) > 0).all() and (pr[seg] == r).all()
+    # pyramid: every level stays Morton / batch sorted and the maps agree canonically
+    cur, prev = tuple(size.tolist()), None
+    for lvl in range(3):
+        go, gg = to.metadata.grids[cur], tg.metadata.levels[cur]
+        kg, og, ig = canon(gg.locations())
+        ko, oo, io = canon(go.coords)
+        assert np.array_equal(kg, ko)
+        mk = _morton_np(gg.locations().numpy())
+        assert (mk[:-1] < mk[1:]).all()
+        assert np.array_equal(canon_map(gg.subm_map(3).cpu().numpy(), og, ig),
+                              canon_map(R.rules_to_map(to.metadata.subm_rules(cur, 3), go.n), oo, io))
+        if prev is not None:
+            ps, pog, pig, poo, pio = prev
+            _, rules, parent, _ = to.metadata.conv_rules(ps, 2, 2)
+            r = tg.metadata.strided_rules(ps, 2, 2)
+            assert np.array_equal(canon_map(r.cmap.cpu().numpy(), og, pig), canon_map(R.rules_to_map(rules, go.n), oo, pio))
+        ok, _, _, _ = to.metadata.conv_rules(cur, 2, 2)
+        tg.metadata.strided_rules(cur, 2, 2)
+        prev, cur = (cur, og, ig, oo, io), ok
+
+
+def test_mode0_keeps_input_order(cuda):
+    from sparse_rcnn_b200 import scn
+    coords, feats, size = random_scene(3, dup=1.0)
+    _, idx = np.unique(R.pack_keys(coords.numpy()), return_index=True)
+    idx = np.sort(idx)
+    coords, feats = coords[idx], feats[idx]
+    to, tg = make_pair(scn, coords, feats, size, cuda, mode=0)
+    assert tg.metadata.row_order == "first"
+    assert torch.equal(tg.get_spatial_locations(), coords) and torch.equal(tg.features.cpu(), feats)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 2e-3)])
+def test_conv_layer_in_morton_order(cuda, precision, tol):
+    from sparse_rcnn_b200 import scn
+    scn.set_precision(precision)
+    try:
+        coords, feats, size = random_scene(5, size=(40, 40, 16), n_samples=2, density=0.06, channels=32)
+        to, tg = make_pair(scn, coords, feats, size, cuda)
+        _, og, ig = canon(tg.get_spatial_locations())
+        _, oo, io = canon(to.get_spatial_locations())
+        lo = O.SubmanifoldConvolution(3, 32, 48, 3, True)
+        lo.bias.data.normal_()
+        lg = scn.SubmanifoldConvolution(3, 32, 48, 3, True)
+        lg.load_state_dict(lo.state_dict())
+        lg.to(cuda)
+        xo = to.features.clone().requires_grad_(True)
+        xg = tg.features.clone().requires_grad_(True)
+        yo = lo(O.SparseConvNetTensor(xo, to.metadata, size)).features
+        yg = lg(scn.SparseConvNetTensor(xg, tg.metadata, size)).features
+        og_t, oo_t = torch.from_numpy(og), torch.from_numpy(oo)
+        assert rel_err(yg.detach().cpu()[og_t], yo.detach()[oo_t]) <= tol
+        gc = torch.randn(yo.shape, generator=torch.Generator().manual_seed(1))      # canonical output gradient
+        yo.backward(gc[torch.from_numpy(io)])
+        yg.backward(gc[torch.from_numpy(ig)].to(cuda))
+        assert rel_err(xg.grad.cpu()[og_t], xo.grad[oo_t]) <= tol
+        assert rel_err(lg.weight.grad, lo.weight.grad) <= 5 * tol and rel_err(lg.bias.grad, lo.bias.grad) <= 5 * tol
+    finally:
+        scn.set_precision("tf32")

@@ -7,7 +7,7 @@ import scn_oracle as O
 from scn_oracle import rules as R
 from tests.util import make_pair, random_scene
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("first_rows")]
 
 
 def _scn():

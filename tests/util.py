@@ -64,3 +64,17 @@ def reinit_by_name(module, scale=1.0):
             std = (2.0 / max(v.numel() // v.shape[-1], 1)) ** 0.5 if v.dim() >= 2 else 0.05
             v.copy_(torch.randn(v.shape, generator=g) * std * scale)
     return module
+
+
+def canon_order(loc):
+    """locations [n,4] (x,y,z,b) -> LongTensor of rows in canonical (b, x, y, z) order."""
+    keys = R.pack_keys(loc.numpy() if isinstance(loc, torch.Tensor) else loc)
+    return torch.from_numpy(np.argsort(keys, kind="stable"))
+
+
+def canon_features(t):
+    """(sorted keys, features in canonical row order) of a SparseConvNetTensor from either backend."""
+    loc = t.get_spatial_locations()
+    order = canon_order(loc)
+    keys = np.sort(R.pack_keys(loc.numpy()))
+    return keys, t.features.detach().cpu()[order]
