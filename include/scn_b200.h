@@ -164,6 +164,19 @@ int scn_conv_pack_weights(const float* w, int K, int Cin, int Cout, int transpos
  * ~120 launches per training step otherwise).  table: device array of n rows of 7 int64
  * {w pointer, image pointer, K, Cin, Cout, transpose, reverse}. */
 int scn_conv_pack_weights_multi(const int64_t* table, int n, scn_stream_t stream);
+/* Tile book of a 3x3x3 submanifold neighbour map over spatially coherent (Morton-ordered) rows (round 2, csrc/conv_ts.cu;
+ * the reference side is the same SubmanifoldConvolution call sites, module_factory.py:377-414): for every 128-row output
+ * tile the list of DISTINCT input rows its 27 x 128 neighbour references touch, the map re-expressed as 16-bit indices into
+ * that list, and a bit mask of offsets with at least one active pair.  scn_tile_book_attach associates a built book with
+ * the device pointer of its map: scn_conv_fwd_tf32 (and the fused entry points on top of it) then run the tile-local
+ * tensor-memory kernel for that map when the layer qualifies (C in {16, 32, 48, 64}, >= 2 tiles per SM) -- same results up
+ * to fp32 summation order.  The caller owns both buffers and detaches before freeing them. */
+int64_t scn_tile_book_bytes(int n_out);
+int scn_tile_book_build(const int32_t* map, int n_out, int K, void* book, scn_stream_t stream);
+int scn_tile_book_attach(const int32_t* map, const void* book, int n_out);
+int scn_tile_book_detach(const int32_t* map);
+/* launches of the tile-local kernel so far (tests assert that the path under test really ran) */
+int64_t scn_conv_ts_launch_count(void);
 /* TF32 tcgen05 implicit gather-GEMM (sm_100a).  Cin/Cout here are the GEMM's K/N widths, i.e.
  * after any transpose; n_in = rows of `in`.  residual (may be NULL) is [n_out, Cout] with leading
  * dimension ld_res.  When `in` and its row stride are 16-byte aligned the rows are gathered by TMA

@@ -962,6 +962,13 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     static int is100 = -1;
     if (is100 < 0) is100 = scn_device_is_sm100();
     SCN_REQUIRE(is100 == 1, "conv_fwd_tf32: needs an sm_100 device (tcgen05)");
+    {
+        // submanifold 3^3 layers over a map with an attached tile book (Morton-ordered rows): tile-local kernel, conv_ts.cu
+        const int ts = scn::conv_ts_try(in, ld_in, Cin, map, n_out, K, image, bias, residual, ld_res, mask, ld_mask, out, ld_out,
+                                        Cout, epi_flags, as_stream(stream));
+        if (ts > 0) return SCN_OK;
+        if (ts < 0) return -ts;
+    }
 
     ConvTcParams p;
     p.in = in, p.ld_in = ld_in, p.Cin = Cin, p.map = map, p.n_out = n_out, p.K = K;

@@ -1,0 +1,736 @@
+// Tile-local TF32 gather-GEMM for submanifold 3^3 convolutions on spatially coherent (Morton-ordered) rows.
+//
+//   out[r, :] = epi( bias + sum_o  in[map[o][r], :] . W[o] )       r in [0, n_out),  27 offsets
+//
+// Round 1's kernel (conv_tc.cu) gathers the 128 input rows of every (tile, offset) unit from L2 with cp.async: 27 x 128
+// row copies per tile of which 63 % are zero fill, bounded by the LDGSTS rate (8 cycles per 512-byte instruction whether
+// the rows are real or zeros; profiles/r2_a_row_order.md).  With Morton-ordered rows the 27 x 128 references of a tile hit
+// only ~280 distinct rows, so here
+//   * a per-level TILE BOOK (k_tile_book, built once per rulebook) lists each tile's distinct input rows (its halo set)
+//     and re-expresses the neighbour map as 16-bit indices into that list;
+//   * loader warps copy the halo set of the NEXT tile into shared memory once (cp.async, 8 lanes per 128-byte row);
+//   * gather warps, thread = output row, read the row's neighbour for one offset from shared memory (LDS.128, XOR-swizzled
+//     against bank conflicts; inactive neighbour = zeros in registers, no memory traffic at all) and store it into TENSOR
+//     MEMORY (tcgen05.st.32x32b): the A operand of the MMA lives in TMEM, there is no shared-memory A stage to fill or to
+//     keep clean;
+//   * one elected thread issues tcgen05.mma kind::tf32 in the TS form (A from TMEM, B = W[o] from shared memory), fp32
+//     accumulation in TMEM across the tile's offsets, double-buffered accumulators, same epilogue as conv_tc.cu.
+// Weights stay RESIDENT in shared memory for the whole kernel when all 27 blocks fit (C <= 32: 108 KB); otherwise they are
+// streamed through a ring by cp.async.bulk.  One persistent CTA per SM (24 warps):
+//   warps 0-3 epilogue | 4-19 gather (4 groups x 4 TMEM lane quarters; group g fills every 4th unit) | 20-21 halo loaders |
+//   22 weight streamer | 23 MMA issuer + TMEM owner (highest warp id = highest issue priority).
+// Rows whose local index does not fit the shared-memory halo buffer (rare: tiles touching > cap rows) are gathered from
+// global memory through the ordinary neighbour map by the same thread.
+// Per-unit cost model (B300 guide): LDS 16 KB / 128 B per cycle = 128 cycles, TMEM store 64, MMA (N = 32) 64.
+#include <atomic>
+#include <mutex>
+#include <type_traits>
+#include <unordered_map>
+#include "tc_common.cuh"
+
+namespace scn {
+
+constexpr int TS_K = 27;
+constexpr int TS_ROWS_CAP = 512;                     // rows stored per tile in the book (local ids beyond: 0xFFFE)
+constexpr int TS_LMAP_BYTES = TS_K * TILE_M * 2;     // 6912
+constexpr int TS_THREADS = 768;
+constexpr int TS_GROUPS = 4;
+constexpr uint32_t TS_INACTIVE = 0xFFFFu, TS_GLOBAL = 0xFFFEu;
+
+struct TileBook {
+    const uint16_t* lmap;      // [n_tiles][27][128] local index | 0xFFFF inactive | 0xFFFE "use the global map"
+    const int32_t* rows;       // [n_tiles][TS_ROWS_CAP] distinct input rows of the tile
+    const int32_t* nloc;       // [n_tiles] rows stored
+    const uint32_t* umask;     // [n_tiles] bit o: some row of the tile has an active neighbour at offset o
+    int n_out, n_tiles;
+};
+static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+static TileBook book_layout(const void* base, int n_out) {
+    TileBook b;
+    b.n_out = n_out, b.n_tiles = (n_out + TILE_M - 1) / TILE_M;
+    const char* p = reinterpret_cast<const char*>(base);
+    int64_t off = 0;
+    b.lmap = reinterpret_cast<const uint16_t*>(p + off), off += align256((int64_t)b.n_tiles * TS_LMAP_BYTES);
+    b.rows = reinterpret_cast<const int32_t*>(p + off), off += align256((int64_t)b.n_tiles * TS_ROWS_CAP * 4);
+    b.nloc = reinterpret_cast<const int32_t*>(p + off), off += align256((int64_t)b.n_tiles * 4);
+    b.umask = reinterpret_cast<const uint32_t*>(p + off), off += align256((int64_t)b.n_tiles * 4);
+    return b;
+}
+static int64_t book_bytes(int n_out) {
+    const int64_t nt = (n_out + TILE_M - 1) / TILE_M;
+    return align256(nt * TS_LMAP_BYTES) + align256(nt * TS_ROWS_CAP * 4) + 2 * align256(nt * 4);
+}
+
+// ------------------------------------------------------------------------------------------------ tile book builder
+constexpr int TBB_THREADS = 256;
+constexpr int TBB_SLOTS = 4096;      // >= 27 * 128 = 3456 distinct rows in the worst case
+constexpr int TBB_SORT_MAX = 1024;   // halo sets beyond this are not coherent anyway: keep list order
+
+__global__ void __launch_bounds__(TBB_THREADS) k_tile_book(const int32_t* __restrict__ map, int n_out, uint16_t* __restrict__ lmap,
+                                                           int32_t* __restrict__ rows, int32_t* __restrict__ nloc,
+                                                           uint32_t* __restrict__ umask) {
+    __shared__ int32_t tab[TBB_SLOTS];
+    __shared__ uint16_t ids[TBB_SLOTS];
+    __shared__ int32_t vals[TS_K * TILE_M];
+    __shared__ uint16_t rank[TS_K * TILE_M];
+    __shared__ int warp_sums[TBB_THREADS / 32];
+    __shared__ uint32_t s_mask;
+    const int tile = blockIdx.x, row0 = tile * TILE_M, tid = threadIdx.x;
+    for (int i = tid; i < TBB_SLOTS; i += TBB_THREADS) tab[i] = -1;
+    if (tid == 0) s_mask = 0;
+    __syncthreads();
+    auto slot_of = [](int v) { return (int)(((uint32_t)v * 2654435761u) >> 20); };      // 12 bits
+    for (int e = tid; e < TS_K * TILE_M; e += TBB_THREADS) {
+        const int o = e >> 7, row = row0 + (e & 127);
+        const int v = row < n_out ? __ldg(map + (int64_t)o * n_out + row) : -1;
+        if (v >= 0) {
+            int s = slot_of(v);
+            while (true) {
+                const int prev = atomicCAS(&tab[s], -1, v);
+                if (prev == -1 || prev == v) break;
+                s = (s + 1) & (TBB_SLOTS - 1);
+            }
+        }
+    }
+    __syncthreads();
+    // distinct rows -> compact list (slot order), then local id = RANK of the row among the tile's rows: ids ascend with the
+    // global (Morton) row index, so the 8 consecutive output rows a quarter warp gathers for one offset read mostly
+    // consecutive halo rows -- conflict-free under the XOR swizzle of conv_ts (a hash-order numbering measured 6.5
+    // wavefronts per LDS.128 instead of 4)
+    constexpr int PER = TBB_SLOTS / TBB_THREADS;      // 16 consecutive slots per thread
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) cnt += tab[tid * PER + j] >= 0 ? 1 : 0;
+    const int lane = tid & 31, w = tid >> 5;
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int j = 0; j < TBB_THREADS / 32; ++j) {
+        if (j < w) off += warp_sums[j];
+        total += warp_sums[j];
+    }
+    int run = off + inc - cnt;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int s = tid * PER + j, v = tab[s];
+        if (v >= 0) {
+            vals[run] = v;
+            ids[s] = (uint16_t)run;      // position in the compact list, replaced by the rank below
+            ++run;
+        }
+    }
+    __syncthreads();
+    if (total <= TBB_SORT_MAX) {
+        for (int i = tid; i < total; i += TBB_THREADS) {
+            const int v = vals[i];
+            int r = 0;
+            for (int k = 0; k < total; ++k) r += vals[k] < v ? 1 : 0;      // all threads read the same word: broadcast
+            rank[i] = (uint16_t)r;
+        }
+    } else {
+        for (int i = tid; i < total; i += TBB_THREADS) rank[i] = (uint16_t)(i < 65534 ? i : 65534);
+    }
+    __syncthreads();
+    for (int i = tid; i < total; i += TBB_THREADS) {
+        const int r = rank[i];
+        if (r < TS_ROWS_CAP) rows[(int64_t)tile * TS_ROWS_CAP + r] = vals[i];
+    }
+    if (tid == 0) nloc[tile] = total < TS_ROWS_CAP ? total : TS_ROWS_CAP;
+    __syncthreads();
+    for (int e = tid; e < TS_K * TILE_M; e += TBB_THREADS) {
+        const int o = e >> 7, row = row0 + (e & 127);
+        const int v = row < n_out ? __ldg(map + (int64_t)o * n_out + row) : -1;
+        uint32_t code = TS_INACTIVE;
+        if (v >= 0) {
+            int s = slot_of(v);
+            while (tab[s] != v) s = (s + 1) & (TBB_SLOTS - 1);
+            const uint32_t r = rank[ids[s]];
+            code = r < (uint32_t)TS_ROWS_CAP ? r : TS_GLOBAL;
+            atomicOr(&s_mask, 1u << o);
+        }
+        lmap[(int64_t)tile * (TS_K * TILE_M) + e] = (uint16_t)code;
+    }
+    __syncthreads();
+    if (tid == 0) umask[tile] = s_mask;
+}
+
+// ------------------------------------------------------------------------------------------------ the convolution
+struct ConvTsParams {
+    const float* in;
+    int ld_in;
+    TileBook book;
+    const int32_t* map;      // global neighbour map [27][n_out] (rows beyond the shared-memory halo)
+    const uint8_t* image;
+    const float* bias;
+    const float* residual;
+    int ld_res;
+    const float* mask;
+    int ld_mask;
+    float* out;
+    int ld_out, epi;
+    int cap;                 // halo rows per shared-memory buffer; row `cap` of each buffer is the all-zero row
+    int skip_units;
+};
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// physical 16-byte chunk of logical chunk c of halo row r: XOR swizzle inside groups of 8 chunks (4 in a trailing half group)
+__device__ __forceinline__ int halo_chunk(int c, int r, int cpr) {
+    const int grp = c & ~7;
+    const int m = (cpr - grp) >= 8 ? 7 : 3;
+    return grp | ((c & 7) ^ (r & m));
+}
+
+#ifdef SCN_TS_TRACE
+// timing experiment: clock64 stamps of CTA 0 (slot -> SM cycles), read back with scn_debug_ts_trace
+__device__ long long g_ts_trace[16384];
+#define TS_STAMP(slot)                                                        \
+    do {                                                                      \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (slot) < 16384) g_ts_trace[slot] = clock64(); \
+    } while (0)
+#else
+#define TS_STAMP(slot) \
+    do {               \
+    } while (0)
+#endif
+
+struct UnitRing {      // position in a ring of `n` stages + the parity of the current round
+    int s;
+    uint32_t par;
+    __device__ __forceinline__ void step(int n) {
+        if (++s == n) s = 0, par ^= 1;
+    }
+};
+
+// compile-time shape of a layer: C input = output channels, weights resident in shared memory or streamed
+template <int C, bool RESIDENT, int GROUPS = 4>
+struct TsShape {
+    static constexpr int NKB = (C + KB - 1) / KB;
+    static constexpr int PITCH = C * 4, CPR = C / 4;
+    static constexpr int WBLOCK = NKB * C * 128;                    // bytes of one offset's packed weights
+    static constexpr int NWB = RESIDENT ? TS_K : (WBLOCK <= 8192 ? 4 : 3);
+    static constexpr int NW = RESIDENT ? 1 : NWB;                   // weight barriers
+    static constexpr int NA_MAX = ((512 - 2 * C) / C) > 12 ? 12 : ((512 - 2 * C) / C);
+    static constexpr int NA = NA_MAX / GROUPS * GROUPS;             // a multiple of the group count (see the gather loop)
+    static constexpr int NK8 = C / 8;
+    static constexpr int G = GROUPS;                                // gather groups (x 4 warps each); must divide NA
+    static constexpr int THREADS = (8 + 4 * G) * 32;
+    static constexpr int N_BARS = 8 + 2 * NA + 2 * NW;
+    static constexpr int FIXED_SMEM = 1024 + NWB * WBLOCK + 2 * TS_LMAP_BYTES + 512;      // + 2 * (cap + 1) * PITCH
+};
+
+// the loop every role walks: the active offsets of a tile in ascending order
+#define TS_FOR_UNITS(um, o) for (int o; (um) != 0u && ((o) = __ffs(um) - 1, (um) &= (um) - 1, true);)
+
+template <int C, bool RESIDENT, int GROUPS>
+__global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_conv_ts(const ConvTsParams p) {
+    using S = TsShape<C, RESIDENT, GROUPS>;
+    constexpr int NA = S::NA, NW = S::NW, PITCH = S::PITCH, CPR = S::CPR, G = S::G;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_base = smem_base;
+    const uint32_t halo_bytes = (uint32_t)(p.cap + 1) * PITCH;
+    const uint32_t halo0 = w_base + (uint32_t)(S::NWB * S::WBLOCK);
+    const uint32_t lmap0 = halo0 + 2u * halo_bytes;
+    const uint32_t bars = lmap0 + 2u * TS_LMAP_BYTES;
+    auto halo_full = [&](int b) { return bars + 8u * b; };
+    auto halo_empty = [&](int b) { return bars + 8u * (2 + b); };
+    auto acc_full = [&](int b) { return bars + 8u * (4 + b); };
+    auto acc_empty = [&](int b) { return bars + 8u * (6 + b); };
+    auto a_full = [&](int s) { return bars + 8u * (8 + s); };
+    auto a_empty = [&](int s) { return bars + 8u * (8 + NA + s); };
+    auto w_full = [&](int s) { return bars + 8u * (8 + 2 * NA + s); };
+    auto w_empty = [&](int s) { return bars + 8u * (8 + 2 * NA + NW + s); };
+    const uint32_t tmem_slot = bars + 8u * S::N_BARS;
+
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    // warp roles; the issue arbiter of an SM sub-partition prefers the HIGHEST warp id (B300 guide), so the warp whose serial
+    // instruction stream paces the whole CTA -- the MMA issuer -- sits on top, the streaming roles below it
+    constexpr int W_GATHER0 = 4, W_LOAD0 = 4 + 4 * G, W_WEIGHTS = W_LOAD0 + 2, W_MMA = W_LOAD0 + 3;
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(halo_full(b), 64 + 1);            // 2 loader warps x 32 lanes (cp.async arrivals) + the lmap bulk copy
+            mbar_init(halo_empty(b), 4 * G);            // one arrival per gather warp
+            mbar_init(acc_full(b), 1);
+            mbar_init(acc_empty(b), 4);                 // one arrival per epilogue warp
+        }
+        for (int s = 0; s < NA; ++s) {
+            mbar_init(a_full(s), 4);                    // one arrival per warp of the unit's gather group
+            mbar_init(a_empty(s), 1);
+        }
+        for (int s = 0; s < NW; ++s) {
+            mbar_init(w_full(s), 1);
+            mbar_init(w_empty(s), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the all-zero row of both halo buffers (index `cap`): inactive neighbours read it, no predication in the gather loop
+    if (tid < 2 * CPR) {
+        const uint32_t a = halo0 + (uint32_t)(tid / CPR) * halo_bytes + (uint32_t)p.cap * PITCH + (uint32_t)(tid % CPR) * 16u;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
+    }
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_trigger();
+    pdl_wait();
+
+    const int n_tiles = p.book.n_tiles;
+    constexpr uint32_t A_COL0 = 2u * C;      // A stages follow the two accumulators
+    constexpr uint32_t ALL_UNITS = (1u << TS_K) - 1u;
+
+    if (warp >= W_GATHER0 && warp < W_LOAD0) {
+        // ===================== gather warps: shared-memory halo -> registers -> tensor memory =====================
+        const int g = (warp - W_GATHER0) >> 2, q = warp & 3;
+        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0;
+        const int cap = p.cap;
+        uint32_t uc = 0;      // units of this CTA before the current tile (every role counts them the same way)
+        int it = 0;
+        int nl_next = blockIdx.x < n_tiles ? __ldg(p.book.nloc + blockIdx.x) : 0;
+        uint32_t um_next = blockIdx.x < n_tiles && p.skip_units ? __ldg(p.book.umask + blockIdx.x) : ALL_UNITS;
+        // one unit of this warp: rows q*32 .. q*32+31 of offset o into A stage (uc + ord) % NA
+        auto do_unit = [&](auto slow_tag, uint32_t cur, int o, uint32_t u, uint32_t hb, int row) {
+            constexpr bool SLOW = decltype(slow_tag)::value;
+            const uint32_t st = u % NA, par = (u / NA) & 1u;
+            const bool local = cur < (uint32_t)cap;
+            const uint32_t rb = hb + cur * PITCH;
+            const uint32_t x7 = (cur & 7u) << 4, x3 = (cur & 3u) << 4;
+            const float* gsrc = nullptr;
+            if (SLOW && !local && cur != TS_INACTIVE)
+                gsrc = p.in + (int64_t)__ldg(p.map + (int64_t)o * p.book.n_out + row) * p.ld_in;
+            if (q == 0) TS_STAMP(4096 + (int)u * 4);
+            mbar_wait(a_empty(st), par ^ 1u);
+            tc_fence_after();
+            if (q == 0) TS_STAMP(4096 + (int)u * 4 + 1);
+            const uint32_t tcol = tq + st * C;
+#pragma unroll
+            for (int c0 = 0; c0 < C; c0 += 32) {      // 32 columns (one 128-byte block) per step, 16 for a trailing half
+                const int w = (C - c0) >= 32 ? 32 : 16;
+                uint32_t v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+                if (local) {      // inactive neighbours issue no shared-memory request at all
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (4 * j < w) {
+                            const uint32_t xs = (w == 32) ? x7 : x3;
+                            const uint32_t a = rb + (uint32_t)(c0 * 4) + (((uint32_t)j << 4) ^ xs);
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
+                                         : "r"(a));
+                        }
+                    }
+                }
+                if (SLOW) {
+                    if (gsrc) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (4 * j < w) {
+                                const uint4 t = __ldg(reinterpret_cast<const uint4*>(gsrc + c0) + j);
+                                v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (w == 32) tmem_st32(tcol + (uint32_t)c0, v);
+                else tmem_st16(tcol + (uint32_t)c0, v);
+            }
+            if (q == 0) TS_STAMP(4096 + (int)u * 4 + 2);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(a_full(st));
+            if (q == 0) TS_STAMP(4096 + (int)u * 4 + 3);
+        };
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int nl = nl_next;
+            const uint32_t um = um_next;
+            {      // the next tile's header, one tile ahead (an L2 round trip per tile otherwise sits in every warp's chain)
+                const int tn = tile + gridDim.x;
+                if (tn < n_tiles) {
+                    nl_next = __ldg(p.book.nloc + tn);
+                    if (p.skip_units) um_next = __ldg(p.book.umask + tn);
+                }
+            }
+            const bool slow = nl > cap || nl >= TS_ROWS_CAP;      // some references live outside the shared-memory halo
+            // this group's units of the tile: every G-th ACTIVE offset, counted through the CTA's running unit number (with
+            // G dividing NA a group then always alternates between the same NA / G stages and can never be more than one
+            // round ahead of the MMA warp on any of them -- an mbarrier wait only sees the phase parity)
+            auto drop = [](uint32_t t, int n) {      // clear the n lowest set bits
+                for (int i = 0; i < n; ++i) t &= t - 1u;
+                return t;
+            };
+            const int skip = (int)(((uint32_t)g + G - uc % G) % G);
+            uint32_t t = drop(um, skip);
+            uint32_t u = uc + (uint32_t)skip;
+            if (g == 0 && q == 0) TS_STAMP(13000 + it * 2);
+            mbar_wait(halo_full(buf), (uint32_t)(it >> 1) & 1u);
+            if (g == 0 && q == 0) TS_STAMP(13000 + it * 2 + 1);
+            const uint32_t hb = halo0 + (uint32_t)buf * halo_bytes;
+            const uint32_t lm = lmap0 + (uint32_t)buf * TS_LMAP_BYTES + (uint32_t)(q * 32 + lane) * 2u;
+            const int row = tile * TILE_M + q * 32 + lane;
+            uint32_t code = TS_INACTIVE;      // the neighbour code of a unit is read one own unit ahead
+            if (t) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(lm + (uint32_t)(__ffs(t) - 1) * (TILE_M * 2)));
+            while (t) {
+                const int o = __ffs(t) - 1;
+                const uint32_t cur = code;
+                t = drop(t, G);
+                if (t) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(lm + (uint32_t)(__ffs(t) - 1) * (TILE_M * 2)));
+                if (slow) do_unit(std::true_type{}, cur, o, u, hb, row);
+                else do_unit(std::false_type{}, cur, o, u, hb, row);
+                u += G;
+            }
+            uc += (uint32_t)__popc(um);
+            __syncwarp();
+            if (elect_one()) mbar_arrive(halo_empty(buf));
+        }
+    } else if (warp == W_LOAD0 || warp == W_LOAD0 + 1) {
+        // ===================== halo loaders: the next tile's distinct input rows, once =====================
+        const int lw = warp - W_LOAD0;
+        int it = 0;
+        const char* in_c = reinterpret_cast<const char*>(p.in);
+        const uint32_t row_bytes = (uint32_t)p.ld_in * 4u;
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            int cnt = __ldg(p.book.nloc + tile);
+            if (cnt > p.cap) cnt = p.cap;
+            const int32_t* rl = p.book.rows + (int64_t)tile * TS_ROWS_CAP;
+            // super-round = 32 consecutive rows of the list: lane L reads the index of row base + L (one coalesced load,
+            // issued one super-round ahead), the copies fetch it by shuffle; the two loader warps alternate super-rounds
+            int base = lw * 32;
+            int mine = base + lane < cnt ? __ldg(rl + base + lane) : -1;
+            if (lw == 0) TS_STAMP(12000 + it * 4);
+            mbar_wait(halo_empty(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            if (lw == 0) TS_STAMP(12000 + it * 4 + 1);
+            const uint32_t hb = halo0 + (uint32_t)buf * halo_bytes;
+            if (lw == 0 && elect_one()) {
+                mbar_arrive_expect_tx(halo_full(buf), TS_LMAP_BYTES);
+                bulk_g2s(lmap0 + (uint32_t)buf * TS_LMAP_BYTES, p.book.lmap + (int64_t)tile * (TS_K * TILE_M), TS_LMAP_BYTES,
+                         halo_full(buf));
+            }
+            while (base < cnt) {
+                const int nbase = base + 64;
+                const int next = nbase + lane < cnt ? __ldg(rl + nbase + lane) : -1;
+#pragma unroll
+                for (int i = 0; i < CPR; ++i) {
+                    const int t = lane + 32 * i;              // chunk t of the super-round: row t / CPR, chunk t % CPR
+                    const int jr = t / CPR, c = t % CPR;
+                    const int ridx = __shfl_sync(0xffffffffu, mine, jr);
+                    if (ridx >= 0) {
+                        const int j = base + jr;
+                        const char* src = in_c + (uint64_t)(uint32_t)ridx * row_bytes + c * 16;
+                        const uint32_t dst = hb + (uint32_t)j * PITCH + (uint32_t)(halo_chunk(c, j, CPR) << 4);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    }
+                }
+                mine = next;
+                base = nbase;
+            }
+            cp_async_mbar_arrive_noinc(halo_full(buf));
+            if (lw == 0) TS_STAMP(12000 + it * 4 + 2);
+        }
+        cp_async_wait_all();
+    } else if (warp == W_WEIGHTS) {
+        // ===================== weights: resident (one load) or streamed through a ring, one block per unit =====================
+        if (RESIDENT) {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(w_full(0), (uint32_t)(TS_K * S::WBLOCK));
+                for (int o = 0; o < TS_K; ++o)
+                    bulk_g2s(w_base + (uint32_t)(o * S::WBLOCK), p.image + (size_t)o * S::WBLOCK, (uint32_t)S::WBLOCK, w_full(0));
+            }
+        } else {
+            UnitRing wr{0, 0};
+#pragma unroll 1
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                uint32_t um = p.skip_units ? __ldg(p.book.umask + tile) : ALL_UNITS;
+                TS_FOR_UNITS(um, o) {
+                    mbar_wait(w_empty(wr.s), wr.par ^ 1u);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(w_full(wr.s), (uint32_t)S::WBLOCK);
+                        bulk_g2s(w_base + (uint32_t)(wr.s * S::WBLOCK), p.image + (size_t)o * S::WBLOCK, (uint32_t)S::WBLOCK,
+                                 w_full(wr.s));
+                    }
+                    wr.step(NW);
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ===================== MMA issuer: A from tensor memory, B = W[o] from shared memory =====================
+        const uint32_t idesc = make_idesc_tf32(TILE_M, C);
+        const uint64_t wdesc0 = make_desc_sw128(w_base);
+        constexpr uint32_t WBLOCK_D = (uint32_t)S::WBLOCK >> 4, KB_D = (uint32_t)(C * 128) >> 4;
+        const uint32_t ta0 = tmem_base + A_COL0;
+        UnitRing ar{0, 0}, wr{0, 0};
+        int it = 0;
+        int mma_n = 0;
+        (void)mma_n;
+        if (RESIDENT) mbar_wait(w_full(0), 0);
+        TS_STAMP(16000);
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int b = it & 1;
+            uint32_t um = p.skip_units ? __ldg(p.book.umask + tile) : ALL_UNITS;
+            mbar_wait(acc_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(b * C);
+            uint32_t accum = 0;
+            TS_FOR_UNITS(um, o) {
+                TS_STAMP(mma_n * 4);
+                mbar_wait(a_full(ar.s), ar.par);
+                if (!RESIDENT) mbar_wait(w_full(wr.s), wr.par);
+                tc_fence_after();
+                TS_STAMP(mma_n * 4 + 1);
+                if (elect_one()) {
+                    const uint32_t ta = ta0 + (uint32_t)(ar.s * C);
+                    const uint64_t wd = wdesc0 + (uint64_t)((uint32_t)(RESIDENT ? o : wr.s) * WBLOCK_D);
+#pragma unroll
+                    for (int k = 0; k < S::NK8; ++k)
+                        mma_tf32_ts(tmem_d, ta + (uint32_t)(k * 8), wd + (uint64_t)((uint32_t)(k >> 2) * KB_D + (uint32_t)((k & 3) * 2)),
+                                    idesc, k == 0 ? accum : 1u);
+                    mma_commit(a_empty(ar.s));
+                    if (!RESIDENT) mma_commit(w_empty(wr.s));
+                }
+                accum = 1u;
+                ar.step(NA);
+                if (!RESIDENT) wr.step(NW);
+                TS_STAMP(mma_n * 4 + 2);
+                ++mma_n;
+            }
+            if (elect_one()) mma_commit(acc_full(b));
+        }
+    } else if (warp < 4) {
+        // ===================== epilogue warps 0..3 (as conv_tc.cu, whole tiles only) =====================
+        const int epi = p.epi;
+        const bool vec_ok = (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                            (!(epi & SCN_EPI_ADD) || ((p.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
+                            (!(epi & SCN_EPI_MASK) || ((p.ld_mask % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+        auto finish = [&](float x, float m, float r) {      // order: (bias), MASK, ADD, RELU, ROUND
+            if ((epi & SCN_EPI_MASK) && !(m > 0.f)) x = 0.f;
+            if (epi & SCN_EPI_ADD) x += r;
+            if (epi & SCN_EPI_RELU) x = fmaxf(x, 0.f);
+            if (epi & SCN_EPI_ROUND) {
+                uint32_t t;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+                x = __uint_as_float(t);
+            }
+            return x;
+        };
+        int it = 0;
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int b = it & 1;
+            if (warp == 0) TS_STAMP(14000 + it * 4);
+            mbar_wait<2000>(acc_full(b), (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            if (warp == 0) TS_STAMP(14000 + it * 4 + 1);
+            const int row = tile * TILE_M + warp * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * C);
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (row < p.book.n_out) {
+                    float* orow = p.out + (int64_t)row * p.ld_out + c0;
+                    const float* rrow = (epi & SCN_EPI_ADD) ? p.residual + (int64_t)row * p.ld_res + c0 : nullptr;
+                    const float* mrow = (epi & SCN_EPI_MASK) ? p.mask + (int64_t)row * p.ld_mask + c0 : nullptr;
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
+                    }
+                    if (vec_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 r4 = rrow ? *reinterpret_cast<const float4*>(rrow + j) : make_float4(0, 0, 0, 0);
+                            const float4 m4 = mrow ? *reinterpret_cast<const float4*>(mrow + j) : make_float4(1, 1, 1, 1);
+                            float4 x;
+                            x.x = finish(v[j], m4.x, r4.x), x.y = finish(v[j + 1], m4.y, r4.y);
+                            x.z = finish(v[j + 2], m4.z, r4.z), x.w = finish(v[j + 3], m4.w, r4.w);
+                            *reinterpret_cast<float4*>(orow + j) = x;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) orow[j] = finish(v[j], mrow ? mrow[j] : 1.f, rrow ? rrow[j] : 0.f);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(acc_empty(b));
+            if (warp == 0) TS_STAMP(14000 + it * 4 + 2);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ registry: map -> book
+struct BookEntry {
+    const void* book;
+    int n_out;
+};
+static std::unordered_map<const void*, BookEntry> g_books;
+static std::mutex g_books_mutex;
+static std::atomic<int64_t> g_ts_launches{0};
+
+template <int C, bool RESIDENT, int GROUPS>
+static int launch_ts(ConvTsParams& p, cudaStream_t stream) {
+    using S = TsShape<C, RESIDENT, GROUPS>;
+    constexpr int MAX_SMEM = 227 * 1024;
+    int cap = (MAX_SMEM - S::FIXED_SMEM) / (2 * S::PITCH) - 1;      // -1: the zero row of each buffer
+    if (cap > TS_ROWS_CAP) cap = TS_ROWS_CAP;
+    cap &= ~7;
+    if (cap < 192) return 0;
+    p.cap = cap;
+    const int smem = S::FIXED_SMEM + 2 * (cap + 1) * S::PITCH;
+    auto kern = k_conv_ts<C, RESIDENT, GROUPS>;
+    cudaError_t e = (cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("conv_ts: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
+        return -SCN_ERR_CUDA;
+    }
+    const int grid = p.book.n_tiles < sm_count() ? p.book.n_tiles : sm_count();
+    PdlLaunch L(dim3(grid), dim3(S::THREADS), smem, stream);
+    e = cudaLaunchKernelEx(&L.cfg, kern, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("conv_ts: launch failed: %s", cudaGetErrorString(e));
+        return -SCN_ERR_CUDA;
+    }
+    const int rc = check_launch("conv_ts");
+    if (!rc) ++g_ts_launches;
+    return rc ? -rc : 1;
+}
+
+// Launches the tile-local kernel when a tile book is attached to `map` and the layer qualifies; returns 1 if it did,
+// 0 if the caller should use conv_tc.cu, < 0 (negated status) on error.
+int conv_ts_try(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const void* image, const float* bias,
+                const float* residual, int ld_res, const float* mask, int ld_mask, float* out, int ld_out, int Cout, int epi,
+                cudaStream_t stream) {
+    if (K != TS_K || !map || Cin != Cout) return 0;
+    const char* ev = getenv("SCN_CONV_TS");      // read per call: tests run both kernels in one process
+    if (ev && ev[0] == '0') return 0;
+    if ((Cin != 16 && Cin != 32 && Cin != 48 && Cin != 64) || ld_in % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15)) return 0;
+    static int min_tiles = -1;
+    if (min_tiles < 0) {
+        const char* e = getenv("SCN_CONV_TS_MIN_TILES");
+        min_tiles = e ? atoi(e) : 2 * sm_count();
+    }
+    const int n_tiles = (n_out + TILE_M - 1) / TILE_M;
+    if (n_tiles < min_tiles) return 0;
+    BookEntry be;
+    {
+        std::lock_guard<std::mutex> lock(g_books_mutex);
+        auto it = g_books.find(map);
+        if (it == g_books.end() || it->second.n_out != n_out) return 0;
+        be = it->second;
+    }
+    ConvTsParams p;
+    p.in = in, p.ld_in = ld_in, p.book = book_layout(be.book, n_out), p.map = map;
+    p.image = reinterpret_cast<const uint8_t*>(image), p.bias = bias, p.residual = residual, p.ld_res = ld_res;
+    p.mask = mask, p.ld_mask = ld_mask, p.out = out, p.ld_out = ld_out, p.epi = epi;
+    static int skip_units = -1;
+    if (skip_units < 0) {
+        const char* e = getenv("SCN_CONV_TS_SKIP");
+        skip_units = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.skip_units = skip_units;
+    static int groups = -1;
+    if (groups < 0) {
+        const char* e = getenv("SCN_CONV_TS_GROUPS");
+        groups = e ? atoi(e) : 4;
+    }
+    switch (Cin) {
+        case 16: return groups == 6 ? launch_ts<16, true, 6>(p, stream) : launch_ts<16, true, 4>(p, stream);
+        case 32: return groups == 6 ? launch_ts<32, true, 6>(p, stream) : launch_ts<32, true, 4>(p, stream);
+        case 48: return launch_ts<48, false, 4>(p, stream);
+        default: return launch_ts<64, false, 4>(p, stream);
+    }
+}
+
+}  // namespace scn
+
+using namespace scn;
+
+extern "C" {
+
+int64_t scn_tile_book_bytes(int n_out) { return n_out > 0 ? book_bytes(n_out) : 256; }
+
+int scn_tile_book_build(const int32_t* map, int n_out, int K, void* book, scn_stream_t stream) {
+    SCN_REQUIRE(K == TS_K, "tile_book: 3x3x3 submanifold maps only (K = %d)", K);
+    SCN_REQUIRE(n_out >= 0 && (n_out == 0 || (map && book)), "tile_book: bad arguments");
+    if (n_out == 0) return SCN_OK;
+    SCN_REQUIRE((reinterpret_cast<uintptr_t>(book) & 255) == 0, "tile_book: buffer must be 256-byte aligned");
+    TileBook b = book_layout(book, n_out);
+    k_tile_book<<<b.n_tiles, TBB_THREADS, 0, as_stream(stream)>>>(map, n_out, const_cast<uint16_t*>(b.lmap), const_cast<int32_t*>(b.rows),
+                                                                  const_cast<int32_t*>(b.nloc), const_cast<uint32_t*>(b.umask));
+    return check_launch("tile_book");
+}
+
+int scn_tile_book_attach(const int32_t* map, const void* book, int n_out) {
+    SCN_REQUIRE(map && book && n_out > 0, "tile_book_attach: bad arguments");
+    std::lock_guard<std::mutex> lock(g_books_mutex);
+    g_books[map] = BookEntry{book, n_out};
+    return SCN_OK;
+}
+
+#ifdef SCN_TS_TRACE
+int scn_debug_ts_trace(long long* out) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, scn::g_ts_trace, sizeof(long long) * 16384) == cudaSuccess ? 0 : 1;
+}
+#endif
+int64_t scn_conv_ts_launch_count(void) { return g_ts_launches.load(); }
+
+int scn_tile_book_detach(const int32_t* map) {
+    std::lock_guard<std::mutex> lock(g_books_mutex);
+    g_books.erase(map);
+    return SCN_OK;
+}
+
+}  // extern "C"

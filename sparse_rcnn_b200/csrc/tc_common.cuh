@@ -8,6 +8,10 @@
 
 namespace scn {
 
+// conv_ts.cu: tile-local submanifold kernel; 1 = launched, 0 = not applicable (use conv_tc.cu), < 0 = -status
+int conv_ts_try(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const void* image, const float* bias,
+                const float* residual, int ld_res, const float* mask, int ld_mask, float* out, int ld_out, int Cout, int epi,
+                cudaStream_t stream);
 int make_gather_tmap(CUtensorMap* tm, const float* base, int rows, int C, int ld, CUtensorMapSwizzle swz);
 
 constexpr int TILE_M = 128;

@@ -94,6 +94,15 @@ class Level:
         self.subm = {}                # filter triple -> int32 [K, n] (None for 1x1x1 = identity)
         self._locations = None
         self._batch_ptr = {}
+        self.coherent = False         # rows follow the Morton curve (set by the builders): tile books are worth building
+        self._books = {}              # map data_ptr -> tile book buffer (attached in the library, detached in __del__)
+
+    def __del__(self):
+        try:
+            for ptr in self._books:
+                _lib.call("scn_tile_book_detach", ptr)
+        except Exception:      # interpreter shutdown
+            pass
 
     def locations(self):
         """int64 CPU [n, 4] (x,y,z,b), row aligned (reference contract: custom_operations.py:26-32)."""
@@ -122,7 +131,16 @@ class Level:
                 _lib.call("scn_subm_map", _ptr(self.keys), self.n, _ptr(self.tab_keys), _ptr(self.tab_vals),
                           self.cap, f[0], f[1], f[2], _ptr(m), _stream())
                 self.subm[f] = m
+                if f == (3, 3, 3) and self.coherent and self.n >= TILE_BOOK_MIN_ROWS:
+                    # tile book for the tile-local convolution kernel (csrc/conv_ts.cu): halo lists + 16-bit local maps
+                    book = torch.empty(int(_lib.raw("scn_tile_book_bytes")(self.n)), dtype=torch.uint8, device=m.device)
+                    _lib.call("scn_tile_book_build", _ptr(m), self.n, K, _ptr(book), _stream())
+                    _lib.call("scn_tile_book_attach", _ptr(m), _ptr(book), self.n)
+                    self._books[m.data_ptr()] = book
         return self.subm[f]
+
+
+TILE_BOOK_MIN_ROWS = 128 * 148 * 2      # levels with fewer tiles run conv_tc.cu's cluster-split mode anyway
 
 
 def build_level(keys, morton_bits=None):
@@ -157,7 +175,9 @@ def build_level(keys, morton_bits=None):
     if perm is not None:      # back to the caller's point order
         sorted_rows, point_row = point_row, torch.empty(P, dtype=torch.int32, device=dev)
         _lib.call("scn_scatter_i32", _ptr(sorted_rows), _ptr(perm), P, _ptr(point_row), s)
-    return Level(row_keys, tab_keys, tab_vals, cap, n), point_row
+    level = Level(row_keys, tab_keys, tab_vals, cap, n)
+    level.coherent = perm is not None
+    return level, point_row
 
 
 class Strided:
@@ -326,6 +346,7 @@ class Metadata:
             _lib.call("scn_strided_level_finish", _ptr(pkeys), _ptr(offs), P, _ptr(tab_keys), _ptr(tab_vals), cap,
                       _ptr(rank), _ptr(parent_row), _ptr(row_keys), n, K, _ptr(cmap), _ptr(dmap), s)
             lout = Level(row_keys, tab_keys, tab_vals, cap, n)
+            lout.coherent = lin.coherent      # coarse rows are numbered by their first fine row: a Morton code's parent is its prefix
             self.levels[out_size] = lout
         r = Strided(out_size, cmap, dmap, parent_row, K)
         self.strided[key] = r

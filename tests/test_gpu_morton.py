@@ -126,3 +126,94 @@ def test_conv_layer_in_morton_order(cuda, precision, tol):
         assert rel_err(lg.weight.grad, lo.weight.grad) <= 5 * tol and rel_err(lg.bias.grad, lo.bias.grad) <= 5 * tol
     finally:
         scn.set_precision("tf32")
+
+
+# ------------------------------------------------------------------ tile books + the tile-local tensor-memory kernel
+@pytest.fixture(scope="module")
+def bench_level():
+    from sparse_rcnn_b200 import scn
+    from sparse_rcnn_b200.synthetic import make_batch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dev = torch.device("cuda:0")
+    coords, feats, size, bs, _ = make_batch(1, 0)
+    md = scn.Metadata(3)
+    scn.ioLayers.InputLayerFunction.apply(3, md, size, coords, feats.to(dev), bs, 4)
+    return md, size
+
+
+def test_tile_book_reproduces_the_map(cuda, bench_level):
+    """lmap / rows / nloc / umask of every tile against the neighbour map they were built from (integer work: exact)."""
+    from sparse_rcnn_b200 import _lib
+    md, size = bench_level
+    lvl = md.level(size)
+    m = lvl.subm_map(3)
+    assert lvl.coherent and m.data_ptr() in lvl._books
+    book = lvl._books[m.data_ptr()].cpu().numpy()
+    n = lvl.n
+    nt = (n + 127) // 128
+    a256 = lambda v: (v + 255) // 256 * 256
+    o0 = a256(nt * 27 * 128 * 2)
+    o1 = o0 + a256(nt * 512 * 4)
+    o2 = o1 + a256(nt * 4)
+    assert int(_lib.raw("scn_tile_book_bytes")(n)) == o2 + a256(nt * 4)
+    lmap = book[:nt * 27 * 128 * 2].view(np.uint16).reshape(nt, 27, 128)
+    rows = book[o0:o0 + nt * 512 * 4].view(np.int32).reshape(nt, 512)
+    nloc = book[o1:o1 + nt * 4].view(np.int32)
+    umask = book[o2:o2 + nt * 4].view(np.uint32)
+    mp = np.full((27, nt * 128), -1, np.int32)
+    mp[:, :n] = m.cpu().numpy()
+    mp = mp.reshape(27, nt, 128).transpose(1, 0, 2)                   # [tile, offset, row]
+    assert nloc.max() <= 512 and nloc.min() >= 1
+    active = lmap != 0xFFFF
+    assert np.array_equal(active, mp >= 0)
+    assert not (lmap == 0xFFFE).any()                                 # Morton order: every halo set fits the book
+    t_idx = np.broadcast_to(np.arange(nt)[:, None, None], lmap.shape)
+    assert np.array_equal(rows[t_idx[active], lmap[active]], mp[active])
+    assert (lmap[active] < nloc[t_idx[active]]).all()
+    for t in (0, nt // 2, nt - 1):                                    # lists hold DISTINCT rows
+        assert len(np.unique(rows[t, :nloc[t]])) == nloc[t] == len(np.unique(mp[t][mp[t] >= 0]))
+    ref_mask = ((mp >= 0).any(2) * (1 << np.arange(27))[None]).sum(1).astype(np.uint32)
+    assert np.array_equal(umask, ref_mask)
+    print("halo rows per tile: mean %.0f max %d; empty units %.1f %%" % (
+        nloc.mean(), nloc.max(), 100.0 * (1 - np.unpackbits(umask.view(np.uint8)).sum() / (27.0 * nt))))
+
+
+@pytest.mark.parametrize("C", [32, 16, 48, 64])
+def test_tile_local_kernel_equals_rule_kernel(cuda, bench_level, monkeypatch, C):
+    """conv_ts.cu (halo set in shared memory, A operand in tensor memory) against conv_tc.cu (cp.async gather per offset) on
+    the bench scene: same TF32 products accumulated in the same offset order; forward with every epilogue, input gradient."""
+    from sparse_rcnn_b200 import networks, scn
+    scn.set_precision("tf32")
+    md, size = bench_level
+    lvl = md.level(size)
+    n = lvl.n
+    torch.manual_seed(C)
+    conv = scn.SubmanifoldConvolution(3, C, C, 3, True).to(cuda)
+    conv.bias.data.normal_()
+    x0 = torch.randn(n, C, device=cuda)
+    go = torch.randn(n, C, device=cuda)
+    unit = networks.residual_unit(scn, C, C).to(cuda)
+
+    def run():
+        x = x0.clone().requires_grad_(True)
+        y = conv(scn.SparseConvNetTensor(x, md, size)).features
+        y.backward(go)
+        x2 = x0.clone().requires_grad_(True)
+        unit.zero_grad()
+        z = unit(scn.SparseConvNetTensor(x2, md, size)).features      # ReLU|ROUND, ADD epilogues; backward: MASK|ROUND, MASK|ADD
+        z.backward(go)
+        return [y.detach(), x.grad, z.detach(), x2.grad]
+    monkeypatch.setenv("SCN_CONV_TS", "0")
+    monkeypatch.setenv("SCN_CONV_TAILSPLIT", "0")
+    ref = run()
+    monkeypatch.setenv("SCN_CONV_TS", "1")
+    from sparse_rcnn_b200 import _lib
+    before = int(_lib.raw("scn_conv_ts_launch_count")())
+    got = run()
+    assert int(_lib.raw("scn_conv_ts_launch_count")()) == before + 6      # conv fwd + dx, unit: 2 fwd + 2 bwd
+    got2 = run()
+    for a, b, c, name in zip(got, ref, got2, ("conv fwd", "conv dx", "unit fwd", "unit dx")):
+        assert rel_err(a, b) <= 1e-6, (name, rel_err(a, b))
+        assert torch.equal(a, c), name                                # deterministic
+    monkeypatch.setenv("SCN_CONV_TS_SKIP", "0")
