@@ -29,29 +29,27 @@ assert dll.scn_debug_ts_trace(buf) == 0
 t = np.array(buf[:], dtype=np.int64)
 t0 = t[16000]
 mma = t[:4096].reshape(-1, 4)[:, :3]
-nu = int((mma[:, 0] > 0).sum())
-mma = mma[:nu] - t0
-ga = t[4096:4096 + 4 * nu].reshape(-1, 4) - t0
-print("units of CTA 0:", nu, " total cycles (first MMA stamp -> last):", int(mma[-1, 2] - mma[0, 0]))
+nb = int((mma[:, 0] > 0).sum())
+mma = mma[:nb] - t0
+ga = t[4096:4096 + 16 * nb].reshape(nb, 4, 4) - t0      # [batch, group, stamp]
+print("batches of CTA 0:", nb, " cycles first->last MMA stamp:", int(mma[-1, 2] - mma[0, 0]))
 d = np.diff(mma[:, 0])
-print("MMA loop period per unit: mean %.0f median %.0f p90 %.0f" % (d.mean(), np.median(d), np.percentile(d, 90)))
-print("MMA wait for a_full: mean %.0f median %.0f ; issue+commit+step: mean %.0f" % (
-    (mma[:, 1] - mma[:, 0]).mean(), np.median(mma[:, 1] - mma[:, 0]), (mma[:, 2] - mma[:, 1]).mean()))
-ok = ga[:, 0] > -10**12
-print("gather (q=0 warp of each group) per unit: wait a_empty %.0f | LDS+STTM issue %.0f | wait::st+arrive %.0f | total %.0f" % (
-    (ga[ok, 1] - ga[ok, 0]).mean(), (ga[ok, 2] - ga[ok, 1]).mean(), (ga[ok, 3] - ga[ok, 2]).mean(), (ga[ok, 3] - ga[ok, 0]).mean()))
-print("gather arrive -> MMA sees it (mma after-wait - gather arrive): mean %.0f median %.0f" % (
-    (mma[:, 1] - ga[:nu, 3]).mean(), np.median(mma[:, 1] - ga[:nu, 3])))
+print("MMA period per batch: mean %.0f median %.0f p90 %.0f | wait b_full mean %.0f median %.0f | issue+commit mean %.0f" % (
+    d.mean(), np.median(d), np.percentile(d, 90), (mma[:, 1] - mma[:, 0]).mean(), np.median(mma[:, 1] - mma[:, 0]),
+    (mma[:, 2] - mma[:, 1]).mean()))
+ok = ga[:, :, 0] > -10**12
 for g in range(4):
-    own = ga[g::4]
-    dd = np.diff(own[:, 0])
-    print(" group %d: period between own units: mean %.0f ; busy %.0f" % (g, dd.mean(), (own[:, 3] - own[:, 0]).mean()))
-ld = t[12000:12000 + 4 * 12].reshape(-1, 4)[:, :3] - t0
-ep = t[14000:14000 + 4 * 12].reshape(-1, 4)[:, :3] - t0
-hf = t[13000:13000 + 2 * 12].reshape(-1, 2) - t0
-print("loader per tile (start, after halo_empty wait, copies issued):"); print(ld[:10])
-print("gather waits halo_full (before, after):"); print(hf[:10])
-print("epilogue per tile (start wait, acc_full seen, done):"); print(ep[:10])
-print("first 40 units: MMA (top, ready, done) | gather (start, a_empty ok, sttm issued, arrived)")
-for i in range(40):
-    print(i, mma[i], ga[i])
+    x = ga[:, g][ok[:, g]]
+    print(" group %d (units %d): wait b_empty %.0f | LDS+STTM issue %.0f | wait::st+arrive %.0f | period %.0f" % (
+        g, len(x), (x[:, 1] - x[:, 0]).mean(), (x[:, 2] - x[:, 1]).mean(), (x[:, 3] - x[:, 2]).mean(), np.diff(x[:, 0]).mean()))
+last = np.where(ok, ga[:, :, 3], -10**15).max(1)
+print("last gather arrival of a batch -> MMA past its wait: mean %.0f median %.0f" % ((mma[:, 1] - last).mean(), np.median(mma[:, 1] - last)))
+ld = t[12000:12000 + 4 * 10].reshape(-1, 4)[:, :3] - t0
+ep = t[14000:14000 + 4 * 10].reshape(-1, 4)[:, :3] - t0
+hf = t[13000:13000 + 2 * 10].reshape(-1, 2) - t0
+print("loader per tile (start, after halo_empty wait, copies issued):"); print(ld[:9])
+print("gather g0 waits halo_full (before, after):"); print(hf[:9])
+print("epilogue per tile (start wait, acc_full seen, done):"); print(ep[:9])
+print("first 24 batches: MMA (top, ready, done) | last gather arrival | group0 (start, b_empty ok, sttm, arrived)")
+for i in range(24):
+    print(i, mma[i], int(last[i]), ga[i, 0])

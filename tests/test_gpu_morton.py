@@ -153,14 +153,16 @@ def test_tile_book_reproduces_the_map(cuda, bench_level):
     n = lvl.n
     nt = (n + 127) // 128
     a256 = lambda v: (v + 255) // 256 * 256
-    o0 = a256(nt * 27 * 128 * 2)
+    BLOB = 64 + 27 * 128 * 2
+    o0 = a256(nt * BLOB)
     o1 = o0 + a256(nt * 512 * 4)
     o2 = o1 + a256(nt * 4)
     assert int(_lib.raw("scn_tile_book_bytes")(n)) == o2 + a256(nt * 4)
-    lmap = book[:nt * 27 * 128 * 2].view(np.uint16).reshape(nt, 27, 128)
+    blobs = book[:nt * BLOB].reshape(nt, BLOB)
+    lmap = np.ascontiguousarray(blobs[:, 64:]).view(np.uint16).reshape(nt, 27, 128)
     rows = book[o0:o0 + nt * 512 * 4].view(np.int32).reshape(nt, 512)
     nloc = book[o1:o1 + nt * 4].view(np.int32)
-    umask = book[o2:o2 + nt * 4].view(np.uint32)
+    useq = book[o2:o2 + nt * 4].view(np.uint32)
     mp = np.full((27, nt * 128), -1, np.int32)
     mp[:, :n] = m.cpu().numpy()
     mp = mp.reshape(27, nt, 128).transpose(1, 0, 2)                   # [tile, offset, row]
@@ -171,12 +173,19 @@ def test_tile_book_reproduces_the_map(cuda, bench_level):
     t_idx = np.broadcast_to(np.arange(nt)[:, None, None], lmap.shape)
     assert np.array_equal(rows[t_idx[active], lmap[active]], mp[active])
     assert (lmap[active] < nloc[t_idx[active]]).all()
-    for t in (0, nt // 2, nt - 1):                                    # lists hold DISTINCT rows
+    for t in (0, nt // 2, nt - 1):                                    # lists hold DISTINCT rows in ascending order
         assert len(np.unique(rows[t, :nloc[t]])) == nloc[t] == len(np.unique(mp[t][mp[t] >= 0]))
-    ref_mask = ((mp >= 0).any(2) * (1 << np.arange(27))[None]).sum(1).astype(np.uint32)
-    assert np.array_equal(umask, ref_mask)
+        assert (np.diff(rows[t, :nloc[t]]) > 0).all()
+    # processing order: centre offset first, then the other active offsets ascending
+    for t in (0, 1, nt // 3, nt - 1):
+        act = np.nonzero(active[t].any(1))[0].tolist()
+        want = [13] + [o for o in act if o != 13]
+        assert blobs[t, 0] == len(want) and blobs[t, 1:1 + len(want)].tolist() == want
+        # the same order as a bit sequence: bit 0 = centre, bits 1..13 = offsets 0..12, bits 14..26 = offsets 14..26
+        bits = [b for b in range(27) if (int(useq[t]) >> b) & 1]
+        assert [13 if b == 0 else (b - 1 if b <= 13 else b) for b in bits] == want
     print("halo rows per tile: mean %.0f max %d; empty units %.1f %%" % (
-        nloc.mean(), nloc.max(), 100.0 * (1 - np.unpackbits(umask.view(np.uint8)).sum() / (27.0 * nt))))
+        nloc.mean(), nloc.max(), 100.0 * (1 - blobs[:, 0].astype(float).sum() / (27.0 * nt))))
 
 
 @pytest.mark.parametrize("C", [32, 16, 48, 64])
@@ -213,7 +222,10 @@ def test_tile_local_kernel_equals_rule_kernel(cuda, bench_level, monkeypatch, C)
     got = run()
     assert int(_lib.raw("scn_conv_ts_launch_count")()) == before + 6      # conv fwd + dx, unit: 2 fwd + 2 bwd
     got2 = run()
+    # Same TF32 products; the tile-local kernel adds the centre offset first, so fp32 sums differ in their last bit.  Through
+    # a residual unit that bit can flip the TF32 rounding (2^-11) of the inner activation: 1e-4 there, 1e-6 for a single layer.
     for a, b, c, name in zip(got, ref, got2, ("conv fwd", "conv dx", "unit fwd", "unit dx")):
-        assert rel_err(a, b) <= 1e-6, (name, rel_err(a, b))
+        assert rel_err(a, b) <= {"unit fwd": 1e-4, "unit dx": 2e-3}.get(name, 1e-6), (name, rel_err(a, b))
+        if name == "unit dx":      # ... and where that bit flips a ReLU mask, one gradient element toggles: rare
+            assert ((a - b).abs() > 1e-5 * b.abs().max()).float().mean() < 2e-3
         assert torch.equal(a, c), name                                # deterministic
-    monkeypatch.setenv("SCN_CONV_TS_SKIP", "0")
