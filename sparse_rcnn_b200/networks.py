@@ -82,77 +82,26 @@ class UNet(nn.Module):
 
 
 # ----------------------------------------------------------------------------- blocks
-FUSE = {"residual": True}      # set False to run the unfused scn.* module graph (identical numerics in fp32 mode)
+def _fuse_switch():
+    from .scn import layers
+    return layers.FUSE
+
+
+FUSE = _fuse_switch()          # the B200 backend's switch (scn/layers.py): False runs the unfused scn.* module graph
 
 
 def residual_unit(scn, cin, cout):
+    """module_factory.py:127-183 (relu_first, main_path_relu=False, bottleneck_divisor=0).  On the B200 backend
+    `scn.Sequential` recognises this module pattern itself and runs it fused -- also when the unmodified reference builds it."""
     shortcut = scn.Identity() if cin == cout else scn.NetworkInNetwork(cin, cout, True)
     inner = scn.Sequential(
         scn.ReLU(), scn.SubmanifoldConvolution(3, cin, cout, 3, True),
         scn.ReLU(), scn.SubmanifoldConvolution(3, cout, cout, 3, True))
-    unit = scn.Sequential(scn.ConcatTable(shortcut, inner), scn.AddTable())
-    if getattr(scn, "BACKEND", "") == "b200-cuda" and cin == cout:
-        unit.__class__ = _fused_class(scn)
-    return unit
-
-
-_FUSED_CLASSES = {}
-
-
-def _fused_class(scn):
-    """Same module tree (=> same state_dict keys) as the reference's residual unit, but forward runs
-    scn.functions.ResidualUnitFunction: two convolution launches + one elementwise pass."""
-    if scn not in _FUSED_CLASSES:
-        from .scn.functions import ResidualUnitFunction
-
-        class FusedResidualUnit(scn.Sequential):
-            def forward(self, x):
-                if not FUSE["residual"]:
-                    return super().forward(x)
-                inner = self[0]._modules["1"]
-                c1, c2 = inner[1], inner[3]
-                lvl = x.metadata.level(x.spatial_size)
-                f = ResidualUnitFunction.run(x.features, lvl.subm_map(c1.filter_size), lvl.n,
-                                               c1.weight, c1.bias, c2.weight, c2.bias)
-                return scn.SparseConvNetTensor(f, x.metadata, x.spatial_size)
-
-        _FUSED_CLASSES[scn] = FusedResidualUnit
-    return _FUSED_CLASSES[scn]
+    return scn.Sequential(scn.ConcatTable(shortcut, inner), scn.AddTable())
 
 
 def unit_stage(scn, channels, num_units):
-    stage = scn.Sequential(*[residual_unit(scn, channels, channels) for _ in range(num_units)])
-    if getattr(scn, "BACKEND", "") == "b200-cuda":
-        stage.__class__ = _fused_stage_class(scn)
-    return stage
-
-
-_FUSED_STAGES = {}
-
-
-def _fused_stage_class(scn):
-    """Same module tree as the reference's stack of residual units; forward runs the whole stack as ONE autograd node."""
-    if scn not in _FUSED_STAGES:
-        from .scn.functions import ResidualUnitFunction
-        fused_unit = _fused_class(scn)
-
-        class FusedUnitStage(scn.Sequential):
-            def forward(self, x):
-                units = list(self._modules.values())
-                if not FUSE["residual"] or not units or not all(type(u) is fused_unit for u in units):
-                    return super().forward(x)
-                params, fs = [], None
-                for u in units:
-                    inner = u[0]._modules["1"]
-                    c1, c2 = inner[1], inner[3]
-                    fs = c1.filter_size
-                    params += [c1.weight, c1.bias, c2.weight, c2.bias]
-                lvl = x.metadata.level(x.spatial_size)
-                f = ResidualUnitFunction.run(x.features, lvl.subm_map(fs), lvl.n, *params)
-                return scn.SparseConvNetTensor(f, x.metadata, x.spatial_size)
-
-        _FUSED_STAGES[scn] = FusedUnitStage
-    return _FUSED_STAGES[scn]
+    return scn.Sequential(*[residual_unit(scn, channels, channels) for _ in range(num_units)])
 
 
 def encoder_level(scn, cin, cout, stride, num_units):

@@ -48,10 +48,86 @@ def _like(x, features):
     return SparseConvNetTensor(features, x.metadata, x.spatial_size)
 
 
+FUSE = {"residual": True}      # False: run the plain module graph (identical numerics in fp32 mode; tests compare both)
+
+
+def _match_residual_unit(m):
+    """(conv1, conv2) if `m` is the residual unit that the reference's module_factory.py:51-57,127-183 builds for the
+    shipped sparse configuration (relu_first, no batch norm, identity shortcut):
+        Sequential(ConcatTable(Identity, Sequential(ReLU, SubM 3^3 C->C, ReLU, SubM 3^3 C->C)), AddTable)
+    else None.  Exact types only: a subclass may override forward."""
+    if type(m) is not Sequential or len(m) != 2:
+        return None
+    table, add = m[0], m[1]
+    if type(table) is not ConcatTable or type(add) is not AddTable or len(table._modules) != 2:
+        return None
+    shortcut, inner = table._modules["0"], table._modules["1"]
+    if type(shortcut) is not Identity or type(inner) is not Sequential or len(inner) != 4:
+        return None
+    r1, c1, r2, c2 = inner[0], inner[1], inner[2], inner[3]
+    if type(r1) is not ReLU or type(r2) is not ReLU:
+        return None
+    for c in (c1, c2):
+        if type(c) is not SubmanifoldConvolution or c.filter_size != (3, 3, 3) or c.dimension != 3:
+            return None
+    if not (c1.nIn == c1.nOut == c2.nIn == c2.nOut) or (c1.bias is None) != (c2.bias is None):
+        return None
+    return c1, c2
+
+
 class Sequential(nn.Sequential):
+    """Runs its children in order -- except that maximal runs of residual units over one level (the reference's
+    `unit_stage`, module_factory.py:438-578) execute as ONE autograd node, `functions.ResidualUnitFunction`: per unit one
+    elementwise pass + two gather-GEMMs whose epilogues carry ReLU, residual add and TF32 rounding.  The module tree, the
+    parameters and the state_dict keys are untouched, so the UNMODIFIED `ndsis.modules` graph gets the fused path; a
+    Sequential that is itself one residual unit is handled the same way."""
+
     def append(self, module):
         self.add_module(str(len(self._modules)), module)
         return self
+
+    def _plan(self):
+        mods = tuple(self._modules.values())
+        cached = self.__dict__.get("_scn_plan")
+        if cached is not None and cached[0] == tuple(id(m) for m in mods):
+            return cached[1]
+        plan = []
+        me = _match_residual_unit(self)
+        if me is not None:
+            plan.append(("units", [me]))
+        else:
+            for m in mods:
+                u = _match_residual_unit(m)
+                if u is None:
+                    plan.append(("module", m))
+                elif plan and plan[-1][0] == "units" and plan[-1][1][-1][1].nOut == u[0].nIn:
+                    plan[-1][1].append(u)
+                else:
+                    plan.append(("units", [u]))
+        if not any(kind == "units" for kind, _ in plan):
+            plan = None
+        self.__dict__["_scn_plan"] = (tuple(id(m) for m in mods), plan)
+        return plan
+
+    def forward(self, x):
+        plan = self._plan() if FUSE["residual"] else None
+        if plan is None:
+            for m in self._modules.values():
+                x = m(x)
+            return x
+        for kind, item in plan:
+            if kind == "module":
+                x = item(x)
+                continue
+            if not isinstance(x, SparseConvNetTensor) or not x.features.is_cuda:
+                raise RuntimeError("sparse_rcnn_b200.scn modules need CUDA SparseConvNetTensors (there is no CPU fallback)")
+            params = []
+            for c1, c2 in item:
+                params += [c1.weight, c1.bias, c2.weight, c2.bias]
+            lvl = x.metadata.level(x.spatial_size)
+            f = F.ResidualUnitFunction.run(x.features, lvl.subm_map(item[0][0].filter_size), lvl.n, *params)
+            x = SparseConvNetTensor(f, x.metadata, x.spatial_size)
+        return x
 
     def input_spatial_size(self, out_size):
         for m in reversed(list(self._modules.values())):

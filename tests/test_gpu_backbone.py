@@ -81,7 +81,7 @@ def test_fused_residual_unit_equals_module_graph(cuda, precision, tol):
     coords, feats, size = random_scene(3, channels=32, size=(28, 24, 16))
     _, tg = make_pair(scn, coords, feats, size, cuda)
     unit = networks.residual_unit(scn, 32, 32).to(cuda)
-    assert type(unit).__name__ == "FusedResidualUnit"
+    assert unit._plan() is not None and unit._plan()[0][0] == "units"      # scn.Sequential recognises the pattern
     outs, grads = [], []
     for fuse in (True, False):
         networks.FUSE["residual"] = fuse
