@@ -336,6 +336,29 @@ int scn_crop_select(const uint64_t* keys, const int32_t* sample_ptr, const int32
                     int P, int32_t* sel_pt, uint64_t* new_keys, uint8_t* is_inside,
                     scn_stream_t stream);
 
+/* ------------------------------------------------------------------ sparse U-Net executor ----
+ * FeatureExtractor.forward model.py:414-446 over the graph module_factory.py:438-578,789-830 builds (encoder levels:
+ * entry convolution + residual units; decoder levels: ReLU, Deconvolution, JoinTable with the skip connection,
+ * NetworkInNetwork, residual units) as ONE call per direction that enqueues every kernel of the pass
+ * (sparse_rcnn_b200/csrc/unet_exec.cu; host mirror: sparse_rcnn_b200/executor.py).
+ *   net : int64 layer table   [L] ; per encoder level [kind K cin cout w b img_f img_b n_units] + n_units x
+ *         [w1 b1 w2 b2 img1_f img2_f img1_b img2_b] ; per decoder level [K cin cout w b img_f img_b] (Deconvolution)
+ *         [cin cout w b img_f img_b] (NetworkInNetwork) [n_units] + units.  kind: 0 pass-through (level 0 only),
+ *         1 submanifold (K = 1 or 27), 2 Convolution 2^3/s2 (K = 8).  img_*: packed weight images (forward / transposed),
+ *         packed by the caller (scn_conv_pack_weights_multi); unused in fp32 mode.
+ *   geo : int64 geometry table, per level [rows, subm_map(3^3) ptr, cmap ptr (to the next coarser level), dmap ptr].
+ * scn_unet_plan: out[0..L) = offsets (floats) of the encoder outputs E_i in the forward arena (-1: the input itself),
+ * out[L..2L-1) = decoder outputs D_j, out[2L-1] = forward arena floats, out[2L] = backward arena floats. */
+int scn_unet_plan(const int64_t* net, const int64_t* geo, int64_t* out);
+int scn_unet_fwd(const int64_t* net, const int64_t* geo, const float* x, float* arena, int n_decoder_levels,
+                 int use_tf32, scn_stream_t stream);
+/* seeds[k]: incoming gradient of output k (order of scn_unet_plan) or 0.  pgrads: one pointer per parameter in table
+ * order (0 = not wanted); gradients are ADDED (zeroed buffers or the parameters' gradient buckets, training.py:458).
+ * gx: gradient wrt the input or NULL.  phases: bit 0 decoder, bit 1 encoder. */
+int scn_unet_bwd(const int64_t* net, const int64_t* geo, const float* x, const float* arena, float* bwd_arena,
+                 const int64_t* seeds, const int64_t* pgrads, float* gx, int phases, int use_tf32,
+                 scn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,417 @@
+// Native executor of the sparse U-Net (encoder pyramid + decoder with skip connections) that the reference assembles in
+// ndsis/modules/module_factory.py:438-578,789-830 and runs through model.py:414-446 (FeatureExtractor.forward):
+//
+//   encoder level i : [SubM K^3 | Convolution 2^3/s2]  ->  num_units residual units            E_i
+//   decoder level j : ReLU -> Deconvolution 2^3/s2 -> JoinTable(up, skip E_l) -> NetworkInNetwork -> residual units   D_j
+//
+// One C-ABI call per direction walks a LAYER TABLE (static: channel counts, parameter / packed-image pointers) against a
+// GEOMETRY TABLE (per scene: rows per level, neighbour maps) and enqueues every kernel of the pass on the caller's stream;
+// all activations live in ONE caller-allocated arena whose layout `scn_unet_plan` computes from the two tables.  Why: the
+// training step was host bound (profiles/r1_i_host_bound.md: 195 Python->C calls, 305 allocations, 47 autograd nodes per
+// step for ~380 kernels); the executor turns the backbone into 2 calls, 2 allocations and 1 autograd node without changing
+// which kernels run or in which order -- results are bit-identical to the per-layer entry points it sequences
+// (scn_conv_layer_*, scn_residual_unit_*; tests/test_gpu_executor.py).
+#include <cstring>
+#include "common.cuh"
+
+using namespace scn;
+
+#define SCN_TRY(call)          \
+    do {                       \
+        int rc__ = (call);     \
+        if (rc__) return rc__; \
+    } while (0)
+
+namespace {
+
+constexpr int MAX_LEVELS = 8, MAX_UNITS = 4;
+
+struct Conv {      // one convolution layer; kind 0 = absent (the level passes its input through)
+    int kind, K, cin, cout;
+    const float *w, *b;
+    void *img_f, *img_b;
+};
+struct Unit {
+    const float *w1, *b1, *w2, *b2;
+    void *i1f, *i2f, *i1b, *i2b;
+};
+struct Net {
+    int L;                                    // encoder levels; decoder levels = L - 1
+    Conv enc[MAX_LEVELS];
+    int enc_units[MAX_LEVELS];
+    Unit eu[MAX_LEVELS][MAX_UNITS];
+    Conv deconv[MAX_LEVELS], nin[MAX_LEVELS];      // decoder level j writes level l = L - 2 - j
+    int dec_units[MAX_LEVELS];
+    Unit du[MAX_LEVELS][MAX_UNITS];
+    int C[MAX_LEVELS];                        // channels of E_i
+    int CD[MAX_LEVELS];                       // channels of D_j
+};
+struct Geo {
+    int n[MAX_LEVELS];
+    const int32_t* subm[MAX_LEVELS];          // [27, n_i]
+    const int32_t* cmap[MAX_LEVELS];          // level i -> i+1: [8, n_{i+1}] children of each coarse row
+    const int32_t* dmap[MAX_LEVELS];          // level i+1 -> i: [8, n_i]   parent of each fine row per in-box offset
+};
+
+// ---- table formats (int64 words), written by sparse_rcnn_b200/executor.py -------------------------------------------------
+//  net : [L] then per encoder level  [kind K cin cout w b img_f img_b n_units] + n_units x [w1 b1 w2 b2 i1f i2f i1b i2b]
+//        then per decoder level      [K cin cout w b img_f img_b] (deconvolution) [cin cout w b img_f img_b] (1x1 layer)
+//                                    [n_units] + n_units x unit record
+//  geo : per level [n subm_map cmap_to_next dmap_from_next]
+template <class T>
+static T* as_ptr(int64_t v) { return reinterpret_cast<T*>(static_cast<uintptr_t>(v)); }
+
+static const int64_t* read_unit(const int64_t* p, Unit& u) {
+    u.w1 = as_ptr<const float>(p[0]), u.b1 = as_ptr<const float>(p[1]), u.w2 = as_ptr<const float>(p[2]), u.b2 = as_ptr<const float>(p[3]);
+    u.i1f = as_ptr<void>(p[4]), u.i2f = as_ptr<void>(p[5]), u.i1b = as_ptr<void>(p[6]), u.i2b = as_ptr<void>(p[7]);
+    return p + 8;
+}
+
+static int parse_net(const int64_t* p, Net& net) {
+    std::memset(&net, 0, sizeof(net));
+    net.L = (int)*p++;
+    SCN_REQUIRE(net.L >= 1 && net.L <= MAX_LEVELS, "unet: %d levels (1..%d supported)", net.L, MAX_LEVELS);
+    for (int i = 0; i < net.L; ++i) {
+        Conv& c = net.enc[i];
+        c.kind = (int)p[0], c.K = (int)p[1], c.cin = (int)p[2], c.cout = (int)p[3];
+        c.w = as_ptr<const float>(p[4]), c.b = as_ptr<const float>(p[5]), c.img_f = as_ptr<void>(p[6]), c.img_b = as_ptr<void>(p[7]);
+        net.enc_units[i] = (int)p[8];
+        p += 9;
+        SCN_REQUIRE(net.enc_units[i] >= 0 && net.enc_units[i] <= MAX_UNITS, "unet: %d units per level (max %d)", net.enc_units[i], MAX_UNITS);
+        SCN_REQUIRE(c.kind == 0 ? (i == 0 && net.enc_units[i] == 0) : (c.kind == 1 ? (c.K == 1 || c.K == 27) : (c.kind == 2 && c.K == 8 && i > 0)),
+                    "unet: bad entry layer at level %d", i);
+        for (int u = 0; u < net.enc_units[i]; ++u) p = read_unit(p, net.eu[i][u]);
+        net.C[i] = c.cout;
+    }
+    for (int j = 0; j < net.L - 1; ++j) {
+        Conv& d = net.deconv[j];
+        d.kind = 3, d.K = (int)p[0], d.cin = (int)p[1], d.cout = (int)p[2];
+        d.w = as_ptr<const float>(p[3]), d.b = as_ptr<const float>(p[4]), d.img_f = as_ptr<void>(p[5]), d.img_b = as_ptr<void>(p[6]);
+        p += 7;
+        Conv& m = net.nin[j];
+        m.kind = 4, m.K = 1, m.cin = (int)p[0], m.cout = (int)p[1];
+        m.w = as_ptr<const float>(p[2]), m.b = as_ptr<const float>(p[3]), m.img_f = as_ptr<void>(p[4]), m.img_b = as_ptr<void>(p[5]);
+        p += 6;
+        net.dec_units[j] = (int)*p++;
+        SCN_REQUIRE(net.dec_units[j] >= 0 && net.dec_units[j] <= MAX_UNITS, "unet: %d units per level (max %d)", net.dec_units[j], MAX_UNITS);
+        for (int u = 0; u < net.dec_units[j]; ++u) p = read_unit(p, net.du[j][u]);
+        const int l = net.L - 2 - j;
+        SCN_REQUIRE(d.K == 8 && d.cin == (j == 0 ? net.C[net.L - 1] : net.CD[j - 1]) && m.cin == d.cout + net.C[l],
+                    "unet: decoder level %d does not fit the encoder (channels)", j);
+        net.CD[j] = m.cout;
+    }
+    return SCN_OK;
+}
+
+static void parse_geo(const int64_t* p, const Net& net, Geo& g) {
+    std::memset(&g, 0, sizeof(g));
+    for (int i = 0; i < net.L; ++i, p += 4) {
+        g.n[i] = (int)p[0];
+        g.subm[i] = as_ptr<const int32_t>(p[1]), g.cmap[i] = as_ptr<const int32_t>(p[2]), g.dmap[i] = as_ptr<const int32_t>(p[3]);
+    }
+}
+
+// ---- arena layout -----------------------------------------------------------------------------------------------------------
+struct Cursor {
+    int64_t off = 0;      // in floats; every buffer starts on a 256-byte boundary
+    int64_t take(int64_t rows, int64_t cols) {
+        const int64_t at = off;
+        off += (rows * cols + 63) / 64 * 64;
+        return at;
+    }
+};
+struct Plan {
+    // forward (kept for the backward)
+    int64_t xr[MAX_LEVELS], c[MAX_LEVELS], er[MAX_LEVELS][MAX_UNITS], eh[MAX_LEVELS][MAX_UNITS], ey[MAX_LEVELS][MAX_UNITS];
+    int64_t rl[MAX_LEVELS], cat[MAX_LEVELS], catr[MAX_LEVELS], nin[MAX_LEVELS];
+    int64_t dr[MAX_LEVELS][MAX_UNITS], dh[MAX_LEVELS][MAX_UNITS], dy[MAX_LEVELS][MAX_UNITS];
+    int64_t E[MAX_LEVELS], D[MAX_LEVELS];      // outputs (E[0] = -1 when level 0 passes the input through)
+    int64_t fwd_total;
+    // backward
+    int64_t gD[MAX_LEVELS], gE[MAX_LEVELS], tmp[MAX_LEVELS];      // gradient wrt D_j / E_i, a level-sized temporary
+    int64_t u_gyr[MAX_LEVELS], u_gh[MAX_LEVELS], u_gx[MAX_LEVELS][2];      // unit scratch per level (shared by its stages)
+    int64_t g_round[MAX_LEVELS], g_cat[MAX_LEVELS], g_up[MAX_LEVELS], g_skip[MAX_LEVELS], g_rl[MAX_LEVELS];
+    int64_t bwd_total;
+};
+
+static void make_plan(const Net& net, const Geo& g, Plan& P) {
+    std::memset(&P, 0, sizeof(P));
+    Cursor f;
+    for (int i = 0; i < net.L; ++i) {
+        const Conv& e = net.enc[i];
+        const int n = g.n[i], n_in = i == 0 ? g.n[0] : g.n[i - 1];
+        if (e.kind) {
+            P.xr[i] = f.take(n_in, e.cin);
+            P.c[i] = f.take(n, e.cout);
+        }
+        for (int u = 0; u < net.enc_units[i]; ++u)
+            P.er[i][u] = f.take(n, net.C[i]), P.eh[i][u] = f.take(n, net.C[i]), P.ey[i][u] = f.take(n, net.C[i]);
+        P.E[i] = net.enc_units[i] ? P.ey[i][net.enc_units[i] - 1] : (e.kind ? P.c[i] : -1);
+    }
+    for (int j = 0; j < net.L - 1; ++j) {
+        const int l = net.L - 2 - j, n = g.n[l], c = net.CD[j], cw = net.nin[j].cin;
+        P.rl[j] = f.take(g.n[l + 1], net.deconv[j].cin);
+        P.cat[j] = f.take(n, cw), P.catr[j] = f.take(n, cw), P.nin[j] = f.take(n, c);
+        for (int u = 0; u < net.dec_units[j]; ++u) P.dr[j][u] = f.take(n, c), P.dh[j][u] = f.take(n, c), P.dy[j][u] = f.take(n, c);
+        P.D[j] = net.dec_units[j] ? P.dy[j][net.dec_units[j] - 1] : P.nin[j];
+    }
+    P.fwd_total = f.off;
+    Cursor b;
+    for (int i = 0; i < net.L; ++i) {
+        int cmax = net.C[i];
+        for (int j = 0; j < net.L - 1; ++j)
+            if (net.L - 2 - j == i && net.nin[j].cin > cmax) cmax = net.nin[j].cin;
+        const int n = g.n[i];
+        P.gE[i] = b.take(n, net.C[i]), P.tmp[i] = b.take(n, cmax);
+        P.u_gyr[i] = b.take(n, cmax), P.u_gh[i] = b.take(n, cmax), P.u_gx[i][0] = b.take(n, cmax), P.u_gx[i][1] = b.take(n, cmax);
+        P.g_round[i] = b.take(n, cmax);
+    }
+    for (int j = 0; j < net.L - 1; ++j) {
+        const int l = net.L - 2 - j, n = g.n[l];
+        P.gD[j] = b.take(n, net.CD[j]);
+        P.g_cat[j] = b.take(n, net.nin[j].cin), P.g_up[j] = b.take(n, net.deconv[j].cout), P.g_skip[j] = b.take(n, net.C[l]);
+        P.g_rl[j] = b.take(g.n[l + 1], net.deconv[j].cin);
+    }
+    P.bwd_total = b.off;
+}
+
+static int copy_cols(float* dst, int ld_dst, const float* src, int ld_src, int n, int cols, cudaStream_t st) {
+    if (n <= 0 || cols <= 0) return SCN_OK;
+    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)ld_dst * 4, src, (size_t)ld_src * 4, (size_t)cols * 4, (size_t)n,
+                                      cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) {
+        set_error("unet: cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
+        return SCN_ERR_CUDA;
+    }
+    return SCN_OK;
+}
+
+// a chain of residual units over one level, forward
+static int stage_fwd(const Unit* units, int U, const float* x, int n, int C, const int32_t* map, float* base, const int64_t* r,
+                     const int64_t* h, const int64_t* y, int tf32, scn_stream_t s) {
+    for (int u = 0; u < U; ++u) {
+        const Unit& q = units[u];
+        SCN_TRY(scn_residual_unit_fwd(x, n, C, map, 27, q.w1, q.b1, q.w2, q.b2, q.i1f, q.i2f, 0, base + r[u], base + h[u], base + y[u],
+                                      tf32, s));
+        x = base + y[u];
+    }
+    return SCN_OK;
+}
+
+// ... backward: gy -> gradient wrt the stage input (returned through *gx_out; it lives in the level's unit scratch)
+static int stage_bwd(const Unit* units, int U, const float* gy, int n, int C, const int32_t* map, const float* fbase, const int64_t* r,
+                     const int64_t* h, float* bbase, const Plan& P, int level, float* const* pg, int tf32, scn_stream_t s,
+                     const float** gx_out) {
+    for (int u = U - 1; u >= 0; --u) {
+        const Unit& q = units[u];
+        float* gx = bbase + P.u_gx[level][u & 1];
+        SCN_TRY(scn_residual_unit_bwd(gy, fbase + r[u], fbase + h[u], n, C, map, 27, q.w1, q.w2, q.i1b, q.i2b, 0, bbase + P.u_gyr[level],
+                                      bbase + P.u_gh[level], gx, pg[4 * u], pg[4 * u + 1], pg[4 * u + 2], pg[4 * u + 3], 1, tf32, s));
+        gy = gx;
+    }
+    *gx_out = gy;
+    return SCN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// offsets (in floats) of the outputs inside the forward arena: out[0 .. L) = E_i (-1: the input itself), out[L .. 2L-1) = D_j;
+// out[2L-1] = forward arena size, out[2L] = backward arena size (floats)
+int scn_unet_plan(const int64_t* net_table, const int64_t* geo_table, int64_t* out) {
+    SCN_REQUIRE(net_table && geo_table && out, "unet_plan: null table");
+    Net net;
+    SCN_TRY(parse_net(net_table, net));
+    Geo g;
+    parse_geo(geo_table, net, g);
+    Plan P;
+    make_plan(net, g, P);
+    for (int i = 0; i < net.L; ++i) out[i] = P.E[i];
+    for (int j = 0; j < net.L - 1; ++j) out[net.L + j] = P.D[j];
+    out[2 * net.L - 1] = P.fwd_total, out[2 * net.L] = P.bwd_total;
+    return SCN_OK;
+}
+
+int scn_unet_fwd(const int64_t* net_table, const int64_t* geo_table, const float* x, float* arena, int n_decoder_levels,
+                 int use_tf32, scn_stream_t stream) {
+    SCN_REQUIRE(net_table && geo_table && arena, "unet_fwd: null argument");
+    Net net;
+    SCN_TRY(parse_net(net_table, net));
+    Geo g;
+    parse_geo(geo_table, net, g);
+    Plan P;
+    make_plan(net, g, P);
+    cudaStream_t st = as_stream(stream);
+    const int tf32 = use_tf32 ? 1 : 0;
+    const float* cur = x;      // E_{i-1}
+    for (int i = 0; i < net.L; ++i) {
+        const Conv& e = net.enc[i];
+        const int n = g.n[i], n_in = i == 0 ? g.n[0] : g.n[i - 1];
+        if (e.kind) {
+            const int32_t* map = e.kind == 2 ? g.cmap[i - 1] : (e.K == 1 ? nullptr : g.subm[i]);
+            SCN_TRY(scn_conv_layer_fwd(cur, e.cin, n_in, e.cin, 0, arena + P.xr[i], map, n, e.K, e.w, e.img_f, 0, e.b, arena + P.c[i],
+                                       e.cout, tf32, stream));
+            cur = arena + P.c[i];
+        }
+        SCN_TRY(stage_fwd(net.eu[i], net.enc_units[i], cur, n, net.C[i], g.subm[i], arena, P.er[i], P.eh[i], P.ey[i], tf32, stream));
+        if (net.enc_units[i]) cur = arena + P.E[i];
+    }
+    const int nd = n_decoder_levels < net.L - 1 ? n_decoder_levels : net.L - 1;
+    for (int j = 0; j < nd; ++j) {
+        const int l = net.L - 2 - j, n = g.n[l], n_in = g.n[l + 1];
+        const Conv &d = net.deconv[j], &m = net.nin[j];
+        // ReLU (rounded in tf32 mode: a valid tensor-core operand) -> transposed convolution over dmap, written into the left
+        // columns of the joined buffer; the skip connection is copied beside it (JoinTable)
+        SCN_TRY(scn_relu_fwd(cur, arena + P.rl[j], (int64_t)n_in * d.cin, tf32, stream));
+        if (n > 0) {
+            if (tf32)
+                SCN_TRY(scn_conv_fwd_tf32(arena + P.rl[j], d.cin, d.cin, n_in, g.dmap[l], n, d.K, d.img_f, d.b, nullptr, 0, nullptr, 0,
+                                          arena + P.cat[j], m.cin, d.cout, 0, stream));
+            else
+                SCN_TRY(scn_conv_fwd_fp32(arena + P.rl[j], d.cin, d.cin, g.dmap[l], n, d.K, d.w, 0, 0, d.b, nullptr, 0, nullptr, 0,
+                                          arena + P.cat[j], m.cin, d.cout, 0, stream));
+        }
+        const float* skip = P.E[l] >= 0 ? arena + P.E[l] : x;
+        SCN_TRY(copy_cols(arena + P.cat[j] + d.cout, m.cin, skip, net.C[l], n, net.C[l], st));
+        SCN_TRY(scn_conv_layer_fwd(arena + P.cat[j], m.cin, n, m.cin, 0, arena + P.catr[j], nullptr, n, 1, m.w, m.img_f, 0, m.b,
+                                   arena + P.nin[j], m.cout, tf32, stream));
+        SCN_TRY(stage_fwd(net.du[j], net.dec_units[j], arena + P.nin[j], n, net.CD[j], g.subm[l], arena, P.dr[j], P.dh[j], P.dy[j], tf32,
+                          stream));
+        cur = arena + P.D[j];
+    }
+    return SCN_OK;
+}
+
+// seeds[k] (k as in scn_unet_plan's output order): incoming gradient of output k or NULL.  pgrads: one pointer per parameter in
+// table order (encoder level: entry w, b, then per unit w1 b1 w2 b2; decoder level: deconvolution w, b, 1x1 w, b, units), NULL =
+// not wanted; every gradient is ADDED to its buffer (zeroed by the caller, or the parameter's gradient bucket).  gx: gradient
+// wrt the network input or NULL.  phases: bit 0 = decoder, bit 1 = encoder (two calls let the caller start the allreduce of
+// the decoder's gradients while the encoder's backward runs; the second call must see the same seeds).
+int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float* x, const float* arena, float* barena,
+                 const int64_t* seeds, const int64_t* pgrads, float* gx, int phases, int use_tf32, scn_stream_t stream) {
+    SCN_REQUIRE(net_table && geo_table && arena && barena && seeds && pgrads, "unet_bwd: null argument");
+    Net net;
+    SCN_TRY(parse_net(net_table, net));
+    Geo g;
+    parse_geo(geo_table, net, g);
+    Plan P;
+    make_plan(net, g, P);
+    cudaStream_t st = as_stream(stream);
+    const int tf32 = use_tf32 ? 1 : 0, L = net.L;
+    const bool run_dec = phases & 1, run_enc = phases & 2;
+    // parameter-gradient pointers in table order
+    float* pg_enc[MAX_LEVELS][2 + 4 * MAX_UNITS];
+    float* pg_dec[MAX_LEVELS][4 + 4 * MAX_UNITS];
+    {
+        const int64_t* q = pgrads;
+        for (int i = 0; i < L; ++i) {
+            if (net.enc[i].kind) pg_enc[i][0] = as_ptr<float>(*q++), pg_enc[i][1] = as_ptr<float>(*q++);
+            else pg_enc[i][0] = pg_enc[i][1] = nullptr;
+            for (int u = 0; u < 4 * net.enc_units[i]; ++u) pg_enc[i][2 + u] = as_ptr<float>(*q++);
+        }
+        for (int j = 0; j < L - 1; ++j)
+            for (int u = 0; u < 4 + 4 * net.dec_units[j]; ++u) pg_dec[j][u] = as_ptr<float>(*q++);
+    }
+    // gradient of an output: nothing yet / the caller's seed (read only) / this call's buffer
+    struct Grad {
+        const float* seed;
+        float* buf;
+        bool have;      // buf holds a value
+    };
+    Grad gE[MAX_LEVELS], gD[MAX_LEVELS];
+    for (int i = 0; i < L; ++i) gE[i] = Grad{as_ptr<const float>(seeds[i]), barena + P.gE[i], false};
+    for (int j = 0; j < L - 1; ++j) gD[j] = Grad{as_ptr<const float>(seeds[L + j]), barena + P.gD[j], false};
+    // add a contribution that a kernel is about to write: returns where to write it; `commit` folds it in afterwards
+    auto target = [&](Grad& G, float* tmp) -> float* { return G.have ? tmp : G.buf; };
+    auto commit = [&](Grad& G, float* written, int64_t count, bool run) -> int {
+        if (G.have) {
+            if (run && count > 0) SCN_TRY(scn_add(G.buf, written, G.buf, count, stream));
+        } else {
+            G.have = true;
+        }
+        return SCN_OK;
+    };
+    // the value to back-propagate: seed + buffer
+    auto resolve = [&](Grad& G, int64_t count, bool run, const float** out) -> int {
+        if (G.have && G.seed) {
+            if (run && count > 0) SCN_TRY(scn_add(G.buf, G.seed, G.buf, count, stream));
+            *out = G.buf;
+        } else {
+            *out = G.have ? G.buf : G.seed;      // may be NULL: no gradient reaches this output
+        }
+        return SCN_OK;
+    };
+
+    for (int j = L - 2; j >= 0; --j) {
+        const int l = L - 2 - j, n = g.n[l], n_in = g.n[l + 1], c = net.CD[j];
+        const Conv &d = net.deconv[j], &m = net.nin[j];
+        const float* gy = nullptr;
+        SCN_TRY(resolve(gD[j], (int64_t)n * c, run_dec, &gy));
+        if (!gy) continue;
+        Grad& below = j == 0 ? gE[L - 1] : gD[j - 1];      // gradient of this level's input
+        if (run_dec) {
+            const float* g_nin = gy;
+            SCN_TRY(stage_bwd(net.du[j], net.dec_units[j], gy, n, c, g.subm[l], arena, P.dr[j], P.dh[j], barena, P, l, pg_dec[j] + 4, tf32,
+                              stream, &g_nin));
+            // 1x1 layer over the joined columns: input gradient [n, cin], weight + bias gradient
+            SCN_TRY(scn_conv_layer_bwd(g_nin, n, m.cout, 0, barena + P.g_round[l], arena + P.cat[j], m.cin, n, m.cin, nullptr, nullptr, 1, m.w,
+                                       m.img_b, 0, 0, barena + P.g_cat[j], pg_dec[j][2], pg_dec[j][3], tf32, stream));
+            // split the joined gradient: left columns -> transposed convolution, right columns -> the skip connection
+            SCN_TRY(copy_cols(barena + P.g_up[j], d.cout, barena + P.g_cat[j], m.cin, n, d.cout, st));
+        }
+        {
+            float* skip_to = target(gE[l], barena + P.g_skip[j]);
+            if (run_dec) SCN_TRY(copy_cols(skip_to, net.C[l], barena + P.g_cat[j] + d.cout, m.cin, n, net.C[l], st));
+            SCN_TRY(commit(gE[l], skip_to, (int64_t)n * net.C[l], run_dec));
+        }
+        if (run_dec) {
+            // transposed convolution backward: the input gradient runs over cmap (children of each coarse row)
+            SCN_TRY(scn_conv_layer_bwd(barena + P.g_up[j], n, d.cout, 0, barena + P.g_round[l], arena + P.rl[j], d.cin, n_in, d.cin, g.dmap[l],
+                                       g.cmap[l], d.K, d.w, d.img_b, 0, 0, barena + P.g_rl[j], pg_dec[j][0], pg_dec[j][1], tf32, stream));
+        }
+        {
+            float* to = target(below, barena + P.tmp[l + 1]);
+            if (run_dec) SCN_TRY(scn_relu_bwd(arena + P.rl[j], barena + P.g_rl[j], to, (int64_t)n_in * d.cin, tf32, stream));
+            SCN_TRY(commit(below, to, (int64_t)n_in * d.cin, run_dec));
+        }
+    }
+    for (int i = L - 1; i >= 0; --i) {
+        const Conv& e = net.enc[i];
+        const int n = g.n[i], n_in = i == 0 ? g.n[0] : g.n[i - 1];
+        const float* gy = nullptr;
+        SCN_TRY(resolve(gE[i], (int64_t)n * net.C[i], run_enc, &gy));
+        if (!gy) continue;
+        const float* g_c = gy;
+        if (run_enc)
+            SCN_TRY(stage_bwd(net.eu[i], net.enc_units[i], gy, n, net.C[i], g.subm[i], arena, P.er[i], P.eh[i], barena, P, i, pg_enc[i] + 2, tf32,
+                              stream, &g_c));
+        if (!e.kind) {      // pass-through level 0: its gradient IS the input gradient
+            if (gx && run_enc && n > 0) {
+                cudaError_t err = cudaMemcpyAsync(gx, g_c, (size_t)n * net.C[i] * 4, cudaMemcpyDeviceToDevice, st);
+                SCN_REQUIRE(err == cudaSuccess, "unet_bwd: copy of the input gradient: %s", cudaGetErrorString(err));
+            }
+            continue;
+        }
+        const int32_t* fmap = e.kind == 2 ? g.cmap[i - 1] : (e.K == 1 ? nullptr : g.subm[i]);
+        const int32_t* bmap = e.kind == 2 ? g.dmap[i - 1] : fmap;
+        // the layer's input as the forward received it (the weight-gradient MMAs truncate it, exactly like the per-layer path
+        // that saves the unrounded tensor); xr / catr are only the forward's rounded operands
+        const float* x_in = (i == 0 || P.E[i - 1] < 0) ? x : arena + P.E[i - 1];
+        const int reverse = e.kind == 1 ? 1 : 0;
+        if (i == 0) {
+            if (run_enc)
+                SCN_TRY(scn_conv_layer_bwd(g_c, n, e.cout, 0, barena + P.g_round[i], x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w,
+                                           e.img_b, 0, reverse, gx, pg_enc[i][0], pg_enc[i][1], tf32, stream));
+        } else {
+            float* to = target(gE[i - 1], barena + P.tmp[i - 1]);
+            if (run_enc)
+                SCN_TRY(scn_conv_layer_bwd(g_c, n, e.cout, 0, barena + P.g_round[i], x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w,
+                                           e.img_b, 0, reverse, to, pg_enc[i][0], pg_enc[i][1], tf32, stream));
+            SCN_TRY(commit(gE[i - 1], to, (int64_t)n_in * e.cin, run_enc));
+        }
+    }
+    return SCN_OK;
+}
+
+}  // extern "C"

@@ -76,7 +76,23 @@ class UNet(nn.Module):
         super().__init__()
         self.downsampling_layer, self.upsampling_layer = down, up
 
+    def _executor(self, x):
+        """Native executor program for this U-Net on the B200 backend (same rule as FeatureExtractor._executor)."""
+        if not hasattr(getattr(x, "metadata", None), "prebuild"):
+            return None
+        from . import executor
+        if not (executor.ENABLED["unet"] and FUSE["residual"]):
+            return None
+        if "_program" not in self.__dict__:
+            self.__dict__["_program"] = executor.UNetProgram.compile(list(self.downsampling_layer),
+                                                                     list(self.upsampling_layer.module_list))
+        return self.__dict__["_program"]
+
     def forward(self, x):
+        prog = self._executor(x)
+        if prog is not None:
+            inter, ups = prog.run(x)
+            return ups if isinstance(self.upsampling_layer, ReuniteInterims) else ups[-1]
         *skip, out = self.downsampling_layer(x)
         return self.upsampling_layer(out, skip[::-1])
 
@@ -194,13 +210,34 @@ class FeatureExtractor(nn.Module):
         else:
             self.unet = None
 
+    def _executor(self):
+        """Compiled layer table of main_network + unet for the native executor, or None (other backends, switched off,
+        or a module tree the compiler does not recognise)."""
+        if getattr(self.scn, "BACKEND", "") != "b200-cuda":
+            return None
+        from . import executor
+        if not (executor.ENABLED["unet"] and FUSE["residual"]):
+            return None
+        if "_program" not in self.__dict__:
+            ups = list(self.unet.module_list) if self.include_unet else []
+            self.__dict__["_program"] = executor.UNetProgram.compile(list(self.main_network), ups)
+        return self.__dict__["_program"]
+
     def forward(self, data):
         scene_size, batch_size, x = self.input_stage(data)
         if hasattr(x.metadata, "prebuild"):         # B200 backend: front-load the rulebook builder's host syncs
             x.metadata.prebuild(len(self.channels) - 1)
-        inter = self.main_network(x)
+        prog = self._executor()
+        if prog is not None:
+            # B200 backend: encoder + decoder as ONE native call per direction (executor.py / csrc/unet_exec.cu); the same
+            # kernels in the same order as the module graph below
+            inter, unet_out = prog.run(x)
+            if not self.include_unet:
+                unet_out = None
+        else:
+            inter = self.main_network(x)
+            unet_out = self.unet(inter[-1], inter[:-1][::-1]) if self.include_unet else None
         extended = [x] + inter
-        unet_out = self.unet(inter[-1], inter[:-1][::-1]) if self.include_unet else None
         class_out = extended[self.class_output_index]
         return scene_size, batch_size, [], class_out, inter, unet_out
 

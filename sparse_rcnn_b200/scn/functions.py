@@ -32,6 +32,9 @@ class _NullCtx:
     def save_for_backward(self, *tensors):
         pass
 
+    def set_materialize_grads(self, value):
+        pass
+
 
 class Function(torch.autograd.Function):
     """torch.autograd.Function plus `run`: the same as `apply` while gradients are recorded; under `torch.no_grad()`
