@@ -11,7 +11,10 @@
 // step for ~380 kernels); the executor turns the backbone into 2 calls, 2 allocations and 1 autograd node without changing
 // which kernels run or in which order -- results are bit-identical to the per-layer entry points it sequences
 // (scn_conv_layer_*, scn_residual_unit_*; tests/test_gpu_executor.py).
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include "common.cuh"
 
 using namespace scn;
@@ -129,8 +132,12 @@ struct Plan {
     int64_t fwd_total;
     // backward
     int64_t gD[MAX_LEVELS], gE[MAX_LEVELS], tmp[MAX_LEVELS];      // gradient wrt D_j / E_i, a level-sized temporary
-    int64_t u_gyr[MAX_LEVELS], u_gh[MAX_LEVELS], u_gx[MAX_LEVELS][2];      // unit scratch per level (shared by its stages)
-    int64_t g_round[MAX_LEVELS], g_cat[MAX_LEVELS], g_up[MAX_LEVELS], g_skip[MAX_LEVELS], g_rl[MAX_LEVELS];
+    // scratch of every unit and layer is its own: the weight gradients run on a side stream and read these buffers while
+    // the main stream is already working on the next layer
+    int64_t e_gyr[MAX_LEVELS][MAX_UNITS], e_gh[MAX_LEVELS][MAX_UNITS], e_gx[MAX_LEVELS][MAX_UNITS], e_round[MAX_LEVELS];
+    int64_t d_gyr[MAX_LEVELS][MAX_UNITS], d_gh[MAX_LEVELS][MAX_UNITS], d_gx[MAX_LEVELS][MAX_UNITS], d_round_nin[MAX_LEVELS],
+        d_round_up[MAX_LEVELS];
+    int64_t g_cat[MAX_LEVELS], g_up[MAX_LEVELS], g_skip[MAX_LEVELS], g_rl[MAX_LEVELS];
     int64_t bwd_total;
 };
 
@@ -163,12 +170,16 @@ static void make_plan(const Net& net, const Geo& g, Plan& P) {
             if (net.L - 2 - j == i && net.nin[j].cin > cmax) cmax = net.nin[j].cin;
         const int n = g.n[i];
         P.gE[i] = b.take(n, net.C[i]), P.tmp[i] = b.take(n, cmax);
-        P.u_gyr[i] = b.take(n, cmax), P.u_gh[i] = b.take(n, cmax), P.u_gx[i][0] = b.take(n, cmax), P.u_gx[i][1] = b.take(n, cmax);
-        P.g_round[i] = b.take(n, cmax);
+        P.e_round[i] = b.take(n, net.C[i]);
+        for (int u = 0; u < net.enc_units[i]; ++u)
+            P.e_gyr[i][u] = b.take(n, net.C[i]), P.e_gh[i][u] = b.take(n, net.C[i]), P.e_gx[i][u] = b.take(n, net.C[i]);
     }
     for (int j = 0; j < net.L - 1; ++j) {
         const int l = net.L - 2 - j, n = g.n[l];
         P.gD[j] = b.take(n, net.CD[j]);
+        P.d_round_nin[j] = b.take(n, net.CD[j]), P.d_round_up[j] = b.take(n, net.deconv[j].cout);
+        for (int u = 0; u < net.dec_units[j]; ++u)
+            P.d_gyr[j][u] = b.take(n, net.CD[j]), P.d_gh[j][u] = b.take(n, net.CD[j]), P.d_gx[j][u] = b.take(n, net.CD[j]);
         P.g_cat[j] = b.take(n, net.nin[j].cin), P.g_up[j] = b.take(n, net.deconv[j].cout), P.g_skip[j] = b.take(n, net.C[l]);
         P.g_rl[j] = b.take(g.n[l + 1], net.deconv[j].cin);
     }
@@ -198,18 +209,145 @@ static int stage_fwd(const Unit* units, int U, const float* x, int n, int C, con
     return SCN_OK;
 }
 
-// ... backward: gy -> gradient wrt the stage input (returned through *gx_out; it lives in the level's unit scratch)
+// ---- weight gradients on a side stream -----------------------------------------------------------------------------------------
+// In the backward pass only the input gradients form a dependency chain; a layer's weight (+ bias) gradient is needed by
+// nobody before the optimizer.  They are enqueued on a second stream that forks from the main stream where their operands
+// are ready and joins it at the end of the call: on the small levels (a handful of tiles, latency bound) they run beside
+// the chain instead of in it; on the large levels the SMs are full either way.  SCN_EXEC_SIDE=0 keeps everything in line.
+struct Side {
+    cudaStream_t main, side;
+    bool on;
+    cudaEvent_t ev[8];
+    int next = 0;
+    bool used = false;
+    int fork() {      // the side stream waits for everything enqueued on the main stream so far
+        if (!on) return SCN_OK;
+        cudaEvent_t e = ev[next++ & 7];
+        if (cudaEventRecord(e, main) != cudaSuccess || cudaStreamWaitEvent(side, e, 0) != cudaSuccess) {
+            set_error("unet_bwd: stream fork: %s", cudaGetErrorString(cudaGetLastError()));
+            return SCN_ERR_CUDA;
+        }
+        used = true;
+        return SCN_OK;
+    }
+    int join() {
+        if (!on || !used) return SCN_OK;
+        cudaEvent_t e = ev[next++ & 7];
+        if (cudaEventRecord(e, side) != cudaSuccess || cudaStreamWaitEvent(main, e, 0) != cudaSuccess) {
+            set_error("unet_bwd: stream join: %s", cudaGetErrorString(cudaGetLastError()));
+            return SCN_ERR_CUDA;
+        }
+        used = false;
+        return SCN_OK;
+    }
+    scn_stream_t wstream() const { return reinterpret_cast<scn_stream_t>(on ? side : main); }
+};
+
+struct SideResources {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev[8];
+};
+static int side_for(cudaStream_t main, Side& S) {
+    static std::mutex mu;
+    static std::unordered_map<cudaStream_t, SideResources> pool;      // one side stream per calling stream (host threads)
+    static int enabled = -1;
+    std::lock_guard<std::mutex> lock(mu);
+    if (enabled < 0) {
+        const char* e = getenv("SCN_EXEC_SIDE");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    S.main = main, S.side = main, S.on = false;
+    if (!enabled) return SCN_OK;
+    auto it = pool.find(main);
+    if (it == pool.end()) {
+        SideResources r;
+        if (cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error("unet_bwd: cudaStreamCreate: %s", cudaGetErrorString(cudaGetLastError()));
+            return SCN_ERR_CUDA;
+        }
+        for (auto& e : r.ev)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+                set_error("unet_bwd: cudaEventCreate: %s", cudaGetErrorString(cudaGetLastError()));
+                return SCN_ERR_CUDA;
+            }
+        it = pool.emplace(main, r).first;
+    }
+    S.side = it->second.side, S.on = true;
+    for (int i = 0; i < 8; ++i) S.ev[i] = it->second.ev[i];
+    return SCN_OK;
+}
+
+// one residual unit backward: the kernels of scn_residual_unit_bwd (accumulate mode), input-gradient chain on the main
+// stream, the two weight gradients on the side stream
+static int unit_bwd(const Unit& q, const float* gy, const float* r, const float* h, int n, int C, const int32_t* map, float* gyr,
+                    float* gh, float* gx, float* gw1, float* gb1, float* gw2, float* gb2, int tf32, scn_stream_t s, Side& side) {
+    if (n == 0) return SCN_OK;
+    const int K = 27;
+    const int64_t total = (int64_t)n * C;
+    const float* g_op = gy;
+    if (tf32) {
+        SCN_TRY(scn_round_tf32(gy, gyr, total, s));
+        g_op = gyr;
+    }
+    if (gw2 || gb2) {
+        SCN_TRY(side.fork());
+        if (gw2) SCN_TRY(scn_conv_bwd_weight(h, C, C, map, n, K, g_op, C, C, gw2, gb2, tf32, side.wstream()));
+        else SCN_TRY(scn_col_sum_add(gy, C, n, C, gb2, side.wstream()));
+    }
+    if (tf32)
+        SCN_TRY(scn_conv_fwd_tf32(g_op, C, C, n, map, n, K, q.i2b, nullptr, nullptr, 0, h, C, gh, C, C, SCN_EPI_MASK | SCN_EPI_ROUND, s));
+    else
+        SCN_TRY(scn_conv_fwd_fp32(g_op, C, C, map, n, K, q.w2, 1, 1, nullptr, nullptr, 0, h, C, gh, C, C, SCN_EPI_MASK, s));
+    if (gw1 || gb1) {
+        SCN_TRY(side.fork());
+        if (gw1) SCN_TRY(scn_conv_bwd_weight(r, C, C, map, n, K, gh, C, C, gw1, gb1, tf32, side.wstream()));
+        else SCN_TRY(scn_col_sum_add(gh, C, n, C, gb1, side.wstream()));
+    }
+    if (tf32)
+        SCN_TRY(scn_conv_fwd_tf32(gh, C, C, n, map, n, K, q.i1b, nullptr, gy, C, r, C, gx, C, C, SCN_EPI_MASK | SCN_EPI_ADD, s));
+    else
+        SCN_TRY(scn_conv_fwd_fp32(gh, C, C, map, n, K, q.w1, 1, 1, nullptr, gy, C, r, C, gx, C, C, SCN_EPI_MASK | SCN_EPI_ADD, s));
+    return SCN_OK;
+}
+
+// ... a chain of units: gy -> gradient wrt the stage input (returned through *gx_out)
 static int stage_bwd(const Unit* units, int U, const float* gy, int n, int C, const int32_t* map, const float* fbase, const int64_t* r,
-                     const int64_t* h, float* bbase, const Plan& P, int level, float* const* pg, int tf32, scn_stream_t s,
-                     const float** gx_out) {
+                     const int64_t* h, float* bbase, const int64_t* gyr, const int64_t* gh, const int64_t* gxs, float* const* pg, int tf32,
+                     scn_stream_t s, Side& side, const float** gx_out) {
     for (int u = U - 1; u >= 0; --u) {
-        const Unit& q = units[u];
-        float* gx = bbase + P.u_gx[level][u & 1];
-        SCN_TRY(scn_residual_unit_bwd(gy, fbase + r[u], fbase + h[u], n, C, map, 27, q.w1, q.w2, q.i1b, q.i2b, 0, bbase + P.u_gyr[level],
-                                      bbase + P.u_gh[level], gx, pg[4 * u], pg[4 * u + 1], pg[4 * u + 2], pg[4 * u + 3], 1, tf32, s));
+        float* gx = bbase + gxs[u];
+        SCN_TRY(unit_bwd(units[u], gy, fbase + r[u], fbase + h[u], n, C, map, bbase + gyr[u], bbase + gh[u], gx, pg[4 * u], pg[4 * u + 1],
+                         pg[4 * u + 2], pg[4 * u + 3], tf32, s, side));
         gy = gx;
     }
     *gx_out = gy;
+    return SCN_OK;
+}
+
+// one convolution layer backward: the kernels of scn_conv_layer_bwd, weight gradient on the side stream
+static int conv_bwd(const float* go, int n_out, int Cout, float* go_round, const float* x, int ld_x, int n_in, int Cin,
+                    const int32_t* fmap, const int32_t* bmap, int K, const float* w, void* image_t, int reverse, float* gx, float* gw,
+                    float* gb, int tf32, scn_stream_t s, Side& side) {
+    if (n_out == 0) {
+        if (gx && n_in > 0) cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)n_in * Cin, as_stream(s));
+        return check_launch("unet_bwd(memset)");
+    }
+    const float* g = go;
+    if (tf32 && (gx || gw)) {
+        SCN_TRY(scn_round_tf32(go, go_round, (int64_t)n_out * Cout, s));
+        g = go_round;
+    }
+    if (gw || gb) {
+        SCN_TRY(side.fork());
+        if (gw) SCN_TRY(scn_conv_bwd_weight(x, ld_x, Cin, fmap, n_out, K, g, Cout, Cout, gw, gb, tf32, side.wstream()));
+        else SCN_TRY(scn_col_sum_add(go, Cout, n_out, Cout, gb, side.wstream()));
+    }
+    if (gx && n_in > 0) {
+        if (tf32)
+            SCN_TRY(scn_conv_fwd_tf32(g, Cout, Cout, n_out, bmap, n_in, K, image_t, nullptr, nullptr, 0, nullptr, 0, gx, Cin, Cin, 0, s));
+        else
+            SCN_TRY(scn_conv_fwd_fp32(g, Cout, Cout, bmap, n_in, K, w, 1, reverse, nullptr, nullptr, 0, nullptr, 0, gx, Cin, Cin, 0, s));
+    }
     return SCN_OK;
 }
 
@@ -300,6 +438,8 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
     cudaStream_t st = as_stream(stream);
     const int tf32 = use_tf32 ? 1 : 0, L = net.L;
     const bool run_dec = phases & 1, run_enc = phases & 2;
+    Side side;
+    SCN_TRY(side_for(st, side));
     // parameter-gradient pointers in table order
     float* pg_enc[MAX_LEVELS][2 + 4 * MAX_UNITS];
     float* pg_dec[MAX_LEVELS][4 + 4 * MAX_UNITS];
@@ -352,11 +492,11 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         Grad& below = j == 0 ? gE[L - 1] : gD[j - 1];      // gradient of this level's input
         if (run_dec) {
             const float* g_nin = gy;
-            SCN_TRY(stage_bwd(net.du[j], net.dec_units[j], gy, n, c, g.subm[l], arena, P.dr[j], P.dh[j], barena, P, l, pg_dec[j] + 4, tf32,
-                              stream, &g_nin));
+            SCN_TRY(stage_bwd(net.du[j], net.dec_units[j], gy, n, c, g.subm[l], arena, P.dr[j], P.dh[j], barena, P.d_gyr[j], P.d_gh[j],
+                              P.d_gx[j], pg_dec[j] + 4, tf32, stream, side, &g_nin));
             // 1x1 layer over the joined columns: input gradient [n, cin], weight + bias gradient
-            SCN_TRY(scn_conv_layer_bwd(g_nin, n, m.cout, 0, barena + P.g_round[l], arena + P.cat[j], m.cin, n, m.cin, nullptr, nullptr, 1, m.w,
-                                       m.img_b, 0, 0, barena + P.g_cat[j], pg_dec[j][2], pg_dec[j][3], tf32, stream));
+            SCN_TRY(conv_bwd(g_nin, n, m.cout, barena + P.d_round_nin[j], arena + P.cat[j], m.cin, n, m.cin, nullptr, nullptr, 1, m.w, m.img_b,
+                             0, barena + P.g_cat[j], pg_dec[j][2], pg_dec[j][3], tf32, stream, side));
             // split the joined gradient: left columns -> transposed convolution, right columns -> the skip connection
             SCN_TRY(copy_cols(barena + P.g_up[j], d.cout, barena + P.g_cat[j], m.cin, n, d.cout, st));
         }
@@ -367,8 +507,8 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         }
         if (run_dec) {
             // transposed convolution backward: the input gradient runs over cmap (children of each coarse row)
-            SCN_TRY(scn_conv_layer_bwd(barena + P.g_up[j], n, d.cout, 0, barena + P.g_round[l], arena + P.rl[j], d.cin, n_in, d.cin, g.dmap[l],
-                                       g.cmap[l], d.K, d.w, d.img_b, 0, 0, barena + P.g_rl[j], pg_dec[j][0], pg_dec[j][1], tf32, stream));
+            SCN_TRY(conv_bwd(barena + P.g_up[j], n, d.cout, barena + P.d_round_up[j], arena + P.rl[j], d.cin, n_in, d.cin, g.dmap[l], g.cmap[l],
+                             d.K, d.w, d.img_b, 0, barena + P.g_rl[j], pg_dec[j][0], pg_dec[j][1], tf32, stream, side));
         }
         {
             float* to = target(below, barena + P.tmp[l + 1]);
@@ -384,8 +524,8 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         if (!gy) continue;
         const float* g_c = gy;
         if (run_enc)
-            SCN_TRY(stage_bwd(net.eu[i], net.enc_units[i], gy, n, net.C[i], g.subm[i], arena, P.er[i], P.eh[i], barena, P, i, pg_enc[i] + 2, tf32,
-                              stream, &g_c));
+            SCN_TRY(stage_bwd(net.eu[i], net.enc_units[i], gy, n, net.C[i], g.subm[i], arena, P.er[i], P.eh[i], barena, P.e_gyr[i], P.e_gh[i],
+                              P.e_gx[i], pg_enc[i] + 2, tf32, stream, side, &g_c));
         if (!e.kind) {      // pass-through level 0: its gradient IS the input gradient
             if (gx && run_enc && n > 0) {
                 cudaError_t err = cudaMemcpyAsync(gx, g_c, (size_t)n * net.C[i] * 4, cudaMemcpyDeviceToDevice, st);
@@ -401,17 +541,17 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         const int reverse = e.kind == 1 ? 1 : 0;
         if (i == 0) {
             if (run_enc)
-                SCN_TRY(scn_conv_layer_bwd(g_c, n, e.cout, 0, barena + P.g_round[i], x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w,
-                                           e.img_b, 0, reverse, gx, pg_enc[i][0], pg_enc[i][1], tf32, stream));
+                SCN_TRY(conv_bwd(g_c, n, e.cout, barena + P.e_round[i], x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w, e.img_b, reverse, gx,
+                                 pg_enc[i][0], pg_enc[i][1], tf32, stream, side));
         } else {
             float* to = target(gE[i - 1], barena + P.tmp[i - 1]);
             if (run_enc)
-                SCN_TRY(scn_conv_layer_bwd(g_c, n, e.cout, 0, barena + P.g_round[i], x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w,
-                                           e.img_b, 0, reverse, to, pg_enc[i][0], pg_enc[i][1], tf32, stream));
+                SCN_TRY(conv_bwd(g_c, n, e.cout, barena + P.e_round[i], x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w, e.img_b, reverse, to,
+                                 pg_enc[i][0], pg_enc[i][1], tf32, stream, side));
             SCN_TRY(commit(gE[i - 1], to, (int64_t)n_in * e.cin, run_enc));
         }
     }
-    return SCN_OK;
+    return side.join();      // the caller's stream continues (optimizer, allreduce) only after every weight gradient
 }
 
 }  // extern "C"
