@@ -143,40 +143,59 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def time_dominant_kernel(dev, trainer_backbone_md, n_iter=20):
-    """Live roofline measurement of k_conv_tc on the L0 SubM 3^3 32->32 layer (CUDA events on the
-    launching stream, L2 flushed between launches)."""
+def time_kernels(dev, md_size, n_iter=20):
+    """Live roofline measurements on the level-0 geometry of a bench scene: the dominant kernel (SubM 3^3 32->32 forward,
+    k_conv_ts), its weight gradient (k_conv_wgrad_tc) and the rulebook kernel (k_subm_map).  Each kernel is launched through
+    its C-ABI entry point directly (no Python layer code between the events), n_iter times with an L2 flush (256 MB memset)
+    in front of every launch; all event pairs are queued before the one synchronisation, and the flush kernel in front of
+    each pair gives the host ~80 us to enqueue the next launch, so host jitter is not inside any pair."""
     from sparse_rcnn_b200 import scn, _lib
-    md, size = trainer_backbone_md
-    lvl = md.level(size)
-    n = lvl.n
-    C = 32
-    conv = scn.SubmanifoldConvolution(3, C, C, 3, True).to(dev)
-    x = torch.randn(n, C, device=dev)
     from sparse_rcnn_b200.scn import functions as Fn
-    xr = Fn.tf32_exact(x)
-    t = scn.SparseConvNetTensor(xr, md, size)
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    from sparse_rcnn_b200.scn.metadata import _stream
+    md, size = md_size
+    lvl = md.level(size)
+    n, C, K = lvl.n, 32, 27
+    P = lambda t: t.data_ptr()
+    s = _stream()
     m = lvl.subm_map(3)
     pairs = int((m >= 0).sum().item())
-    with torch.no_grad():
+    w = torch.randn(K, C, C, device=dev) * 0.05
+    img = torch.empty(int(_lib.raw("scn_conv_weight_image_bytes")(K, C, C)), dtype=torch.uint8, device=dev)
+    _lib.call("scn_conv_pack_weights", P(w), K, C, C, 0, 0, P(img), s)
+    x = Fn.tf32_exact(torch.randn(n, C, device=dev))
+    go = Fn.tf32_exact(torch.randn(n, C, device=dev))
+    out = torch.empty(n, C, device=dev)
+    gw, gb = torch.zeros(K, C, C, device=dev), torch.zeros(C, device=dev)
+    m2 = torch.empty_like(m)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    ts0 = int(_lib.raw("scn_conv_ts_launch_count")())
+    calls = {
+        "conv": lambda: _lib.call("scn_conv_fwd_tf32", P(x), C, C, n, P(m), n, K, P(img), None, None, 0, None, 0, P(out), C, C, 0, s),
+        "wgrad": lambda: _lib.call("scn_conv_bwd_weight", P(x), C, C, P(m), n, K, P(go), C, C, P(gw), P(gb), 1, s),
+        "rulebook": lambda: _lib.call("scn_subm_map", P(lvl.keys), n, P(lvl.tab_keys), P(lvl.tab_vals), lvl.cap, 3, 3, 3, P(m2), s),
+    }
+    ms = {}
+    for name, fn in calls.items():
         for _ in range(3):
-            conv(t)
+            fn()
         torch.cuda.synchronize()
-        total = 0.0
+        evs = []
         for _ in range(n_iter):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            conv(t)
+            fn()
             e1.record()
-            torch.cuda.synchronize()
-            total += e0.elapsed_time(e1)
-    ms = total / n_iter
-    K = 27
-    alg_bytes = n * C * 4 + n * C * 4 + K * C * C * 4 + 4 * K * n          # SURVEY.md 8d, s = 4 (fp32 storage)
-    flops = 2.0 * pairs * C * C
-    return ms, alg_bytes, flops, n, pairs
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms[name] = sum(a.elapsed_time(b) for a, b in evs) / n_iter
+    used_ts = int(_lib.raw("scn_conv_ts_launch_count")()) > ts0
+    assert torch.equal(m2, m)
+    # algorithmic bytes, SURVEY.md 8d with s = 4 (fp32 storage)
+    alg = {"conv": n * C * 4 + n * C * 4 + K * C * C * 4 + 4 * K * n,
+           "wgrad": n * C * 4 + n * C * 4 + K * C * C * 4 + 4 * K * n,
+           "rulebook": 8 * n + K * n * (8 + 4)}
+    return ms, alg, 2.0 * pairs * C * C, n, pairs, used_ts
 
 
 def main():
@@ -195,14 +214,17 @@ def main():
                     help="build each step's rulebooks between the previous step's forward and backward (the next batch is "
                          "known one step ahead, as with a DataLoader).  Off by default: measured 7.89 vs 7.80 ms -- the "
                          "host is busy, not blocked, so moving its synchronisation points buys nothing")
-    ap.add_argument("--stage", action="store_true",
-                    help="upload each batch one step ahead on a copy stream (BackboneTrainer.stage).  Off by default: measured "
-                         "e2e 9.49 vs 8.86 ms -- the inline upload already overlaps the host's issue of the rulebook kernels, "
-                         "staging only adds host work to a host-bound step")
+    ap.add_argument("--no-stage", dest="stage", action="store_false",
+                    help="do NOT upload each batch one step ahead on a copy stream (BackboneTrainer.stage).  Staging is on by "
+                         "default since the native executor freed the host (e2e 6.4 -> 5.8 ms); every step still uploads "
+                         "exactly one batch from pinned host memory inside the timed region")
     ap.add_argument("--prefetch", action="store_true",
-                    help="build each step's rulebooks one step ahead on a side stream (scn.GeometryPrefetcher).  Off by "
-                         "default: measured neutral (7.8 vs 7.8 ms) to harmful here, the worker thread shares the GIL with "
-                         "an already host-bound training thread (profiles/r1_i_host_bound.md)")
+                    help="build each step's rulebooks one step ahead on a side stream from a worker thread "
+                         "(scn.GeometryPrefetcher).  Off by default: with the native executor it reaches 5.3 ms per step in "
+                         "good runs but is not stable (3 runs: 6.5 / 6.4 / 7.0 ms, e2e 6.1 / 5.8 / 20.9 ms -- the worker shares "
+                         "the GIL and the launch queue with the training thread); without it 6.22 +- 0.01 ms "
+                         "(profiles/r2_e_executor.md)")
+    ap.set_defaults(stage=True)
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -303,26 +325,33 @@ def main():
     ms_e2e, vox_e2e, _, _ = timed(pinned, read_loss=True)
     clocks = sampler.stop() if rank == 0 else None
 
-    roof = None
+    roof = roof_w = roof_r = None
     if rank == 0:
         data, _ = resident[0]
         md = scn.Metadata(3)
         scn.ioLayers.InputLayerFunction.apply(3, md, data[2], data[0], data[1], data[3], 4)
-        kms, alg_bytes, flops, n0, pairs = time_dominant_kernel(dev, (md, data[2]))
+        kms, alg, flops, n0, pairs, used_ts = time_kernels(dev, (md, data[2]))
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk):
             peaks = json.load(open(pk))
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg_bytes / (kms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_conv_tc<4> SubM 3^3 32->32, N=%d, %d pairs" % (n0, pairs),
-                "achieved": achieved, "peak": peak, "peak_source": "measured" if peaks else "fallback",
-                "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this layer from the ncu --set full
-                # capture summarised in profiles/r1_p_final_state.md section 7 (39.66 MB + 0.53 MB; the output stays in L2)
-                "traffic": 40.19e6,
-                "ms_per_launch": kms, "algorithmic_bytes": alg_bytes,
-                "tflops_useful": flops / (kms * 1e-3) / 1e12, "l2": "flushed between launches"}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of these kernels on this layer, from the committed ncu
+        # capture (profiles/roofline_traffic.json says which report each number comes from)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+
+        def roofline(key, kernel):
+            achieved = alg[key] / (kms[key] * 1e-3) / 1e9
+            return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
+                    "peak_source": "measured" if peaks else "fallback", "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic.get(key, {}).get("bytes_per_launch"), "ms_per_launch": kms[key],
+                    "algorithmic_bytes": alg[key], "l2": "flushed before every launch"}
+        roof = roofline("conv", "%s SubM 3^3 32->32 forward, N=%d, %d pairs" % (
+            "k_conv_ts<32> (tile-local, A operand in tensor memory)" if used_ts else "k_conv_tc<4>", n0, pairs))
+        roof["tflops_useful"] = flops / (kms["conv"] * 1e-3) / 1e12
+        roof_w = roofline("wgrad", "k_conv_wgrad_tc<4> weight + bias gradient of the same layer")
+        roof_w["tflops_useful"] = flops / (kms["wgrad"] * 1e-3) / 1e12
+        roof_r = roofline("rulebook", "k_subm_map 3^3 neighbour map of level 0 (13 N hash probes)")
 
     # metric part (ii): sparse inference scenes/s (backbone + segmentation + class network + sparse mask network on
     # 256 proposal boxes per scene), every rank runs its own scenes (no collective), pinned host inputs.
@@ -386,7 +415,8 @@ def main():
                     "loss_read": "blocking .item() per step" if args.sync_loss else
                     "every step, async copy into pinned memory, read by the host one step late",
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "inference": inference,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_wgrad": roof_w,
+            "roofline_rulebook": roof_r, "inference": inference,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -477,16 +477,25 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
         int it = 0;
         const char* in_c = reinterpret_cast<const char*>(p.in);
         const uint32_t row_bytes = (uint32_t)p.ld_in * 4u;
+        int cnt_next = blockIdx.x < n_tiles ? __ldg(p.book.nloc + blockIdx.x) : 0;      // one tile ahead: no dependent load chain
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            int cnt = __ldg(p.book.nloc + tile);
+            int cnt = cnt_next;
+            if (tile + (int)gridDim.x < n_tiles) cnt_next = __ldg(p.book.nloc + tile + gridDim.x);
             if (cnt > p.cap) cnt = p.cap;
             const int32_t* rl = p.book.rows + (int64_t)tile * TS_ROWS_CAP;
-            // super-round = 32 consecutive rows of the list: lane L reads the index of row base + L (one coalesced load,
-            // issued one super-round ahead), the copies fetch it by shuffle; the two loader warps alternate super-rounds
-            int base = lw * 32;
-            int mine = base + lane < cnt ? __ldg(rl + base + lane) : -1;
+            // super-round = 32 consecutive rows of the list: lane L holds the index of row base + L, the copies fetch it by
+            // shuffle; the two loader warps alternate super-rounds.  All of a tile's indices are requested up front (one
+            // coalesced load per super-round, independent of each other): with a cold L2 a load-per-round chain cost one
+            // DRAM latency per 32 rows, more than the tile's compute time (bench.py flushes L2 before every launch)
+            constexpr int ROUNDS = TS_ROWS_CAP / 64;
+            int idx[ROUNDS];
+#pragma unroll
+            for (int k = 0; k < ROUNDS; ++k) {
+                const int at = lw * 32 + 64 * k + lane;
+                idx[k] = at < cnt ? __ldg(rl + at) : -1;
+            }
             if (lw == 0) TS_STAMP(12000 + 4 * it);
             mbar_wait(halo_empty(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
             if (lw == 0) TS_STAMP(12000 + 4 * it + 1);
@@ -496,22 +505,23 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
                 bulk_g2s(blob0 + (uint32_t)buf * TS_BLOB_BYTES, p.book.blobs + (int64_t)tile * TS_BLOB_BYTES, TS_BLOB_BYTES,
                          halo_full(buf));
             }
-            while (base < cnt) {
-                const int nbase = base + 64;
-                const int next = nbase + lane < cnt ? __ldg(rl + nbase + lane) : -1;
 #pragma unroll
-                for (int i = 0; i < CPR; ++i) {
-                    const int t = lane + 32 * i;              // chunk t of the super-round: row t / CPR, chunk t % CPR
-                    const int jr = t / CPR, c = t % CPR;
-                    const int ridx = __shfl_sync(0xffffffffu, mine, jr);
-                    if (ridx >= 0) {
-                        const char* src = in_c + (uint64_t)(uint32_t)ridx * row_bytes + c * 16;
-                        const uint32_t dst = hb + (uint32_t)(base + jr) * PITCH + (uint32_t)(c * 16);
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            for (int k = 0; k < ROUNDS; ++k) {
+                const int base = lw * 32 + 64 * k;
+                if (base < cnt) {
+                    const int mine = idx[k];
+#pragma unroll
+                    for (int i = 0; i < CPR; ++i) {
+                        const int t = lane + 32 * i;              // chunk t of the super-round: row t / CPR, chunk t % CPR
+                        const int jr = t / CPR, c = t % CPR;
+                        const int ridx = __shfl_sync(0xffffffffu, mine, jr);
+                        if (ridx >= 0) {
+                            const char* src = in_c + (uint64_t)(uint32_t)ridx * row_bytes + c * 16;
+                            const uint32_t dst = hb + (uint32_t)(base + jr) * PITCH + (uint32_t)(c * 16);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                        }
                     }
                 }
-                mine = next;
-                base = nbase;
             }
             cp_async_mbar_arrive_noinc(halo_full(buf));
             if (lw == 0) TS_STAMP(12000 + 4 * it + 2);

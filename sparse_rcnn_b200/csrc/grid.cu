@@ -263,31 +263,32 @@ __global__ void k_rule_sort(const int32_t* __restrict__ row_ptr, int N, int32_t*
 }
 
 // ------------------------------------------------------------------------------ neighbour maps
-// One thread per output row, looping the filter box with the last dimension fastest.  Writes are
-// coalesced per offset (map is offset-major); probes of spatially adjacent sites share L2 lines
-// only by luck (rows are in scan order), so this kernel is L2-latency bound: keep many rows in flight.
+// Neighbour map of an odd filter box, offsets enumerated with the last dimension fastest (SparseConvNet order).
+// The map is symmetric: map[o][r] == q  <=>  map[K-1-o][q] == r, so only the first K/2 offsets are probed -- ONE thread per
+// (offset, row) pair, 13 N independent probes for a 3^3 filter instead of 27 dependent ones per thread.  Threads of a warp
+// share the offset and hold consecutive rows: the key read and the write of map[o][r] are coalesced, the mirrored write
+// map[K-1-o][q] goes to rows near r (Morton order keeps neighbours close).  Entries of the upper half without a neighbour keep
+// the -1 that scn_subm_map fills in first.  Round 1 walked all 27 probes of a row serially in one thread: 21-35 us per level
+// whatever its size (a chain of L2 misses); measured after the rewrite in profiles/r2_c_kernel_table.md.
 __global__ void k_subm_map(const uint64_t* __restrict__ row_keys, int N, const uint64_t* __restrict__ tk,
                            const int32_t* __restrict__ tv, uint32_t mask, int fx, int fy, int fz,
                            int32_t* __restrict__ map) {
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
-        uint64_t k = row_keys[r];
-        int x = key_x(k), y = key_y(k), z = key_z(k), b = key_b(k);
-        int o = 0;
-        for (int dx = -(fx / 2); dx <= fx / 2; ++dx)
-            for (int dy = -(fy / 2); dy <= fy / 2; ++dy)
-                for (int dz = -(fz / 2); dz <= fz / 2; ++dz, ++o) {
-                    int v;
-                    if (dx == 0 && dy == 0 && dz == 0) {
-                        v = r;
-                    } else {
-                        int qx = x + dx, qy = y + dy, qz = z + dz;
-                        v = -1;
-                        if (qx >= 0 && qy >= 0 && qz >= 0 && qx < 65535 && qy < 65535 && qz < 65535)
-                            v = hash_lookup(tk, tv, mask, make_key(qx, qy, qz, b));
-                    }
-                    map[(int64_t)o * N + r] = v;
-                }
+    const int K = fx * fy * fz, half = K / 2;
+    const int64_t total = (int64_t)half * N;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int o = (int)(p / N), r = (int)(p - (int64_t)o * N);
+        const uint64_t k = __ldg(row_keys + r);
+        const int dz = o % fz - fz / 2, dy = (o / fz) % fy - fy / 2, dx = o / (fz * fy) - fx / 2;
+        const int qx = key_x(k) + dx, qy = key_y(k) + dy, qz = key_z(k) + dz;
+        int v = -1;
+        if (qx >= 0 && qy >= 0 && qz >= 0 && qx < 65535 && qy < 65535 && qz < 65535)
+            v = hash_lookup(tk, tv, mask, make_key(qx, qy, qz, key_b(k)));
+        map[(int64_t)o * N + r] = v;
+        if (v >= 0) map[(int64_t)(K - 1 - o) * N + v] = r;
+        if (o == 0) map[(int64_t)half * N + r] = r;      // the centre offset
     }
+    if (half == 0)      // 1^3 filter: the identity
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) map[r] = r;
 }
 
 __global__ void k_stride_keys(const uint64_t* __restrict__ row_keys, int N, int sx, int sy, int sz,
@@ -462,7 +463,11 @@ int scn_subm_map(const uint64_t* row_keys, int N, const uint64_t* tk, const int3
     SCN_REQUIRE((fx & 1) && (fy & 1) && (fz & 1) && fx > 0 && fy > 0 && fz > 0 && fx * fy * fz <= 343,
                 "subm_map: filter must be odd and <= 7^3 (got %dx%dx%d)", fx, fy, fz);
     if (N <= 0) return SCN_OK;
-    k_subm_map<<<grid_for(N, 128, 16), 128, 0, as_stream(stream)>>>(row_keys, N, tk, tv, cap - 1, fx, fy, fz, map);
+    const int K = fx * fy * fz, half = K / 2;
+    if (half > 0)      // upper half: -1 wherever the mirrored write does not land
+        cudaMemsetAsync(map + (int64_t)(half + 1) * N, 0xFF, sizeof(int32_t) * (size_t)half * N, as_stream(stream));
+    k_subm_map<<<grid_for((int64_t)(half > 0 ? half : 1) * N, 256, 8), 256, 0, as_stream(stream)>>>(row_keys, N, tk, tv, cap - 1, fx, fy,
+                                                                                                   fz, map);
     return check_launch("subm_map");
 }
 int scn_stride_keys(const uint64_t* row_keys, int N, int sx, int sy, int sz, uint64_t* parent_keys, int32_t* offs,
