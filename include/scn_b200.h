@@ -177,6 +177,8 @@ int scn_tile_book_attach(const int32_t* map, const void* book, int n_out);
 int scn_tile_book_detach(const int32_t* map);
 /* launches of the tile-local kernel so far (tests assert that the path under test really ran) */
 int64_t scn_conv_ts_launch_count(void);
+/* launches of the tile-local weight-gradient kernel (csrc/conv_wgrad_ts.cu) so far */
+int64_t scn_conv_wgrad_ts_launch_count(void);
 /* TF32 tcgen05 implicit gather-GEMM (sm_100a).  Cin/Cout here are the GEMM's K/N widths, i.e.
  * after any transpose; n_in = rows of `in`.  residual (may be NULL) is [n_out, Cout] with leading
  * dimension ld_res.  When `in` and its row stride are 16-byte aligned the rows are gathered by TMA

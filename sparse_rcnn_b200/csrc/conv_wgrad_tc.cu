@@ -403,6 +403,11 @@ extern "C" int scn_conv_bwd_weight(const float* in, int ld_in, int Cin, const in
         return scn_col_sum_add(grad_out, ld_go, n_out, Cout, grad_bias, stream);
     }
 
+    {      // Morton-ordered level with a tile book, C -> C, 3^3: the tile-local deterministic kernel (conv_wgrad_ts.cu)
+        const int rc = scn::conv_wgrad_ts_try(in, ld_in, Cin, map, n_out, K, grad_out, ld_go, Cout, grad_w, grad_bias, as_stream(stream));
+        if (rc < 0) return -rc;
+        if (rc == 1) return SCN_OK;
+    }
     WgradParams p;
     p.in = in, p.ld_in = ld_in, p.Cin = Cin, p.map = map, p.n_out = n_out, p.K = K;
     p.go = grad_out, p.ld_go = ld_go, p.Cout = Cout, p.gw = grad_w, p.gb = grad_bias;

@@ -12,6 +12,9 @@ namespace scn {
 int conv_ts_try(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const void* image, const float* bias,
                 const float* residual, int ld_res, const float* mask, int ld_mask, float* out, int ld_out, int Cout, int epi,
                 cudaStream_t stream);
+// conv_wgrad_ts.cu: tile-local, deterministic weight gradient; same return convention
+int conv_wgrad_ts_try(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const float* go, int ld_go, int Cout,
+                      float* gw, float* gb, cudaStream_t stream);
 int make_gather_tmap(CUtensorMap* tm, const float* base, int rows, int C, int ld, CUtensorMapSwizzle swz);
 
 constexpr int TILE_M = 128;

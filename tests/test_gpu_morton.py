@@ -229,3 +229,46 @@ def test_tile_local_kernel_equals_rule_kernel(cuda, bench_level, monkeypatch, C)
         if name == "unit dx":      # ... and where that bit flips a ReLU mask, one gradient element toggles: rare
             assert ((a - b).abs() > 1e-5 * b.abs().max()).float().mean() < 2e-3
         assert torch.equal(a, c), name                                # deterministic
+
+
+@pytest.mark.parametrize("C", [32, 48])
+def test_tile_local_weight_gradient(cuda, bench_level, monkeypatch, C):
+    """conv_wgrad_ts.cu (halo set in shared memory, A = [(offset, channel)] x [row] in tensor memory, per-CTA partial sums reduced
+    in CTA order) against conv_wgrad_tc.cu (cp.async gather per offset, floating-point atomics) on the bench scene: the same
+    TF32 products, another summation order -> 1e-5; and against itself: bit-reproducible."""
+    from sparse_rcnn_b200 import _lib, scn
+    from sparse_rcnn_b200.scn import functions as Fn
+    from sparse_rcnn_b200.scn.metadata import _stream
+    scn.set_precision("tf32")
+    md, size = bench_level
+    lvl = md.level(size)
+    n, K = lvl.n, 27
+    m = lvl.subm_map(3)
+    torch.manual_seed(C)
+    x = Fn.tf32_exact(torch.randn(n, C, device=cuda))
+    go = Fn.tf32_exact(torch.randn(n, C, device=cuda))
+    P = lambda t: t.data_ptr()
+
+    def run(ts, fill=0.0):
+        monkeypatch.setenv("SCN_WGRAD_TS", ("48" if C == 48 else "1") if ts else "0")      # C = 48 is opt-in (slower)
+        gw = torch.full((K, C, C), fill, device=cuda)
+        gb = torch.full((C,), fill, device=cuda)
+        _lib.call("scn_conv_bwd_weight", P(x), C, C, P(m), n, K, P(go), C, C, P(gw), P(gb), 1, _stream())
+        torch.cuda.synchronize()
+        return gw, gb
+    ref_w, ref_b = run(False)
+    before = int(_lib.raw("scn_conv_wgrad_ts_launch_count")())
+    w1, b1 = run(True)
+    assert int(_lib.raw("scn_conv_wgrad_ts_launch_count")()) == before + 1
+    w2, b2 = run(True)
+    assert rel_err(w1, ref_w) <= 1e-5, rel_err(w1, ref_w)
+    assert rel_err(b1, ref_b) <= 1e-5, rel_err(b1, ref_b)
+    assert torch.equal(w1, w2) and torch.equal(b1, b2)              # deterministic
+    w3, b3 = run(True, fill=1.0)                                     # gradients are ADDED to what the buffers hold
+    assert rel_err(w3 - 1.0, w1) <= 1e-5 and rel_err(b3 - 1.0, b1) <= 1e-5
+    # independent check of a few offsets in float64 (exact products of TF32-representable operands)
+    mm = m.long()
+    for o in (0, 13, 26):
+        act = mm[o] >= 0
+        want = x.double()[mm[o][act]].t() @ go.double()[act]
+        assert rel_err(w1[o], want) <= 2e-5, (o, rel_err(w1[o], want))
