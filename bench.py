@@ -92,6 +92,32 @@ def make_inputs(seed, in_channels=6, scene_kw=SCENE, num_classes=20):
     return data, labels
 
 
+def active_voxels(data):
+    c = data[0].numpy()
+    key = (c[:, 3].astype("int64") << 48) | (c[:, 0].astype("int64") << 32) | (c[:, 1].astype("int64") << 16) | c[:, 2].astype("int64")
+    import numpy as np
+    return int(np.unique(key).size)
+
+
+def balanced_inputs(rank, i, tol=0.01, tries=40):
+    """Scene i of rank `rank`: rank 0 uses seed i; every other rank draws its OWN scenes (different geometry) but keeps only
+    one whose active-voxel count is within 1 % of rank 0's scene i, so that at N > 1 the max-over-ranks step time measures
+    the collective and not which rank happened to draw the largest scene."""
+    ref = make_inputs(i)
+    if rank == 0:
+        return ref
+    want = active_voxels(ref[0])
+    best, best_err = None, None
+    for k in range(tries):
+        cand = make_inputs(1000 * rank + i + 100 * k)
+        err = abs(active_voxels(cand[0]) - want) / want
+        if best is None or err < best_err:
+            best, best_err = cand, err
+        if err <= tol:
+            break
+    return best
+
+
 def run_cpu_oracle(steps, warmup, sample_kw=SCENE):
     """Backbone fwd+bwd on the CPU oracle (the SparseConvNet-CPU-style path); returns (voxels/s, info)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -249,7 +275,7 @@ def main():
 
     # weak scaling: every rank owns its own scene(s); a different scene per step so nothing is cached
     n_distinct = 4
-    host = [make_inputs(1000 * rank + i) for i in range(n_distinct)]
+    host = [balanced_inputs(rank, i) for i in range(n_distinct)]
     pinned = [((d[0].pin_memory(), d[1].pin_memory(), d[2], d[3], d[4]), l.pin_memory()) for d, l in host]
     resident = [((d[0].to(dev), d[1].to(dev), d[2], d[3], d[4]), l.to(dev)) for d, l in host]
 

@@ -356,7 +356,8 @@ int scn_unet_fwd(const int64_t* net, const int64_t* geo, const float* x, float* 
                  int use_tf32, scn_stream_t stream);
 /* seeds[k]: incoming gradient of output k (order of scn_unet_plan) or 0.  pgrads: one pointer per parameter in table
  * order (0 = not wanted); gradients are ADDED (zeroed buffers or the parameters' gradient buckets, training.py:458).
- * gx: gradient wrt the input or NULL.  phases: bit 0 decoder, bit 1 encoder. */
+ * gx: gradient wrt the input or NULL.  phases: bit 0 decoder, bit 1 encoder levels >= split, bit 2 encoder levels < split,
+ * split = phases >> 8 (7 = everything in one call). */
 int scn_unet_bwd(const int64_t* net, const int64_t* geo, const float* x, const float* arena, float* bwd_arena,
                  const int64_t* seeds, const int64_t* pgrads, float* gx, int phases, int use_tf32,
                  scn_stream_t stream);

@@ -424,8 +424,9 @@ int scn_unet_fwd(const int64_t* net_table, const int64_t* geo_table, const float
 // seeds[k] (k as in scn_unet_plan's output order): incoming gradient of output k or NULL.  pgrads: one pointer per parameter in
 // table order (encoder level: entry w, b, then per unit w1 b1 w2 b2; decoder level: deconvolution w, b, 1x1 w, b, units), NULL =
 // not wanted; every gradient is ADDED to its buffer (zeroed by the caller, or the parameter's gradient bucket).  gx: gradient
-// wrt the network input or NULL.  phases: bit 0 = decoder, bit 1 = encoder (two calls let the caller start the allreduce of
-// the decoder's gradients while the encoder's backward runs; the second call must see the same seeds).
+// wrt the network input or NULL.  phases: bit 0 = decoder, bit 1 = encoder levels >= split, bit 2 = encoder levels < split,
+// split = phases >> 8 (several calls let the caller start the allreduce of a finished group's gradients while the rest of the
+// backward runs; every call must see the same seeds).
 int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float* x, const float* arena, float* barena,
                  const int64_t* seeds, const int64_t* pgrads, float* gx, int phases, int use_tf32, scn_stream_t stream) {
     SCN_REQUIRE(net_table && geo_table && arena && barena && seeds && pgrads, "unet_bwd: null argument");
@@ -437,7 +438,10 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
     make_plan(net, g, P);
     cudaStream_t st = as_stream(stream);
     const int tf32 = use_tf32 ? 1 : 0, L = net.L;
-    const bool run_dec = phases & 1, run_enc = phases & 2;
+    // phases: bit 0 = decoder, bit 1 = encoder levels >= split, bit 2 = encoder levels < split, split = phases >> 8
+    const int split = phases >> 8;
+    const bool run_dec = phases & 1;
+    auto enc_runs = [&](int level) { return (phases & (level >= split ? 2 : 4)) != 0; };
     Side side;
     SCN_TRY(side_for(st, side));
     // parameter-gradient pointers in table order
@@ -519,6 +523,7 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
     for (int i = L - 1; i >= 0; --i) {
         const Conv& e = net.enc[i];
         const int n = g.n[i], n_in = i == 0 ? g.n[0] : g.n[i - 1];
+        const bool run_enc = enc_runs(i);
         const float* gy = nullptr;
         SCN_TRY(resolve(gE[i], (int64_t)n * net.C[i], run_enc, &gy));
         if (!gy) continue;

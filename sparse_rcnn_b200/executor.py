@@ -19,6 +19,7 @@ from .scn import layers as L
 from .scn.metadata import _ptr, _stream
 
 ENABLED = {"unet": True}      # False: always run the module graph (tests compare both)
+ENCODER_PHASE_SPLIT = 2       # bucketed backward: encoder levels >= this finish in the second call, the finer ones in the third
 
 
 def _units_of(stage):
@@ -107,6 +108,11 @@ class UNetProgram:
         n_enc_slots = sum((2 if conv is not None else 0) + 4 * len(units) for kind, conv, units in prog.enc)
         prog.n_encoder_params = sum(1 for p in prog.params[:n_enc_slots] if p is not None)
         return prog
+
+    def encoder_params_below(self, level):
+        """Number of (non-None) parameters of the encoder levels < level, in table order."""
+        slots = sum((2 if conv is not None else 0) + 4 * len(units) for kind, conv, units in self.enc[:level])
+        return sum(1 for p in self.params[:slots] if p is not None)
 
     def channels_in(self):
         kind, conv, _ = self.enc[0]
@@ -267,18 +273,24 @@ class UNetFunction(F.Function):
         args = (net.ctypes.data, geo.ctypes.data, _ptr(x), _ptr(arena), _ptr(barena), seeds.ctypes.data, pg.ctypes.data, _ptr(gx))
         s = _stream()
         if bucketed and prog.dec:
-            # decoder first, its parameters' hooks fire (the bucket's allreduce starts), then the encoder
-            _lib.call("scn_unet_bwd", *args, 1, int(tf32), s)
-            n_enc = prog.n_encoder_params
-            for p, want in list(zip(params, need))[n_enc:]:
-                if want:
-                    p._scn_grad_hook(p)
-            _lib.call("scn_unet_bwd", *args, 2, int(tf32), s)
-            for p, want in list(zip(params, need))[:n_enc]:
-                if want:
-                    p._scn_grad_hook(p)
+            # three calls: decoder | coarse encoder levels | fine encoder levels; after each one the hooks of its parameters
+            # fire, so that a gradient bucket cut along these boundaries is all-reduced while the rest of the backward runs
+            pw = list(zip(params, need))
+            n_enc, split = prog.n_encoder_params, min(ENCODER_PHASE_SPLIT, len(prog.enc))
+            n_fine = prog.encoder_params_below(split)
+
+            def fire(lo, hi):
+                for p, want in pw[lo:hi]:
+                    if want:
+                        p._scn_grad_hook(p)
+            _lib.call("scn_unet_bwd", *args, 1 | (split << 8), int(tf32), s)
+            fire(n_enc, len(pw))
+            _lib.call("scn_unet_bwd", *args, 2 | (split << 8), int(tf32), s)
+            fire(n_fine, n_enc)
+            _lib.call("scn_unet_bwd", *args, 4 | (split << 8), int(tf32), s)
+            fire(0, n_fine)
         else:
-            _lib.call("scn_unet_bwd", *args, 3, int(tf32), s)
+            _lib.call("scn_unet_bwd", *args, 7, int(tf32), s)
             if bucketed:
                 for p, want in zip(params, need):
                     if want:

@@ -22,23 +22,42 @@ def shard_scenes(n_scenes, rank, world):
 class GradientBuckets:
     """Flat gradient buckets with overlapped asynchronous allreduce (mean)."""
 
-    def __init__(self, params, n_buckets=2, process_group=None):
+    def __init__(self, params, n_buckets=2, process_group=None, groups=None):
+        """params: parameters in registration order, cut into `n_buckets` equal-sized buckets in reverse order -- or
+        `groups`: explicit buckets, given in the order in which the backward pass completes them (the native U-Net executor
+        finishes decoder / coarse encoder levels / fine encoder levels in three calls and fires each group's hooks at once,
+        so buckets cut along those boundaries start their allreduce as early as possible)."""
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        params = [p for p in params if p.requires_grad]
-        # reverse registration order ~ order in which backward produces gradients
-        order = list(reversed(params))
-        total = sum(p.numel() for p in order)
-        target = (total + n_buckets - 1) // n_buckets
-        self.buckets, cur, cur_n = [], [], 0
-        for p in order:
-            cur.append(p)
-            cur_n += p.numel()
-            if cur_n >= target and len(self.buckets) < n_buckets - 1:
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then divide
+        self.average_in_collective = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
+        if groups is not None:
+            self.buckets = [[p for p in g if p.requires_grad] for g in groups]
+            self.buckets = [b for b in self.buckets if b]
+            seen = set()
+            for b in self.buckets:
+                for p in b:
+                    if id(p) in seen:
+                        raise ValueError("a parameter appears in two gradient buckets")
+                    seen.add(id(p))
+            missing = [p for p in params if p.requires_grad and id(p) not in seen]
+            if missing:
+                self.buckets.append(missing)
+        else:
+            params = [p for p in params if p.requires_grad]
+            # reverse registration order ~ order in which backward produces gradients
+            order = list(reversed(params))
+            total = sum(p.numel() for p in order)
+            target = (total + n_buckets - 1) // n_buckets
+            self.buckets, cur, cur_n = [], [], 0
+            for p in order:
+                cur.append(p)
+                cur_n += p.numel()
+                if cur_n >= target and len(self.buckets) < n_buckets - 1:
+                    self.buckets.append(cur)
+                    cur, cur_n = [], 0
+            if cur:
                 self.buckets.append(cur)
-                cur, cur_n = [], 0
-        if cur:
-            self.buckets.append(cur)
         self.flats, self._pending, self._handles = [], [], []
         self._fired = set()
         self._launched = []
@@ -88,7 +107,8 @@ class GradientBuckets:
     def _launch(self, bi):
         self._launched[bi] = True
         if self.world > 1:
-            self._handles.append(dist.all_reduce(self.flats[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            op = dist.ReduceOp.AVG if self.average_in_collective else dist.ReduceOp.SUM
+            self._handles.append(dist.all_reduce(self.flats[bi], op=op, group=self.group, async_op=True))
 
     def flatten_parameters(self):
         """Make every parameter a view of one flat buffer per bucket (same order as its gradient view) and return the flat
@@ -130,9 +150,9 @@ class GradientBuckets:
             if not self._launched[bi]:
                 self._launch(bi)
         for h in self._handles:
-            h.wait()
+            h.wait()      # NCCL: the current stream waits for the collective's stream, the host does not block
         self._handles = []
-        if self.world > 1:
+        if self.world > 1 and not self.average_in_collective:
             for f in self.flats:
                 f.div_(self.world)
 

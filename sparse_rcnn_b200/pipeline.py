@@ -8,7 +8,7 @@ features may be host (pinned) or device tensors; the host->device copies happen 
 import torch
 import torch.nn as nn
 
-from . import networks, roi, scn
+from . import executor, networks, roi, scn
 from .parallel import GradientBuckets
 from .scn.metadata import stage_to_device, take_staged
 
@@ -34,7 +34,14 @@ class BackboneTrainer(nn.Module):
         self.backbone = networks.FeatureExtractor(scn, input_channels=in_channels)
         self.seg = networks.SegmentationNetwork(scn, 32, num_classes)
         self.to(device)
-        self.buckets = GradientBuckets(list(self.parameters()), n_buckets=2)
+        # gradient buckets cut where the backward pass completes them: segmentation head + decoder, coarse encoder levels
+        # (most of the parameters), fine encoder levels (most of the time) -- the executor fires each group's hooks at once
+        enc = list(self.backbone.main_network)
+        split = executor.ENCODER_PHASE_SPLIT
+        groups = [list(self.seg.parameters()) + list(self.backbone.unet.parameters()),
+                  [p for lev in enc[split:] for p in lev.parameters()],
+                  [p for lev in enc[:split] for p in lev.parameters()]]
+        self.buckets = GradientBuckets(list(self.parameters()), groups=groups)
         self.buckets.enabled = True
         # torch.optim.Adam as in the reference (ndsis/training/training.py:386); the fused implementation is the same
         # update in one multi-tensor kernel (the foreach path costs ~1.2 ms of host time per step, and the step is host bound)

@@ -179,3 +179,54 @@ def test_flat_parameters_expose_the_optimizers_version_counter():
     # fused optimizers do not even move the flat buffer's counter (measured on the B200 box): the global optimizer-step
     # hook must have bumped the generation
     assert _wver(w)[3] > before[3]
+
+
+def _worker_groups(rank, world, port, q):
+    """Explicit buckets (the executor's decoder / coarse / fine phases): mean over the ranks, parameters that were not listed
+    land in a last bucket, duplicates are rejected."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    a, b, c = nn.Linear(4, 8), nn.Linear(8, 8), nn.Linear(8, 2)
+    params = list(a.parameters()) + list(b.parameters()) + list(c.parameters())
+    try:
+        GradientBuckets(params, groups=[list(c.parameters()), list(c.parameters())])
+        dup = False
+    except ValueError:
+        dup = True
+    buckets = GradientBuckets(params, groups=[list(c.parameters()), list(b.parameters())])      # `a` is not listed
+    assert not buckets.average_in_collective                                                   # gloo: sum, then divide
+    g = torch.Generator().manual_seed(11 + rank)
+    x = torch.randn(6, 4, generator=g)
+    # this rank's own gradients from an untouched copy (the buckets' allreduce may already run during the backward below)
+    import copy
+    a2, b2, c2 = copy.deepcopy(a), copy.deepcopy(b), copy.deepcopy(c)
+    for m in (a2, b2, c2):
+        for p in m.parameters():
+            p.grad = None
+    c2(b2(a2(x))).sum().backward()
+    local = [p.grad.clone() for m in (a2, b2, c2) for p in m.parameters()]
+    buckets.zero()
+    c(b(a(x))).sum().backward()
+    buckets.finish()
+    gathered = [[torch.zeros_like(t) for _ in range(world)] for t in local]
+    for t, out in zip(local, gathered):
+        dist.all_gather(out, t)
+    err = max(float((p.grad - sum(out) / world).abs().max()) for p, out in zip(params, gathered))
+    q.put((rank, dup, [len(bk) for bk in buckets.buckets], err))
+    dist.destroy_process_group()
+
+
+def test_explicit_bucket_groups():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_groups, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, dup, sizes, err in res:
+        assert dup and sizes == [2, 2, 2] and err < 1e-6, (rank, dup, sizes, err)
