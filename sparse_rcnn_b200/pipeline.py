@@ -8,7 +8,7 @@ features may be host (pinned) or device tensors; the host->device copies happen 
 import torch
 import torch.nn as nn
 
-from . import executor, networks, roi, scn
+from . import executor, networks, proposal, roi, scn
 from .parallel import GradientBuckets
 from .scn.metadata import stage_to_device, take_staged
 
@@ -101,7 +101,8 @@ class SparseInference(nn.Module):
     them is out of scope): feature extractor -> segmentation logits per point,
     class logits per box, mask logits per (box, point)."""
 
-    def __init__(self, device, in_channels=6, num_seg_classes=20, num_classes=18, seed=0):
+    def __init__(self, device, in_channels=6, num_seg_classes=20, num_classes=18, seed=0, num_keep_pre_nms=1024,
+                 num_keep_post_nms=256, thresh_nms=0.5):
         super().__init__()
         torch.manual_seed(seed)
         self.device = device
@@ -111,22 +112,37 @@ class SparseInference(nn.Module):
         self.class_network = networks.ClassNetwork(scn, cut, input_channels=64, stride=4, num_classes=num_classes)
         self.mask_network = networks.SparseMaskNetwork(scn, cut, input_channels=in_channels,
                                                        channel_list=(32, num_classes))
+        # proposal selection of the shipped configuration (run.py: 1024 highest scores -> NMS 0.5 -> 256 RoIs)
+        self.roi_selector = proposal.ProposalSelector(num_keep_pre_nms, num_keep_post_nms, thresh_nms)
         self.to(device)
         self.eval()
 
     @torch.no_grad()
-    def forward(self, data, boxes):
+    def forward(self, data, boxes=None, rpn=None):
+        """boxes: proposal boxes per sample (list of [n_i, 2, 3], voxel units) -- or rpn = (score [B, A], bbox [B, A, 2, 3]):
+        the raw proposal scores / boxes a region-proposal head would emit (model.py:990-1010 hands them to the RoiSelector),
+        reduced on the device by `proposal.ProposalSelector` (top-k, 3-D NMS kernel, first num_keep_post_nms survivors)."""
         data = _to_device(data, self.device)
         roi.clear_key_cache()
+        selected = None
+        if boxes is None:
+            if rpn is None:
+                raise ValueError("SparseInference needs proposal boxes or raw RPN outputs")
+            score, bbox = (t.to(self.device, non_blocking=True) for t in rpn)
+            selected = self.roi_selector(score, bbox)              # (scores, boxes, indices) lists over the batch
+            boxes = selected[1]
         scene_size, batch_size, _, class_map, inter, unet = self.backbone(data)
         roi.register_keys(data[0], inter[0].metadata.point_keys)     # packed once per forward
         seg = self.seg(unet)
         cls, cls_sel = self.class_network(class_map, boxes)
         mask, mask_sel = self.mask_network(data, unet, boxes)
-        return dict(segmentation=seg, mpn_class=cls, mpn_mask=mask, class_selection=cls_sel, mask_selection=mask_sel,
-                    n_active=inter[0].features.shape[0])
+        out = dict(segmentation=seg, mpn_class=cls, mpn_mask=mask, class_selection=cls_sel, mask_selection=mask_sel,
+                   n_active=inter[0].features.shape[0])
+        if selected is not None:
+            out["roi_score"], out["roi_bbox"], out["roi_index"] = selected
+        return out
 
-    def run_many(self, scenes, boxes, workers=2, consume=None):
+    def run_many(self, scenes, boxes=None, workers=2, consume=None, rpn=None):
         """Inference over independent scenes from `workers` host threads, one CUDA stream each (scene i -> worker
         i mod workers).  Why: one scene's pass is a ping-pong between host and GPU -- 16 host reads of row counts (every
         level of three pyramids and two crops) during which the host waits for the GPU, each followed by a stretch in which
@@ -141,7 +157,7 @@ class SparseInference(nn.Module):
         if workers <= 1 or n <= 1:
             out = []
             for i in range(n):
-                r = self(scenes[i], boxes[i])
+                r = self(scenes[i], None if boxes is None else boxes[i], rpn=None if rpn is None else rpn[i])
                 out.append(consume(i, r) if consume is not None else r)
             return out
         workers = min(workers, n)
@@ -162,7 +178,7 @@ class SparseInference(nn.Module):
                 with torch.cuda.stream(streams[k]):
                     streams[k].wait_event(ready)      # weights / packed images written on the caller's stream
                     for i in range(k, n, workers):
-                        r = self(scenes[i], boxes[i])
+                        r = self(scenes[i], None if boxes is None else boxes[i], rpn=None if rpn is None else rpn[i])
                         results[i] = consume(i, r) if consume is not None else r
                     done[k].record(streams[k])
             except BaseException as e:      # surfaced in the calling thread

@@ -153,3 +153,38 @@ def make_mask_loss_case(seed, boxes_per_sample, max_points=400, num_classes=18, 
         outs.append(so), tgts.append(st)
         cls.append(torch.randint(0, num_classes, (nb,), generator=g))
     return outs, tgts, cls
+
+
+def make_rpn_outputs(coords, n_anchors=30000, n_objects=256, seed=0, spatial_size=(256, 256, 128), copies=4):
+    """Raw region-proposal outputs of one batch as the RoiSelector receives them (model.py:990-1010): -> (score [B, A],
+    bbox [B, A, 2, 3]) fp32 CPU.  `n_objects` object boxes per sample (make_boxes: centred on real points, anchor-shaped),
+    each present `copies` times with a small jitter (the lower-scored copies overlap the best one with IoU > 0.5, so NMS
+    removes them) and the highest scores; the remaining anchors are random boxes with low scores.  With 1024 -> NMS 0.5 ->
+    256 selection this yields ~n_objects RoIs per sample, i.e. the mask / class workload of make_boxes."""
+    import torch
+    rng = np.random.default_rng(seed + 104729)
+    obj = make_boxes(coords, n_objects, seed, spatial_size)
+    hi = np.asarray(spatial_size, np.float32)
+    scores, boxes = [], []
+    for b in range(len(obj)):
+        base = obj[b].numpy()
+        size = base[:, 1] - base[:, 0]
+        reps = [base]
+        for _ in range(copies - 1):
+            j = rng.uniform(-0.02, 0.02, base.shape).astype(np.float32) * size[:, None, :]
+            reps.append(np.clip(base + j, 0, hi))
+        top = np.concatenate(reps)
+        n_fill = n_anchors - len(top)
+        c = rng.uniform(0, 1, (n_fill, 3)).astype(np.float32) * hi
+        e = rng.uniform(4, 40, (n_fill, 3)).astype(np.float32)
+        fill = np.clip(np.stack([c - e / 2, c + e / 2], 1), 0, hi)
+        bx = np.concatenate([top, fill]).astype(np.float32)
+        # unique scores: copy k of object i scores above every copy k+1, all above the filler
+        sc = np.empty(n_anchors, np.float32)
+        order = rng.permutation(n_objects)
+        for k in range(copies):
+            sc[k * n_objects:(k + 1) * n_objects] = 1.0 - (k * n_objects + order + 0.5) / (2.0 * copies * n_objects)
+        sc[len(top):] = 0.4 * (rng.permutation(n_fill) + 0.5) / n_fill
+        perm = rng.permutation(n_anchors)
+        scores.append(sc[perm]), boxes.append(bx[perm])
+    return torch.from_numpy(np.stack(scores)), torch.from_numpy(np.stack(boxes))

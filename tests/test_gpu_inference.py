@@ -62,3 +62,31 @@ def test_run_many_surfaces_worker_errors(cuda):
         inf.run_many([d, bad, d], [b, b, b], workers=2)
     res = inf.run_many([d, d], [b, b], workers=2)                    # the pipeline is usable afterwards
     assert res[0]["mpn_class"].shape == res[1]["mpn_class"].shape
+
+
+def test_inference_from_raw_rpn_outputs(cuda):
+    """configs[1] with the proposal selection inside (SURVEY 8f #1 wired in): SparseInference fed with raw RPN scores / boxes
+    runs proposal.ProposalSelector (top-k, scn_nms3d, first num_keep_post_nms survivors) on the device and must return what
+    the same pass returns when it is handed the selector's boxes; the selection itself equals the reference restatement
+    (oracle/scn_oracle/nms_ref.py, pinned by the unmodified reference's goldens in test_golden.py / test_gpu_proposal.py)."""
+    from scn_oracle import nms_ref
+    from sparse_rcnn_b200 import pipeline, scn
+    from sparse_rcnn_b200.synthetic import make_batch, make_proposals
+    scn.set_precision("tf32")
+    size = (64, 64, 32)
+    d = make_batch(2, 21, spatial_size=size, room=(44, 44, 22), room_offset=(8, 8, 2), n_furniture=3)
+    score, bbox = make_proposals(5, 2, 600, scene=(64.0, 64.0, 32.0))
+    bbox = bbox.clamp(min=0.0).minimum(torch.tensor([64.0, 64.0, 32.0]))
+    inf = pipeline.SparseInference(cuda, num_keep_pre_nms=256, num_keep_post_nms=24, thresh_nms=0.3)
+    a = inf(d, rpn=(score, bbox))
+    s_ref, b_ref, i_ref = nms_ref.select(score, bbox, 256, 24, 0.3)
+    for k in range(2):
+        assert torch.equal(a["roi_index"][k], i_ref[k]) and torch.equal(a["roi_bbox"][k].cpu(), b_ref[k])
+        assert 0 < len(i_ref[k]) <= 24
+    b = inf(d, boxes=[t.cpu() for t in a["roi_bbox"]])
+    for key in ("segmentation", "mpn_class", "mpn_mask"):
+        assert a[key].shape == b[key].shape and rel_err(a[key], b[key]) < 2e-4, key
+    many = inf.run_many([d, d], rpn=[(score, bbox)] * 2, workers=2)
+    torch.cuda.synchronize()
+    for m in many:
+        assert rel_err(m["mpn_class"], a["mpn_class"]) < 2e-4
