@@ -338,6 +338,21 @@ int scn_crop_select(const uint64_t* keys, const int32_t* sample_ptr, const int32
                     int P, int32_t* sel_pt, uint64_t* new_keys, uint8_t* is_inside,
                     scn_stream_t stream);
 
+/* ------------------------------------------------------------------ dense stage -------------
+ * get_dilation_network module_factory.py:581-611 (SparseToDense + num_dilations x [Conv3d 3^3 'same', dilated + ReLU]),
+ * the trunk of the region-proposal network (anchor_network.py:127-219 consumes its [B, C, X, Y, Z] output).  The dense
+ * grid is kept channels-last ([B*X*Y*Z, C] rows in (b, x, y, z) order) so that its convolutions run on the gather-GEMM
+ * entry points above (scn_conv_fwd_tf32 / _fp32, scn_conv_bwd_weight) over the trivial map built here. */
+/* map [27][B*X*Y*Z]: map[o][r] = r + delta(o) * dilation, -1 outside the grid; offsets last-dimension-fastest */
+int scn_dense_map(int B, int X, int Y, int Z, int dilation, int32_t* map, scn_stream_t stream);
+/* sparse rows -> dense rows, zero fill fused (scn.SparseToDense, module_factory.py:429-435, channels-last) */
+int scn_sparse_to_dense_rows_fwd(const float* in, int C, const uint64_t* tab_keys, const int32_t* tab_vals,
+                                 uint32_t cap, int B, int X, int Y, int Z, float* out, scn_stream_t stream);
+int scn_sparse_to_dense_rows_bwd(const float* grad_dense, const uint64_t* row_keys, int N, int C, int X, int Y,
+                                 int Z, float* grad_in, scn_stream_t stream);
+/* out[b][c][r] = in[b][r][c]: dense rows <-> [B, C, X*Y*Z] */
+int scn_transpose_batched(const float* in, int batches, int rows, int cols, float* out, scn_stream_t stream);
+
 /* ------------------------------------------------------------------ sparse U-Net executor ----
  * FeatureExtractor.forward model.py:414-446 over the graph module_factory.py:438-578,789-830 builds (encoder levels:
  * entry convolution + residual units; decoder levels: ReLU, Deconvolution, JoinTable with the skip connection,
