@@ -133,6 +133,17 @@ class CropSelection:
         return self.sel_pt.numel()
 
     def is_inside(self, cpu=False):
+        """The reference's dense [n_boxes, n_points] bool matrix (roi_select_sparse.py:125-135).  The hot path works on the
+        (box, point) CSR the crop kernel emits; the dense matrix (70 MB at 256 boxes x 273 k points) is only materialised
+        when somebody asks for it -- here, from the CSR, once."""
+        if self._is_inside is None:
+            dev = self.sel_pt.device
+            m = torch.zeros(self.n_boxes * self.n_points, dtype=torch.uint8, device=dev)
+            if self.total:
+                per_box = (self.box_ptr[1:] - self.box_ptr[:-1]).long()
+                box_of = torch.repeat_interleave(torch.arange(self.n_boxes, device=dev), per_box, output_size=self.total)
+                m[box_of * self.n_points + self.sel_pt.long()] = 1
+            self._is_inside = m
         m = self._is_inside.view(self.n_boxes, self.n_points).bool()
         return m.cpu() if cpu else m
 
@@ -209,6 +220,9 @@ class SparseRoiCut(nn.Module):
         self.raw_scene = raw_scene
         self.bbox_transformer = BBoxTransformerSlice(clip=clip_boxes, resize=resize_boxes)
         self.combine, self.cpu_selection = combine, cpu_selection
+        # True: the crop kernel also writes the dense [BB, P] byte matrix (zero fill + one byte per tested pair); False
+        # (default): `selection.is_inside()` builds it from the (box, point) CSR on request
+        self.dense_selection = False
 
     def forward(self, feature_map, bbox_batch):
         feats0 = feature_map[1] if self.raw_scene else feature_map.features
@@ -216,7 +230,7 @@ class SparseRoiCut(nn.Module):
         keys, feats, spatial_size, splits, ptr, max_len = (RawScene if self.raw_scene else TensorScene).extract(
             feature_map, dev)
         boxes, counts, assoc = self.bbox_transformer(bbox_batch, spatial_size)
-        sel_pt, new_keys, box_ptr, total, inside = crop(keys, ptr, max_len, boxes, assoc)
+        sel_pt, new_keys, box_ptr, total, inside = crop(keys, ptr, max_len, boxes, assoc, want_is_inside=self.dense_selection)
         sel = CropSelection(sel_pt, new_keys, box_ptr, boxes.shape[0], keys.numel(), inside, counts, splits)
         new_feats = GatherRowsFunction.run(feats, sel_pt)
         out = combine_crop(self.scn, self.combine, new_keys, new_feats, spatial_size, boxes.shape[0],

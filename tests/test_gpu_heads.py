@@ -25,8 +25,12 @@ def test_crop_kernel_matches_reference_golden(cuda, name):
     scene = (coords, feats.to(cuda), g["size"], len(splits), splits)
     cut = roi.SparseRoiCut(scn, raw_scene=True, clip_boxes=g["clip"], resize_boxes=g["resize"], combine="raw")
     (new_keys, new_feats, size, n_boxes), sel = cut(scene, g["boxes"])
+    assert sel._is_inside is None                                                     # built from the CSR on request ...
     inside = sel.is_inside(cpu=True).numpy()
     assert np.array_equal(np.packbits(inside, axis=1), g["inside_packed"])           # bit-exact selection
+    cut.dense_selection = True                                                        # ... or written by the crop kernel
+    _, sel2 = cut(scene, g["boxes"])
+    assert sel2._is_inside is not None and np.array_equal(sel2.is_inside(cpu=True).numpy(), inside)
     from sparse_rcnn_b200 import _lib
     loc = torch.empty((new_keys.numel(), 4), dtype=torch.int64, device=cuda)
     _lib.call("scn_unpack_keys", new_keys.data_ptr(), new_keys.numel(), loc.data_ptr(), 0)
