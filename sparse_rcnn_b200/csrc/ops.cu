@@ -2,6 +2,8 @@
 // All of these are HBM-bound: every kernel streams each tensor once with coalesced (and, where
 // the row width allows, 128-bit) accesses; grids are sized as multiples of the SM count.
 #include <float.h>
+#include <mutex>
+#include <unordered_map>
 #include "common.cuh"
 
 namespace scn {
@@ -506,29 +508,43 @@ static int col_reduce(const float* in, int ld, int n, int C, const float* mean, 
     return check_launch("col_reduce");
 }
 
-// scratch for the two-stage column reductions: one persistent buffer per process/device
-static float* g_scratch = nullptr;
-static size_t g_scratch_bytes = 0;
-static unsigned int* g_tickets = nullptr;       // 64 self-resetting ticket counters (C <= 2048)
-static int ensure_scratch(size_t bytes) {
-    if (!g_tickets) {
-        if (cudaMalloc(&g_tickets, 64 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(g_tickets, 0, 64 * sizeof(unsigned int)) != cudaSuccess) {
+// scratch + ticket counters of the two-stage column reductions: one set PER STREAM (host threads drive one stream each in
+// SparseInference.run_many, the executor runs weight / bias gradients on a side stream), created under a mutex and only ever
+// grown after the stream has drained (an earlier launch may still read the old buffer).  ADVICE r1.
+struct ColScratch {
+    float* buf = nullptr;
+    size_t bytes = 0;
+    unsigned int* tickets = nullptr;      // 64 self-resetting ticket counters (bias sums / BN mean use 0..31, BN variance 32..63)
+};
+static int col_scratch(cudaStream_t st, size_t bytes, ColScratch* out) {
+    static std::mutex mu;
+    static std::unordered_map<cudaStream_t, ColScratch> pool;
+    std::lock_guard<std::mutex> lock(mu);
+    ColScratch& w = pool[st];
+    if (!w.tickets) {
+        if (cudaMalloc(&w.tickets, 64 * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemsetAsync(w.tickets, 0, 64 * sizeof(unsigned int), st) != cudaSuccess) {
             cudaGetLastError();
+            w.tickets = nullptr;
             set_error("ticket alloc failed");
             return SCN_ERR_CUDA;
         }
     }
-    if (bytes <= g_scratch_bytes) return SCN_OK;
-    if (g_scratch) cudaFree(g_scratch);
-    g_scratch = nullptr;
-    g_scratch_bytes = 0;
-    cudaError_t e = cudaMalloc(&g_scratch, bytes);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        set_error("scratch alloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-        return SCN_ERR_CUDA;
+    if (bytes > w.bytes) {
+        if (w.buf) {
+            cudaStreamSynchronize(st);
+            cudaFree(w.buf);
+        }
+        w.buf = nullptr, w.bytes = 0;
+        cudaError_t e = cudaMalloc(&w.buf, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("scratch alloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return SCN_ERR_CUDA;
+        }
+        w.bytes = bytes;
     }
-    g_scratch_bytes = bytes;
+    *out = w;
     return SCN_OK;
 }
 constexpr int NSLAB = 296;  // 2 x 148 SMs
@@ -578,26 +594,30 @@ int scn_add(const float* a, const float* b, float* out, int64_t n, scn_stream_t 
 }
 int scn_col_sum(const float* in, int ld, int n, int C, float* out, scn_stream_t stream) {
     SCN_REQUIRE(C > 0 && n >= 0, "col_sum: bad shape");
-    int rc = ensure_scratch((size_t)NSLAB * 2 * C * sizeof(float));
+    ColScratch ws;
+    int rc = col_scratch(as_stream(stream), (size_t)NSLAB * 2 * C * sizeof(float), &ws);
     if (rc) return rc;
     SCN_REQUIRE(C <= 2048, "col_sum: C > 2048 not supported");
-    return col_reduce(in, ld, n, C, nullptr, 1.f, out, g_scratch, g_tickets, NSLAB, as_stream(stream));
+    return col_reduce(in, ld, n, C, nullptr, 1.f, out, ws.buf, ws.tickets, NSLAB, as_stream(stream));
 }
 int scn_col_sum_add(const float* in, int ld, int n, int C, float* out, scn_stream_t stream) {
     SCN_REQUIRE(C > 0 && n >= 0, "col_sum_add: bad shape");
     if (n == 0) return SCN_OK;
-    int rc = ensure_scratch((size_t)NSLAB * 2 * C * sizeof(float));
+    ColScratch ws;
+    int rc = col_scratch(as_stream(stream), (size_t)NSLAB * 2 * C * sizeof(float), &ws);
     if (rc) return rc;
     SCN_REQUIRE(C <= 2048, "col_sum_add: C > 2048 not supported");
-    return col_reduce(in, ld, n, C, nullptr, 1.f, out, g_scratch, g_tickets, NSLAB, as_stream(stream), 1);
+    return col_reduce(in, ld, n, C, nullptr, 1.f, out, ws.buf, ws.tickets, NSLAB, as_stream(stream), 1);
 }
 int scn_bn_stats(const float* in, int n, int C, float* mean, float* var, scn_stream_t stream) {
     SCN_REQUIRE(C > 0 && n > 0, "bn_stats: needs at least one active row");
-    int rc = ensure_scratch((size_t)NSLAB * 2 * C * sizeof(float));
+    SCN_REQUIRE(C <= 1024, "bn_stats: C > 1024 not supported (mean and variance share the 64 ticket counters)");
+    ColScratch ws;
+    int rc = col_scratch(as_stream(stream), (size_t)NSLAB * 2 * C * sizeof(float), &ws);
     if (rc) return rc;
-    rc = col_reduce(in, C, n, C, nullptr, 1.f / n, mean, g_scratch, g_tickets, NSLAB, as_stream(stream));
+    rc = col_reduce(in, C, n, C, nullptr, 1.f / n, mean, ws.buf, ws.tickets, NSLAB, as_stream(stream));
     if (rc) return rc;
-    return col_reduce(in, C, n, C, mean, 1.f / n, var, g_scratch + (size_t)NSLAB * C, g_tickets + 32, NSLAB, as_stream(stream));
+    return col_reduce(in, C, n, C, mean, 1.f / n, var, ws.buf + (size_t)NSLAB * C, ws.tickets + 32, NSLAB, as_stream(stream));
 }
 int scn_bn_apply(const float* in, int n, int C, const float* mean, const float* var, const float* gamma,
                  const float* beta, float eps, float leak, float* out, scn_stream_t stream) {
@@ -610,14 +630,15 @@ int scn_bn_bwd(const float* x, const float* y, const float* dy, int n, int C, co
                const float* gamma, float eps, float leak, int training, float* dx, float* dgamma, float* dbeta,
                float* tmp2C, scn_stream_t stream) {
     if (n <= 0) return SCN_OK;
-    int rc = ensure_scratch((size_t)NSLAB * 2 * C * sizeof(float));
+    ColScratch ws;
+    int rc = col_scratch(as_stream(stream), (size_t)NSLAB * 2 * C * sizeof(float), &ws);
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
     dim3 grid(NSLAB, cdiv(C, 32)), block(32, 8);
-    k_bn_bwd_partial<<<grid, block, 0, st>>>(x, y, dy, n, C, mean, var, eps, leak, g_scratch);
+    k_bn_bwd_partial<<<grid, block, 0, st>>>(x, y, dy, n, C, mean, var, eps, leak, ws.buf);
     rc = check_launch("bn_bwd_partial");
     if (rc) return rc;
-    k_bn_bwd_final<<<cdiv(C, 128), 128, 0, st>>>(g_scratch, NSLAB, C, tmp2C);
+    k_bn_bwd_final<<<cdiv(C, 128), 128, 0, st>>>(ws.buf, NSLAB, C, tmp2C);
     rc = check_launch("bn_bwd_final");
     if (rc) return rc;
     k_bn_bwd_dx<<<grid_for((int64_t)n * C, TB), TB, 0, st>>>(x, y, dy, n, C, mean, var, gamma, eps, leak, training, tmp2C, dx);
@@ -707,9 +728,10 @@ int scn_cross_entropy_fwd(const float* logits, int ld, int64_t n, int C, const i
     k_ce_rows<<<grid_for(n, TB), TB, 0, as_stream(stream)>>>(logits, ld, n, C, labels, weight, ignore_index, lse, row_scratch);
     int rc = check_launch("cross_entropy_rows");
     if (rc) return rc;
-    rc = ensure_scratch((size_t)NSLAB * 2 * 2 * sizeof(float));
+    ColScratch ws;
+    rc = col_scratch(as_stream(stream), (size_t)NSLAB * 2 * 2 * sizeof(float), &ws);
     if (rc) return rc;
-    return col_reduce(row_scratch, 2, (int)n, 2, nullptr, 1.f, stats, g_scratch, g_tickets, NSLAB, as_stream(stream));
+    return col_reduce(row_scratch, 2, (int)n, 2, nullptr, 1.f, stats, ws.buf, ws.tickets, NSLAB, as_stream(stream));
 }
 int scn_cross_entropy_bwd(const float* logits, int ld, int64_t n, int C, const int64_t* labels, const float* weight,
                           int64_t ignore_index, const float* lse, const float* stats, const float* grad_loss, float* dlogits,
