@@ -247,9 +247,18 @@ struct TsShape {
     static constexpr int FIXED_SMEM = 1024 + NWB * WBLOCK + 2 * TS_BLOB_BYTES + 512;      // + 2 * cap * PITCH
 };
 
-template <int C, bool RESIDENT, int GROUPS>
+// CL > 1 (streamed weights only): the CTAs of a cluster work on consecutive tiles IN LOCKSTEP -- every tile walks all 27
+// offsets in the same order -- so that a weight block is read from L2 ONCE per cluster: CTA r fetches the r-th 1/CL of the
+// block and multicasts it into the same ring stage of every CTA of the cluster (cp.async.bulk ... .multicast::cluster, the
+// completion bytes land on each CTA's own barrier); a stage is refilled when all CL consumers have released it
+// (tcgen05.commit ... .multicast::cluster arrives on every CTA's w_empty).  Why: with streamed weights every CTA pulled
+// every 12-16 KB block it used from L2 -- 390 MB per level-0-sized layer at C = 48, 6 TB/s at 65 us: L2 -> SM bandwidth
+// on the WEIGHTS was the bound (profiles/r2_b).
+template <int C, bool RESIDENT, int GROUPS, int CL = 1>
 __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_conv_ts(const ConvTsParams p) {
     using S = TsShape<C, RESIDENT, GROUPS>;
+    constexpr bool MC = CL > 1 && !RESIDENT;
+    constexpr uint32_t ALL_UNITS = (1u << TS_K) - 1u;
     constexpr int NB = S::NB, NW = S::NW, PITCH = S::PITCH, CPR = S::CPR, G = S::G;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -287,7 +296,7 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
         }
         for (int s = 0; s < NW; ++s) {
             mbar_init(w_full(s), 1);
-            mbar_init(w_empty(s), 1);
+            mbar_init(w_empty(s), MC ? CL : 1);      // every consumer CTA of the cluster releases the stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -300,6 +309,7 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (MC) cluster_sync_all();      // every CTA's barriers exist before a peer multicasts into them
     pdl_trigger();
     pdl_wait();
     if (warp == 0) TS_STAMP(16000);
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const int nl = nl_next;
-            uint32_t seq = seq_next;
+            uint32_t seq = MC ? ALL_UNITS : seq_next;
             {
                 const int tn = tile + gridDim.x;      // the next tile's header, one tile ahead
                 if (tn < n_tiles) nl_next = __ldg(p.book.nloc + tn), seq_next = __ldg(p.book.useq + tn);
@@ -489,17 +499,26 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
             }
         } else {
             UnitRing wr{0, 0};
+            const uint32_t rank = MC ? cluster_ctarank() : 0u;
+            constexpr uint32_t PART = (uint32_t)S::WBLOCK / (MC ? CL : 1);
+            // MC: every CTA of the cluster runs the same number of rounds (a CTA without a tile in the last round still
+            // fetches its share of every block and releases the stages: its peers depend on both)
+            const int rounds = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
 #pragma unroll 1
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                uint32_t seq = __ldg(p.book.useq + tile);      // the tile's units in processing order
+            for (int it = 0; it < rounds; ++it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                if (!MC && tile >= n_tiles) break;
+                uint32_t seq = MC ? ALL_UNITS : __ldg(p.book.useq + tile);      // the tile's units in processing order
 #pragma unroll 1
                 for (; seq; seq &= seq - 1u) {
                     const int o = (int)seq_offset((uint32_t)__ffs((int)seq) - 1u);
                     mbar_wait(w_empty(wr.s), wr.par ^ 1u);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(w_full(wr.s), (uint32_t)S::WBLOCK);
-                        bulk_g2s(w_base + (uint32_t)(wr.s * S::WBLOCK), p.image + (size_t)o * S::WBLOCK, (uint32_t)S::WBLOCK,
-                                 w_full(wr.s));
+                        const uint32_t dst = w_base + (uint32_t)(wr.s * S::WBLOCK) + rank * PART;
+                        const uint8_t* src = p.image + (size_t)o * S::WBLOCK + rank * PART;
+                        if (MC) bulk_g2s_multicast(dst, src, PART, w_full(wr.s), (uint16_t)((1u << CL) - 1u));
+                        else bulk_g2s(dst, src, PART, w_full(wr.s));
                     }
                     wr.step(NW);
                 }
@@ -515,10 +534,26 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
         int it = 0;
         [[maybe_unused]] int tb = 0;
         if (RESIDENT) mbar_wait(w_full(0), 0);
+        const int rounds = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
 #pragma unroll 1
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; it < rounds; tile += gridDim.x, ++it) {
+            if (tile >= n_tiles) {
+                if constexpr (MC) {
+                    // no tile in the last round: consume the weight stages like the peers do, multiply nothing
+#pragma unroll 1
+                    for (int u = 0; u < TS_K; ++u) {
+                        mbar_wait(w_full(wr.s), wr.par);
+                        if (elect_one()) mma_commit_multicast(w_empty(wr.s), (uint16_t)((1u << CL) - 1u));
+                        __syncwarp();
+                        wr.step(NW);
+                    }
+                    continue;
+                } else {
+                    break;
+                }
+            }
             const int b = it & 1;
-            uint32_t seq = __ldg(p.book.useq + tile);      // the tile's units; this warp issues no shared-memory loads at all
+            uint32_t seq = MC ? ALL_UNITS : __ldg(p.book.useq + tile);      // the tile's units; this warp reads no shared memory
             mbar_wait(acc_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(b * C);
@@ -556,7 +591,8 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
                                             wd + (uint64_t)((uint32_t)(kk >> 2) * KB_D + (uint32_t)((kk & 3) * 2)), idesc,
                                             (i == 0 && kk == 0) ? accum : 1u);
                             if (!RESIDENT) {
-                                mma_commit(w_empty(wr.s));
+                                if (MC) mma_commit_multicast(w_empty(wr.s), (uint16_t)((1u << CL) - 1u));
+                                else mma_commit(w_empty(wr.s));
                                 wr.step(NW);
                             }
                         }
@@ -641,6 +677,7 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();      // no CTA leaves while a peer may still write into its shared memory / barriers
     if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
@@ -661,7 +698,7 @@ bool tile_book_lookup(const int32_t* map, int n_out, TileBook* out) {
     return true;
 }
 
-template <int C, bool RESIDENT, int GROUPS>
+template <int C, bool RESIDENT, int GROUPS, int CL = 1>
 static int launch_ts(ConvTsParams& p, cudaStream_t stream) {
     using S = TsShape<C, RESIDENT, GROUPS>;
     constexpr int MAX_SMEM = 227 * 1024;
@@ -671,15 +708,17 @@ static int launch_ts(ConvTsParams& p, cudaStream_t stream) {
     if (cap < 192) return 0;
     p.cap = cap;
     const int smem = S::FIXED_SMEM + 2 * cap * S::PITCH;
-    auto kern = k_conv_ts<C, RESIDENT, GROUPS>;
+    auto kern = k_conv_ts<C, RESIDENT, GROUPS, CL>;
     cudaError_t e = (cudaError_t)ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
     if (e != cudaSuccess) {
         cudaGetLastError();
         set_error("conv_ts: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
         return -SCN_ERR_CUDA;
     }
-    const int grid = p.book.n_tiles < sm_count() ? p.book.n_tiles : sm_count();
-    PdlLaunch L(dim3(grid), dim3(S::THREADS), smem, stream);
+    int grid = p.book.n_tiles < sm_count() ? p.book.n_tiles : sm_count();
+    grid = grid / CL * CL;      // whole clusters
+    if (grid < CL) return 0;
+    PdlLaunch L(dim3(grid), dim3(S::THREADS), smem, stream, CL);
     e = cudaLaunchKernelEx(&L.cfg, kern, p);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -723,11 +762,17 @@ int conv_ts_try(const float* in, int ld_in, int Cin, const int32_t* map, int n_o
         const char* e = getenv("SCN_CONV_TS_GROUPS");
         groups = e ? atoi(e) : 4;
     }
+    // streamed weights: CTAs per cluster sharing each weight block by multicast.  Parity-tested (SCN_CONV_TS_CLUSTER=2) but
+    // measured neutral (C = 48: 69.2 vs 68.1 us, C = 64: 94.6 vs 89.8 us): halving the L2 -> SM weight bytes does not help
+    // because the ring is bound by the LATENCY of a refill behind its own release, not by bandwidth; off by default
+    const char* ce = getenv("SCN_CONV_TS_CLUSTER");
+    const int cluster = ce ? atoi(ce) : 1;
     switch (Cin) {
         case 16: return groups == 6 ? launch_ts<16, true, 6>(p, stream) : launch_ts<16, true, 4>(p, stream);
         case 32: return groups == 6 ? launch_ts<32, true, 6>(p, stream) : launch_ts<32, true, 4>(p, stream);
-        case 48: return launch_ts<48, false, 4>(p, stream);
-        default: return launch_ts<64, false, 3>(p, stream);      // 6 A stages of 64 columns: two batches of three
+        case 48: return cluster == 2 ? launch_ts<48, false, 4, 2>(p, stream) : launch_ts<48, false, 4>(p, stream);
+        default:      // 6 A stages of 64 columns: two batches of three
+            return cluster == 2 ? launch_ts<64, false, 3, 2>(p, stream) : launch_ts<64, false, 3>(p, stream);
     }
 }
 

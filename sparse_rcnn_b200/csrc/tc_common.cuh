@@ -144,6 +144,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
+// the same copy delivered to the same shared-memory offset of every CTA in cta_mask; each destination CTA's barrier (same
+// offset) receives the completion bytes
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+        : "memory");
+}
+// arrive (once all tcgen05 operations issued so far by this thread have completed) on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 in
 // [0,14), LBO>>4 in [16,30) (unused for swizzled K-major, set to 1), SBO>>4 in [32,46) = 1024 B
 // between 8-row groups, version=1 in [46,48), layout_type=2 (SWIZZLE_128B) in [61,64).

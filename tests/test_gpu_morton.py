@@ -188,8 +188,13 @@ def test_tile_book_reproduces_the_map(cuda, bench_level):
         nloc.mean(), nloc.max(), 100.0 * (1 - blobs[:, 0].astype(float).sum() / (27.0 * nt))))
 
 
-@pytest.mark.parametrize("C", [32, 16, 48, 64])
+@pytest.mark.parametrize("C", [32, 16, 48, 64, -48, -64])
 def test_tile_local_kernel_equals_rule_kernel(cuda, bench_level, monkeypatch, C):
+    if C < 0:      # streamed weights shared by the two CTAs of a cluster (multicast); opt-in variant
+        monkeypatch.setenv("SCN_CONV_TS_CLUSTER", "2")
+        C = -C
+    else:
+        monkeypatch.setenv("SCN_CONV_TS_CLUSTER", "1")
     """conv_ts.cu (halo set in shared memory, A operand in tensor memory) against conv_tc.cu (cp.async gather per offset) on
     the bench scene: same TF32 products accumulated in the same offset order; forward with every epilogue, input gradient."""
     from sparse_rcnn_b200 import networks, scn
