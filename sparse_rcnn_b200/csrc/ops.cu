@@ -382,6 +382,8 @@ __global__ void __launch_bounds__(256) k_crop_select(const uint64_t* __restrict_
     __shared__ int bx[6];
     __shared__ int wcnt[8];
     __shared__ int base;
+    // most (box, chunk) pairs select nothing (a box covers a small part of its scene): the count pass already knows
+    if (offsets[box * n_chunks + chunk + 1] == offsets[box * n_chunks + chunk] && !is_inside) return;
     if (threadIdx.x < 6) bx[threadIdx.x] = boxes[box * 6 + threadIdx.x];
     if (threadIdx.x == 0) base = offsets[box * n_chunks + chunk];
     __syncthreads();

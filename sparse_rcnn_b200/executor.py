@@ -172,7 +172,11 @@ class UNetProgram:
             g[4 * i] = lvl.n
             needs_subm = bool(self.enc[i][2]) or (self.enc[i][0] == 1 and self.enc[i][1].filter_size == (3, 3, 3)) or \
                 (i < nl - 1 and self.dec and bool(self.dec[nl - 2 - i][2]))
-            m = lvl.subm_map(3) if (needs_subm and lvl.n) else None
+            m = lvl.subm_map(3, tile_book=False) if (needs_subm and lvl.n) else None
+            if m is not None:      # tile book only where a layer of a width the tile-local kernels implement runs
+                units = self.enc[i][2] or (self.dec[nl - 2 - i][2] if (i < nl - 1 and self.dec) else [])
+                if units:
+                    lvl.ensure_tile_book(units[0][0].nIn)
             g[4 * i + 1] = 0 if m is None else m.data_ptr()
             if i < nl - 1:
                 r = md.strided_rules(size, 2, 2)

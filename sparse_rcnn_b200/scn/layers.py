@@ -125,7 +125,9 @@ class Sequential(nn.Sequential):
             for c1, c2 in item:
                 params += [c1.weight, c1.bias, c2.weight, c2.bias]
             lvl = x.metadata.level(x.spatial_size)
-            f = F.ResidualUnitFunction.run(x.features, lvl.subm_map(item[0][0].filter_size), lvl.n, *params)
+            fmap = lvl.subm_map(item[0][0].filter_size, tile_book=False)
+            lvl.ensure_tile_book(item[0][0].nIn)
+            f = F.ResidualUnitFunction.run(x.features, fmap, lvl.n, *params)
             x = SparseConvNetTensor(f, x.metadata, x.spatial_size)
         return x
 
@@ -231,7 +233,9 @@ class SubmanifoldConvolution(nn.Module):
 
     def forward(self, x):
         lvl = x.metadata.level(x.spatial_size)
-        m = lvl.subm_map(self.filter_size)
+        m = lvl.subm_map(self.filter_size, tile_book=False)
+        if self.nIn == self.nOut and self.filter_size == (3, 3, 3):
+            lvl.ensure_tile_book(self.nIn)
         f = F.ConvFunction.run(x.features, self.weight, self.bias, m, m, lvl.n, 1)
         return _like(x, f)
 

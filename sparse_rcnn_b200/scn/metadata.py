@@ -8,6 +8,8 @@ here every scale is a `Level` living in HBM: packed row keys, an open-addressing
 table key->row, and cached output-stationary neighbour maps.  All buffers are torch
 tensors (caching allocator); the C ABI only sees raw pointers.
 """
+import os
+
 import numpy as np
 import threading
 
@@ -122,7 +124,10 @@ class Level:
             self._batch_ptr[n_seg] = p
         return self._batch_ptr[n_seg]
 
-    def subm_map(self, filter_size):
+    def subm_map(self, filter_size, tile_book=True):
+        """Neighbour map [K, n] of an odd filter.  tile_book=True also builds the tile book of a 3^3 map right away (direct
+        users of the C ABI); the module / executor paths pass False and call `ensure_tile_book(channels)` when a layer that
+        the tile-local kernels can take actually runs on this level (a 22-channel mask-network level never needs one)."""
         f = _triple(filter_size)
         if f not in self.subm:
             if f == (1, 1, 1):
@@ -133,16 +138,28 @@ class Level:
                 _lib.call("scn_subm_map", _ptr(self.keys), self.n, _ptr(self.tab_keys), _ptr(self.tab_vals),
                           self.cap, f[0], f[1], f[2], _ptr(m), _stream())
                 self.subm[f] = m
-                if f == (3, 3, 3) and self.coherent and self.n >= TILE_BOOK_MIN_ROWS:
-                    # tile book for the tile-local convolution kernel (csrc/conv_ts.cu): halo lists + 16-bit local maps
-                    book = torch.empty(int(_lib.raw("scn_tile_book_bytes")(self.n)), dtype=torch.uint8, device=m.device)
-                    _lib.call("scn_tile_book_build", _ptr(m), self.n, K, _ptr(book), _stream())
-                    _lib.call("scn_tile_book_attach", _ptr(m), _ptr(book), self.n)
-                    self._books[m.data_ptr()] = book
+        if (tile_book or _EAGER_BOOKS) and f == (3, 3, 3):
+            self.ensure_tile_book()
         return self.subm[f]
+
+    def ensure_tile_book(self, channels=None):
+        """Tile book of the 3^3 map for the tile-local kernels (csrc/conv_ts.cu, conv_wgrad_ts.cu): halo lists + 16-bit local
+        maps, built once per level -- only for Morton-ordered levels with enough tiles, and (when the caller names its layer
+        width) only for widths those kernels implement."""
+        m = self.subm.get((3, 3, 3))
+        if m is None or not self.coherent or self.n < TILE_BOOK_MIN_ROWS or m.data_ptr() in self._books:
+            return
+        if channels is not None and channels not in TILE_LOCAL_CHANNELS:
+            return
+        book = torch.empty(int(_lib.raw("scn_tile_book_bytes")(self.n)), dtype=torch.uint8, device=m.device)
+        _lib.call("scn_tile_book_build", _ptr(m), self.n, 27, _ptr(book), _stream())
+        _lib.call("scn_tile_book_attach", _ptr(m), _ptr(book), self.n)
+        self._books[m.data_ptr()] = book
 
 
 TILE_BOOK_MIN_ROWS = 128 * 148 * 2      # levels with fewer tiles run conv_tc.cu's cluster-split mode anyway
+TILE_LOCAL_CHANNELS = (16, 32, 48, 64)    # C -> C layers csrc/conv_ts.cu implements
+_EAGER_BOOKS = os.environ.get("SCN_TILE_BOOK_EAGER", "0") == "1"      # A/B switch: a book for every large Morton level
 
 
 def build_level(keys, morton_bits=None):
@@ -292,7 +309,7 @@ class Metadata:
 
             def own_maps(lvl=lvl):      # this level's neighbour map (+ tile book): independent of the next level's count
                 if subm_filter and lvl.n:
-                    lvl.subm_map(subm_filter)
+                    lvl.subm_map(subm_filter, tile_book=False)
             if _ == n_levels or any(s % 2 for s in size) or min(size) < 2:
                 own_maps()
                 break
