@@ -250,7 +250,11 @@ def main():
                          "good runs but is not stable (3 runs: 6.5 / 6.4 / 7.0 ms, e2e 6.1 / 5.8 / 20.9 ms -- the worker shares "
                          "the GIL and the launch queue with the training thread); without it 6.22 +- 0.01 ms "
                          "(profiles/r2_e_executor.md)")
-    ap.set_defaults(stage=True)
+    ap.add_argument("--no-build-late", dest="build_late", action="store_false",
+                    help="do NOT build the following batch's rulebooks at the end of each step on a side stream "
+                         "(BackboneTrainer.build_late; the batch is known one step ahead, as with a DataLoader).  Every step "
+                         "still builds exactly one geometry inside the timed loop")
+    ap.set_defaults(stage=True, build_late=True)
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -292,7 +296,8 @@ def main():
         # (--no-build-ahead: at the head of its own step); every step still builds exactly one geometry and uploads exactly
         # one batch inside the loop (h2d_bytes_per_step)
         trainer.stage_uploads, trainer.build_ahead = args.stage, args.build_ahead
-        nb = (lambda i: inputs[(i + 1) % n_distinct]) if (args.stage or args.build_ahead) else (lambda i: None)
+        trainer.build_late = args.build_late and not args.prefetch
+        nb = (lambda i: inputs[(i + 1) % n_distinct]) if (args.stage or args.build_ahead or args.build_late) else (lambda i: None)
         # every distinct scene once before the warm-up proper: first-touch costs of a new geometry (caching-allocator growth,
         # dynamic-smem attributes) must not land in the timed region when W < n_distinct
         for i in range(n_distinct):

@@ -188,6 +188,14 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
                       const void* image, const float* bias, const float* residual, int ld_res,
                       const float* mask, int ld_mask, float* out, int ld_out, int Cout, int epi_flags,
                       scn_stream_t stream);
+/* Same with a second output (out2 may be NULL): out2 = epi2(out), epi2_flags a subset of SCN_EPI_RELU | SCN_EPI_ROUND.
+ * In the reference's graph (module_factory.py:127-183) every residual unit starts with scn.ReLU on a tensor whose
+ * unrectified value the AddTable shortcut still needs; the producing convolution writes both instead of a separate
+ * elementwise pass per unit. */
+int scn_conv_fwd_tf32_dual(const float* in, int ld_in, int Cin, int n_in, const int32_t* map, int n_out, int K,
+                           const void* image, const float* bias, const float* residual, int ld_res,
+                           const float* mask, int ld_mask, float* out, int ld_out, int Cout, int epi_flags,
+                           float* out2, int ld_out2, int epi2_flags, scn_stream_t stream);
 /* exact fp32 FFMA path (verification mode, <=1e-5).  w is the raw [K, Cin_w, Cout_w] tensor;
  * transpose/reverse as above. */
 int scn_conv_fwd_fp32(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K,

@@ -66,6 +66,22 @@ struct PdlLaunch {
     }
 };
 
+// ---------------------------------------------------------------- second output of a convolution epilogue
+// out2 = epi2(out): ReLU and / or round-to-nearest TF32 of the value just written -- the operand the NEXT gather-GEMM reads
+// (the residual chain keeps the unrounded value), saving that layer's separate elementwise pass.
+__device__ __forceinline__ float epi2_apply(float x, int epi2) {
+    if (epi2 & SCN_EPI_RELU) x = fmaxf(x, 0.f);
+    if (epi2 & SCN_EPI_ROUND) {
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+        x = __uint_as_float(t);
+    }
+    return x;
+}
+__device__ __forceinline__ float4 epi2_apply4(float4 v, int epi2) {
+    return make_float4(epi2_apply(v.x, epi2), epi2_apply(v.y, epi2), epi2_apply(v.z, epi2), epi2_apply(v.w, epi2));
+}
+
 // ---------------------------------------------------------------- packed voxel keys
 __host__ __device__ __forceinline__ uint64_t make_key(uint32_t x, uint32_t y, uint32_t z, uint32_t b) {
     return ((uint64_t)b << 48) | ((uint64_t)x << 32) | ((uint64_t)y << 16) | (uint64_t)z;

@@ -58,6 +58,8 @@ struct ConvTcParams {
     int ld_mask;
     float* out;
     int ld_out, Cout, epi;
+    float* out2;          // optional second output: out2 = epi2(out) (RELU and / or ROUND), the next layer's operand
+    int ld_out2, epi2;
     int cout_pad, n_kb, cin_pad8, stages, tmem_cols, n_tiles;
     int osplit, opg;      // offsets of a tile are split over `osplit` work items of `opg` offsets each (small levels)
     float* scratch;       // split mode: accumulation buffer [n_out][Cout], all-zero between launches
@@ -495,6 +497,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
         int it = 0;
         const int epi = p.epi;
         const bool vec_ok = (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                            (!p.out2 || ((p.ld_out2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out2) & 15) == 0))) &&
                             (!(epi & SCN_EPI_ADD) ||
                              ((p.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
                             (!(epi & SCN_EPI_MASK) ||
@@ -517,6 +520,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
         // bias / mask / residual / ReLU / rounding of 16 accumulator columns of one row, then the store
         auto finish_store = [&](float (&v)[16], int row, int c0) {
             float* orow = p.out + (int64_t)row * p.ld_out + c0;
+            float* orow2 = p.out2 ? p.out2 + (int64_t)row * p.ld_out2 + c0 : nullptr;
             const float* rrow = (epi & SCN_EPI_ADD) ? p.residual + (int64_t)row * p.ld_res + c0 : nullptr;
             const float* mrow = (epi & SCN_EPI_MASK) ? p.mask + (int64_t)row * p.ld_mask + c0 : nullptr;
             if (p.bias) {
@@ -533,11 +537,16 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                     x.x = finish(v[j], m4.x, r4.x), x.y = finish(v[j + 1], m4.y, r4.y);
                     x.z = finish(v[j + 2], m4.z, r4.z), x.w = finish(v[j + 3], m4.w, r4.w);
                     *reinterpret_cast<float4*>(orow + j) = x;
+                    if (orow2) *reinterpret_cast<float4*>(orow2 + j) = epi2_apply4(x, p.epi2);
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (c0 + j < p.Cout) orow[j] = finish(v[j], mrow ? mrow[j] : 1.f, rrow ? rrow[j] : 0.f);
+                    if (c0 + j < p.Cout) {
+                        const float y = finish(v[j], mrow ? mrow[j] : 1.f, rrow ? rrow[j] : 0.f);
+                        orow[j] = y;
+                        if (orow2) orow2[j] = epi2_apply(y, p.epi2);
+                    }
             }
         };
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
@@ -642,6 +651,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                                     y.x = fin1(x[u].x, gr, c), y.y = fin1(x[u].y, gr, c + 1);
                                     y.z = fin1(x[u].z, gr, c + 2), y.w = fin1(x[u].w, gr, c + 3);
                                     *reinterpret_cast<float4*>(p.out + (int64_t)gr * p.ld_out + c) = y;
+                                    if (p.out2) *reinterpret_cast<float4*>(p.out2 + (int64_t)gr * p.ld_out2 + c) = epi2_apply4(y, p.epi2);
                                 }
                             }
                         }
@@ -651,7 +661,9 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                             const int r = e / p.Cout, c = e - r * p.Cout;
                             const float x = __ldcg(abase + e);
                             __stcg(abase + e, 0.f);
-                            p.out[(int64_t)(row0 + r) * p.ld_out + c] = fin1(x, row0 + r, c);
+                            const float y = fin1(x, row0 + r, c);
+                            p.out[(int64_t)(row0 + r) * p.ld_out + c] = y;
+                            if (p.out2) p.out2[(int64_t)(row0 + r) * p.ld_out2 + c] = epi2_apply(y, p.epi2);
                         }
                     }
                 }
@@ -693,7 +705,8 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                 return x;
             };
             if (r_hi > r_lo) {
-                const bool v4 = (p.Cout & 3) == 0 && (p.ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+                const bool v4 = (p.Cout & 3) == 0 && (p.ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+                                (!p.out2 || ((p.ld_out2 & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out2) & 15) == 0));
                 if (v4) {
                     const int q = p.Cout >> 2, total = (r_hi - r_lo) * q;
                     for (int e = tid; e < total; e += 128) {
@@ -710,6 +723,7 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
                         acc.x = fin1(acc.x, gr, c), acc.y = fin1(acc.y, gr, c + 1), acc.z = fin1(acc.z, gr, c + 2);
                         acc.w = fin1(acc.w, gr, c + 3);
                         *reinterpret_cast<float4*>(p.out + (int64_t)gr * p.ld_out + c) = acc;
+                        if (p.out2) *reinterpret_cast<float4*>(p.out2 + (int64_t)gr * p.ld_out2 + c) = epi2_apply4(acc, p.epi2);
                     }
                 } else {
                     const int total = (r_hi - r_lo) * p.Cout;
@@ -720,7 +734,9 @@ __global__ void __launch_bounds__(TMA ? 192 : CONV_THREADS, TMA ? 2 : 3) k_conv_
 #pragma unroll
                         for (int rr = 0; rr < 8; ++rr)
                             if (rr < cs) acc += ld_dsmem_f32(rbase[rr] + off);
-                        p.out[(int64_t)(row0 + r) * p.ld_out + c] = fin1(acc, row0 + r, c);
+                        acc = fin1(acc, row0 + r, c);
+                        p.out[(int64_t)(row0 + r) * p.ld_out + c] = acc;
+                        if (p.out2) p.out2[(int64_t)(row0 + r) * p.ld_out2 + c] = epi2_apply(acc, p.epi2);
                     }
                 }
             }
@@ -951,6 +967,15 @@ int scn_conv_pack_weights_multi(const int64_t* table, int n, scn_stream_t stream
 int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32_t* map, int n_out, int K, const void* image,
                       const float* bias, const float* residual, int ld_res, const float* mask, int ld_mask, float* out,
                       int ld_out, int Cout, int epi_flags, scn_stream_t stream) {
+    return scn_conv_fwd_tf32_dual(in, ld_in, Cin, n_in, map, n_out, K, image, bias, residual, ld_res, mask, ld_mask, out, ld_out, Cout,
+                                  epi_flags, nullptr, 0, 0, stream);
+}
+
+int scn_conv_fwd_tf32_dual(const float* in, int ld_in, int Cin, int n_in, const int32_t* map, int n_out, int K, const void* image,
+                           const float* bias, const float* residual, int ld_res, const float* mask, int ld_mask, float* out,
+                           int ld_out, int Cout, int epi_flags, float* out2, int ld_out2, int epi2_flags, scn_stream_t stream) {
+    SCN_REQUIRE(!out2 || (ld_out2 >= Cout && !(epi2_flags & ~(SCN_EPI_RELU | SCN_EPI_ROUND)) && out2 != out),
+                "conv_fwd_tf32: second output takes RELU / ROUND only and its own buffer");
     SCN_REQUIRE(Cin > 0 && Cout > 0 && K > 0, "conv_fwd_tf32: bad shape Cin=%d Cout=%d K=%d", Cin, Cout, K);
     SCN_REQUIRE(Cout <= 256, "conv_fwd_tf32: Cout > 256 not supported (got %d)", Cout);
     SCN_REQUIRE(map || K == 1, "conv_fwd_tf32: identity map requires K == 1");
@@ -965,7 +990,7 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     {
         // submanifold 3^3 layers over a map with an attached tile book (Morton-ordered rows): tile-local kernel, conv_ts.cu
         const int ts = scn::conv_ts_try(in, ld_in, Cin, map, n_out, K, image, bias, residual, ld_res, mask, ld_mask, out, ld_out,
-                                        Cout, epi_flags, as_stream(stream));
+                                        Cout, epi_flags, out2, ld_out2, epi2_flags, as_stream(stream));
         if (ts > 0) return SCN_OK;
         if (ts < 0) return -ts;
     }
@@ -975,6 +1000,7 @@ int scn_conv_fwd_tf32(const float* in, int ld_in, int Cin, int n_in, const int32
     p.image = reinterpret_cast<const uint8_t*>(image), p.bias = bias, p.residual = residual, p.ld_res = ld_res;
     p.mask = mask, p.ld_mask = ld_mask;
     p.out = out, p.ld_out = ld_out, p.Cout = Cout, p.epi = epi_flags;
+    p.out2 = out2, p.ld_out2 = ld_out2, p.epi2 = epi2_flags;
     p.cout_pad = pad16(Cout), p.n_kb = n_kblocks(Cin), p.cin_pad8 = (Cin + 7) / 8 * 8;
     p.n_tiles = cdiv(n_out, TILE_M);
     int cols = 2 * p.cout_pad, tc = 32;

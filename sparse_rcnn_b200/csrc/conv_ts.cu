@@ -163,6 +163,8 @@ struct ConvTsParams {
     int ld_mask;
     float* out;
     int ld_out, epi;
+    float* out2;             // optional second output, out2 = epi2(out) (common.cuh: epi2_apply)
+    int ld_out2, epi2;
     int cap;                 // halo rows per shared-memory buffer
 };
 
@@ -618,6 +620,7 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
         // ===================== epilogue warps 0..3 (as conv_tc.cu, whole tiles only) =====================
         const int epi = p.epi;
         const bool vec_ok = (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                            (!p.out2 || ((p.ld_out2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out2) & 15) == 0))) &&
                             (!(epi & SCN_EPI_ADD) || ((p.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
                             (!(epi & SCN_EPI_MASK) || ((p.ld_mask % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
         auto finish = [&](float x, float m, float r) {      // order: (bias), MASK, ADD, RELU, ROUND
@@ -647,6 +650,7 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
                 tmem_ld16(taddr + c0, v);
                 if (row < p.book.n_out) {
                     float* orow = p.out + (int64_t)row * p.ld_out + c0;
+                    float* orow2 = p.out2 ? p.out2 + (int64_t)row * p.ld_out2 + c0 : nullptr;
                     const float* rrow = (epi & SCN_EPI_ADD) ? p.residual + (int64_t)row * p.ld_res + c0 : nullptr;
                     const float* mrow = (epi & SCN_EPI_MASK) ? p.mask + (int64_t)row * p.ld_mask + c0 : nullptr;
                     if (p.bias) {
@@ -662,10 +666,15 @@ __global__ void __launch_bounds__(TsShape<C, RESIDENT, GROUPS>::THREADS, 1) k_co
                             x.x = finish(v[j], m4.x, r4.x), x.y = finish(v[j + 1], m4.y, r4.y);
                             x.z = finish(v[j + 2], m4.z, r4.z), x.w = finish(v[j + 3], m4.w, r4.w);
                             *reinterpret_cast<float4*>(orow + j) = x;
+                            if (orow2) *reinterpret_cast<float4*>(orow2 + j) = epi2_apply4(x, p.epi2);
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) orow[j] = finish(v[j], mrow ? mrow[j] : 1.f, rrow ? rrow[j] : 0.f);
+                        for (int j = 0; j < 16; ++j) {
+                            const float y = finish(v[j], mrow ? mrow[j] : 1.f, rrow ? rrow[j] : 0.f);
+                            orow[j] = y;
+                            if (orow2) orow2[j] = epi2_apply(y, p.epi2);
+                        }
                     }
                 }
             }
@@ -734,7 +743,7 @@ static int launch_ts(ConvTsParams& p, cudaStream_t stream) {
 // 0 if the caller should use conv_tc.cu, < 0 (negated status) on error.
 int conv_ts_try(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const void* image, const float* bias,
                 const float* residual, int ld_res, const float* mask, int ld_mask, float* out, int ld_out, int Cout, int epi,
-                cudaStream_t stream) {
+                float* out2, int ld_out2, int epi2, cudaStream_t stream) {
     if (K != TS_K || !map || Cin != Cout) return 0;
     const char* ev = getenv("SCN_CONV_TS");      // read per call: tests run both kernels in one process
     if (ev && ev[0] == '0') return 0;
@@ -757,6 +766,7 @@ int conv_ts_try(const float* in, int ld_in, int Cin, const int32_t* map, int n_o
     p.in = in, p.ld_in = ld_in, p.book = book_layout(be.book, n_out), p.map = map;
     p.image = reinterpret_cast<const uint8_t*>(image), p.bias = bias, p.residual = residual, p.ld_res = ld_res;
     p.mask = mask, p.ld_mask = ld_mask, p.out = out, p.ld_out = ld_out, p.epi = epi;
+    p.out2 = out2, p.ld_out2 = ld_out2, p.epi2 = epi2;
     static int groups = -1;
     if (groups < 0) {
         const char* e = getenv("SCN_CONV_TS_GROUPS");

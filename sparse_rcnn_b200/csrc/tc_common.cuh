@@ -11,7 +11,7 @@ namespace scn {
 // conv_ts.cu: tile-local submanifold kernel; 1 = launched, 0 = not applicable (use conv_tc.cu), < 0 = -status
 int conv_ts_try(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const void* image, const float* bias,
                 const float* residual, int ld_res, const float* mask, int ld_mask, float* out, int ld_out, int Cout, int epi,
-                cudaStream_t stream);
+                float* out2, int ld_out2, int epi2, cudaStream_t stream);
 // conv_wgrad_ts.cu: tile-local, deterministic weight gradient; same return convention
 int conv_wgrad_ts_try(const float* in, int ld_in, int Cin, const int32_t* map, int n_out, int K, const float* go, int ld_go, int Cout,
                       float* gw, float* gb, cudaStream_t stream);

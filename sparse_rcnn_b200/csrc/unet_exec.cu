@@ -137,7 +137,7 @@ struct Plan {
     int64_t e_gyr[MAX_LEVELS][MAX_UNITS], e_gh[MAX_LEVELS][MAX_UNITS], e_gx[MAX_LEVELS][MAX_UNITS], e_round[MAX_LEVELS];
     int64_t d_gyr[MAX_LEVELS][MAX_UNITS], d_gh[MAX_LEVELS][MAX_UNITS], d_gx[MAX_LEVELS][MAX_UNITS], d_round_nin[MAX_LEVELS],
         d_round_up[MAX_LEVELS];
-    int64_t g_cat[MAX_LEVELS], g_up[MAX_LEVELS], g_skip[MAX_LEVELS], g_rl[MAX_LEVELS];
+    int64_t g_cat[MAX_LEVELS], g_up[MAX_LEVELS], g_skip[MAX_LEVELS], g_rl[MAX_LEVELS], g_catr[MAX_LEVELS];
     int64_t bwd_total;
 };
 
@@ -182,6 +182,7 @@ static void make_plan(const Net& net, const Geo& g, Plan& P) {
             P.d_gyr[j][u] = b.take(n, net.CD[j]), P.d_gh[j][u] = b.take(n, net.CD[j]), P.d_gx[j][u] = b.take(n, net.CD[j]);
         P.g_cat[j] = b.take(n, net.nin[j].cin), P.g_up[j] = b.take(n, net.deconv[j].cout), P.g_skip[j] = b.take(n, net.C[l]);
         P.g_rl[j] = b.take(g.n[l + 1], net.deconv[j].cin);
+        P.g_catr[j] = b.take(n, net.nin[j].cin);
     }
     P.bwd_total = b.off;
 }
@@ -197,13 +198,38 @@ static int copy_cols(float* dst, int ld_dst, const float* src, int ld_src, int n
     return SCN_OK;
 }
 
-// a chain of residual units over one level, forward
-static int stage_fwd(const Unit* units, int U, const float* x, int n, int C, const int32_t* map, float* base, const int64_t* r,
-                     const int64_t* h, const int64_t* y, int tf32, scn_stream_t s) {
+// Second outputs (scn_conv_fwd_tf32_dual): in TF32 mode the convolution that produces a tensor also writes the operand its
+// consumer gathers -- relu + round for the next residual unit / the decoder's ReLU -> Deconvolution, round for the next
+// level's strided convolution, round of a gradient for the next transposed convolution -- instead of one elementwise
+// kernel per consumer (54 of the ~380 launches of a training step; every one of them sat on the dependency chain).  Same
+// values as the separate passes, bit for bit.  SCN_EXEC_DUAL=0 restores the separate kernels (read per call: tests).
+static bool dual_outputs() {
+    const char* e = getenv("SCN_EXEC_DUAL");
+    return !(e && e[0] == '0');
+}
+struct Out2 {
+    float* p;
+    int epi;
+};
+static const Out2 NO_OUT2 = {nullptr, 0};
+
+// a chain of residual units over one level, forward.  r_ready: r[0] already holds relu(x) (rounded), written by x's producer;
+// tail: second output of the chain's last convolution
+static int stage_fwd(const Unit* units, int U, const float* x, bool r_ready, int n, int C, const int32_t* map, float* base,
+                     const int64_t* r, const int64_t* h, const int64_t* y, bool dual, Out2 tail, int tf32, scn_stream_t s) {
     for (int u = 0; u < U; ++u) {
         const Unit& q = units[u];
-        SCN_TRY(scn_residual_unit_fwd(x, n, C, map, 27, q.w1, q.b1, q.w2, q.b2, q.i1f, q.i2f, 0, base + r[u], base + h[u], base + y[u],
-                                      tf32, s));
+        if (!tf32) {
+            SCN_TRY(scn_residual_unit_fwd(x, n, C, map, 27, q.w1, q.b1, q.w2, q.b2, q.i1f, q.i2f, 0, base + r[u], base + h[u], base + y[u],
+                                          tf32, s));
+        } else if (n > 0) {
+            if (!(dual && (u > 0 || r_ready))) SCN_TRY(scn_relu_fwd(x, base + r[u], (int64_t)n * C, 1, s));
+            SCN_TRY(scn_conv_fwd_tf32(base + r[u], C, C, n, map, n, 27, q.i1f, q.b1, nullptr, 0, nullptr, 0, base + h[u], C, C,
+                                      SCN_EPI_RELU | SCN_EPI_ROUND, s));
+            const Out2 o = !dual ? NO_OUT2 : (u + 1 < U ? Out2{base + r[u + 1], SCN_EPI_RELU | SCN_EPI_ROUND} : tail);
+            SCN_TRY(scn_conv_fwd_tf32_dual(base + h[u], C, C, n, map, n, 27, q.i2f, q.b2, x, C, nullptr, 0, base + y[u], C, C, SCN_EPI_ADD,
+                                           o.p, C, o.epi, s));
+        }
         x = base + y[u];
     }
     return SCN_OK;
@@ -278,15 +304,17 @@ static int side_for(cudaStream_t main, Side& S) {
 }
 
 // one residual unit backward: the kernels of scn_residual_unit_bwd (accumulate mode), input-gradient chain on the main
-// stream, the two weight gradients on the side stream
-static int unit_bwd(const Unit& q, const float* gy, const float* r, const float* h, int n, int C, const int32_t* map, float* gyr,
-                    float* gh, float* gx, float* gw1, float* gb1, float* gw2, float* gb2, int tf32, scn_stream_t s, Side& side) {
+// stream, the two weight gradients on the side stream.  gyr_ready: gyr already holds round(gy) (second output of gy's
+// producer); gx2: second output of the convolution that produces gx
+static int unit_bwd(const Unit& q, const float* gy, bool gyr_ready, const float* r, const float* h, int n, int C, const int32_t* map,
+                    float* gyr, float* gh, float* gx, Out2 gx2, float* gw1, float* gb1, float* gw2, float* gb2, int tf32, scn_stream_t s,
+                    Side& side) {
     if (n == 0) return SCN_OK;
     const int K = 27;
     const int64_t total = (int64_t)n * C;
     const float* g_op = gy;
     if (tf32) {
-        SCN_TRY(scn_round_tf32(gy, gyr, total, s));
+        if (!gyr_ready) SCN_TRY(scn_round_tf32(gy, gyr, total, s));
         g_op = gyr;
     }
     if (gw2 || gb2) {
@@ -304,47 +332,56 @@ static int unit_bwd(const Unit& q, const float* gy, const float* r, const float*
         else SCN_TRY(scn_col_sum_add(gh, C, n, C, gb1, side.wstream()));
     }
     if (tf32)
-        SCN_TRY(scn_conv_fwd_tf32(gh, C, C, n, map, n, K, q.i1b, nullptr, gy, C, r, C, gx, C, C, SCN_EPI_MASK | SCN_EPI_ADD, s));
+        SCN_TRY(scn_conv_fwd_tf32_dual(gh, C, C, n, map, n, K, q.i1b, nullptr, gy, C, r, C, gx, C, C, SCN_EPI_MASK | SCN_EPI_ADD, gx2.p, C,
+                                       gx2.epi, s));
     else
         SCN_TRY(scn_conv_fwd_fp32(gh, C, C, map, n, K, q.w1, 1, 1, nullptr, gy, C, r, C, gx, C, C, SCN_EPI_MASK | SCN_EPI_ADD, s));
     return SCN_OK;
 }
 
-// ... a chain of units: gy -> gradient wrt the stage input (returned through *gx_out)
+// ... a chain of units: gy -> gradient wrt the stage input (returned through *gx_out).  head: where the layer in front of the
+// stage wants round(gradient of the stage input) (second output of unit 0's last convolution)
 static int stage_bwd(const Unit* units, int U, const float* gy, int n, int C, const int32_t* map, const float* fbase, const int64_t* r,
-                     const int64_t* h, float* bbase, const int64_t* gyr, const int64_t* gh, const int64_t* gxs, float* const* pg, int tf32,
-                     scn_stream_t s, Side& side, const float** gx_out) {
+                     const int64_t* h, float* bbase, const int64_t* gyr, const int64_t* gh, const int64_t* gxs, float* const* pg, bool dual,
+                     Out2 head, int tf32, scn_stream_t s, Side& side, const float** gx_out) {
+    bool ready = false;
     for (int u = U - 1; u >= 0; --u) {
         float* gx = bbase + gxs[u];
-        SCN_TRY(unit_bwd(units[u], gy, fbase + r[u], fbase + h[u], n, C, map, bbase + gyr[u], bbase + gh[u], gx, pg[4 * u], pg[4 * u + 1],
-                         pg[4 * u + 2], pg[4 * u + 3], tf32, s, side));
+        const Out2 o = !dual ? NO_OUT2 : (u > 0 ? Out2{bbase + gyr[u - 1], SCN_EPI_ROUND} : head);
+        SCN_TRY(unit_bwd(units[u], gy, ready, fbase + r[u], fbase + h[u], n, C, map, bbase + gyr[u], bbase + gh[u], gx, o, pg[4 * u],
+                         pg[4 * u + 1], pg[4 * u + 2], pg[4 * u + 3], tf32, s, side));
         gy = gx;
+        ready = dual && n > 0;
     }
     *gx_out = gy;
     return SCN_OK;
 }
 
-// one convolution layer backward: the kernels of scn_conv_layer_bwd, weight gradient on the side stream
-static int conv_bwd(const float* go, int n_out, int Cout, float* go_round, const float* x, int ld_x, int n_in, int Cin,
-                    const int32_t* fmap, const int32_t* bmap, int K, const float* w, void* image_t, int reverse, float* gx, float* gw,
-                    float* gb, int tf32, scn_stream_t s, Side& side) {
+// one convolution layer backward: the kernels of scn_conv_layer_bwd, weight gradient on the side stream.  go_exact: go_round
+// already holds round(go), both with leading dimension ld_gr; gx2: second output of the input-gradient convolution
+static int conv_bwd(const float* go, int n_out, int Cout, bool go_exact, float* go_round, int ld_gr, const float* x, int ld_x, int n_in,
+                    int Cin, const int32_t* fmap, const int32_t* bmap, int K, const float* w, void* image_t, int reverse, float* gx, Out2 gx2,
+                    float* gw, float* gb, int tf32, scn_stream_t s, Side& side) {
     if (n_out == 0) {
         if (gx && n_in > 0) cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)n_in * Cin, as_stream(s));
+        if (gx && gx2.p && n_in > 0) cudaMemsetAsync(gx2.p, 0, sizeof(float) * (size_t)n_in * Cin, as_stream(s));
         return check_launch("unet_bwd(memset)");
     }
     const float* g = go;
+    int ld_g = Cout;
     if (tf32 && (gx || gw)) {
-        SCN_TRY(scn_round_tf32(go, go_round, (int64_t)n_out * Cout, s));
-        g = go_round;
+        if (!go_exact) SCN_TRY(scn_round_tf32(go, go_round, (int64_t)n_out * Cout, s));
+        g = go_round, ld_g = go_exact ? ld_gr : Cout;
     }
     if (gw || gb) {
         SCN_TRY(side.fork());
-        if (gw) SCN_TRY(scn_conv_bwd_weight(x, ld_x, Cin, fmap, n_out, K, g, Cout, Cout, gw, gb, tf32, side.wstream()));
-        else SCN_TRY(scn_col_sum_add(go, Cout, n_out, Cout, gb, side.wstream()));
+        if (gw) SCN_TRY(scn_conv_bwd_weight(x, ld_x, Cin, fmap, n_out, K, g, ld_g, Cout, gw, gb, tf32, side.wstream()));
+        else SCN_TRY(scn_col_sum_add(go, go_exact ? ld_gr : Cout, n_out, Cout, gb, side.wstream()));
     }
     if (gx && n_in > 0) {
         if (tf32)
-            SCN_TRY(scn_conv_fwd_tf32(g, Cout, Cout, n_out, bmap, n_in, K, image_t, nullptr, nullptr, 0, nullptr, 0, gx, Cin, Cin, 0, s));
+            SCN_TRY(scn_conv_fwd_tf32_dual(g, ld_g, Cout, n_out, bmap, n_in, K, image_t, nullptr, nullptr, 0, nullptr, 0, gx, Cin, Cin, 0,
+                                           gx2.p, Cin, gx2.epi, s));
         else
             SCN_TRY(scn_conv_fwd_fp32(g, Cout, Cout, bmap, n_in, K, w, 1, reverse, nullptr, nullptr, 0, nullptr, 0, gx, Cin, Cin, 0, s));
     }
@@ -382,26 +419,45 @@ int scn_unet_fwd(const int64_t* net_table, const int64_t* geo_table, const float
     make_plan(net, g, P);
     cudaStream_t st = as_stream(stream);
     const int tf32 = use_tf32 ? 1 : 0;
+    const bool dual = tf32 && dual_outputs();
+    const int RR = SCN_EPI_RELU | SCN_EPI_ROUND;
+    const int nd = n_decoder_levels < net.L - 1 ? n_decoder_levels : net.L - 1;
     const float* cur = x;      // E_{i-1}
+    bool operand_ready = false;      // the consumer's operand of `cur` (xr[i] / rl[0]) was written by cur's producer
     for (int i = 0; i < net.L; ++i) {
         const Conv& e = net.enc[i];
         const int n = g.n[i], n_in = i == 0 ? g.n[0] : g.n[i - 1];
+        const int U = net.enc_units[i];
+        // what the consumer of E_i gathers: the next level's entry layer reads round(E_i), the first decoder level relu(E_i)
+        const Out2 tail = !dual ? NO_OUT2
+                          : i + 1 < net.L ? (net.enc[i + 1].kind ? Out2{arena + P.xr[i + 1], SCN_EPI_ROUND} : NO_OUT2)
+                                          : (nd > 0 ? Out2{arena + P.rl[0], RR} : NO_OUT2);
+        bool r_ready = false;
         if (e.kind) {
             const int32_t* map = e.kind == 2 ? g.cmap[i - 1] : (e.K == 1 ? nullptr : g.subm[i]);
-            SCN_TRY(scn_conv_layer_fwd(cur, e.cin, n_in, e.cin, 0, arena + P.xr[i], map, n, e.K, e.w, e.img_f, 0, e.b, arena + P.c[i],
-                                       e.cout, tf32, stream));
+            if (!tf32) {
+                SCN_TRY(scn_conv_layer_fwd(cur, e.cin, n_in, e.cin, 0, arena + P.xr[i], map, n, e.K, e.w, e.img_f, 0, e.b, arena + P.c[i],
+                                           e.cout, tf32, stream));
+            } else if (n > 0) {
+                if (!operand_ready) SCN_TRY(scn_round_tf32(cur, arena + P.xr[i], (int64_t)n_in * e.cin, stream));
+                const Out2 o = !dual ? NO_OUT2 : (U ? Out2{arena + P.er[i][0], RR} : tail);
+                SCN_TRY(scn_conv_fwd_tf32_dual(arena + P.xr[i], e.cin, e.cin, n_in, map, n, e.K, e.img_f, e.b, nullptr, 0, nullptr, 0,
+                                               arena + P.c[i], e.cout, e.cout, 0, o.p, e.cout, o.epi, stream));
+                r_ready = dual && U > 0;
+            }
             cur = arena + P.c[i];
         }
-        SCN_TRY(stage_fwd(net.eu[i], net.enc_units[i], cur, n, net.C[i], g.subm[i], arena, P.er[i], P.eh[i], P.ey[i], tf32, stream));
-        if (net.enc_units[i]) cur = arena + P.E[i];
+        SCN_TRY(stage_fwd(net.eu[i], U, cur, r_ready, n, net.C[i], g.subm[i], arena, P.er[i], P.eh[i], P.ey[i], dual, tail, tf32, stream));
+        if (U) cur = arena + P.E[i];
+        operand_ready = dual && tail.p && n > 0 && (e.kind || U);
     }
-    const int nd = n_decoder_levels < net.L - 1 ? n_decoder_levels : net.L - 1;
     for (int j = 0; j < nd; ++j) {
         const int l = net.L - 2 - j, n = g.n[l], n_in = g.n[l + 1];
         const Conv &d = net.deconv[j], &m = net.nin[j];
+        const int U = net.dec_units[j];
         // ReLU (rounded in tf32 mode: a valid tensor-core operand) -> transposed convolution over dmap, written into the left
         // columns of the joined buffer; the skip connection is copied beside it (JoinTable)
-        SCN_TRY(scn_relu_fwd(cur, arena + P.rl[j], (int64_t)n_in * d.cin, tf32, stream));
+        if (!operand_ready) SCN_TRY(scn_relu_fwd(cur, arena + P.rl[j], (int64_t)n_in * d.cin, tf32, stream));
         if (n > 0) {
             if (tf32)
                 SCN_TRY(scn_conv_fwd_tf32(arena + P.rl[j], d.cin, d.cin, n_in, g.dmap[l], n, d.K, d.img_f, d.b, nullptr, 0, nullptr, 0,
@@ -412,11 +468,22 @@ int scn_unet_fwd(const int64_t* net_table, const int64_t* geo_table, const float
         }
         const float* skip = P.E[l] >= 0 ? arena + P.E[l] : x;
         SCN_TRY(copy_cols(arena + P.cat[j] + d.cout, m.cin, skip, net.C[l], n, net.C[l], st));
-        SCN_TRY(scn_conv_layer_fwd(arena + P.cat[j], m.cin, n, m.cin, 0, arena + P.catr[j], nullptr, n, 1, m.w, m.img_f, 0, m.b,
-                                   arena + P.nin[j], m.cout, tf32, stream));
-        SCN_TRY(stage_fwd(net.du[j], net.dec_units[j], arena + P.nin[j], n, net.CD[j], g.subm[l], arena, P.dr[j], P.dh[j], P.dy[j], tf32,
-                          stream));
+        const Out2 tail = (dual && j + 1 < nd) ? Out2{arena + P.rl[j + 1], RR} : NO_OUT2;
+        bool r_ready = false;
+        if (!tf32) {
+            SCN_TRY(scn_conv_layer_fwd(arena + P.cat[j], m.cin, n, m.cin, 0, arena + P.catr[j], nullptr, n, 1, m.w, m.img_f, 0, m.b,
+                                       arena + P.nin[j], m.cout, tf32, stream));
+        } else if (n > 0) {
+            SCN_TRY(scn_round_tf32(arena + P.cat[j], arena + P.catr[j], (int64_t)n * m.cin, stream));
+            const Out2 o = !dual ? NO_OUT2 : (U ? Out2{arena + P.dr[j][0], RR} : tail);
+            SCN_TRY(scn_conv_fwd_tf32_dual(arena + P.catr[j], m.cin, m.cin, n, nullptr, n, 1, m.img_f, m.b, nullptr, 0, nullptr, 0,
+                                           arena + P.nin[j], m.cout, m.cout, 0, o.p, m.cout, o.epi, stream));
+            r_ready = dual && U > 0;
+        }
+        SCN_TRY(stage_fwd(net.du[j], U, arena + P.nin[j], r_ready, n, net.CD[j], g.subm[l], arena, P.dr[j], P.dh[j], P.dy[j], dual, tail,
+                          tf32, stream));
         cur = arena + P.D[j];
+        operand_ready = dual && tail.p && n > 0;
     }
     return SCN_OK;
 }
@@ -487,6 +554,7 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         return SCN_OK;
     };
 
+    const bool dual = tf32 && dual_outputs();
     for (int j = L - 2; j >= 0; --j) {
         const int l = L - 2 - j, n = g.n[l], n_in = g.n[l + 1], c = net.CD[j];
         const Conv &d = net.deconv[j], &m = net.nin[j];
@@ -496,13 +564,18 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         Grad& below = j == 0 ? gE[L - 1] : gD[j - 1];      // gradient of this level's input
         if (run_dec) {
             const float* g_nin = gy;
-            SCN_TRY(stage_bwd(net.du[j], net.dec_units[j], gy, n, c, g.subm[l], arena, P.dr[j], P.dh[j], barena, P.d_gyr[j], P.d_gh[j],
-                              P.d_gx[j], pg_dec[j] + 4, tf32, stream, side, &g_nin));
+            const int U = net.dec_units[j];
+            // unit 0 hands round(gradient of the 1x1 layer's output) to that layer; the 1x1 layer hands round(gradient of the
+            // joined columns) to the transposed convolution, which reads its left columns in place (no copy, no rounding pass)
+            SCN_TRY(stage_bwd(net.du[j], U, gy, n, c, g.subm[l], arena, P.dr[j], P.dh[j], barena, P.d_gyr[j], P.d_gh[j], P.d_gx[j],
+                              pg_dec[j] + 4, dual, dual ? Out2{barena + P.d_round_nin[j], SCN_EPI_ROUND} : NO_OUT2, tf32, stream, side,
+                              &g_nin));
             // 1x1 layer over the joined columns: input gradient [n, cin], weight + bias gradient
-            SCN_TRY(conv_bwd(g_nin, n, m.cout, barena + P.d_round_nin[j], arena + P.cat[j], m.cin, n, m.cin, nullptr, nullptr, 1, m.w, m.img_b,
-                             0, barena + P.g_cat[j], pg_dec[j][2], pg_dec[j][3], tf32, stream, side));
+            SCN_TRY(conv_bwd(g_nin, n, m.cout, dual && U > 0, barena + P.d_round_nin[j], m.cout, arena + P.cat[j], m.cin, n, m.cin, nullptr,
+                             nullptr, 1, m.w, m.img_b, 0, barena + P.g_cat[j], dual ? Out2{barena + P.g_catr[j], SCN_EPI_ROUND} : NO_OUT2,
+                             pg_dec[j][2], pg_dec[j][3], tf32, stream, side));
             // split the joined gradient: left columns -> transposed convolution, right columns -> the skip connection
-            SCN_TRY(copy_cols(barena + P.g_up[j], d.cout, barena + P.g_cat[j], m.cin, n, d.cout, st));
+            if (!dual) SCN_TRY(copy_cols(barena + P.g_up[j], d.cout, barena + P.g_cat[j], m.cin, n, d.cout, st));
         }
         {
             float* skip_to = target(gE[l], barena + P.g_skip[j]);
@@ -511,8 +584,14 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         }
         if (run_dec) {
             // transposed convolution backward: the input gradient runs over cmap (children of each coarse row)
-            SCN_TRY(conv_bwd(barena + P.g_up[j], n, d.cout, barena + P.d_round_up[j], arena + P.rl[j], d.cin, n_in, d.cin, g.dmap[l], g.cmap[l],
-                             d.K, d.w, d.img_b, 0, barena + P.g_rl[j], pg_dec[j][0], pg_dec[j][1], tf32, stream, side));
+            if (dual)
+                SCN_TRY(conv_bwd(barena + P.g_cat[j], n, d.cout, n > 0, barena + P.g_catr[j], m.cin, arena + P.rl[j], d.cin, n_in, d.cin,
+                                 g.dmap[l], g.cmap[l], d.K, d.w, d.img_b, 0, barena + P.g_rl[j], NO_OUT2, pg_dec[j][0], pg_dec[j][1], tf32,
+                                 stream, side));
+            else
+                SCN_TRY(conv_bwd(barena + P.g_up[j], n, d.cout, false, barena + P.d_round_up[j], d.cout, arena + P.rl[j], d.cin, n_in, d.cin,
+                                 g.dmap[l], g.cmap[l], d.K, d.w, d.img_b, 0, barena + P.g_rl[j], NO_OUT2, pg_dec[j][0], pg_dec[j][1], tf32,
+                                 stream, side));
         }
         {
             float* to = target(below, barena + P.tmp[l + 1]);
@@ -524,13 +603,15 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         const Conv& e = net.enc[i];
         const int n = g.n[i], n_in = i == 0 ? g.n[0] : g.n[i - 1];
         const bool run_enc = enc_runs(i);
+        const int U = net.enc_units[i];
         const float* gy = nullptr;
         SCN_TRY(resolve(gE[i], (int64_t)n * net.C[i], run_enc, &gy));
         if (!gy) continue;
         const float* g_c = gy;
         if (run_enc)
-            SCN_TRY(stage_bwd(net.eu[i], net.enc_units[i], gy, n, net.C[i], g.subm[i], arena, P.er[i], P.eh[i], barena, P.e_gyr[i], P.e_gh[i],
-                              P.e_gx[i], pg_enc[i] + 2, tf32, stream, side, &g_c));
+            SCN_TRY(stage_bwd(net.eu[i], U, gy, n, net.C[i], g.subm[i], arena, P.er[i], P.eh[i], barena, P.e_gyr[i], P.e_gh[i], P.e_gx[i],
+                              pg_enc[i] + 2, dual, (dual && e.kind) ? Out2{barena + P.e_round[i], SCN_EPI_ROUND} : NO_OUT2, tf32, stream, side,
+                              &g_c));
         if (!e.kind) {      // pass-through level 0: its gradient IS the input gradient
             if (gx && run_enc && n > 0) {
                 cudaError_t err = cudaMemcpyAsync(gx, g_c, (size_t)n * net.C[i] * 4, cudaMemcpyDeviceToDevice, st);
@@ -544,15 +625,16 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         // that saves the unrounded tensor); xr / catr are only the forward's rounded operands
         const float* x_in = (i == 0 || P.E[i - 1] < 0) ? x : arena + P.E[i - 1];
         const int reverse = e.kind == 1 ? 1 : 0;
+        const bool go_exact = dual && U > 0 && n > 0;
         if (i == 0) {
             if (run_enc)
-                SCN_TRY(conv_bwd(g_c, n, e.cout, barena + P.e_round[i], x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w, e.img_b, reverse, gx,
-                                 pg_enc[i][0], pg_enc[i][1], tf32, stream, side));
+                SCN_TRY(conv_bwd(g_c, n, e.cout, go_exact, barena + P.e_round[i], e.cout, x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w,
+                                 e.img_b, reverse, gx, NO_OUT2, pg_enc[i][0], pg_enc[i][1], tf32, stream, side));
         } else {
             float* to = target(gE[i - 1], barena + P.tmp[i - 1]);
             if (run_enc)
-                SCN_TRY(conv_bwd(g_c, n, e.cout, barena + P.e_round[i], x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w, e.img_b, reverse, to,
-                                 pg_enc[i][0], pg_enc[i][1], tf32, stream, side));
+                SCN_TRY(conv_bwd(g_c, n, e.cout, go_exact, barena + P.e_round[i], e.cout, x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w,
+                                 e.img_b, reverse, to, NO_OUT2, pg_enc[i][0], pg_enc[i][1], tf32, stream, side));
             SCN_TRY(commit(gE[i - 1], to, (int64_t)n_in * e.cin, run_enc));
         }
     }

@@ -53,12 +53,15 @@ class BackboneTrainer(nn.Module):
         self.prefetcher = None
         self.build_ahead = False       # next_batch: build its rulebooks between this step's forward and backward (no gain)
         self.stage_uploads = False     # next_batch: also issue its host->device copies now (measured: no gain)
+        self.build_late = False        # next_batch: build its rulebooks on a side stream at the END of this step (same thread)
 
-    def prefetch(self, data):
+    def prefetch(self, data, threaded=True):
         """Start building the geometry (voxel hash, level pyramid, neighbour maps) of an upcoming batch on a side stream;
-        the step() that later receives the same coords tensor picks it up (scn.GeometryPrefetcher)."""
+        the step() that later receives the same coords tensor picks it up (scn.GeometryPrefetcher).  threaded=False: built
+        by the calling thread, inline (see GeometryPrefetcher)."""
         if self.prefetcher is None:
-            self.prefetcher = scn.GeometryPrefetcher(self.device, n_levels=len(self.backbone.channels) - 1)
+            self.prefetcher = scn.GeometryPrefetcher(self.device, n_levels=len(self.backbone.channels) - 1, threaded=threaded,
+                                                     book_channels=list(self.backbone.channels))
             self.backbone.input_stage.prefetcher = self.prefetcher
         coords, _, size, bs = data[:4]
         self.prefetcher.submit(coords.long(), torch.as_tensor(size, dtype=torch.long), bs)
@@ -92,6 +95,10 @@ class BackboneTrainer(nn.Module):
         self.buckets.finish()
         self.optimizer.step()
         scn.functions.weights_changed()            # packed TF32 weight images are stale now (re-packed by the next pack_all)
+        if next_batch is not None and self.build_late:
+            # the whole step is enqueued: the following batch's rulebooks now, on the high-priority side stream -- the six
+            # row-count round trips wait for that stream only, while the GPU still has this step's backward to run
+            self.prefetch(next_batch[0], threaded=False)
         self.last_active = out[4][0].features.shape[0]
         return loss.detach()
 

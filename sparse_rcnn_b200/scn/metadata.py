@@ -297,19 +297,23 @@ class Metadata:
             self.row_pts = torch.arange(self.n_points, dtype=torch.int32, device=dev)
         return self.row_ptr, self.row_pts
 
-    def prebuild(self, n_levels, filter_size=2, stride=2, subm_filter=3):
+    def prebuild(self, n_levels, filter_size=2, stride=2, subm_filter=3, book_channels=None):
         """Build `n_levels` strided levels below the input level (and the submanifold maps of every level) NOW.
         Each new level costs one host sync (its active-row count sizes the buffers).  Done lazily, those syncs land
         in the middle of the network and drain a full launch queue every time; done here, right after the input
         layer, they cost ~30 us each and everything after runs asynchronously.  Purely an ordering change: the
-        same cached rulebooks are produced."""
+        same cached rulebooks are produced.  book_channels: layer width per level (level 0 first) -- the tile book of a level
+        whose width the tile-local kernels implement is built here too (a prefetched geometry is then complete; otherwise
+        the first layer that runs on the level builds it)."""
         size = self.input_size
         for _ in range(n_levels + 1):
             lvl = self.levels[size]
 
-            def own_maps(lvl=lvl):      # this level's neighbour map (+ tile book): independent of the next level's count
+            def own_maps(lvl=lvl, i=_):      # this level's neighbour map (+ tile book): independent of the next level's count
                 if subm_filter and lvl.n:
                     lvl.subm_map(subm_filter, tile_book=False)
+                    if book_channels is not None and i < len(book_channels) and _triple(subm_filter) == (3, 3, 3):
+                        lvl.ensure_tile_book(book_channels[i])
             if _ == n_levels or any(s % 2 for s in size) or min(size) < 2:
                 own_maps()
                 break
@@ -470,12 +474,19 @@ class GeometryPrefetcher:
     (ndsis/data/data.py:88-115).  Without it the step has a bubble at its start: the host waits for the previous step
     to drain before it can read the first count, then the GPU waits for the host (profiles/r1_i_host_bound.md)."""
 
-    def __init__(self, device, n_levels, mode=4, dimension=3):
-        import concurrent.futures
+    def __init__(self, device, n_levels, mode=4, dimension=3, threaded=True, book_channels=None):
+        """threaded=False: `submit` builds inline on the side stream from the CALLING thread (no worker, no GIL hand-offs).
+        Called at the end of a training step -- after the step's forward, backward and optimizer kernels are enqueued --
+        the builder's host round trips wait only for the side stream's own kernels while the GPU works through the queued
+        step, and the next step starts without the host <-> GPU ping-pong of six row-count reads at its head."""
         self.device = torch.device(device)
         self.n_levels, self.mode, self.dimension = n_levels, mode, dimension
+        self.book_channels = book_channels
         self.stream = torch.cuda.Stream(self.device, priority=-1)
-        self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="scn-geometry")
+        self.pool = None
+        if threaded:
+            import concurrent.futures
+            self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="scn-geometry")
         self.pending = {}
 
     def _build(self, coords, spatial_size, batch_size):
@@ -483,7 +494,7 @@ class GeometryPrefetcher:
         with torch.cuda.stream(self.stream):
             md = Metadata(self.dimension)
             md.set_input(spatial_size, coords, batch_size, self.mode, self.device)
-            md.prebuild(self.n_levels)
+            md.prebuild(self.n_levels, book_channels=self.book_channels)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         md._prebuilt_for = coords
@@ -494,7 +505,10 @@ class GeometryPrefetcher:
         """Start building the geometry of `coords` (a later InputLayer call with this very tensor picks it up)."""
         if id(coords) in self.pending or not len(coords):
             return
-        self.pending[id(coords)] = (self.pool.submit(self._build, coords, spatial_size, batch_size), coords)
+        if self.pool is None:
+            self.pending[id(coords)] = (_Done(self._build(coords, spatial_size, batch_size)), coords)
+        else:
+            self.pending[id(coords)] = (self.pool.submit(self._build, coords, spatial_size, batch_size), coords)
 
     def take(self, coords):
         """The prefetched Metadata for `coords`, ordered after its build on the current stream; None if not submitted."""
@@ -510,5 +524,16 @@ class GeometryPrefetcher:
         return md
 
     def shutdown(self):
-        self.pool.shutdown(wait=True)
+        if self.pool is not None:
+            self.pool.shutdown(wait=True)
         self.pending.clear()
+
+
+class _Done:
+    """A finished result with the Future interface `take` uses."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def result(self):
+        return self.value

@@ -216,3 +216,42 @@ def test_tail_split_equals_persistent_grid(cuda, monkeypatch, channels):
     xin.grad = None
     conv(scn.SparseConvNetTensor(xin, md, size)).features.backward(go)
     assert rel_err(g_on, xin.grad) < 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,epi2", [(32, 32, 9), (22, 22, 9), (7, 18, 8), (48, 80, 1), (6, 32, 9)])
+@pytest.mark.parametrize("nocluster", ["0", "1"])
+def test_second_output_of_the_epilogue(cuda, monkeypatch, cin, cout, epi2, nocluster):
+    """scn_conv_fwd_tf32_dual: out2 == epi2(out) (ReLU = 1, ROUND = 8) bit for bit, `out` unchanged by the second store; odd
+    widths take the scalar stores, the small scene the cluster reduction or (SCN_CONV_NOCLUSTER=1) the last-arriver pass."""
+    from sparse_rcnn_b200 import _lib, scn
+    from sparse_rcnn_b200.scn import functions as F
+    scn.set_precision("tf32")
+    monkeypatch.setenv("SCN_CONV_NOCLUSTER", nocluster)
+    torch.manual_seed(cin + cout)
+    coords, feats, size = random_scene(cin * 31 + cout, channels=cin)
+    md = scn.Metadata(3)
+    f = scn.ioLayers.InputLayerFunction.apply(3, md, torch.as_tensor(size), coords, feats.to(cuda), 0, 4)
+    lvl = md.level(torch.as_tensor(size))
+    n = f.shape[0]
+    fmap = lvl.subm_map(3)
+    w = torch.randn(27, cin, cout, device=cuda)
+    bias = torch.randn(cout, device=cuda)
+    res = torch.randn(n, cout, device=cuda)
+    x = F.tf32_exact(torch.randn(n, cin, device=cuda))
+    img = F._image(w, 27, cin, cout, 0, 0)
+    ptr, s = F._ptr, F._stream()
+    out = torch.empty(n, cout, device=cuda)
+    _lib.call("scn_conv_fwd_tf32", ptr(x), cin, cin, n, ptr(fmap), n, 27, ptr(img), ptr(bias), ptr(res), cout, 0, 0, ptr(out), cout,
+              cout, 2, s)
+    o1, o2 = torch.full((n, cout), 7.0, device=cuda), torch.full((n, cout + 3), 7.0, device=cuda)
+    _lib.call("scn_conv_fwd_tf32_dual", ptr(x), cin, cin, n, ptr(fmap), n, 27, ptr(img), ptr(bias), ptr(res), cout, 0, 0, ptr(o1), cout,
+              cout, 2, ptr(o2), cout + 3, epi2, s)
+    if nocluster == "0":
+        assert torch.equal(o1, out)
+    else:
+        assert rel_err(o1, out) < 1e-5            # fp32 atomics
+    want = o1.clamp_min(0) if epi2 & 1 else o1
+    if epi2 & 8:
+        want = F.tf32_exact(want.clone())
+    assert torch.equal(o2[:, :cout], want)
+    assert bool((o2[:, cout:] == 7.0).all())      # the padding columns of the wider second buffer are untouched

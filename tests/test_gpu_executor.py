@@ -126,3 +126,32 @@ def test_trainer_steps_with_and_without_executor(cuda, precision):
     for a, b in zip(l1, l0):
         assert abs(a - b) <= (2e-3 if precision == "tf32" else 1e-4) * abs(b), (l1, l0)
     assert l1[2] < l1[0]                                        # it trains
+
+
+@pytest.mark.parametrize("extra_seed", [False, True])
+def test_second_outputs_equal_separate_passes(cuda, monkeypatch, extra_seed):
+    """scn_conv_fwd_tf32_dual inside the executor (the producing convolution also writes relu / round of its result for the
+    next gather) against SCN_EXEC_DUAL=0 (one elementwise kernel per consumer) on the BASELINE scene: every epilogue flavour
+    runs (tile-local kernel on levels 0-1, whole-tile persistent grid, tail split, cluster split on the small levels).
+    Same values from the same fp32 results: activations and the input gradient are identical bits."""
+    from sparse_rcnn_b200 import _lib, scn
+    scn.set_precision("tf32")
+    torch.manual_seed(0)
+    net, seg = networks.FeatureExtractor(scn).to(cuda), networks.SegmentationNetwork(scn).to(cuda)
+    data = make_batch(1, 0)
+    monkeypatch.setenv("SCN_CONV_TAILSPLIT", "0")      # its fp32 atomics reorder sums between any two runs
+    monkeypatch.setenv("SCN_EXEC_DUAL", "1")
+    _run(net, seg, data, cuda, extra_seed, True)
+    l0 = int(_lib.raw("scn_launch_count")())
+    a1, s1, gx1, g1, _ = _run(net, seg, data, cuda, extra_seed, True)
+    l1 = int(_lib.raw("scn_launch_count")())
+    monkeypatch.setenv("SCN_EXEC_DUAL", "0")
+    a0, s0, gx0, g0, _ = _run(net, seg, data, cuda, extra_seed, True)
+    l2 = int(_lib.raw("scn_launch_count")())
+    for x, y in zip(a1, a0):
+        assert torch.equal(x, y)
+    assert torch.equal(s1, s0) and torch.equal(gx1, gx0)
+    for n in g0:      # k_conv_wgrad_tc ends in fp32 atomics
+        assert rel_err(g1[n], g0[n]) <= 2e-5, (n, rel_err(g1[n], g0[n]))
+    print("kernel launches: second outputs %d, separate passes %d" % (l1 - l0, l2 - l1))
+    assert (l2 - l1) - (l1 - l0) >= 50
