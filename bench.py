@@ -250,12 +250,17 @@ def main():
                          "good runs but is not stable (3 runs: 6.5 / 6.4 / 7.0 ms, e2e 6.1 / 5.8 / 20.9 ms -- the worker shares "
                          "the GIL and the launch queue with the training thread); without it 6.22 +- 0.01 ms "
                          "(profiles/r2_e_executor.md)")
-    ap.add_argument("--no-build-late", dest="build_late", action="store_false",
-                    help="do NOT build the following batch's rulebooks at the end of each step on a side stream "
-                         "(BackboneTrainer.build_late; the batch is known one step ahead, as with a DataLoader).  Every step "
-                         "still builds exactly one geometry inside the timed loop")
-    ap.set_defaults(stage=True, build_late=True)
+    ap.add_argument("--geometry-ahead", default="thread", choices=["off", "inline", "thread"],
+                    help="build the following batch's rulebooks one step ahead on a high-priority side stream into a recycled "
+                         "arena (the batch is known one step ahead, as with a DataLoader; every step still builds exactly one "
+                         "geometry inside the timed loop).  thread: a worker thread takes the builder's row-count round trips; "
+                         "inline: the training thread does, after enqueueing the step; off: at the head of its own step")
+    ap.add_argument("--geometry-at", default="end", choices=["start", "forward", "end"],
+                    help="where in the step the worker thread is handed the next batch")
+    ap.set_defaults(stage=True)
     args = ap.parse_args()
+    if os.environ.get("SCN_SWITCH_INTERVAL"):      # experiment: GIL hand-off latency between the training thread and --prefetch's worker
+        sys.setswitchinterval(float(os.environ["SCN_SWITCH_INTERVAL"]))
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -296,8 +301,9 @@ def main():
         # (--no-build-ahead: at the head of its own step); every step still builds exactly one geometry and uploads exactly
         # one batch inside the loop (h2d_bytes_per_step)
         trainer.stage_uploads, trainer.build_ahead = args.stage, args.build_ahead
-        trainer.build_late = args.build_late and not args.prefetch
-        nb = (lambda i: inputs[(i + 1) % n_distinct]) if (args.stage or args.build_ahead or args.build_late) else (lambda i: None)
+        trainer.build_late = False if (args.prefetch or args.geometry_ahead == "off") else args.geometry_ahead
+        trainer.build_late_at = args.geometry_at
+        nb = (lambda i: inputs[(i + 1) % n_distinct]) if (args.stage or args.build_ahead or trainer.build_late) else (lambda i: None)
         # every distinct scene once before the warm-up proper: first-touch costs of a new geometry (caching-allocator growth,
         # dynamic-smem attributes) must not land in the timed region when W < n_distinct
         for i in range(n_distinct):
@@ -306,6 +312,8 @@ def main():
             trainer.step(*inputs[i % n_distinct], next_data=nxt(i), next_batch=nb(i))
         barrier()
         launches0 = _lib.raw("scn_launch_count")()
+        mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+        step_wall = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         voxels, t0 = 0, time.perf_counter()
         e0.record()
@@ -328,6 +336,7 @@ def main():
                         loss_sum += float(slots[pending][0])
                     pending = i & 1
             voxels += trainer.last_active
+            step_wall.append(time.perf_counter())
         if read_loss and pending is not None:
             evs[pending].synchronize()
             loss_sum += float(slots[pending][0])
@@ -338,6 +347,11 @@ def main():
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
         launches = _lib.raw("scn_launch_count")() - launches0
+        # diagnostics of the timed region: cudaMalloc calls of the caching allocator (a steady-state step makes none) and the
+        # host-side duration of the slowest step
+        diag["device_allocs"] = diag.get("device_allocs", 0) + torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0
+        gaps = [b - a for a, b in zip([t0] + step_wall[:-1], step_wall)]
+        diag.setdefault("slowest_step_host_ms", []).append(round(max(gaps) * 1e3, 3) if gaps else None)
         t = torch.tensor([ms, float(voxels), wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             tm = t.clone()
@@ -349,6 +363,7 @@ def main():
             wall_ms = wall * 1e3
         return max(ms, 1e-9), voxels, launches, wall_ms
 
+    diag = {}
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -452,7 +467,7 @@ def main():
                     "loss_read": "blocking .item() per step" if args.sync_loss else
                     "every step, async copy into pinned memory, read by the host one step late",
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_wgrad": roof_w,
+            "gpu_launches": int(launches), "timed_region": diag, "clocks": clocks, "roofline": roof, "roofline_wgrad": roof_w,
             "roofline_rulebook": roof_r, "inference": inference,
         }
         if cpu is not None:

@@ -175,6 +175,8 @@ int64_t scn_tile_book_bytes(int n_out);
 int scn_tile_book_build(const int32_t* map, int n_out, int K, void* book, scn_stream_t stream);
 int scn_tile_book_attach(const int32_t* map, const void* book, int n_out);
 int scn_tile_book_detach(const int32_t* map);
+/* detach only if `map` is still associated with `book` (a caller that recycles device addresses) */
+int scn_tile_book_detach_if(const int32_t* map, const void* book);
 /* launches of the tile-local kernel so far (tests assert that the path under test really ran) */
 int64_t scn_conv_ts_launch_count(void);
 /* launches of the tile-local weight-gradient kernel (csrc/conv_wgrad_ts.cu) so far */

@@ -10,12 +10,14 @@ from sparse_rcnn_b200 import pipeline, scn
 dev = torch.device("cuda:0"); scn.set_precision("tf32")
 tr = pipeline.BackboneTrainer(dev)
 batches = [bench.make_inputs(s) for s in range(4)]
-batches = [((d[0], d[1].to(dev), d[2], d[3], d[4]), l.to(dev)) for d, l in batches]
-for i in range(6): tr.step(*batches[i % 4])
+batches = [((d[0].pin_memory(), d[1].pin_memory(), d[2], d[3], d[4]), l.pin_memory()) for d, l in batches]
+tr.stage_uploads = True
+tr.build_late = os.environ.get("BUILD_LATE", "1") == "1"
+for i in range(8): tr.step(*batches[i % 4], next_batch=batches[(i + 1) % 4])
 torch.cuda.synchronize()
 NS = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    for i in range(NS): tr.step(*batches[i % 4])
+    for i in range(NS): tr.step(*batches[i % 4], next_batch=batches[(i + 1) % 4])
     torch.cuda.synchronize()
 path = os.path.join(tempfile.gettempdir(), "scn_trace.json")
 prof.export_chrome_trace(path)
@@ -44,6 +46,9 @@ for si, st in enumerate(steps[1:], 1):      # the first one starts mid-way (pack
     by_stream = collections.defaultdict(list)
     for e in st: by_stream[e["args"].get("stream")].append((e["ts"], e["ts"] + e["dur"]))
     # phases: up to the first conv kernel = geometry; up to k_ce_bwd = forward; rest = backward (+ optimizer)
+    geo = [e for e in st if any(g in e["name"] for g in GEO)]
+    print("   geometry kernels: %d, busy %.3f ms, from +%.3f to +%.3f ms of the step" % (len(geo), union([(e["ts"], e["ts"] + e["dur"]) for e in geo]) / 1e3,
+          (geo[0]["ts"] - st[0]["ts"]) / 1e3, (geo[-1]["ts"] + geo[-1]["dur"] - st[0]["ts"]) / 1e3))
     i_conv = next(i for i, e in enumerate(st) if "k_conv" in e["name"])
     i_ce = next(i for i, e in enumerate(st) if "k_ce_bwd" in e["name"])
     tg, tf = st[i_conv]["ts"], st[i_ce]["ts"]

@@ -44,6 +44,30 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // SCN_PDL=0 turns the launch attribute off (the device-side instructions are then no-ops)
 bool pdl_enabled();
+// Per-thread exclusion list: launches on these streams go without the attribute while the scope lives.  With TWO streams
+// feeding the GPU (scn_unet_bwd: input-gradient chain + weight gradients) an early-launched dependent grid parks its CTAs
+// -- shared memory and tensor memory included -- in griddepcontrol.wait on SMs the OTHER stream's ready kernel could use
+// (measured: backward call 4.17 ms with the attribute on both streams, 3.91 ms without).
+struct PdlMask {
+    int n = 0;
+    cudaStream_t s[2];
+};
+PdlMask& pdl_mask();
+static inline bool pdl_allowed(cudaStream_t st) {
+    const PdlMask& m = pdl_mask();
+    for (int i = 0; i < m.n; ++i)
+        if (m.s[i] == st) return false;
+    return true;
+}
+struct PdlMaskScope {
+    PdlMask saved;
+    PdlMaskScope() : saved(pdl_mask()) {}
+    void exclude(cudaStream_t st) {
+        PdlMask& m = pdl_mask();
+        if (m.n < 2) m.s[m.n++] = st;
+    }
+    ~PdlMaskScope() { pdl_mask() = saved; }
+};
 // launch config with the PDL attribute (and an optional cluster dimension); attrs must outlive the launch call
 struct PdlLaunch {
     cudaLaunchConfig_t cfg;
@@ -52,7 +76,7 @@ struct PdlLaunch {
         cfg = cudaLaunchConfig_t{};
         cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
         int n = 0;
-        if (pdl_enabled()) {
+        if (pdl_enabled() && pdl_allowed(st)) {
             attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attrs[n].val.programmaticStreamSerializationAllowed = 1;
             ++n;

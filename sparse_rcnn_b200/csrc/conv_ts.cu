@@ -820,6 +820,13 @@ int scn_debug_ts_trace(long long* out) {
 #endif
 int64_t scn_conv_ts_launch_count(void) { return g_ts_launches.load(); }
 
+int scn_tile_book_detach_if(const int32_t* map, const void* book) {
+    std::lock_guard<std::mutex> lock(g_books_mutex);
+    auto it = g_books.find(map);
+    if (it != g_books.end() && it->second.book == book) g_books.erase(it);
+    return SCN_OK;
+}
+
 int scn_tile_book_detach(const int32_t* map) {
     std::lock_guard<std::mutex> lock(g_books_mutex);
     g_books.erase(map);

@@ -39,6 +39,11 @@ bool pdl_enabled() {
     return on == 1;
 }
 
+PdlMask& pdl_mask() {
+    static thread_local PdlMask m;
+    return m;
+}
+
 int sm_count() {
     static int n = -1;
     if (n < 0) {

@@ -28,6 +28,9 @@ using namespace scn;
 namespace {
 
 constexpr int MAX_LEVELS = 8, MAX_UNITS = 4;
+#ifndef SCN_EXEC_BWD_PDL_DEFAULT
+#define SCN_EXEC_BWD_PDL_DEFAULT 3
+#endif
 
 struct Conv {      // one convolution layer; kind 0 = absent (the level passes its input through)
     int kind, K, cin, cout;
@@ -511,6 +514,15 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
     auto enc_runs = [&](int level) { return (phases & (level >= split ? 2 : 4)) != 0; };
     Side side;
     SCN_TRY(side_for(st, side));
+    // programmatic dependent launch per stream while two streams feed the GPU (common.cuh: PdlMask).  SCN_EXEC_BWD_PDL:
+    // bit 0 = main stream keeps the attribute, bit 1 = side stream keeps it
+    PdlMaskScope pdl_scope;
+    if (side.on) {
+        const char* e = getenv("SCN_EXEC_BWD_PDL");
+        const int keep = e ? atoi(e) : SCN_EXEC_BWD_PDL_DEFAULT;
+        if (!(keep & 1)) pdl_scope.exclude(side.main);
+        if (!(keep & 2)) pdl_scope.exclude(side.side);
+    }
     // parameter-gradient pointers in table order
     float* pg_enc[MAX_LEVELS][2 + 4 * MAX_UNITS];
     float* pg_dec[MAX_LEVELS][4 + 4 * MAX_UNITS];

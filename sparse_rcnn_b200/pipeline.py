@@ -53,7 +53,12 @@ class BackboneTrainer(nn.Module):
         self.prefetcher = None
         self.build_ahead = False       # next_batch: build its rulebooks between this step's forward and backward (no gain)
         self.stage_uploads = False     # next_batch: also issue its host->device copies now (measured: no gain)
-        self.build_late = False        # next_batch: build its rulebooks on a side stream at the END of this step (same thread)
+        # next_batch: build its rulebooks one step ahead on a high-priority side stream, into a recycled arena
+        # (scn.GeometryPrefetcher).  "thread": a worker thread issues the builder's kernels and takes its row-count round
+        # trips (blocked ~3 ms per step while the GPU is busy with this step); "inline": the training thread does, after it
+        # has enqueued the whole step.  build_late_at: where in the step the build is started (start | forward | end).
+        self.build_late = False
+        self.build_late_at = "end"
 
     def prefetch(self, data, threaded=True):
         """Start building the geometry (voxel hash, level pyramid, neighbour maps) of an upcoming batch on a side stream;
@@ -78,6 +83,10 @@ class BackboneTrainer(nn.Module):
         (`stage_uploads`).  next_data: build its rulebooks in a worker thread instead (scn.GeometryPrefetcher, opt-in)."""
         if next_data is not None:
             self.prefetch(next_data)
+        ahead = self.build_late if next_batch is not None else False
+        at = "end" if ahead == "inline" else self.build_late_at
+        if ahead and at == "start":
+            self.prefetch(next_batch[0], threaded=True)
         data = _to_device(data, self.device)
         labels = _dev(labels, self.device)
         if next_batch is not None and self.stage_uploads:
@@ -87,6 +96,8 @@ class BackboneTrainer(nn.Module):
         out = self.backbone(data)
         logits = self.seg(out[5])
         loss = scn.functions.cross_entropy(logits, labels)      # nn.CrossEntropyLoss semantics (loss.py:95-97)
+        if ahead and at == "forward":
+            self.prefetch(next_batch[0], threaded=True)
         if next_batch is not None and self.build_ahead:
             # the following batch's rulebooks, between this step's forward and backward: their host round trips wait
             # while the GPU drains the forward instead of idling it at the head of the next step
@@ -95,10 +106,10 @@ class BackboneTrainer(nn.Module):
         self.buckets.finish()
         self.optimizer.step()
         scn.functions.weights_changed()            # packed TF32 weight images are stale now (re-packed by the next pack_all)
-        if next_batch is not None and self.build_late:
+        if ahead and at == "end":
             # the whole step is enqueued: the following batch's rulebooks now, on the high-priority side stream -- the six
             # row-count round trips wait for that stream only, while the GPU still has this step's backward to run
-            self.prefetch(next_batch[0], threaded=False)
+            self.prefetch(next_batch[0], threaded=ahead != "inline")
         self.last_active = out[4][0].features.shape[0]
         return loss.detach()
 

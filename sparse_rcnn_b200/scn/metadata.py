@@ -77,11 +77,49 @@ def _triple(v):
     return tuple(int(a) for a in np.broadcast_to(np.asarray(v), (3,)))
 
 
+# ---------------------------------------------------------------- buffers of the rulebook builder
+# Geometry built ahead on a side stream (GeometryPrefetcher) must not go through the caching allocator: blocks allocated under
+# the side stream and used under the training stream need record_stream, which delays their reuse, and with a different scene
+# every step the pools never settle -- measured 4-13 cudaMalloc calls inside 20 timed steps and single steps of 10-100 ms.
+# While a thread has an arena installed, every buffer of the builder is a 256-byte aligned slice of that one pre-allocated
+# block; without one (the default) buffers come from torch as before.
+_arena_tls = threading.local()
+
+
+class Arena:
+    def __init__(self, nbytes, device):
+        self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        self.off = 0
+        self.event = None      # recorded by the last user when it let go of the arena
+
+    def take(self, shape, dtype):
+        if isinstance(shape, int):
+            shape = (shape,)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * dtype.itemsize
+        start = (self.off + 255) // 256 * 256
+        if start + nbytes > self.buf.numel():
+            return None
+        self.off = start + nbytes
+        return self.buf[start:start + nbytes].view(dtype).view(shape)
+
+
+def _new(shape, dtype, device):
+    a = getattr(_arena_tls, "arena", None)
+    if a is not None:
+        t = a.take(shape, dtype)
+        if t is not None:
+            return t
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
 def exclusive_scan(x):
     """int32 [n] -> int32 [n+1] exclusive prefix sum (own kernel, no CUB)."""
     n = x.numel()
-    out = torch.empty(n + 1, dtype=torch.int32, device=x.device)
-    tmp = torch.empty(int(_lib.raw("scn_scan_tmp_elems")(n)), dtype=torch.int32, device=x.device)
+    out = _new(n + 1, torch.int32, x.device)
+    tmp = _new(int(_lib.raw("scn_scan_tmp_elems")(n)), torch.int32, x.device)
     _lib.call("scn_exclusive_scan", _ptr(x), _ptr(out), n, _ptr(tmp), _stream())
     return out
 
@@ -103,8 +141,8 @@ class Level:
 
     def __del__(self):
         try:
-            for ptr in self._books:
-                _lib.call("scn_tile_book_detach", ptr)
+            for ptr, book in self._books.items():      # only if the registry still holds THIS book (arena addresses recur)
+                _lib.call("scn_tile_book_detach_if", ptr, _ptr(book))
         except Exception:      # interpreter shutdown
             pass
 
@@ -134,7 +172,7 @@ class Level:
                 self.subm[f] = None
             else:
                 K = f[0] * f[1] * f[2]
-                m = torch.empty((K, self.n), dtype=torch.int32, device=self.keys.device)
+                m = _new((K, self.n), torch.int32, self.keys.device)
                 _lib.call("scn_subm_map", _ptr(self.keys), self.n, _ptr(self.tab_keys), _ptr(self.tab_vals),
                           self.cap, f[0], f[1], f[2], _ptr(m), _stream())
                 self.subm[f] = m
@@ -151,7 +189,7 @@ class Level:
             return
         if channels is not None and channels not in TILE_LOCAL_CHANNELS:
             return
-        book = torch.empty(int(_lib.raw("scn_tile_book_bytes")(self.n)), dtype=torch.uint8, device=m.device)
+        book = _new(int(_lib.raw("scn_tile_book_bytes")(self.n)), torch.uint8, m.device)
         _lib.call("scn_tile_book_build", _ptr(m), self.n, 27, _ptr(book), _stream())
         _lib.call("scn_tile_book_attach", _ptr(m), _ptr(book), self.n)
         self._books[m.data_ptr()] = book
@@ -170,29 +208,29 @@ def build_level(keys, morton_bits=None):
     P = keys.numel()
     perm = None
     if morton_bits is not None and P > 1:
-        ws = torch.empty(int(_lib.raw("scn_morton_order_ws_bytes")(P)), dtype=torch.uint8, device=dev)
-        perm = torch.empty(P, dtype=torch.int32, device=dev)
-        skeys = torch.empty(P, dtype=torch.int64, device=dev)
+        ws = _new(int(_lib.raw("scn_morton_order_ws_bytes")(P)), torch.uint8, dev)
+        perm = _new(P, torch.int32, dev)
+        skeys = _new(P, torch.int64, dev)
         _lib.call("scn_morton_order", _ptr(keys), P, int(morton_bits[0]), int(morton_bits[1]), _ptr(perm), _ptr(skeys),
                   _ptr(ws), _stream())
         keys = skeys
     cap = 64
     while cap < 2 * P:
         cap <<= 1
-    tab_keys = torch.empty(cap, dtype=torch.int64, device=dev)
-    tab_vals = torch.empty(cap, dtype=torch.int32, device=dev)
+    tab_keys = _new(cap, torch.int64, dev)
+    tab_vals = _new(cap, torch.int32, dev)
     s = _stream()
-    first = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
-    rank = torch.empty(P + 1, dtype=torch.int32, device=dev)
-    tmp = torch.empty(int(_lib.raw("scn_scan_tmp_elems")(P)), dtype=torch.int32, device=dev)
+    first = _new(max(P, 1), torch.int32, dev)
+    rank = _new(P + 1, torch.int32, dev)
+    tmp = _new(int(_lib.raw("scn_scan_tmp_elems")(P)), torch.int32, dev)
     _lib.call("scn_level_count", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(first), _ptr(rank), _ptr(tmp), s)
     n = int(rank[P].item())
-    point_row = torch.empty(P, dtype=torch.int32, device=dev)
-    row_keys = torch.empty(n, dtype=torch.int64, device=dev)
+    point_row = _new(P, torch.int32, dev)
+    row_keys = _new(n, torch.int64, dev)
     _lib.call("scn_level_finish", _ptr(keys), P, _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(rank), _ptr(point_row),
               _ptr(row_keys), s)
     if perm is not None:      # back to the caller's point order
-        sorted_rows, point_row = point_row, torch.empty(P, dtype=torch.int32, device=dev)
+        sorted_rows, point_row = point_row, _new(P, torch.int32, dev)
         _lib.call("scn_scatter_i32", _ptr(sorted_rows), _ptr(perm), P, _ptr(point_row), s)
     level = Level(row_keys, tab_keys, tab_vals, cap, n)
     level.coherent = perm is not None
@@ -251,8 +289,8 @@ class Metadata:
             if cdev is None:
                 cdev = coords.to(device, non_blocking=True)
             cdev = cdev.contiguous()
-            keys = torch.empty(P, dtype=torch.int64, device=device)
-            err = torch.zeros(1, dtype=torch.int32, device=device)
+            keys = _new(P, torch.int64, device)
+            err = _new(1, torch.int32, device).zero_()
             _lib.call("scn_pack_coords", _ptr(cdev), P, ncol, _ptr(keys), _ptr(err), s)
             self._err = err
         morton_bits = None
@@ -276,10 +314,10 @@ class Metadata:
         self.n_samples = max(int(batch_size), max_b + 1, 1)
         if mode != 0:
             n = level.n
-            cnt = torch.empty(max(n, 1), dtype=torch.int32, device=device)
-            self.row_ptr = torch.empty(n + 1, dtype=torch.int32, device=device)
-            self.row_pts = torch.empty(P, dtype=torch.int32, device=device)
-            tmp = torch.empty(int(_lib.raw("scn_scan_tmp_elems")(n)), dtype=torch.int32, device=device)
+            cnt = _new(max(n, 1), torch.int32, device)
+            self.row_ptr = _new(n + 1, torch.int32, device)
+            self.row_pts = _new(P, torch.int32, device)
+            tmp = _new(int(_lib.raw("scn_scan_tmp_elems")(n)), torch.int32, device)
             _lib.call("scn_input_rule", _ptr(point_row), P, n, _ptr(cnt), _ptr(self.row_ptr), _ptr(self.row_pts), _ptr(tmp), s)
         return level.n
 
@@ -347,18 +385,18 @@ class Metadata:
         dev = lin.keys.device
         s = _stream()
         K = f[0] * f[1] * f[2]
-        pkeys = torch.empty(lin.n, dtype=torch.int64, device=dev)
-        offs = torch.empty(lin.n, dtype=torch.int32, device=dev)
+        pkeys = _new(lin.n, torch.int64, dev)
+        offs = _new(lin.n, torch.int32, dev)
         if out_size in self.levels:
             if between is not None:
                 between()
             _lib.call("scn_stride_keys", _ptr(lin.keys), lin.n, st[0], st[1], st[2], _ptr(pkeys), _ptr(offs), s)
             lout = self.levels[out_size]
-            parent_row = torch.empty(lin.n, dtype=torch.int32, device=dev)
+            parent_row = _new(lin.n, torch.int32, dev)
             _lib.call("scn_hash_lookup", _ptr(pkeys), lin.n, _ptr(lout.tab_keys), _ptr(lout.tab_vals), lout.cap,
                       _ptr(parent_row), s)
-            cmap = torch.full((K, lout.n), -1, dtype=torch.int32, device=dev)
-            dmap = torch.empty((K, lin.n), dtype=torch.int32, device=dev)
+            cmap = _new((K, lout.n), torch.int32, dev).fill_(-1)
+            dmap = _new((K, lin.n), torch.int32, dev)
             _lib.call("scn_strided_maps", _ptr(parent_row), _ptr(offs), lin.n, lout.n, K, _ptr(cmap), _ptr(dmap), s)
         else:
             # new coarse level: two C calls around the one host round trip (its active-row count)
@@ -366,11 +404,11 @@ class Metadata:
             cap = 64
             while cap < 2 * P:
                 cap <<= 1
-            tab_keys = torch.empty(cap, dtype=torch.int64, device=dev)
-            tab_vals = torch.empty(cap, dtype=torch.int32, device=dev)
-            first = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
-            rank = torch.empty(P + 1, dtype=torch.int32, device=dev)
-            tmp = torch.empty(int(_lib.raw("scn_scan_tmp_elems")(P)), dtype=torch.int32, device=dev)
+            tab_keys = _new(cap, torch.int64, dev)
+            tab_vals = _new(cap, torch.int32, dev)
+            first = _new(max(P, 1), torch.int32, dev)
+            rank = _new(P + 1, torch.int32, dev)
+            tmp = _new(int(_lib.raw("scn_scan_tmp_elems")(P)), torch.int32, dev)
             _lib.call("scn_strided_level_count", _ptr(lin.keys), P, st[0], st[1], st[2], _ptr(pkeys), _ptr(offs),
                       _ptr(tab_keys), _ptr(tab_vals), cap, _ptr(first), _ptr(rank), _ptr(tmp), s)
             # The coarse level's row count sizes its buffers: one host round trip.  The count is copied to pinned memory
@@ -385,10 +423,10 @@ class Metadata:
                 between()
             slot[1].synchronize()
             n = int(slot[0][0])
-            parent_row = torch.empty(P, dtype=torch.int32, device=dev)
-            row_keys = torch.empty(n, dtype=torch.int64, device=dev)
-            cmap = torch.empty((K, n), dtype=torch.int32, device=dev)
-            dmap = torch.empty((K, P), dtype=torch.int32, device=dev)
+            parent_row = _new(P, torch.int32, dev)
+            row_keys = _new(n, torch.int64, dev)
+            cmap = _new((K, n), torch.int32, dev)
+            dmap = _new((K, P), torch.int32, dev)
             _lib.call("scn_strided_level_finish", _ptr(pkeys), _ptr(offs), P, _ptr(tab_keys), _ptr(tab_vals), cap,
                       _ptr(rank), _ptr(parent_row), _ptr(row_keys), n, K, _ptr(cmap), _ptr(dmap), s)
             lout = Level(row_keys, tab_keys, tab_vals, cap, n)
@@ -482,6 +520,8 @@ class GeometryPrefetcher:
         self.device = torch.device(device)
         self.n_levels, self.mode, self.dimension = n_levels, mode, dimension
         self.book_channels = book_channels
+        self.use_arena = os.environ.get("SCN_GEOMETRY_ARENA", "1") != "0"
+        self._free, self._lock, self.last_arena_bytes = [], threading.Lock(), 0
         self.stream = torch.cuda.Stream(self.device, priority=-1)
         self.pool = None
         if threaded:
@@ -489,16 +529,42 @@ class GeometryPrefetcher:
             self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="scn-geometry")
         self.pending = {}
 
+    ARENA_BYTES_PER_POINT = 1024      # measured ~420 bytes per point on scan-like scenes (all levels, maps, tile books)
+
+    def _acquire(self, n_points):
+        need = max(int(n_points), 1) * self.ARENA_BYTES_PER_POINT
+        need = (need + (1 << 25) - 1) >> 25 << 25      # 32 MB granules: scenes of similar size share arenas
+        with self._lock:
+            for i, a in enumerate(self._free):
+                if a.buf.numel() >= need:
+                    return self._free.pop(i)
+        return Arena(need, self.device)
+
+    def _release(self, arena, event):
+        arena.event, arena.off = event, 0
+        with self._lock:
+            self._free.append(arena)
+
     def _build(self, coords, spatial_size, batch_size):
         torch.cuda.set_device(self.device)
         with torch.cuda.stream(self.stream):
-            md = Metadata(self.dimension)
-            md.set_input(spatial_size, coords, batch_size, self.mode, self.device)
-            md.prebuild(self.n_levels, book_channels=self.book_channels)
+            arena = self._acquire(len(coords)) if self.use_arena else None
+            if arena is not None and arena.event is not None:
+                self.stream.wait_event(arena.event)      # its previous geometry's last consumer kernels (device-side wait)
+            _arena_tls.arena = arena
+            try:
+                md = Metadata(self.dimension)
+                md.set_input(spatial_size, coords, batch_size, self.mode, self.device)
+                md.prebuild(self.n_levels, book_channels=self.book_channels)
+            finally:
+                _arena_tls.arena = None
             ev = torch.cuda.Event()
             ev.record(self.stream)
         md._prebuilt_for = coords
         md._ready = ev
+        if arena is not None:
+            md._lease = _Lease(self, arena)
+            self.last_arena_bytes = arena.off
         return md
 
     def submit(self, coords, spatial_size, batch_size):
@@ -518,8 +584,10 @@ class GeometryPrefetcher:
         md = item[0].result()
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(md._ready)
+        lease = getattr(md, "_lease", None)
+        base = lease.arena.buf.untyped_storage().data_ptr() if lease is not None else None
         for t in _walk_tensors(md, set()):
-            if t.is_cuda:
+            if t.is_cuda and t.untyped_storage().data_ptr() != base:      # slices of the arena are not the allocator's business
                 t.record_stream(cur)      # allocated on the side stream, used (and later freed) under the training stream
         return md
 
@@ -527,6 +595,23 @@ class GeometryPrefetcher:
         if self.pool is not None:
             self.pool.shutdown(wait=True)
         self.pending.clear()
+
+
+class _Lease:
+    """Returns a geometry's arena to its prefetcher when the Metadata dies.  By then every kernel that reads the geometry has
+    been enqueued (the autograd graph that held it is gone): an event on the releasing thread's current stream orders the
+    arena's next build behind them."""
+
+    def __init__(self, owner, arena):
+        self.owner, self.arena = owner, arena
+
+    def __del__(self):
+        try:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.owner.device))
+            self.owner._release(self.arena, ev)
+        except Exception:      # interpreter shutdown
+            pass
 
 
 class _Done:

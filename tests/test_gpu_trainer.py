@@ -106,23 +106,26 @@ def test_prefetched_geometry_equals_inline(cuda):
     try:
         batches = [bench.make_inputs(s, scene_kw=bench.CPU_SAMPLE) for s in (0, 1, 2)]
         losses = []
-        for prefetch in (False, True, "late"):      # "late": same thread, at the end of the previous step (build_late)
+        batches = batches + batches      # six steps: the prefetcher's arenas are recycled
+        for prefetch in (False, True, "inline", "thread"):      # build_late: training thread / worker thread, recycled arenas
             tr = pipeline.BackboneTrainer(cuda, seed=5)
-            tr.build_late = prefetch == "late"
+            tr.build_late = prefetch if isinstance(prefetch, str) else False
             out = []
             for i, (d, l) in enumerate(batches):
                 nxt = batches[i + 1] if prefetch and i + 1 < len(batches) else None
-                if prefetch == "late":
+                if isinstance(prefetch, str):
                     out.append(float(tr.step(d, l, next_batch=nxt)))
                     assert (tr.prefetcher is not None and len(tr.prefetcher.pending) == 1) or nxt is None
+                    assert nxt is None or tr.prefetcher.last_arena_bytes > 0 or prefetch == "thread"
                 else:
                     out.append(float(tr.step(d, l, next_data=nxt[0] if nxt else None)))
             losses.append(out)
             if prefetch:
                 assert tr.prefetcher is not None and not tr.prefetcher.pending
                 tr.prefetcher.shutdown()
-        assert max(abs(a - b) / abs(a) for a, b in zip(losses[0], losses[1])) < 1e-5, losses
-        assert max(abs(a - b) / abs(a) for a, b in zip(losses[0], losses[2])) < 1e-5, losses
+        for other in losses[1:]:
+            assert max(abs(a - b) / abs(a) for a, b in zip(losses[0], other)) < 1e-5, losses
+        assert len(tr.prefetcher._free) <= 3 and tr.prefetcher.last_arena_bytes > 0      # arenas cycle, nothing leaks
         md = scn.Metadata(3)
         md._prebuilt_for = batches[0][0][0]
         with pytest.raises(RuntimeError):
