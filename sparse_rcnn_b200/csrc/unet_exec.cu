@@ -29,7 +29,7 @@ namespace {
 
 constexpr int MAX_LEVELS = 8, MAX_UNITS = 4;
 #ifndef SCN_EXEC_BWD_PDL_DEFAULT
-#define SCN_EXEC_BWD_PDL_DEFAULT 3
+#define SCN_EXEC_BWD_PDL_DEFAULT 0
 #endif
 
 struct Conv {      // one convolution layer; kind 0 = absent (the level passes its input through)
