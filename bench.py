@@ -195,6 +195,7 @@ def time_kernels(dev, md_size, n_iter=20):
     m2 = torch.empty_like(m)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     ts0 = int(_lib.raw("scn_conv_ts_launch_count")())
+    wts0 = int(_lib.raw("scn_conv_wgrad_ts_launch_count")())
     calls = {
         "conv": lambda: _lib.call("scn_conv_fwd_tf32", P(x), C, C, n, P(m), n, K, P(img), None, None, 0, None, 0, P(out), C, C, 0, s),
         "wgrad": lambda: _lib.call("scn_conv_bwd_weight", P(x), C, C, P(m), n, K, P(go), C, C, P(gw), P(gb), 1, s),
@@ -215,7 +216,7 @@ def time_kernels(dev, md_size, n_iter=20):
             evs.append((e0, e1))
         torch.cuda.synchronize()
         ms[name] = sum(a.elapsed_time(b) for a, b in evs) / n_iter
-    used_ts = int(_lib.raw("scn_conv_ts_launch_count")()) > ts0
+    used_ts = (int(_lib.raw("scn_conv_ts_launch_count")()) > ts0, int(_lib.raw("scn_conv_wgrad_ts_launch_count")()) > wts0)
     assert torch.equal(m2, m)
     # algorithmic bytes, SURVEY.md 8d with s = 4 (fp32 storage)
     alg = {"conv": n * C * 4 + n * C * 4 + K * C * C * 4 + 4 * K * n,
@@ -393,9 +394,10 @@ def main():
                     "traffic": traffic.get(key, {}).get("bytes_per_launch"), "ms_per_launch": kms[key],
                     "algorithmic_bytes": alg[key], "l2": "flushed before every launch"}
         roof = roofline("conv", "%s SubM 3^3 32->32 forward, N=%d, %d pairs" % (
-            "k_conv_ts<32> (tile-local, A operand in tensor memory)" if used_ts else "k_conv_tc<4>", n0, pairs))
+            "k_conv_ts<32> (tile-local, A operand in tensor memory)" if used_ts[0] else "k_conv_tc<4>", n0, pairs))
         roof["tflops_useful"] = flops / (kms["conv"] * 1e-3) / 1e12
-        roof_w = roofline("wgrad", "k_conv_wgrad_tc<4> weight + bias gradient of the same layer")
+        roof_w = roofline("wgrad", "%s weight + bias gradient of the same layer" % (
+            "k_wgrad_ts<32> + k_wgrad_ts_reduce<32> (tile-local, deterministic)" if used_ts[1] else "k_conv_wgrad_tc<4>"))
         roof_w["tflops_useful"] = flops / (kms["wgrad"] * 1e-3) / 1e12
         roof_r = roofline("rulebook", "k_subm_map 3^3 neighbour map of level 0 (13 N hash probes)")
 

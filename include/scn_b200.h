@@ -363,6 +363,27 @@ int scn_sparse_to_dense_rows_bwd(const float* grad_dense, const uint64_t* row_ke
 /* out[b][c][r] = in[b][r][c]: dense rows <-> [B, C, X*Y*Z] */
 int scn_transpose_batched(const float* in, int batches, int rows, int cols, float* out, scn_stream_t stream);
 
+/* ------------------------------------------------------------------ voxelisation + collation ----
+ * the deterministic core of the reference's per-sample conversion for a whole batch on the device --
+ * augment_coords sparse_augmentation.py:81-126 (coords @ (distortion * scale), shift = -min + sub-pixel offset, .long(),
+ * fix_cut_out :41-46 / a drawn random_cut_out :49-78) and collate_fn data.py:88-115 (sample-index column, concatenation).
+ * points fp32 [P, 3], samples concatenated, sample_ptr int32 [B + 1] (device); proj fp32 [B, 9] row-major, offset fp32
+ * [B, 3]; window int32 [B, 9] = start[3] (inside test: start <= c < start + size), size[3], move[3] (added to the
+ * coordinates that stay): fix_cut_out(shift) = {0, size, +shift}, a drawn cut-out = {start, size, -start}.
+ * Outputs: coords int64 [P', 4] (x, y, z, sample; buffer of P rows), kept int32 [P'] = input row of every output row,
+ * out_ptr int32 [B + 1] = first output row of every sample (out_ptr[B] = P'), shift_out fp32 [B, 3] = -min + offset.
+ * fp32 arithmetic is the reference's bit for bit (one rounded product + two fused multiply-adds per output). */
+int64_t scn_voxelize_ws_bytes(int P, int B);
+int scn_voxelize(const float* points, int P, const int32_t* sample_ptr, int B, const float* proj, const float* offset,
+                 const int32_t* window, void* ws, int64_t* coords, int32_t* kept, int32_t* out_ptr, float* shift_out,
+                 scn_stream_t stream);
+/* augment_features sparse_augmentation.py:129-190 for the kept rows: out [n, C] = [colors (+ color_shift[sample]) | ones |
+ * normals @ rotation[sample] (+ normal_shift[sample])]; colors / normals fp32 [P, 3] or NULL, shifts fp32 [B, 3] or NULL,
+ * rotation fp32 [B, 9] or NULL; C = 3 * (colors != NULL) + (use_ones != 0) + 3 * (normals != NULL). */
+int scn_voxelize_features(const int32_t* kept, int n, const int32_t* out_ptr, int B, const float* colors,
+                          const float* color_shift, int use_ones, const float* normals, const float* rotation,
+                          const float* normal_shift, float* out, int C, scn_stream_t stream);
+
 /* ------------------------------------------------------------------ sparse U-Net executor ----
  * FeatureExtractor.forward model.py:414-446 over the graph module_factory.py:438-578,789-830 builds (encoder levels:
  * entry convolution + residual units; decoder levels: ReLU, Deconvolution, JoinTable with the skip connection,

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["grid.cu", "sort.cu", "ops.cu", "conv_fp32.cu", "conv_tc.cu", "conv_ts.cu", "conv_wgrad_tc.cu", "conv_wgrad_ts.cu", "fused.cu", "unet_exec.cu", "dense.cu", "nms.cu"]
+SOURCES = ["grid.cu", "sort.cu", "ops.cu", "conv_fp32.cu", "conv_tc.cu", "conv_ts.cu", "conv_wgrad_tc.cu", "conv_wgrad_ts.cu", "fused.cu", "unet_exec.cu", "dense.cu", "nms.cu", "voxelize.cu"]
 OUT = os.path.join(CSRC, "libscn_b200.so")
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17"]

@@ -1,0 +1,126 @@
+"""Voxelisation + collation of a batch on the device: host mirror of the reference's per-sample conversion
+
+    ndsis/data/sparse_augmentation.py:81-126  augment_coords   (project, shift to the origin, discretise, cut out)
+    ndsis/data/sparse_augmentation.py:129-190 augment_features (rows that stay, normals rotated, common noise vectors)
+    ndsis/data/data.py:88-115                 collate_fn       (batch-index column, concatenation, batch_splits)
+
+for ALL samples of a batch in four kernel launches (csrc/voxelize.cu) instead of ~25 torch ops per sample.  The reference's
+random draws are made HERE, on the host, with the reference's own torch calls in the reference's order (distortion matrix,
+sub-pixel offset, noise vectors), so a seeded run reproduces `convert_sample` bit for bit; the random cut-out draws its start
+positions from data-dependent ranges dimension by dimension (sparse_augmentation.py:49-78), which needs the discrete
+coordinates on the host between draws -- callers that want it pass `start` (drawn by their own policy); `shift` is the
+reference's fixed cut-out (evaluation and the shipped training configuration's `shift=0`).
+
+Output follows the reference's collate contract: (coords int64 [P', 4] (x, y, z, sample), features fp32 [P', C],
+spatial_size, batch_size, batch_splits) -- coords stay ON THE DEVICE (scn.InputLayer accepts them there; `.cpu()` gives the
+reference's host tensor)."""
+from math import pi
+
+import torch
+
+from . import _lib
+from .scn.metadata import _ptr, _stream
+
+
+def coord_distortion_matrix(dtype, coord_noise_sigma, theta, mirror):
+    """The draws of get_coord_distortion_matrix (sparse_augmentation.py:9-38) in its order: randn(3,3), the mirror coin (if
+    not fixed), theta (if not fixed; a list draws one entry).  Returns the almost-orthonormal 3x3 matrix."""
+    m = torch.eye(3, dtype=dtype) + torch.randn((3, 3), dtype=dtype) * coord_noise_sigma
+    m[0, 0] *= (torch.randint(0, 2, ()) * 2 - 1) if mirror is None else (-1 if mirror else 1)
+    if theta is None:
+        theta = torch.rand((), dtype=dtype) * 2 * pi
+    else:
+        theta = torch.tensor(theta, dtype=dtype)
+        if theta.numel() > 1:
+            theta = theta[torch.ones_like(theta).multinomial(1)[0]]
+    c, s = torch.cos(theta), torch.sin(theta)
+    return m @ torch.tensor([[c, s, 0.], [-s, c, 0.], [0., 0., 1.]])
+
+
+def voxelize_batch(points, sample_ptr, proj, offset, spatial_size, shift=None, start=None):
+    """points fp32 [P, 3] (device, samples concatenated), sample_ptr [B + 1] (host ints), proj fp32 [B, 3, 3] = distortion *
+    scale, offset fp32 [B, 3], spatial_size (3 ints), and either shift (int or [B, 3]: fix_cut_out) or start ([B, 3]: the
+    start positions of a drawn cut-out).  -> dict(coords int64 [P', 4], kept int32 [P'] (input row of every output row),
+    out_ptr int32 [B + 1] (device: batch_splits as offsets), complete_shift fp32 [B, 3] as the reference reports it)."""
+    dev = points.device
+    B = len(sample_ptr) - 1
+    P = int(points.shape[0])
+    assert points.dtype == torch.float32 and points.is_contiguous() and int(sample_ptr[-1]) == P and B >= 1
+    size = [int(s) for s in spatial_size]
+    win = torch.zeros((B, 9), dtype=torch.int32)
+    win[:, 3:6] = torch.tensor(size, dtype=torch.int32)
+    if (shift is None) == (start is None):
+        raise ValueError("exactly one of shift (fixed cut-out) / start (drawn start positions) is needed")
+    if shift is not None:
+        win[:, 6:9] = torch.as_tensor(shift, dtype=torch.int32).expand(B, 3) if not isinstance(shift, int) else int(shift)
+        moved = -win[:, 6:9].float()
+    else:
+        st = torch.as_tensor(start, dtype=torch.int32).reshape(B, 3)
+        win[:, 0:3], win[:, 6:9] = st, -st
+        moved = st.float()
+    host = torch.cat([torch.as_tensor(proj, dtype=torch.float32).reshape(B, 9), torch.as_tensor(offset, dtype=torch.float32).reshape(B, 3)], 1)
+    params = host.to(dev, non_blocking=True)
+    ints = torch.cat([torch.as_tensor(sample_ptr, dtype=torch.int32).reshape(-1), win.reshape(-1)]).to(dev, non_blocking=True)
+    sp, window = ints[:B + 1], ints[B + 1:]
+    pr, off = params[:, :9].contiguous(), params[:, 9:].contiguous()
+    ws = torch.empty(int(_lib.raw("scn_voxelize_ws_bytes")(P, B)), dtype=torch.uint8, device=dev)
+    coords = torch.empty((max(P, 1), 4), dtype=torch.int64, device=dev)
+    kept = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    out_ptr = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    shift_out = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    _lib.call("scn_voxelize", _ptr(points), P, _ptr(sp), B, _ptr(pr), _ptr(off), _ptr(window), _ptr(ws), _ptr(coords), _ptr(kept),
+              _ptr(out_ptr), _ptr(shift_out), _stream())
+    splits_end = out_ptr.cpu()              # the one host read: how many points stayed (sizes the outputs)
+    n = int(splits_end[-1])
+    return dict(coords=coords[:n], kept=kept[:n], out_ptr=out_ptr, n=n,
+                batch_splits=[int(b - a) for a, b in zip(splits_end[:-1], splits_end[1:])],
+                complete_shift=shift_out.cpu() - moved)      # coords_shift of the reference: minus the cut-out start
+
+
+def features_batch(vox, B, colors=None, color_shift=None, use_ones=False, normals=None, rotation=None, normal_shift=None):
+    """[colours (+ common shift [B, 3]) | ones | normals @ rotation [B, 3, 3] (+ common shift)] of the kept points."""
+    src = colors if colors is not None else normals
+    dev = vox["coords"].device
+    C = (3 if colors is not None else 0) + (1 if use_ones else 0) + (3 if normals is not None else 0)
+    out = torch.empty((vox["n"], C), dtype=torch.float32, device=dev)
+    up = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32).reshape(B, -1).to(dev).contiguous()
+    cs, rot, ns = up(color_shift), up(rotation), up(normal_shift)
+    assert src is None or src.is_contiguous()
+    _lib.call("scn_voxelize_features", _ptr(vox["kept"]), vox["n"], _ptr(vox["out_ptr"]), B, _ptr(colors), _ptr(cs), int(use_ones),
+              _ptr(normals), _ptr(rot), _ptr(ns), _ptr(out), C, _stream())
+    return out
+
+
+def convert_and_collate(samples, *, spatial_size, scale, shift=0, start=None, coord_noise_sigma=0.0, theta=None, mirror=None,
+                        sub_pixel_offset=None, color_noise_sigma=0.0, normal_noise_sigma=0.0, use_color=True, use_ones=False,
+                        use_normal=True, device="cuda"):
+    """samples: list of (points [n, 3], colors [n, 3], normals [n, 3]) host or device fp32 tensors.  The per-sample draws
+    follow convert_sample (sparse_augmentation.py:250-313 with common_*_noise=True): distortion matrix, sub-pixel offset,
+    colour noise vector, normal noise vector -- sample by sample, as the reference's loop does.  -> (data 5-tuple of
+    collate_fn with coords / features on the device, augmentation list, is_inside-equivalent `kept` rows)."""
+    B = len(samples)
+    projs, rots, offs, cshift, nshift = [], [], [], [], []
+    for pts, _, _ in samples:
+        rot = coord_distortion_matrix(torch.float32, coord_noise_sigma, theta, mirror)
+        rots.append(rot), projs.append(rot * scale)
+        offs.append(torch.rand((3,), dtype=torch.float32) if sub_pixel_offset is None else torch.as_tensor(sub_pixel_offset, dtype=torch.float32))
+        if use_color and color_noise_sigma:
+            cshift.append(color_noise_sigma * torch.randn((3,), dtype=torch.float32))
+        if use_normal and normal_noise_sigma:
+            nshift.append(normal_noise_sigma * torch.randn((3,), dtype=torch.float32))
+    dev = torch.device(device)
+    cat = lambda k: torch.cat([s[k].to(dev, non_blocking=True) for s in samples]).contiguous()
+    ptr = [0]
+    for s in samples:
+        ptr.append(ptr[-1] + len(s[0]))
+    vox = voxelize_batch(cat(0), ptr, torch.stack(projs), torch.stack(offs), spatial_size, shift=None if start is not None else shift,
+                         start=start)
+    feats = features_batch(vox, B, colors=cat(1) if use_color else None, color_shift=torch.stack(cshift) if cshift else None,
+                           use_ones=use_ones, normals=cat(2) if use_normal else None, rotation=torch.stack(rots) if use_normal else None,
+                           normal_shift=torch.stack(nshift) if nshift else None)
+    size = torch.tensor([int(s) for s in spatial_size], dtype=torch.long)
+    data = (vox["coords"], feats, size, B, vox["batch_splits"])
+    augmentation = [dict(coords_projection=projs[i], coords_shift=vox["complete_shift"][i],
+                         **({"color_shift": cshift[i]} if cshift else {}), **({"normals_shift": nshift[i]} if nshift else {}))
+                    for i in range(B)]
+    return data, augmentation, vox["kept"]

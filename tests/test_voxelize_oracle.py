@@ -1,0 +1,64 @@
+"""CPU: the voxelisation / collation oracle (oracle/voxelize_oracle, numpy) against goldens produced by the unmodified
+reference (`augment_coords`, `augment_features`, `collate_fn`; oracle/make_golden_voxelize.py): integer results bit-exact,
+float results bit-exact as well (same fp32 operations in the same order)."""
+import os
+
+import numpy as np
+import torch
+
+import voxelize_oracle as V
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "voxelize.pt")
+
+
+def run_case(case):
+    coords_list, feats_list = [], []
+    for s in case["samples"]:
+        c, inside, cs = V.voxelize_sample(s["points"].numpy(), s["proj"].numpy(), s["offset"].numpy(), case["spatial_size"],
+                                          shift=case["shift"])
+        assert np.array_equal(inside, s["is_inside"].numpy())
+        assert np.array_equal(c, s["coords"].numpy())
+        # complete_shift as the reference reports it: minus the cut-out start (= +shift for fix_cut_out)
+        want = s["complete_shift"].numpy()
+        assert np.array_equal((cs + np.float32(case["shift"])).astype(np.float32), want)
+        cshift = s["color_shift"].numpy() if s["color_shift"].ndim else None
+        nshift = s["normal_shift"].numpy() if s["normal_shift"].ndim else None
+        f = V.features_sample(inside, colors=s["colors"].numpy(), color_shift=cshift, normals=s["normals"].numpy(),
+                              rotation=s["rotation"].numpy(), normal_shift=nshift)
+        assert np.array_equal(f, s["features"].numpy())
+        coords_list.append(c), feats_list.append(f)
+    cb, fb, splits = V.collate(coords_list, feats_list)
+    assert np.array_equal(cb, case["coords_batch"].numpy()) and np.array_equal(fb, case["features_batch"].numpy())
+    assert splits == list(case["batch_splits"])
+
+
+def test_oracle_reproduces_the_reference():
+    cases = torch.load(GOLDEN)
+    assert len(cases) == 4
+    for case in cases[:3]:
+        run_case(case)
+    # the fully seeded case (every draw made by the reference): the oracle with the recorded projection, and the shift the
+    # reference reports minus its own minimum gives back the drawn sub-pixel offset
+    c = cases[3]
+    at = 0
+    for (pts, colors, normals), proj, shift, n in zip(c["inputs"], c["coords_projection"], c["coords_shift"], c["batch_splits"]):
+        aug = V.project(pts.numpy(), proj.numpy())
+        offset = shift.numpy() + aug.min(0)
+        got, inside, _ = V.voxelize_sample(pts.numpy(), proj.numpy(), offset, c["spatial_size"], shift=0)
+        want = c["coords_batch"][at:at + n, :3].numpy()
+        # offset recovered through an fp32 subtraction: a coordinate within one ulp of an integer may land next door
+        assert got.shape == want.shape and (got != want).any(1).mean() < 1e-3
+        at += n
+
+
+def test_start_positions_form_and_empty_sample():
+    rng = np.random.default_rng(0)
+    pts = rng.random((500, 3)).astype(np.float32) * 4
+    proj = (np.eye(3) * 20).astype(np.float32)
+    c0, in0, _ = V.voxelize_sample(pts, proj, [0.5, 0.5, 0.5], (32, 32, 32), shift=0)
+    c1, in1, _ = V.voxelize_sample(pts, proj, [0.5, 0.5, 0.5], (32, 32, 32), start=(0, 0, 0))
+    assert np.array_equal(c0, c1) and np.array_equal(in0, in1)
+    c2, in2, _ = V.voxelize_sample(pts, proj, [0.5, 0.5, 0.5], (32, 32, 32), start=(10, 5, 0))
+    assert in2.sum() < in0.sum() + 500 and (c2 >= 0).all() and (c2 < 32).all()
+    e, ine, cs = V.voxelize_sample(np.zeros((0, 3), np.float32), proj, [0, 0, 0], (8, 8, 8), shift=0)
+    assert e.shape == (0, 3) and ine.shape == (0,)
