@@ -233,7 +233,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
-    ap.add_argument("--infer-workers", type=int, default=2,
+    ap.add_argument("--infer-workers", type=int, default=3,
                     help="host threads (one CUDA stream each) of the sparse inference measurement; 1 = one scene at a time")
     ap.add_argument("--sync-loss", action="store_true",
                     help="e2e: read every step's loss with a blocking .item() right after the step instead of one step late")
