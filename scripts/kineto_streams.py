@@ -73,3 +73,15 @@ for si, st in enumerate(steps[1:], 1):      # the first one starts mid-way (pack
                 end = max(end, e["ts"] + e["dur"])
             print("      idle gaps > 4 us: %d, total %.3f ms; largest: %s" % (len(gaps), sum(g for g, _ in gaps) / 1e3,
                   ", ".join("%.0f us before %s" % g for g in sorted(gaps, reverse=True)[:8])))
+
+# effective cost of every kernel of the first steady step's forward chain: start-to-start intervals on the main stream
+st = steps[1]
+i_conv = next(i for i, e in enumerate(st) if "k_conv" in e["name"])
+i_ce = next(i for i, e in enumerate(st) if "k_ce_bwd" in e["name"])
+main = max(collections.Counter(e["args"].get("stream") for e in st).items(), key=lambda x: x[1])[0]
+chain = [e for e in st[i_conv:i_ce] if e["args"].get("stream") == main]
+print("forward chain on stream %s: kernel, grid, duration us, start-to-next-start us" % main)
+for a, b in zip(chain, chain[1:] + [None]):
+    nxt = (b["ts"] - a["ts"]) if b is not None else a["dur"]
+    print("   %-36s grid %5s  dur %6.1f  step %6.1f" % (a["name"].split("(")[0].replace("void scn::", "").replace("scn::", "")[:34],
+                                                       a["args"].get("grid", ["?"])[0], a["dur"], nxt))
