@@ -305,10 +305,10 @@ def main():
         trainer.build_late = False if (args.prefetch or args.geometry_ahead == "off") else args.geometry_ahead
         trainer.build_late_at = args.geometry_at
         nb = (lambda i: inputs[(i + 1) % n_distinct]) if (args.stage or args.build_ahead or trainer.build_late) else (lambda i: None)
-        # every distinct scene once before the warm-up proper: first-touch costs of a new geometry (caching-allocator growth,
-        # dynamic-smem attributes) must not land in the timed region when W < n_distinct
-        for i in range(n_distinct):
-            trainer.step(*inputs[i])
+        # every distinct scene twice before the warm-up proper: first-touch costs of a new geometry (caching-allocator growth,
+        # dynamic-smem attributes, the recycled arenas of the prefetcher / staging ring) must not land in the timed region
+        for i in range(2 * n_distinct):
+            trainer.step(*inputs[i % n_distinct])
         for i in range(W):
             trainer.step(*inputs[i % n_distinct], next_data=nxt(i), next_batch=nb(i))
         barrier()

@@ -243,57 +243,71 @@ static int stage_fwd(const Unit* units, int U, const float* x, bool r_ready, int
 // nobody before the optimizer.  They are enqueued on a second stream that forks from the main stream where their operands
 // are ready and joins it at the end of the call: on the small levels (a handful of tiles, latency bound) they run beside
 // the chain instead of in it; on the large levels the SMs are full either way.  SCN_EXEC_SIDE=0 keeps everything in line.
+// SCN_EXEC_SIDE_STREAMS=n (default 1) takes n side streams round robin.  Measured and left off: most weight-gradient launches
+// belong to the small levels (44 of 68 per step, a handful of CTAs each), so several streams should overlap their latency
+// chains -- but the backward call stays at 3.90 / 4.07 / 3.97 / 3.92 ms with 1 / 2 / 3 / 4 side streams (profiles/r2_h): the
+// backward is bound by the two big levels' throughput, not by the small levels' serialisation.
+constexpr int MAX_SIDE = 4;
 struct Side {
-    cudaStream_t main, side;
+    cudaStream_t main, sides[MAX_SIDE];
+    int n_side = 0;
     bool on;
-    cudaEvent_t ev[8];
-    int next = 0;
-    bool used = false;
-    int fork() {      // the side stream waits for everything enqueued on the main stream so far
+    cudaEvent_t ev[16];
+    int next = 0, cur = 0;
+    unsigned used = 0;      // bit i: sides[i] has work of this call
+    int fork() {      // the next side stream waits for everything enqueued on the main stream so far
         if (!on) return SCN_OK;
-        cudaEvent_t e = ev[next++ & 7];
-        if (cudaEventRecord(e, main) != cudaSuccess || cudaStreamWaitEvent(side, e, 0) != cudaSuccess) {
+        cur = (cur + 1) % n_side;
+        cudaEvent_t e = ev[next++ & 15];
+        if (cudaEventRecord(e, main) != cudaSuccess || cudaStreamWaitEvent(sides[cur], e, 0) != cudaSuccess) {
             set_error("unet_bwd: stream fork: %s", cudaGetErrorString(cudaGetLastError()));
             return SCN_ERR_CUDA;
         }
-        used = true;
+        used |= 1u << cur;
         return SCN_OK;
     }
     int join() {
-        if (!on || !used) return SCN_OK;
-        cudaEvent_t e = ev[next++ & 7];
-        if (cudaEventRecord(e, side) != cudaSuccess || cudaStreamWaitEvent(main, e, 0) != cudaSuccess) {
-            set_error("unet_bwd: stream join: %s", cudaGetErrorString(cudaGetLastError()));
-            return SCN_ERR_CUDA;
+        if (!on) return SCN_OK;
+        for (int i = 0; i < n_side; ++i) {
+            if (!(used >> i & 1u)) continue;
+            cudaEvent_t e = ev[next++ & 15];
+            if (cudaEventRecord(e, sides[i]) != cudaSuccess || cudaStreamWaitEvent(main, e, 0) != cudaSuccess) {
+                set_error("unet_bwd: stream join: %s", cudaGetErrorString(cudaGetLastError()));
+                return SCN_ERR_CUDA;
+            }
         }
-        used = false;
+        used = 0;
         return SCN_OK;
     }
-    scn_stream_t wstream() const { return reinterpret_cast<scn_stream_t>(on ? side : main); }
+    scn_stream_t wstream() const { return reinterpret_cast<scn_stream_t>(on ? sides[cur] : main); }
 };
 
 struct SideResources {
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev[8];
+    cudaStream_t sides[MAX_SIDE];
+    cudaEvent_t ev[16];
 };
 static int side_for(cudaStream_t main, Side& S) {
     static std::mutex mu;
-    static std::unordered_map<cudaStream_t, SideResources> pool;      // one side stream per calling stream (host threads)
-    static int enabled = -1;
+    static std::unordered_map<cudaStream_t, SideResources> pool;      // side streams per calling stream (host threads)
+    static int enabled = -1, n_side = 1;
     std::lock_guard<std::mutex> lock(mu);
     if (enabled < 0) {
         const char* e = getenv("SCN_EXEC_SIDE");
         enabled = (e && e[0] == '0') ? 0 : 1;
+        const char* ns = getenv("SCN_EXEC_SIDE_STREAMS");
+        if (ns) n_side = atoi(ns);
+        n_side = n_side < 1 ? 1 : (n_side > MAX_SIDE ? MAX_SIDE : n_side);
     }
-    S.main = main, S.side = main, S.on = false;
+    S.main = main, S.on = false, S.n_side = 0;
     if (!enabled) return SCN_OK;
     auto it = pool.find(main);
     if (it == pool.end()) {
         SideResources r;
-        if (cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking) != cudaSuccess) {
-            set_error("unet_bwd: cudaStreamCreate: %s", cudaGetErrorString(cudaGetLastError()));
-            return SCN_ERR_CUDA;
-        }
+        for (auto& st : r.sides)
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+                set_error("unet_bwd: cudaStreamCreate: %s", cudaGetErrorString(cudaGetLastError()));
+                return SCN_ERR_CUDA;
+            }
         for (auto& e : r.ev)
             if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
                 set_error("unet_bwd: cudaEventCreate: %s", cudaGetErrorString(cudaGetLastError()));
@@ -301,8 +315,9 @@ static int side_for(cudaStream_t main, Side& S) {
             }
         it = pool.emplace(main, r).first;
     }
-    S.side = it->second.side, S.on = true;
-    for (int i = 0; i < 8; ++i) S.ev[i] = it->second.ev[i];
+    S.on = true, S.n_side = n_side;
+    for (int i = 0; i < MAX_SIDE; ++i) S.sides[i] = it->second.sides[i];
+    for (int i = 0; i < 16; ++i) S.ev[i] = it->second.ev[i];
     return SCN_OK;
 }
 
@@ -521,7 +536,8 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         const char* e = getenv("SCN_EXEC_BWD_PDL");
         const int keep = e ? atoi(e) : SCN_EXEC_BWD_PDL_DEFAULT;
         if (!(keep & 1)) pdl_scope.exclude(side.main);
-        if (!(keep & 2)) pdl_scope.exclude(side.side);
+        if (!(keep & 2))
+            for (int i = 0; i < side.n_side; ++i) pdl_scope.exclude(side.sides[i]);
     }
     // parameter-gradient pointers in table order
     float* pg_enc[MAX_LEVELS][2 + 4 * MAX_UNITS];

@@ -158,6 +158,23 @@ def test_staged_uploads_equal_inline(cuda):
         scn.set_precision("tf32")
 
 
+def test_staged_copy_that_is_never_taken_cannot_go_stale(cuda):
+    """The staging buffers are recycled (two alternating arenas): a tensor that was staged but never picked up -- a warm-up
+    loop that ends one batch early, as bench.py's does -- must not be handed out later, after its buffer has been rewritten
+    (regression: the geometry worker packed garbage coordinates four steps later)."""
+    from sparse_rcnn_b200.scn import metadata as M
+    g = torch.Generator().manual_seed(0)
+    host = [torch.randint(0, 1000, (5000 + 100 * i, 4), generator=g).pin_memory() for i in range(5)]      # three recycled buffers
+    M.stage_to_device([host[0]], cuda)                  # staged, never taken
+    for i in (1, 2, 3, 4, 1, 2):                        # its buffer is rewritten twice meanwhile
+        M.stage_to_device([host[i]], cuda)
+        assert torch.equal(M.take_staged(host[i]).cpu(), host[i])
+    assert M.take_staged(host[0]) is None               # the stale entry is gone: the caller uploads it again
+    M.stage_to_device([host[0]], cuda)
+    assert torch.equal(M.take_staged(host[0]).cpu(), host[0])
+    assert not M._staged
+
+
 def test_geometry_built_ahead_equals_inline(cuda):
     """next_batch: rulebooks built between the previous step's forward and backward (InputStage.build_ahead) give the same
     losses as building them at the head of the step."""
