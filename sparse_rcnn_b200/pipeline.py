@@ -160,7 +160,19 @@ class SparseInference(nn.Module):
             out["roi_score"], out["roi_bbox"], out["roi_index"] = selected
         return out
 
-    def run_many(self, scenes, boxes=None, workers=2, consume=None, rpn=None):
+    def _geometry_prefetcher(self):
+        pf = getattr(self, "_prefetcher", None)
+        if pf is None:
+            ch = list(self.backbone.channels)
+            pf = self._prefetcher = scn.GeometryPrefetcher(self.device, n_levels=len(ch) - 1, book_channels=ch)
+            self.backbone.input_stage.prefetcher = pf
+        return pf
+
+    def _submit_geometry(self, pf, scene):
+        coords, _, size, bs = scene[:4]
+        pf.submit(coords.long(), torch.as_tensor(size, dtype=torch.long), bs, again=True)
+
+    def run_many(self, scenes, boxes=None, workers=2, consume=None, rpn=None, geometry_ahead=False):
         """Inference over independent scenes from `workers` host threads, one CUDA stream each (scene i -> worker
         i mod workers).  Why: one scene's pass is a ping-pong between host and GPU -- 16 host reads of row counts (every
         level of three pyramids and two crops) during which the host waits for the GPU, each followed by a stretch in which
@@ -172,13 +184,31 @@ class SparseInference(nn.Module):
         its return value replaces the result; returned tensors are `record_stream`-ed for the caller's stream."""
         import threading
         n = len(scenes)
+        # geometry_ahead: the BACKBONE geometry of the scenes ahead (voxel hash, six-level pyramid, maps, tile books: 6 of a
+        # scene's 16 host round trips) is built by the prefetcher's thread on its own stream into recycled arenas; every
+        # worker hands in scene i + workers before it runs scene i.  Same geometry, same results.  OFF by default -- measured
+        # slower (profiles/r2_h section 8: 8.4 -> 9.5 ms per scene with one worker, 7.2 -> 7.6-7.9 with three): the pass is
+        # bound by Python under the GIL, which a further thread does not shorten, and the builder's kernels then queue
+        # behind other scenes' persistent convolution CTAs.
+        pf = self._geometry_prefetcher() if (geometry_ahead and n > 1) else None
         if workers <= 1 or n <= 1:
             out = []
-            for i in range(n):
-                r = self(scenes[i], None if boxes is None else boxes[i], rpn=None if rpn is None else rpn[i])
-                out.append(consume(i, r) if consume is not None else r)
+            try:
+                if pf is not None:
+                    self._submit_geometry(pf, scenes[0])
+                for i in range(n):
+                    if pf is not None and i + 1 < n:
+                        self._submit_geometry(pf, scenes[i + 1])
+                    r = self(scenes[i], None if boxes is None else boxes[i], rpn=None if rpn is None else rpn[i])
+                    out.append(consume(i, r) if consume is not None else r)
+            finally:
+                if pf is not None:
+                    pf.drain()
             return out
         workers = min(workers, n)
+        if pf is not None:
+            for i in range(workers):
+                self._submit_geometry(pf, scenes[i])
         streams = getattr(self, "_streams", None)
         if streams is None or len(streams) < workers:
             streams = self._streams = [torch.cuda.Stream(device=self.device) for _ in range(workers)]
@@ -196,6 +226,8 @@ class SparseInference(nn.Module):
                 with torch.cuda.stream(streams[k]):
                     streams[k].wait_event(ready)      # weights / packed images written on the caller's stream
                     for i in range(k, n, workers):
+                        if pf is not None and i + workers < n:
+                            self._submit_geometry(pf, scenes[i + workers])
                         r = self(scenes[i], None if boxes is None else boxes[i], rpn=None if rpn is None else rpn[i])
                         results[i] = consume(i, r) if consume is not None else r
                     done[k].record(streams[k])
@@ -207,6 +239,8 @@ class SparseInference(nn.Module):
             t.start()
         for t in threads:
             t.join()
+        if pf is not None:
+            pf.drain()
         if errors:
             raise errors[0]
         for d in done:

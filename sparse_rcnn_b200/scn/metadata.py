@@ -592,18 +592,26 @@ class GeometryPrefetcher:
             self.last_arena_bytes = arena.off
         return md
 
-    def submit(self, coords, spatial_size, batch_size):
-        """Start building the geometry of `coords` (a later InputLayer call with this very tensor picks it up)."""
-        if id(coords) in self.pending or not len(coords):
+    def submit(self, coords, spatial_size, batch_size, again=False):
+        """Start building the geometry of `coords` (a later InputLayer call with this very tensor picks it up).  A tensor
+        that is already pending is not built twice unless `again` (inference over a scene list that repeats tensors: one
+        geometry per occurrence, handed out in submission order)."""
+        if not len(coords) or (id(coords) in self.pending and not again):
             return
         if self.pool is None:
-            self.pending[id(coords)] = (_Done(self._build(coords, spatial_size, batch_size)), coords)
+            item = (_Done(self._build(coords, spatial_size, batch_size)), coords)
         else:
-            self.pending[id(coords)] = (self.pool.submit(self._build, coords, spatial_size, batch_size), coords)
+            item = (self.pool.submit(self._build, coords, spatial_size, batch_size), coords)
+        with self._lock:
+            self.pending.setdefault(id(coords), []).append(item)
 
     def take(self, coords):
         """The prefetched Metadata for `coords`, ordered after its build on the current stream; None if not submitted."""
-        item = self.pending.pop(id(coords), None)
+        with self._lock:
+            items = self.pending.get(id(coords))
+            item = items.pop(0) if items else None
+            if items is not None and not items:
+                del self.pending[id(coords)]
         if item is None:
             return None
         md = item[0].result()
@@ -615,6 +623,17 @@ class GeometryPrefetcher:
             if t.is_cuda and t.untyped_storage().data_ptr() != base:      # slices of the arena are not the allocator's business
                 t.record_stream(cur)      # allocated on the side stream, used (and later freed) under the training stream
         return md
+
+    def drain(self):
+        """Forget geometries that were submitted and never taken (after an aborted run); waits for builds in flight."""
+        with self._lock:
+            items = [it for lst in self.pending.values() for it in lst]
+            self.pending.clear()
+        for fut, _ in items:
+            try:
+                fut.result()
+            except Exception:
+                pass
 
     def shutdown(self):
         if self.pool is not None:
