@@ -190,8 +190,35 @@ static void make_plan(const Net& net, const Geo& g, Plan& P) {
     P.bwd_total = b.off;
 }
 
-static int copy_cols(float* dst, int ld_dst, const float* src, int ld_src, int n, int cols, cudaStream_t st) {
+// dst[r][0:cols] = src[r][0:cols] (+ dst2 = round-to-nearest TF32 of the same values): the column blocks of JoinTable and its
+// backward.  Own kernel instead of cudaMemcpy2DAsync: the 2-D copy engine path moved the 21 MB of a level-0 skip connection
+// in 34 us, 16-byte vector accesses in a grid-stride loop take ~12 us, and the optional second output replaces the rounding
+// pass over the joined buffer.
+template <bool DUAL>
+__global__ void __launch_bounds__(256) k_copy_cols(float* __restrict__ dst, int ld_dst, float* __restrict__ dst2, int ld_dst2,
+                                                   const float* __restrict__ src, int ld_src, int64_t total, int q) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t r = i / q;
+        const int c = (int)(i - r * q) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+        *reinterpret_cast<float4*>(dst + r * ld_dst + c) = v;
+        if (DUAL) *reinterpret_cast<float4*>(dst2 + r * ld_dst2 + c) = epi2_apply4(v, SCN_EPI_ROUND);
+    }
+}
+
+static int copy_cols(float* dst, int ld_dst, const float* src, int ld_src, int n, int cols, cudaStream_t st, float* dst2 = nullptr,
+                     int ld_dst2 = 0) {
     if (n <= 0 || cols <= 0) return SCN_OK;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst2);
+    if ((cols | ld_dst | ld_src | ld_dst2) % 4 == 0 && (al & 15) == 0) {
+        const int q = cols / 4;
+        const int64_t total = (int64_t)n * q;
+        const int grid = grid_for(total, 256);
+        if (dst2) k_copy_cols<true><<<grid, 256, 0, st>>>(dst, ld_dst, dst2, ld_dst2, src, ld_src, total, q);
+        else k_copy_cols<false><<<grid, 256, 0, st>>>(dst, ld_dst, nullptr, 0, src, ld_src, total, q);
+        return check_launch("unet: copy_cols");
+    }
+    SCN_REQUIRE(!dst2, "unet: copy_cols with a second output needs 16-byte aligned column blocks");
     cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)ld_dst * 4, src, (size_t)ld_src * 4, (size_t)cols * 4, (size_t)n,
                                       cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) {
@@ -476,23 +503,28 @@ int scn_unet_fwd(const int64_t* net_table, const int64_t* geo_table, const float
         // ReLU (rounded in tf32 mode: a valid tensor-core operand) -> transposed convolution over dmap, written into the left
         // columns of the joined buffer; the skip connection is copied beside it (JoinTable)
         if (!operand_ready) SCN_TRY(scn_relu_fwd(cur, arena + P.rl[j], (int64_t)n_in * d.cin, tf32, stream));
+        // second outputs of the join: the transposed convolution also writes its columns of catr (rounded), the skip copy
+        // writes the other columns of cat and catr -- no rounding pass over the joined buffer
+        const bool join2 = dual && (d.cout % 4 == 0) && (m.cin % 4 == 0) && (net.C[l] % 4 == 0);
         if (n > 0) {
             if (tf32)
-                SCN_TRY(scn_conv_fwd_tf32(arena + P.rl[j], d.cin, d.cin, n_in, g.dmap[l], n, d.K, d.img_f, d.b, nullptr, 0, nullptr, 0,
-                                          arena + P.cat[j], m.cin, d.cout, 0, stream));
+                SCN_TRY(scn_conv_fwd_tf32_dual(arena + P.rl[j], d.cin, d.cin, n_in, g.dmap[l], n, d.K, d.img_f, d.b, nullptr, 0, nullptr, 0,
+                                               arena + P.cat[j], m.cin, d.cout, 0, join2 ? arena + P.catr[j] : nullptr, m.cin,
+                                               SCN_EPI_ROUND, stream));
             else
                 SCN_TRY(scn_conv_fwd_fp32(arena + P.rl[j], d.cin, d.cin, g.dmap[l], n, d.K, d.w, 0, 0, d.b, nullptr, 0, nullptr, 0,
                                           arena + P.cat[j], m.cin, d.cout, 0, stream));
         }
         const float* skip = P.E[l] >= 0 ? arena + P.E[l] : x;
-        SCN_TRY(copy_cols(arena + P.cat[j] + d.cout, m.cin, skip, net.C[l], n, net.C[l], st));
+        SCN_TRY(copy_cols(arena + P.cat[j] + d.cout, m.cin, skip, net.C[l], n, net.C[l], st, join2 ? arena + P.catr[j] + d.cout : nullptr,
+                          m.cin));
         const Out2 tail = (dual && j + 1 < nd) ? Out2{arena + P.rl[j + 1], RR} : NO_OUT2;
         bool r_ready = false;
         if (!tf32) {
             SCN_TRY(scn_conv_layer_fwd(arena + P.cat[j], m.cin, n, m.cin, 0, arena + P.catr[j], nullptr, n, 1, m.w, m.img_f, 0, m.b,
                                        arena + P.nin[j], m.cout, tf32, stream));
         } else if (n > 0) {
-            SCN_TRY(scn_round_tf32(arena + P.cat[j], arena + P.catr[j], (int64_t)n * m.cin, stream));
+            if (!join2) SCN_TRY(scn_round_tf32(arena + P.cat[j], arena + P.catr[j], (int64_t)n * m.cin, stream));
             const Out2 o = !dual ? NO_OUT2 : (U ? Out2{arena + P.dr[j][0], RR} : tail);
             SCN_TRY(scn_conv_fwd_tf32_dual(arena + P.catr[j], m.cin, m.cin, n, nullptr, n, 1, m.img_f, m.b, nullptr, 0, nullptr, 0,
                                            arena + P.nin[j], m.cout, m.cout, 0, o.p, m.cout, o.epi, stream));

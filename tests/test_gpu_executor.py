@@ -65,8 +65,9 @@ def test_executor_equals_module_graph(cuda, precision, extra_seed):
     for n in g0:
         assert rel_err(g1[n], g0[n]) <= gtol, (n, rel_err(g1[n], g0[n]))
     print("kernel launches: executor %d, module graph %d" % (l1 - l0, l2 - l1))
-    # (the executor's counted launches include the skip-gradient adds that autograd does with uncounted torch kernels)
-    assert l1 - l0 <= l2 - l1 + 2 * 5
+    # (the executor's counted launches include the skip-gradient adds and the column copies of JoinTable and its backward --
+    # own kernels since round 2b -- that the module graph does with uncounted torch kernels: 2 + 3 per decoder level)
+    assert l1 - l0 <= l2 - l1 + (2 + 3) * 5
 
 
 def test_executor_under_no_grad_and_threads(cuda):
