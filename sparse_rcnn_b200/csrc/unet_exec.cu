@@ -197,6 +197,8 @@ static void make_plan(const Net& net, const Geo& g, Plan& P) {
 template <bool DUAL>
 __global__ void __launch_bounds__(256) k_copy_cols(float* __restrict__ dst, int ld_dst, float* __restrict__ dst2, int ld_dst2,
                                                    const float* __restrict__ src, int ld_src, int64_t total, int q) {
+    pdl_trigger();      // PDL (common.cuh): the convolution that follows sets itself up meanwhile
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
         const int64_t r = i / q;
         const int c = (int)(i - r * q) * 4;
@@ -214,8 +216,21 @@ static int copy_cols(float* dst, int ld_dst, const float* src, int ld_src, int n
         const int q = cols / 4;
         const int64_t total = (int64_t)n * q;
         const int grid = grid_for(total, 256);
-        if (dst2) k_copy_cols<true><<<grid, 256, 0, st>>>(dst, ld_dst, dst2, ld_dst2, src, ld_src, total, q);
-        else k_copy_cols<false><<<grid, 256, 0, st>>>(dst, ld_dst, nullptr, 0, src, ld_src, total, q);
+        // programmatic dependent launch for this kernel: measured on one box, three alternations -- forward 1.478-1.479 ms with
+        // the attribute, 1.464-1.466 ms without (a 1184-CTA elementwise grid parked in griddepcontrol.wait takes the SMs the
+        // small-level convolution in front of it is still using); SCN_COPY_PDL=1 turns it on
+        static int copy_pdl = -1;
+        if (copy_pdl < 0) {
+            const char* e = getenv("SCN_COPY_PDL");
+            copy_pdl = (e && e[0] == '1') ? 1 : 0;
+        }
+        PdlMaskScope scope;
+        if (!copy_pdl) scope.exclude(st);
+        PdlLaunch L(dim3(grid), dim3(256), 0, st);
+        float* no2 = nullptr;
+        const int zero = 0;
+        if (dst2) cudaLaunchKernelEx(&L.cfg, k_copy_cols<true>, dst, ld_dst, dst2, ld_dst2, src, ld_src, total, q);
+        else cudaLaunchKernelEx(&L.cfg, k_copy_cols<false>, dst, ld_dst, no2, zero, src, ld_src, total, q);
         return check_launch("unet: copy_cols");
     }
     SCN_REQUIRE(!dst2, "unet: copy_cols with a second output needs 16-byte aligned column blocks");
@@ -349,18 +364,19 @@ static int side_for(cudaStream_t main, Side& S) {
 }
 
 // one residual unit backward: the kernels of scn_residual_unit_bwd (accumulate mode), input-gradient chain on the main
-// stream, the two weight gradients on the side stream.  gyr_ready: gyr already holds round(gy) (second output of gy's
-// producer); gx2: second output of the convolution that produces gx
-static int unit_bwd(const Unit& q, const float* gy, bool gyr_ready, const float* r, const float* h, int n, int C, const int32_t* map,
+// stream, the two weight gradients on the side stream.  gy_state: gyr already holds round(gy) (second output of gy's
+// producer) or gy is rounded itself (written by the rounding ReLU backward); gx2: second output of the convolution that
+// produces gx
+static int unit_bwd(const Unit& q, const float* gy, int gy_state, const float* r, const float* h, int n, int C, const int32_t* map,
                     float* gyr, float* gh, float* gx, Out2 gx2, float* gw1, float* gb1, float* gw2, float* gb2, int tf32, scn_stream_t s,
                     Side& side) {
     if (n == 0) return SCN_OK;
     const int K = 27;
     const int64_t total = (int64_t)n * C;
     const float* g_op = gy;
-    if (tf32) {
-        if (!gyr_ready) SCN_TRY(scn_round_tf32(gy, gyr, total, s));
-        g_op = gyr;
+    if (tf32) {      // gy_state: 0 = round gy into gyr, 1 = gyr already holds round(gy), 2 = gy itself is rounded
+        if (gy_state == 0) SCN_TRY(scn_round_tf32(gy, gyr, total, s));
+        g_op = gy_state == 2 ? gy : gyr;
     }
     if (gw2 || gb2) {
         SCN_TRY(side.fork());
@@ -388,15 +404,15 @@ static int unit_bwd(const Unit& q, const float* gy, bool gyr_ready, const float*
 // stage wants round(gradient of the stage input) (second output of unit 0's last convolution)
 static int stage_bwd(const Unit* units, int U, const float* gy, int n, int C, const int32_t* map, const float* fbase, const int64_t* r,
                      const int64_t* h, float* bbase, const int64_t* gyr, const int64_t* gh, const int64_t* gxs, float* const* pg, bool dual,
-                     Out2 head, int tf32, scn_stream_t s, Side& side, const float** gx_out) {
-    bool ready = false;
+                     Out2 head, bool gy_exact, int tf32, scn_stream_t s, Side& side, const float** gx_out) {
+    int ready = gy_exact ? 2 : 0;
     for (int u = U - 1; u >= 0; --u) {
         float* gx = bbase + gxs[u];
         const Out2 o = !dual ? NO_OUT2 : (u > 0 ? Out2{bbase + gyr[u - 1], SCN_EPI_ROUND} : head);
         SCN_TRY(unit_bwd(units[u], gy, ready, fbase + r[u], fbase + h[u], n, C, map, bbase + gyr[u], bbase + gh[u], gx, o, pg[4 * u],
                          pg[4 * u + 1], pg[4 * u + 2], pg[4 * u + 3], tf32, s, side));
         gy = gx;
-        ready = dual && n > 0;
+        ready = (dual && n > 0) ? 1 : 0;
     }
     *gx_out = gy;
     return SCN_OK;
@@ -589,17 +605,19 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         const float* seed;
         float* buf;
         bool have;      // buf holds a value
+        bool exact;     // ... that is TF32-representable (single contribution written by the rounding ReLU backward)
     };
     Grad gE[MAX_LEVELS], gD[MAX_LEVELS];
-    for (int i = 0; i < L; ++i) gE[i] = Grad{as_ptr<const float>(seeds[i]), barena + P.gE[i], false};
-    for (int j = 0; j < L - 1; ++j) gD[j] = Grad{as_ptr<const float>(seeds[L + j]), barena + P.gD[j], false};
+    for (int i = 0; i < L; ++i) gE[i] = Grad{as_ptr<const float>(seeds[i]), barena + P.gE[i], false, false};
+    for (int j = 0; j < L - 1; ++j) gD[j] = Grad{as_ptr<const float>(seeds[L + j]), barena + P.gD[j], false, false};
     // add a contribution that a kernel is about to write: returns where to write it; `commit` folds it in afterwards
     auto target = [&](Grad& G, float* tmp) -> float* { return G.have ? tmp : G.buf; };
-    auto commit = [&](Grad& G, float* written, int64_t count, bool run) -> int {
+    auto commit = [&](Grad& G, float* written, int64_t count, bool run, bool written_exact = false) -> int {
         if (G.have) {
             if (run && count > 0) SCN_TRY(scn_add(G.buf, written, G.buf, count, stream));
+            G.exact = false;
         } else {
-            G.have = true;
+            G.have = true, G.exact = written_exact;
         }
         return SCN_OK;
     };
@@ -607,8 +625,10 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
     auto resolve = [&](Grad& G, int64_t count, bool run, const float** out) -> int {
         if (G.have && G.seed) {
             if (run && count > 0) SCN_TRY(scn_add(G.buf, G.seed, G.buf, count, stream));
+            G.exact = false;
             *out = G.buf;
         } else {
+            if (!G.have) G.exact = false;      // the caller's seed: any fp32 value
             *out = G.have ? G.buf : G.seed;      // may be NULL: no gradient reaches this output
         }
         return SCN_OK;
@@ -628,8 +648,8 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
             // unit 0 hands round(gradient of the 1x1 layer's output) to that layer; the 1x1 layer hands round(gradient of the
             // joined columns) to the transposed convolution, which reads its left columns in place (no copy, no rounding pass)
             SCN_TRY(stage_bwd(net.du[j], U, gy, n, c, g.subm[l], arena, P.dr[j], P.dh[j], barena, P.d_gyr[j], P.d_gh[j], P.d_gx[j],
-                              pg_dec[j] + 4, dual, dual ? Out2{barena + P.d_round_nin[j], SCN_EPI_ROUND} : NO_OUT2, tf32, stream, side,
-                              &g_nin));
+                              pg_dec[j] + 4, dual, dual ? Out2{barena + P.d_round_nin[j], SCN_EPI_ROUND} : NO_OUT2, tf32 && gD[j].exact, tf32,
+                              stream, side, &g_nin));
             // 1x1 layer over the joined columns: input gradient [n, cin], weight + bias gradient
             SCN_TRY(conv_bwd(g_nin, n, m.cout, dual && U > 0, barena + P.d_round_nin[j], m.cout, arena + P.cat[j], m.cin, n, m.cin, nullptr,
                              nullptr, 1, m.w, m.img_b, 0, barena + P.g_cat[j], dual ? Out2{barena + P.g_catr[j], SCN_EPI_ROUND} : NO_OUT2,
@@ -656,7 +676,7 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         {
             float* to = target(below, barena + P.tmp[l + 1]);
             if (run_dec) SCN_TRY(scn_relu_bwd(arena + P.rl[j], barena + P.g_rl[j], to, (int64_t)n_in * d.cin, tf32, stream));
-            SCN_TRY(commit(below, to, (int64_t)n_in * d.cin, run_dec));
+            SCN_TRY(commit(below, to, (int64_t)n_in * d.cin, run_dec, tf32 != 0));      // k_relu_bwd<true> rounds what it writes
         }
     }
     for (int i = L - 1; i >= 0; --i) {
@@ -670,8 +690,8 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         const float* g_c = gy;
         if (run_enc)
             SCN_TRY(stage_bwd(net.eu[i], U, gy, n, net.C[i], g.subm[i], arena, P.er[i], P.eh[i], barena, P.e_gyr[i], P.e_gh[i], P.e_gx[i],
-                              pg_enc[i] + 2, dual, (dual && e.kind) ? Out2{barena + P.e_round[i], SCN_EPI_ROUND} : NO_OUT2, tf32, stream, side,
-                              &g_c));
+                              pg_enc[i] + 2, dual, (dual && e.kind) ? Out2{barena + P.e_round[i], SCN_EPI_ROUND} : NO_OUT2, tf32 && gE[i].exact,
+                              tf32, stream, side, &g_c));
         if (!e.kind) {      // pass-through level 0: its gradient IS the input gradient
             if (gx && run_enc && n > 0) {
                 cudaError_t err = cudaMemcpyAsync(gx, g_c, (size_t)n * net.C[i] * 4, cudaMemcpyDeviceToDevice, st);
