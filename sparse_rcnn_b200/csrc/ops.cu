@@ -553,15 +553,28 @@ constexpr int NSLAB = 296;  // 2 x 148 SMs
 
 extern "C" {
 
+// SCN_EW_PDL=0: launch the elementwise kernels without the programmatic-dependent-launch attribute (A/B switch)
+static bool ew_pdl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SCN_EW_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 int scn_relu_fwd(const float* in, float* out, int64_t n, int round_tf32, scn_stream_t stream) {
     if (n <= 0) return SCN_OK;
     if (round_tf32)
         {
+            PdlMaskScope ew_scope;
+            if (!ew_pdl()) ew_scope.exclude(as_stream(stream));
             PdlLaunch L(dim3(grid_for((n + 3) / 4, TB)), dim3(TB), 0, as_stream(stream));
             cudaLaunchKernelEx(&L.cfg, k_relu_fwd<1>, in, out, n);
         }
     else
         {
+            PdlMaskScope ew_scope;
+            if (!ew_pdl()) ew_scope.exclude(as_stream(stream));
             PdlLaunch L(dim3(grid_for((n + 3) / 4, TB)), dim3(TB), 0, as_stream(stream));
             cudaLaunchKernelEx(&L.cfg, k_relu_fwd<0>, in, out, n);
         }
@@ -571,11 +584,15 @@ int scn_relu_bwd(const float* y, const float* go, float* gi, int64_t n, int roun
     if (n <= 0) return SCN_OK;
     if (round_tf32)
         {
+            PdlMaskScope ew_scope;
+            if (!ew_pdl()) ew_scope.exclude(as_stream(stream));
             PdlLaunch L(dim3(grid_for(n, TB)), dim3(TB), 0, as_stream(stream));
             cudaLaunchKernelEx(&L.cfg, k_relu_bwd<true>, y, go, gi, n);
         }
     else
         {
+            PdlMaskScope ew_scope;
+            if (!ew_pdl()) ew_scope.exclude(as_stream(stream));
             PdlLaunch L(dim3(grid_for(n, TB)), dim3(TB), 0, as_stream(stream));
             cudaLaunchKernelEx(&L.cfg, k_relu_bwd<false>, y, go, gi, n);
         }
@@ -584,6 +601,8 @@ int scn_relu_bwd(const float* y, const float* go, float* gi, int64_t n, int roun
 int scn_round_tf32(const float* in, float* out, int64_t n, scn_stream_t stream) {
     if (n <= 0) return SCN_OK;
     {
+        PdlMaskScope ew_scope;
+        if (!ew_pdl()) ew_scope.exclude(as_stream(stream));
         PdlLaunch L(dim3(grid_for((n + 3) / 4, TB)), dim3(TB), 0, as_stream(stream));
         cudaLaunchKernelEx(&L.cfg, k_relu_fwd<2>, in, out, n);
     }
