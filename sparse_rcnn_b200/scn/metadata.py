@@ -581,6 +581,12 @@ class GeometryPrefetcher:
                 md = Metadata(self.dimension)
                 md.set_input(spatial_size, coords, batch_size, self.mode, self.device)
                 md.prebuild(self.n_levels, book_channels=self.book_channels)
+            except BaseException:
+                if arena is not None:      # a build that fails (bad coordinates) gives its arena back
+                    back = torch.cuda.Event()
+                    back.record(self.stream)
+                    self._release(arena, back)
+                raise
             finally:
                 _arena_tls.arena = None
             ev = torch.cuda.Event()
