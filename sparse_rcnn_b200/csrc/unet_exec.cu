@@ -404,8 +404,8 @@ static int unit_bwd(const Unit& q, const float* gy, int gy_state, const float* r
 // stage wants round(gradient of the stage input) (second output of unit 0's last convolution)
 static int stage_bwd(const Unit* units, int U, const float* gy, int n, int C, const int32_t* map, const float* fbase, const int64_t* r,
                      const int64_t* h, float* bbase, const int64_t* gyr, const int64_t* gh, const int64_t* gxs, float* const* pg, bool dual,
-                     Out2 head, bool gy_exact, int tf32, scn_stream_t s, Side& side, const float** gx_out) {
-    int ready = gy_exact ? 2 : 0;
+                     Out2 head, int gy_state, int tf32, scn_stream_t s, Side& side, const float** gx_out) {
+    int ready = gy_state;      // of the chain's incoming gradient (unit_bwd)
     for (int u = U - 1; u >= 0; --u) {
         float* gx = bbase + gxs[u];
         const Out2 o = !dual ? NO_OUT2 : (u > 0 ? Out2{bbase + gyr[u - 1], SCN_EPI_ROUND} : head);
@@ -422,10 +422,16 @@ static int stage_bwd(const Unit* units, int U, const float* gy, int n, int C, co
 // already holds round(go), both with leading dimension ld_gr; gx2: second output of the input-gradient convolution
 static int conv_bwd(const float* go, int n_out, int Cout, bool go_exact, float* go_round, int ld_gr, const float* x, int ld_x, int n_in,
                     int Cin, const int32_t* fmap, const int32_t* bmap, int K, const float* w, void* image_t, int reverse, float* gx, Out2 gx2,
-                    float* gw, float* gb, int tf32, scn_stream_t s, Side& side) {
+                    float* gw, float* gb, int tf32, scn_stream_t s, Side& side, const float* add = nullptr, const float* mask = nullptr) {
+    // add / mask (TF32 mode only): epilogue of the input-gradient convolution -- gx = conv + add (`add` may be gx itself:
+    // the skip connection's gradient already sits there) and / or gx = round(mask > 0 ? conv : 0) (the ReLU in front of a
+    // transposed convolution), instead of a k_add / k_relu_bwd launch behind it
     if (n_out == 0) {
-        if (gx && n_in > 0) cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)n_in * Cin, as_stream(s));
-        if (gx && gx2.p && n_in > 0) cudaMemsetAsync(gx2.p, 0, sizeof(float) * (size_t)n_in * Cin, as_stream(s));
+        if (gx && n_in > 0 && !add) cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)n_in * Cin, as_stream(s));
+        if (gx && gx2.p && n_in > 0) {
+            if (add) SCN_TRY(scn_round_tf32(add, gx2.p, (int64_t)n_in * Cin, s));
+            else cudaMemsetAsync(gx2.p, 0, sizeof(float) * (size_t)n_in * Cin, as_stream(s));
+        }
         return check_launch("unet_bwd(memset)");
     }
     const float* g = go;
@@ -441,8 +447,8 @@ static int conv_bwd(const float* go, int n_out, int Cout, bool go_exact, float* 
     }
     if (gx && n_in > 0) {
         if (tf32)
-            SCN_TRY(scn_conv_fwd_tf32_dual(g, ld_g, Cout, n_out, bmap, n_in, K, image_t, nullptr, nullptr, 0, nullptr, 0, gx, Cin, Cin, 0,
-                                           gx2.p, Cin, gx2.epi, s));
+            SCN_TRY(scn_conv_fwd_tf32_dual(g, ld_g, Cout, n_out, bmap, n_in, K, image_t, nullptr, add, Cin, mask, Cin, gx, Cin, Cin,
+                                           (add ? SCN_EPI_ADD : 0) | (mask ? (SCN_EPI_MASK | SCN_EPI_ROUND) : 0), gx2.p, Cin, gx2.epi, s));
         else
             SCN_TRY(scn_conv_fwd_fp32(g, Cout, Cout, bmap, n_in, K, w, 1, reverse, nullptr, nullptr, 0, nullptr, 0, gx, Cin, Cin, 0, s));
     }
@@ -606,10 +612,11 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         float* buf;
         bool have;      // buf holds a value
         bool exact;     // ... that is TF32-representable (single contribution written by the rounding ReLU backward)
+        bool rounded;   // round(buf) already sits in the last unit's gyr scratch (second output of the fused add below)
     };
     Grad gE[MAX_LEVELS], gD[MAX_LEVELS];
-    for (int i = 0; i < L; ++i) gE[i] = Grad{as_ptr<const float>(seeds[i]), barena + P.gE[i], false, false};
-    for (int j = 0; j < L - 1; ++j) gD[j] = Grad{as_ptr<const float>(seeds[L + j]), barena + P.gD[j], false, false};
+    for (int i = 0; i < L; ++i) gE[i] = Grad{as_ptr<const float>(seeds[i]), barena + P.gE[i], false, false, false};
+    for (int j = 0; j < L - 1; ++j) gD[j] = Grad{as_ptr<const float>(seeds[L + j]), barena + P.gD[j], false, false, false};
     // add a contribution that a kernel is about to write: returns where to write it; `commit` folds it in afterwards
     auto target = [&](Grad& G, float* tmp) -> float* { return G.have ? tmp : G.buf; };
     auto commit = [&](Grad& G, float* written, int64_t count, bool run, bool written_exact = false) -> int {
@@ -648,7 +655,7 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
             // unit 0 hands round(gradient of the 1x1 layer's output) to that layer; the 1x1 layer hands round(gradient of the
             // joined columns) to the transposed convolution, which reads its left columns in place (no copy, no rounding pass)
             SCN_TRY(stage_bwd(net.du[j], U, gy, n, c, g.subm[l], arena, P.dr[j], P.dh[j], barena, P.d_gyr[j], P.d_gh[j], P.d_gx[j],
-                              pg_dec[j] + 4, dual, dual ? Out2{barena + P.d_round_nin[j], SCN_EPI_ROUND} : NO_OUT2, tf32 && gD[j].exact, tf32,
+                              pg_dec[j] + 4, dual, dual ? Out2{barena + P.d_round_nin[j], SCN_EPI_ROUND} : NO_OUT2, (tf32 && gD[j].exact) ? 2 : 0, tf32,
                               stream, side, &g_nin));
             // 1x1 layer over the joined columns: input gradient [n, cin], weight + bias gradient
             SCN_TRY(conv_bwd(g_nin, n, m.cout, dual && U > 0, barena + P.d_round_nin[j], m.cout, arena + P.cat[j], m.cin, n, m.cin, nullptr,
@@ -664,10 +671,10 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         }
         if (run_dec) {
             // transposed convolution backward: the input gradient runs over cmap (children of each coarse row)
-            if (dual)
+            if (dual)      // ... with the backward of the ReLU in front of it (mask = its output, rounded result) in the epilogue
                 SCN_TRY(conv_bwd(barena + P.g_cat[j], n, d.cout, n > 0, barena + P.g_catr[j], m.cin, arena + P.rl[j], d.cin, n_in, d.cin,
-                                 g.dmap[l], g.cmap[l], d.K, d.w, d.img_b, 0, barena + P.g_rl[j], NO_OUT2, pg_dec[j][0], pg_dec[j][1], tf32,
-                                 stream, side));
+                                 g.dmap[l], g.cmap[l], d.K, d.w, d.img_b, 0, target(below, barena + P.tmp[l + 1]), NO_OUT2, pg_dec[j][0],
+                                 pg_dec[j][1], tf32, stream, side, nullptr, arena + P.rl[j]));
             else
                 SCN_TRY(conv_bwd(barena + P.g_up[j], n, d.cout, false, barena + P.d_round_up[j], d.cout, arena + P.rl[j], d.cin, n_in, d.cin,
                                  g.dmap[l], g.cmap[l], d.K, d.w, d.img_b, 0, barena + P.g_rl[j], NO_OUT2, pg_dec[j][0], pg_dec[j][1], tf32,
@@ -675,7 +682,7 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         }
         {
             float* to = target(below, barena + P.tmp[l + 1]);
-            if (run_dec) SCN_TRY(scn_relu_bwd(arena + P.rl[j], barena + P.g_rl[j], to, (int64_t)n_in * d.cin, tf32, stream));
+            if (run_dec && !dual) SCN_TRY(scn_relu_bwd(arena + P.rl[j], barena + P.g_rl[j], to, (int64_t)n_in * d.cin, tf32, stream));
             SCN_TRY(commit(below, to, (int64_t)n_in * d.cin, run_dec, tf32 != 0));      // k_relu_bwd<true> rounds what it writes
         }
     }
@@ -690,7 +697,7 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
         const float* g_c = gy;
         if (run_enc)
             SCN_TRY(stage_bwd(net.eu[i], U, gy, n, net.C[i], g.subm[i], arena, P.er[i], P.eh[i], barena, P.e_gyr[i], P.e_gh[i], P.e_gx[i],
-                              pg_enc[i] + 2, dual, (dual && e.kind) ? Out2{barena + P.e_round[i], SCN_EPI_ROUND} : NO_OUT2, tf32 && gE[i].exact,
+                              pg_enc[i] + 2, dual, (dual && e.kind) ? Out2{barena + P.e_round[i], SCN_EPI_ROUND} : NO_OUT2, (tf32 && gE[i].exact) ? 2 : ((tf32 && gE[i].rounded) ? 1 : 0),
                               tf32, stream, side, &g_c));
         if (!e.kind) {      // pass-through level 0: its gradient IS the input gradient
             if (gx && run_enc && n > 0) {
@@ -710,6 +717,17 @@ int scn_unet_bwd(const int64_t* net_table, const int64_t* geo_table, const float
             if (run_enc)
                 SCN_TRY(conv_bwd(g_c, n, e.cout, go_exact, barena + P.e_round[i], e.cout, x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w,
                                  e.img_b, reverse, gx, NO_OUT2, pg_enc[i][0], pg_enc[i][1], tf32, stream, side));
+        } else if (dual && gE[i - 1].have) {
+            // the skip connection's gradient already sits in gE[i-1]: add it in this convolution's epilogue, in place, and
+            // hand round(sum) to the last unit of level i-1 as a second output (nothing else adds to it: no seed)
+            Grad& G = gE[i - 1];
+            const int Ub = net.enc_units[i - 1];
+            const bool hand = Ub > 0 && !G.seed && n_in > 0;
+            if (run_enc)
+                SCN_TRY(conv_bwd(g_c, n, e.cout, go_exact, barena + P.e_round[i], e.cout, x_in, e.cin, n_in, e.cin, fmap, bmap, e.K, e.w,
+                                 e.img_b, reverse, G.buf, hand ? Out2{barena + P.e_gyr[i - 1][Ub - 1], SCN_EPI_ROUND} : NO_OUT2, pg_enc[i][0],
+                                 pg_enc[i][1], tf32, stream, side, G.buf));
+            G.exact = false, G.rounded = hand;
         } else {
             float* to = target(gE[i - 1], barena + P.tmp[i - 1]);
             if (run_enc)
