@@ -53,7 +53,10 @@ def seeded_case(seed, sizes, spatial_size, scale, sigma, noise):
     samples = []
     for i, n in enumerate(sizes):
         pts, colors, normals = sample(seed * 100 + i, n, (5.0, 4.0, 2.5))
-        samples.append(("s%d" % i, pts, colors, normals, torch.zeros(n, dtype=torch.long), torch.zeros(1, dtype=torch.long)))
+        g = torch.Generator().manual_seed(seed * 1000 + i)
+        n_inst = 5 + i
+        samples.append(("s%d" % i, pts, colors, normals, torch.randint(0, n_inst + 1, (n,), generator=g),      # n_inst = no instance
+                        torch.randint(1, 19, (n_inst,), generator=g)))
     torch.manual_seed(seed)
     conv = [A.convert_sample(
         smp, spatial_size=spatial_size, instance_cutoff_threshold=0.5, color_noise_sigma=noise, common_color_noise=True,
@@ -63,7 +66,8 @@ def seeded_case(seed, sizes, spatial_size, scale, sigma, noise):
     batch = collate_fn(conv)
     cb, fb, ss, bs, splits = batch["data"]
     return dict(seed=seed, inputs=[(s[1], s[2], s[3]) for s in samples], spatial_size=list(spatial_size), scale=scale, sigma=sigma,
-                noise=noise, coords_batch=cb, features_batch=fb, batch_splits=splits,
+                noise=noise, coords_batch=cb, features_batch=fb, batch_splits=splits, gt_segmentation=batch["gt_segmentation"],
+                instance_ids=[s[4] for s in samples], semantic_instance_labels=[s[5] for s in samples],
                 coords_shift=[a["coords_shift"] for a in batch["augmentation"]],
                 coords_projection=[a["coords_projection"] for a in batch["augmentation"]])
 

@@ -91,6 +91,33 @@ def features_batch(vox, B, colors=None, color_shift=None, use_ones=False, normal
     return out
 
 
+def load_sample(scene_id, path):
+    """data.py:6-8: the on-disk tuple (coords fp32 [P, 3], colors, normals, instance_ids, semantic_instance_labels_raw)
+    written by the reference's preparation step, prefixed with the scene id."""
+    return (scene_id,) + tuple(torch.load(path))
+
+
+def segmentation_labels_batch(vox, sample_ptr, instance_ids, semantic_instance_labels, background_label, label_mapper=None):
+    """get_semantic_segmentation_labels (sparse_augmentation.py:235-246) for the kept points of a whole batch: every sample's
+    label table, optionally mapped, padded with the background label (the instance id one past the table = "no instance"),
+    gathered through the sample's instance ids.  instance_ids: list of int64 [P_b]; semantic_instance_labels: list of int64
+    [n_instances_b].  -> int64 [P'] on the device, in the collated row order (collate_fn's `gt_segmentation`)."""
+    dev = vox["coords"].device
+    tables, base, at = [], [], 0
+    for lab in semantic_instance_labels:
+        lab = torch.as_tensor(lab, dtype=torch.long)
+        if label_mapper is not None:
+            lab = torch.as_tensor(label_mapper, dtype=torch.long)[lab]
+        tables.append(torch.nn.functional.pad(lab, (0, 1), value=background_label))
+        base.append(at)
+        at += len(lab) + 1
+    table = torch.cat(tables).to(dev)
+    ids = torch.cat([torch.as_tensor(i, dtype=torch.long) for i in instance_ids]).to(dev)
+    kept = vox["kept"].long()
+    sample_of = torch.bucketize(kept, torch.as_tensor(sample_ptr, dtype=torch.long, device=dev), right=True) - 1
+    return table[torch.as_tensor(base, dtype=torch.long, device=dev)[sample_of] + ids[kept]]
+
+
 def convert_and_collate(samples, *, spatial_size, scale, shift=0, start=None, coord_noise_sigma=0.0, theta=None, mirror=None,
                         sub_pixel_offset=None, color_noise_sigma=0.0, normal_noise_sigma=0.0, use_color=True, use_ones=False,
                         use_normal=True, device="cuda"):

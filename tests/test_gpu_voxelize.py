@@ -54,6 +54,13 @@ def test_seeded_conversion_draws_like_the_reference(cuda):
     assert torch.equal(data[1].cpu(), c["features_batch"])
     for a, proj, sh in zip(aug, c["coords_projection"], c["coords_shift"]):
         assert torch.equal(a["coords_projection"], proj) and torch.equal(a["coords_shift"], sh)
+    # labels of the kept points (get_semantic_segmentation_labels + collate_fn's gt_segmentation)
+    ptr = [0]
+    for pts, _, _ in c["inputs"]:
+        ptr.append(ptr[-1] + len(pts))
+    vox = dict(coords=data[0], kept=kept)
+    seg = Z.segmentation_labels_batch(vox, ptr, c["instance_ids"], c["semantic_instance_labels"], background_label=0)
+    assert torch.equal(seg.cpu(), c["gt_segmentation"])
 
 
 @pytest.mark.parametrize("seed,sizes,start", [(0, [5000, 0, 3000, 1], None), (1, [257, 4097], (7, 3, 0)), (2, [1], None)])
