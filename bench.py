@@ -324,7 +324,12 @@ def main():
             torch.cuda.synchronize()
             t_g = time.perf_counter() - t_g
             settle += n_distinct
-            if prev is not None and abs(t_g - prev) <= 0.03 * prev:
+            done = prev is not None and abs(t_g - prev) <= 0.03 * prev
+            if world > 1:      # every rank must run the same number of steps (each one holds an allreduce): stop together
+                flag = torch.tensor([1.0 if done else 0.0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                done = bool(flag.item() > 0.5)
+            if done:
                 break
             prev = t_g
         diag.setdefault("settle_steps", []).append(settle)
