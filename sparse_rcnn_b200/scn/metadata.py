@@ -478,10 +478,12 @@ def stage_to_device(tensors, device):
     need = sum((t.numel() * t.element_size() + 255) // 256 * 256 for t in todo) + 256
     slot = ring[1] % 3
     ring[1] += 1
-    for k in ring[2][slot]:      # copies staged into this buffer and never taken die with its contents
-        _staged.pop(k, None)
-    ring[2][slot] = [id(t) for t in todo]
     arena = ring[0][slot]
+    for k in ring[2][slot]:      # copies staged into THIS buffer and never taken die with its contents
+        hit = _staged.get(k)
+        if hit is not None and arena is not None and hit[1].untyped_storage().data_ptr() == arena.buf.untyped_storage().data_ptr():
+            del _staged[k]
+    ring[2][slot] = [id(t) for t in todo]
     if arena is None or arena.buf.numel() < need:
         arena = ring[0][slot] = Arena((need + (1 << 24) - 1) >> 24 << 24, device)      # 16 MB granules, grow only
     arena.off = 0
