@@ -38,6 +38,15 @@ def test_run_many_equals_one_scene_at_a_time(cuda, monkeypatch, precision, tol, 
                 for k in keys:
                     assert g[k].shape == r[k].shape, k
                     assert rel_err(g[k], r[k]) < tol, (workers, k, rel_err(g[k], r[k]))
+    # backbone geometry built ahead by the prefetcher thread into recycled arenas (off by default: measured slower): same results,
+    # with scene tensors that repeat in the list (one geometry per occurrence) and with one worker as well
+    for workers in (1, 3):
+        got = inf.run_many(scenes + scenes[:2], boxes + boxes[:2], workers=workers, geometry_ahead=True)
+        torch.cuda.synchronize()
+        assert len(got) == len(ref) + 2 and not inf._prefetcher.pending
+        for g, r in zip(got, ref + ref[:2]):
+            for k in keys:
+                assert g[k].shape == r[k].shape and rel_err(g[k], r[k]) < tol, (workers, k, rel_err(g[k], r[k]))
     # consume runs on the worker's stream and replaces the result; order is the scene order
     out = inf.run_many(scenes, boxes, workers=2, consume=lambda i, res: (i, res["mpn_class"].argmax(1).cpu()))
     assert [o[0] for o in out] == list(range(6))
