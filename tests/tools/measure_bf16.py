@@ -3,9 +3,9 @@ the BASELINE scene.  Runs the CPU oracle's FeatureExtractor + segmentation head 
 gathered features and the weights of every convolution rounded to fp32 (reference) / TF32 (10-bit mantissa, round to nearest,
 what the tcgen05 kind::tf32 path computes after scn_round_tf32) / bf16 (7-bit mantissa, round to nearest even), and reports
 the relative error (max |a - b| / max |b|, the tests' rel_err) of every encoder / decoder output and the logits, plus the
-gradient of the loss wrt the input features.  CPU only: python scripts/measure_bf16.py"""
+gradient of the loss wrt the input features.  CPU only: python tests/tools/measure_bf16.py"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
 import scn_oracle as O
