@@ -64,3 +64,24 @@ def collate(coords_list, features_list):
     """collate_fn: coords [sum P', 4] int64 with the sample index in the last column, features concatenated, batch_splits."""
     coords = np.concatenate([np.concatenate([c, np.full((len(c), 1), i, np.int64)], 1) for i, c in enumerate(coords_list)])
     return coords, np.concatenate(features_list), [len(c) for c in coords_list]
+
+
+def random_cut(disc, size, border, order, draws):
+    """random_cut_out :49-78 with its draws given: `order` = the drawn order of the dimensions, `draws` = an iterator of
+    callables (lo, hi) -> int consumed only where the reference calls randint.  -> (start int64 [3], is_inside bool [P])."""
+    disc = np.asarray(disc, np.int64)
+    start = np.zeros(3, np.int64)
+    inside = np.ones(len(disc), bool)
+    for dim in order:
+        if not inside.any():
+            break
+        vals = disc[inside, dim]
+        lo = int(vals.min()) - int(border[dim])
+        hi = int(vals.max()) + 1 - int(size[dim]) + int(border[dim])
+        if hi <= lo:
+            start[dim] = lo
+        else:
+            start[dim] = next(draws)(lo, hi)
+            rel = disc[:, dim] - start[dim]
+            inside &= (rel >= 0) & (rel < int(size[dim]))
+    return start, inside

@@ -63,6 +63,30 @@ def test_seeded_conversion_draws_like_the_reference(cuda):
     assert torch.equal(seg.cpu(), c["gt_segmentation"])
 
 
+def test_training_loader_configuration(cuda):
+    """The shipped TRAINING augmentation (scannet_config/run.py:971-984): random cut-out, random mirror / rotation / offset,
+    coordinate noise, one colour-noise value per kept point -- every draw made by the code under test, sample after sample;
+    golden from the unmodified convert_sample + collate_fn under the same seed."""
+    from sparse_rcnn_b200 import voxelize as Z
+    c = torch.load(GOLDEN)[4]
+    torch.manual_seed(c["seed"])
+    data, aug, kept = Z.convert_and_collate(c["inputs"], spatial_size=c["spatial_size"], scale=c["scale"], shift=None,
+                                            coord_noise_sigma=0.1, color_noise_sigma=0.1, common_color_noise=False,
+                                            normal_noise_sigma=0, common_normal_noise=False, device=cuda)
+    assert data[4] == list(c["batch_splits"]) and 0 < sum(data[4]) < sum(len(p[0]) for p in c["inputs"])      # points were cut away
+    assert torch.equal(data[0].cpu(), c["coords_batch"])
+    assert torch.equal(data[1].cpu(), c["features_batch"])
+    inside = torch.cat(c["remaining"])
+    assert torch.equal(kept.cpu().long(), inside.nonzero().flatten())
+    for a, sh in zip(aug, c["coords_shift"]):
+        assert torch.equal(a["coords_shift"], sh)
+    ptr = [0]
+    for pts, _, _ in c["inputs"]:
+        ptr.append(ptr[-1] + len(pts))
+    seg = Z.segmentation_labels_batch(dict(coords=data[0], kept=kept), ptr, c["instance_ids"], c["semantic_instance_labels"], 0)
+    assert torch.equal(seg.cpu(), c["gt_segmentation"])
+
+
 @pytest.mark.parametrize("seed,sizes,start", [(0, [5000, 0, 3000, 1], None), (1, [257, 4097], (7, 3, 0)), (2, [1], None)])
 def test_against_the_oracle(cuda, seed, sizes, start):
     """Ragged batches with empty and one-point samples, a drawn cut-out, ones column, no normals."""

@@ -34,7 +34,7 @@ def run_case(case):
 
 def test_oracle_reproduces_the_reference():
     cases = torch.load(GOLDEN)
-    assert len(cases) == 4
+    assert len(cases) == 6
     for case in cases[:3]:
         run_case(case)
     # the fully seeded case (every draw made by the reference): the oracle with the recorded projection, and the shift the
@@ -62,3 +62,26 @@ def test_start_positions_form_and_empty_sample():
     assert in2.sum() < in0.sum() + 500 and (c2 >= 0).all() and (c2 < 32).all()
     e, ine, cs = V.voxelize_sample(np.zeros((0, 3), np.float32), proj, [0, 0, 0], (8, 8, 8), shift=0)
     assert e.shape == (0, 3) and ine.shape == (0,)
+
+
+def test_random_cut_out_draws_like_the_reference():
+    """sparse_rcnn_b200.voxelize.draw_random_cut (the host logic of the training loader's random cut-out; pure torch, runs on
+    any device) and the oracle's random_cut against the unmodified reference function's outputs: same start positions, same
+    points inside, same coordinates -- with the reference's RNG calls in the reference's order."""
+    from sparse_rcnn_b200 import voxelize as Z
+    cut = torch.load(GOLDEN)[5]["cut_cases"]
+    assert len(cut) == 4
+    branches = set()
+    for c in cut:
+        torch.manual_seed(c["seed"])
+        start, inside = Z.draw_random_cut(c["disc"], c["size"], c["border"])
+        assert torch.equal(start, c["start"]) and torch.equal(inside, c["is_inside"])
+        assert torch.equal(c["disc"][inside] - start, c["coords"])
+        # the oracle with the same draws
+        torch.manual_seed(c["seed"])
+        order = torch.multinomial(torch.ones(3), 3).tolist()
+        draws = iter(lambda: (lambda lo, hi: int(torch.randint(lo, hi, ()))), None)
+        s2, in2 = V.random_cut(c["disc"].numpy(), c["size"], c["border"], order, draws)
+        assert np.array_equal(s2, c["start"].numpy()) and np.array_equal(in2, c["is_inside"].numpy())
+        branches.add(bool(inside.all()))
+    assert branches == {True, False}      # both the "extent fits" and the "draw and cut" branch were taken
