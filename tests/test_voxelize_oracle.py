@@ -85,3 +85,25 @@ def test_random_cut_out_draws_like_the_reference():
         assert np.array_equal(s2, c["start"].numpy()) and np.array_equal(in2, c["is_inside"].numpy())
         branches.add(bool(inside.all()))
     assert branches == {True, False}      # both the "extent fits" and the "draw and cut" branch were taken
+
+
+def test_host_side_draws_and_label_gather_on_cpu():
+    """Host logic of sparse_rcnn_b200.voxelize that needs no GPU: the first sample's distortion-matrix draws of the seeded
+    golden (get_coord_distortion_matrix with theta / mirror left to the RNG) and the label gather with a label mapper."""
+    from sparse_rcnn_b200 import voxelize as Z
+    c = torch.load(GOLDEN)[3]
+    torch.manual_seed(c["seed"])
+    rot = Z.coord_distortion_matrix(torch.float32, c["sigma"], None, None)
+    assert torch.equal(rot * c["scale"], c["coords_projection"][0])
+    # every point kept (that case cuts nothing away): gt_segmentation == table[instance ids]
+    n = [len(p[0]) for p in c["inputs"]]
+    assert c["batch_splits"] == n
+    ptr = [0, n[0], n[0] + n[1]]
+    vox = dict(coords=torch.zeros(1), kept=torch.arange(ptr[-1], dtype=torch.int32))
+    seg = Z.segmentation_labels_batch(vox, ptr, c["instance_ids"], c["semantic_instance_labels"], background_label=0)
+    assert torch.equal(seg, c["gt_segmentation"])
+    mapper = torch.arange(40) * 2
+    seg2 = Z.segmentation_labels_batch(vox, ptr, c["instance_ids"], c["semantic_instance_labels"], background_label=-100, label_mapper=mapper)
+    want = torch.where(c["gt_segmentation"] == 0, torch.tensor(-100), c["gt_segmentation"] * 2)
+    # label 0 never occurs among the instance labels (drawn from 1..18), so a zero in the golden is the background
+    assert torch.equal(seg2, want)
